@@ -1,0 +1,132 @@
+"""ctypes binding of libmfvidip.so (include/mfvi_dip.h) — the only way the Python host reaches the GPU kernels.
+
+There is no CPU or PyTorch fallback: if the shared library is missing the import fails loudly, and every
+call with a non-zero return code raises `MfviError` carrying `mfvi_last_error()`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libmfvidip.so")
+
+ABI_VERSION = 1
+MATH_FP32 = 0
+MATH_TF32 = 1
+STREAM_WEIGHTS = 0
+STREAM_INPUT_JITTER = 1
+
+
+class MfviError(RuntimeError):
+    pass
+
+
+class PhiloxKey(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("step", C.c_uint32), ("sample0", C.c_uint32), ("step_dev", C.c_void_p)]
+
+
+class View(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("sstride", C.c_longlong), ("hstride", C.c_int), ("wstride", C.c_int)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("S", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int), ("KH", C.c_int), ("KW", C.c_int),
+                ("stride", C.c_int), ("Hin", C.c_int), ("Win", C.c_int), ("Hout", C.c_int), ("Wout", C.c_int),
+                ("math", C.c_int)]
+
+
+_P = C.c_void_p
+_LL = C.c_longlong
+_I = C.c_int
+_F = C.c_float
+_D = C.c_double
+_SZ = C.c_size_t
+_U32 = C.c_uint32
+_CD = C.POINTER(ConvDesc)
+
+# name -> argtypes (the trailing stream argument is appended automatically by `call`)
+_SIGS = {
+    "mfvi_philox_raw_fill": [_P, _SZ, PhiloxKey, _U32],
+    "mfvi_philox_normal_fill": [_P, _SZ, PhiloxKey, _U32],
+    "mfvi_sample_weights": [_P, _P, _SZ, _I, _P, _LL, PhiloxKey, _P, _LL],
+    "mfvi_conv2d_fwd": [_CD, View, _P, _P, _LL, View, _P],
+    "mfvi_conv2d_dgrad": [_CD, View, _P, _LL, View, _I],
+    "mfvi_conv2d_wgrad": [_CD, View, View, _P, _P, _LL],
+    "mfvi_kl_reparam_fwd_bwd": [_P, _P, _SZ, _F, _D, _I, _F, _P, _P, _LL, _I, _P, _LL, PhiloxKey, _F, _P, _P, _P, _I],
+    "mfvi_bn_act_pad_fwd": [View, _I, _I, _I, _I, _P, _P, _P, _I, _I, View],
+    "mfvi_cat_up_fwd": [View, _I, _P, _P, _P, View, _I, _P, _P, _P, _I, _I, _I, _I, View, _P],
+    "mfvi_pad_act_bwd": [View, _I, _I, _I, _I, _I, View, _P, _P, _P, _I, View, _P],
+    "mfvi_bn_bwd_apply": [View, View, _I, _I, _I, _I, _P, _P, _P, View, _P, _P],
+    "mfvi_cat_up_bwd": [View, _I, _I, _I, _I, View, _I, _P, _P, _P, View, _P, View, _I, _P, _P, _P, View, _P],
+    "mfvi_bn_running_update": [_P, _P, _P, _P, _P, _I, _I, _F, _P, _P],
+    "mfvi_gauss_nll_fwd_bwd": [_I, View, _I, _I, _I, _I, _I, _P, _P, _P, View],
+    "mfvi_mse_fwd_bwd": [_P, _LL, _P, _SZ, _I, _P, _P],
+    "mfvi_radon_fwd": [View, _I, _I, _I, _I, _P, _I, _P],
+    "mfvi_radon_bwd": [_P, _I, _I, _I, _I, _P, _I, View],
+    "mfvi_input_jitter_pad": [_P, _P, _I, _I, _I, _F, _I, PhiloxKey, View],
+    "mfvi_adamw_step": [_P, _P, _P, _P, _SZ, _F, _F, _F, _F, _F, _I, _P, _P],
+    "mfvi_counter_add": [_P, _U32],
+    "mfvi_fill_f32": [_P, _SZ, _F],
+    "mfvi_nchw_to_nhwc": [_P, _P, _I, _I, _I, _I],
+    "mfvi_nhwc_to_nchw": [_P, _P, _I, _I, _I, _I],
+}
+
+EXPORTS = ["mfvi_abi_version", "mfvi_last_error"] + list(_SIGS)
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise MfviError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` or "
+            f"`bash mfvi_dip_mia_b200/csrc/build.sh`. There is no CPU/PyTorch fallback for this path.")
+    lib = C.CDLL(LIB_PATH)
+    lib.mfvi_abi_version.restype = C.c_int
+    lib.mfvi_last_error.restype = C.c_char_p
+    got = lib.mfvi_abi_version()
+    if got != ABI_VERSION:
+        raise MfviError(f"libmfvidip ABI version {got}, host expects {ABI_VERSION}: rebuild the library")
+    for name, args in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = list(args) + [_P]
+        fn.restype = C.c_int
+    return lib
+
+
+lib = _load()
+launch_count = 0   # number of kernel-launching C-ABI calls made by this process (bench.py reports it)
+
+
+def call(name: str, *args, stream=None):
+    """Invoke `name(*args, stream)`; raises MfviError on a non-zero return code."""
+    global launch_count
+    if stream is None:
+        stream = torch.cuda.current_stream().cuda_stream
+    rc = getattr(lib, name)(*args, stream)
+    launch_count += 1
+    if rc != 0:
+        raise MfviError(f"{name} failed (rc={rc}): {lib.mfvi_last_error().decode()}")
+
+
+def require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise MfviError(f"{what}: tensor is on {t.device}; this path runs only on a CUDA device (sm_100a) — "
+                        "there is no CPU fallback")
+
+
+def ptr(t):
+    """Device pointer of a tensor (or NULL for None)."""
+    return None if t is None else t.data_ptr()
+
+
+def view(t: torch.Tensor, broadcast: bool = False) -> View:
+    """MfviView of an NHWC tensor (S,H,W,C) (channel stride must be 1; other strides arbitrary, in elements)."""
+    assert t.dim() == 4 and t.dtype == torch.float32 and (t.stride(3) == 1 or t.shape[3] == 1), (t.shape, t.stride())
+    ss = 0 if (broadcast or t.shape[0] == 1) else t.stride(0)
+    return View(t.data_ptr(), ss, t.stride(1), t.stride(2))
+
+
+def key(seed: int, step: int = 0, sample0: int = 0, step_dev: torch.Tensor | None = None) -> PhiloxKey:
+    return PhiloxKey(seed & 0xFFFFFFFFFFFFFFFF, step & 0xFFFFFFFF, sample0, ptr(step_dev))

@@ -1,0 +1,10 @@
+#!/usr/bin/env bash
+# Builds libmfvidip.so in-tree for sm_100a.  Usage: build.sh [extra nvcc flags]
+set -euo pipefail
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+SRCS="basic_kernels.cu elementwise.cu conv_simt.cu conv_dispatch.cu radon.cu"
+[ -f conv_tc.cu ] && SRCS="$SRCS conv_tc.cu"
+$NVCC -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
+  -Xcompiler -fPIC -shared -o libmfvidip.so $SRCS -lcuda "$@"
+echo "built $(pwd)/libmfvidip.so"

@@ -1,0 +1,549 @@
+// Skip-net elementwise path (models/common.py:77-135, models/skip.py:68,102 of the reference):
+// BatchNorm (train mode, per-sample statistics) + LeakyReLU(0.2) + ReflectionPad2d + x2 upsample + concat,
+// forward and backward.  NHWC fp32, HBM-bound: each thread owns one channel quad of one pixel (float4 when
+// C % 4 == 0), threads of a CTA are laid out [pixel-slot][channel-group] so that a warp touches contiguous
+// memory; per-(sample,channel) reductions go registers -> shared -> one double atomic per channel per CTA.
+#include "common.cuh"
+
+namespace mfvi {
+
+constexpr int kEwThreads = 256;
+constexpr int kMaxC = 512;  // per-kernel channel limit of the smem scale/shift tables
+
+struct EwGeom {
+  int V;      // vector width (4 or 1)
+  int G;      // channel groups = ceil(C / V)
+  int PPB;    // pixel slots per CTA iteration
+};
+
+static inline EwGeom ew_geom(int C, bool aligned) {
+  EwGeom g;
+  g.V = (C % 4 == 0 && aligned) ? 4 : 1;
+  g.G = (C + g.V - 1) / g.V;
+  g.PPB = kEwThreads / g.G;
+  if (g.PPB < 1) g.PPB = 1;
+  return g;
+}
+
+static inline bool view_vec_ok(const MfviView& v) {
+  return (reinterpret_cast<uintptr_t>(v.ptr) % 16 == 0) && (v.sstride % 4 == 0) && (v.hstride % 4 == 0) &&
+         (v.wstride % 4 == 0);
+}
+
+template <int V>
+struct Vec;
+template <>
+struct Vec<4> {
+  float v[4];
+  __device__ __forceinline__ void load(const float* p) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <>
+struct Vec<1> {
+  float v[1];
+  __device__ __forceinline__ void load(const float* p) { v[0] = *p; }
+  __device__ __forceinline__ void store(float* p) const { *p = v[0]; }
+};
+
+// Per-CTA tables: scale[c] = gamma*invstd, shift[c] = beta - mean*scale  (z = y*scale + shift),
+// mean[c], invstd[c] for sample s.
+__device__ __forceinline__ void load_bn_tables(const double* __restrict__ sums, const float* __restrict__ gamma,
+                                               const float* __restrict__ beta, int s, int C, double inv_count,
+                                               float* sm_scale, float* sm_shift, float* sm_mean, float* sm_invstd) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean = 0.f, invstd = 1.f;
+    if (sums != nullptr) bn_mean_invstd(sums + ((size_t)s * C + c) * 2, inv_count, mean, invstd);
+    const float g = gamma != nullptr ? gamma[c] : 1.f;
+    const float b = beta != nullptr ? beta[c] : 0.f;
+    const float sc = g * invstd;
+    sm_scale[c] = sc;
+    sm_shift[c] = b - mean * sc;
+    if (sm_mean) sm_mean[c] = mean;
+    if (sm_invstd) sm_invstd[c] = invstd;
+  }
+}
+
+// CTA-level reduction of per-thread partial sums for a fixed channel (threads [slot][group] layout),
+// then one double atomicAdd per channel into dst[c*2 + {0,1}].
+template <int V>
+__device__ __forceinline__ void cta_reduce_2(float (&a)[V], float (&b)[V], int group, int C, float* sm_a, float* sm_b,
+                                             double* __restrict__ dst, bool active) {
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    sm_a[c] = 0.f;
+    sm_b[c] = 0.f;
+  }
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const int c = group * V + j;
+      if (c < C) {
+        atomicAdd(&sm_a[c], a[j]);
+        atomicAdd(&sm_b[c], b[j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(&dst[(size_t)c * 2 + 0], (double)sm_a[c]);
+    atomicAdd(&dst[(size_t)c * 2 + 1], (double)sm_b[c]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// F1: xp = reflect_pad(act(bn(y)))            grid = (chunks, S)
+template <int V>
+__global__ void __launch_bounds__(kEwThreads)
+k_bn_act_pad_fwd(MfviView y, int H, int W, int C, const double* __restrict__ sums, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, int act, int pad, MfviView xp, int G, int PPB) {
+  __shared__ float sm_scale[kMaxC], sm_shift[kMaxC];
+  const int s = blockIdx.y;
+  load_bn_tables(sums, gamma, beta, s, C, 1.0 / ((double)H * W), sm_scale, sm_shift, nullptr, nullptr);
+  __syncthreads();
+  const int group = threadIdx.x % G, slot = threadIdx.x / G;
+  if (slot >= PPB) return;
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  const int npix = Hp * Wp;
+  const int c0 = group * V;
+  for (int p = blockIdx.x * PPB + slot; p < npix; p += gridDim.x * PPB) {
+    const int hp = p / Wp, wp = p % Wp;
+    const int h = reflect_idx(hp - pad, H), w = reflect_idx(wp - pad, W);
+    Vec<V> t;
+    t.load(y.ptr + view_off(y, s, h, w) + c0);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float z = fmaf(t.v[j], sm_scale[c0 + j], sm_shift[c0 + j]);
+      if (act) z = z > 0.f ? z : kLreluSlope * z;
+      t.v[j] = z;
+    }
+    t.store(xp.ptr + view_off(xp, s, hp, wp) + c0);
+  }
+}
+
+// x2 upsample source taps along one dimension (align_corners=False).  i: hi-res index, n: low-res size.
+__device__ __forceinline__ void up_taps(int i, int n, int mode, int& i0, int& i1, float& w0, float& w1) {
+  if (mode == 1) {  // nearest
+    i0 = i >> 1; i1 = i0; w0 = 1.f; w1 = 0.f;
+    return;
+  }
+  float src = 0.5f * (float)i - 0.25f;
+  src = src < 0.f ? 0.f : src;
+  i0 = (int)src;
+  const float f = src - (float)i0;
+  i1 = i0 + 1 < n ? i0 + 1 : n - 1;
+  w0 = 1.f - f;
+  w1 = f;
+}
+
+// F2: A = cat(lrelu(bn(ys)), up2x(lrelu(bn(yd)))), sumsA += (sum, sumsq)      grid = (chunks, S)
+template <int V>
+__global__ void __launch_bounds__(kEwThreads)
+k_cat_up_fwd(MfviView ys, int Cs, const double* __restrict__ sums_s, const float* __restrict__ gamma_s,
+             const float* __restrict__ beta_s, MfviView yd, int Cd, const double* __restrict__ sums_d,
+             const float* __restrict__ gamma_d, const float* __restrict__ beta_d, int H, int W, int mode, MfviView A,
+             double* __restrict__ sumsA, int G, int PPB) {
+  __shared__ float sm_scale[kMaxC], sm_shift[kMaxC], sm_a[kMaxC], sm_b[kMaxC];
+  const int s = blockIdx.y;
+  const int C = Cs + Cd;
+  const int h2 = H / 2, w2 = W / 2;
+  if (Cs > 0) load_bn_tables(sums_s, gamma_s, beta_s, s, Cs, 1.0 / ((double)H * W), sm_scale, sm_shift, nullptr, nullptr);
+  load_bn_tables(sums_d, gamma_d, beta_d, s, Cd, 1.0 / ((double)h2 * w2), sm_scale + Cs, sm_shift + Cs, nullptr, nullptr);
+  __syncthreads();
+  const int group = threadIdx.x % G, slot = threadIdx.x / G;
+  const bool active = slot < PPB;
+  const int c0 = group * V;
+  float acc1[V], acc2[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) acc1[j] = acc2[j] = 0.f;
+  if (active) {
+    const int npix = H * W;
+    for (int p = blockIdx.x * PPB + slot; p < npix; p += gridDim.x * PPB) {
+      const int h = p / W, w = p % W;
+      Vec<V> o;
+      if (c0 < Cs) {  // Cs % V == 0 is guaranteed by the host (V falls back to 1 otherwise)
+        o.load(ys.ptr + view_off(ys, s, h, w) + c0);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const float z = fmaf(o.v[j], sm_scale[c0 + j], sm_shift[c0 + j]);
+          o.v[j] = z > 0.f ? z : kLreluSlope * z;
+        }
+      } else {
+        const int cd = c0 - Cs;
+        int ha, hb, wa, wb;
+        float wha, whb, wwa, wwb;
+        up_taps(h, h2, mode, ha, hb, wha, whb);
+        up_taps(w, w2, mode, wa, wb, wwa, wwb);
+        Vec<V> t00, t01, t10, t11;
+        t00.load(yd.ptr + view_off(yd, s, ha, wa) + cd);
+        t01.load(yd.ptr + view_off(yd, s, ha, wb) + cd);
+        t10.load(yd.ptr + view_off(yd, s, hb, wa) + cd);
+        t11.load(yd.ptr + view_off(yd, s, hb, wb) + cd);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const float sc = sm_scale[c0 + j], sh = sm_shift[c0 + j];
+          float z00 = fmaf(t00.v[j], sc, sh), z01 = fmaf(t01.v[j], sc, sh);
+          float z10 = fmaf(t10.v[j], sc, sh), z11 = fmaf(t11.v[j], sc, sh);
+          z00 = z00 > 0.f ? z00 : kLreluSlope * z00;
+          z01 = z01 > 0.f ? z01 : kLreluSlope * z01;
+          z10 = z10 > 0.f ? z10 : kLreluSlope * z10;
+          z11 = z11 > 0.f ? z11 : kLreluSlope * z11;
+          o.v[j] = wha * (wwa * z00 + wwb * z01) + whb * (wwa * z10 + wwb * z11);
+        }
+      }
+      o.store(A.ptr + view_off(A, s, h, w) + c0);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        acc1[j] += o.v[j];
+        acc2[j] = fmaf(o.v[j], o.v[j], acc2[j]);
+      }
+    }
+  }
+  cta_reduce_2<V>(acc1, acc2, group, C, sm_a, sm_b, sumsA + (size_t)s * C * 2, active);
+}
+
+// number of padded positions (per dimension) that reflect onto source index h: fills q[0..n)
+__device__ __forceinline__ int fold_sources(int h, int n, int pad, int (&q)[3]) {
+  int cnt = 0;
+  q[cnt++] = h + pad;
+  if (h >= 1 && h <= pad) q[cnt++] = pad - h;
+  if (h <= n - 2 && h >= n - 1 - pad) q[cnt++] = 2 * (n - 1) - h + pad;
+  return cnt;
+}
+
+// B1: g = fold_reflect(dxp) * act'(bn(y)), red += (sum g, sum g*xhat)      grid = (chunks, S)
+template <int V>
+__global__ void __launch_bounds__(kEwThreads)
+k_pad_act_bwd(MfviView dxp, int H, int W, int C, int pad, MfviView y, const double* __restrict__ sums,
+              const float* __restrict__ gamma, const float* __restrict__ beta, int act, MfviView g,
+              double* __restrict__ red, int G, int PPB) {
+  __shared__ float sm_scale[kMaxC], sm_shift[kMaxC], sm_mean[kMaxC], sm_invstd[kMaxC];
+  const int s = blockIdx.y;
+  load_bn_tables(sums, gamma, beta, s, C, 1.0 / ((double)H * W), sm_scale, sm_shift, sm_mean, sm_invstd);
+  __syncthreads();
+  const int group = threadIdx.x % G, slot = threadIdx.x / G;
+  const bool active = slot < PPB;
+  const int c0 = group * V;
+  float acc1[V], acc2[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) acc1[j] = acc2[j] = 0.f;
+  if (active) {
+    const int npix = H * W;
+    for (int p = blockIdx.x * PPB + slot; p < npix; p += gridDim.x * PPB) {
+      const int h = p / W, w = p % W;
+      int qh[3], qw[3];
+      const int nh = pad > 0 ? fold_sources(h, H, pad, qh) : (qh[0] = h, 1);
+      const int nw = pad > 0 ? fold_sources(w, W, pad, qw) : (qw[0] = w, 1);
+      Vec<V> a;
+#pragma unroll
+      for (int j = 0; j < V; ++j) a.v[j] = 0.f;
+      for (int ih = 0; ih < nh; ++ih)
+        for (int iw = 0; iw < nw; ++iw) {
+          Vec<V> t;
+          t.load(dxp.ptr + view_off(dxp, s, qh[ih], qw[iw]) + c0);
+#pragma unroll
+          for (int j = 0; j < V; ++j) a.v[j] += t.v[j];
+        }
+      Vec<V> yy;
+      yy.load(y.ptr + view_off(y, s, h, w) + c0);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const float z = fmaf(yy.v[j], sm_scale[c0 + j], sm_shift[c0 + j]);
+        float gg = a.v[j];
+        if (act && z <= 0.f) gg *= kLreluSlope;
+        const float xhat = (yy.v[j] - sm_mean[c0 + j]) * sm_invstd[c0 + j];
+        a.v[j] = gg;
+        acc1[j] += gg;
+        acc2[j] = fmaf(gg, xhat, acc2[j]);
+      }
+      a.store(g.ptr + view_off(g, s, h, w) + c0);
+    }
+  }
+  cta_reduce_2<V>(acc1, acc2, group, C, sm_scale, sm_shift, red + (size_t)s * C * 2, active);
+}
+
+// B2: dy = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)); block (0,0) also writes dgamma/dbeta.
+template <int V>
+__global__ void __launch_bounds__(kEwThreads)
+k_bn_bwd_apply(MfviView g, MfviView y, int S, int H, int W, int C, const double* __restrict__ sums,
+               const double* __restrict__ red, const float* __restrict__ gamma, MfviView dy,
+               float* __restrict__ dgamma, float* __restrict__ dbeta, int G, int PPB) {
+  __shared__ float sm_k[kMaxC], sm_mean[kMaxC], sm_invstd[kMaxC], sm_m1[kMaxC], sm_m2[kMaxC];
+  const int s = blockIdx.y;
+  const double inv_count = 1.0 / ((double)H * W);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean, invstd;
+    bn_mean_invstd(sums + ((size_t)s * C + c) * 2, inv_count, mean, invstd);
+    sm_mean[c] = mean;
+    sm_invstd[c] = invstd;
+    sm_k[c] = (gamma != nullptr ? gamma[c] : 1.f) * invstd;
+    sm_m1[c] = (float)(red[((size_t)s * C + c) * 2 + 0] * inv_count);
+    sm_m2[c] = (float)(red[((size_t)s * C + c) * 2 + 1] * inv_count);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && dgamma != nullptr) {
+      double dg = 0.0, db = 0.0;
+      for (int ss = 0; ss < S; ++ss) {
+        db += red[((size_t)ss * C + c) * 2 + 0];
+        dg += red[((size_t)ss * C + c) * 2 + 1];
+      }
+      dgamma[c] = (float)dg;
+      dbeta[c] = (float)db;
+    }
+  }
+  __syncthreads();
+  const int group = threadIdx.x % G, slot = threadIdx.x / G;
+  if (slot >= PPB) return;
+  const int c0 = group * V;
+  const int npix = H * W;
+  for (int p = blockIdx.x * PPB + slot; p < npix; p += gridDim.x * PPB) {
+    const int h = p / W, w = p % W;
+    Vec<V> gg, yy;
+    gg.load(g.ptr + view_off(g, s, h, w) + c0);
+    yy.load(y.ptr + view_off(y, s, h, w) + c0);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float xhat = (yy.v[j] - sm_mean[c0 + j]) * sm_invstd[c0 + j];
+      gg.v[j] = sm_k[c0 + j] * (gg.v[j] - sm_m1[c0 + j] - xhat * sm_m2[c0 + j]);
+    }
+    gg.store(dy.ptr + view_off(dy, s, h, w) + c0);
+  }
+}
+
+// B3a: skip branch of the concat: gs = dA[:, :Cs] * lrelu'(bn(ys)), red_s += …
+template <int V>
+__global__ void __launch_bounds__(kEwThreads)
+k_cat_bwd_skip(MfviView dA, int H, int W, MfviView ys, int Cs, const double* __restrict__ sums_s,
+               const float* __restrict__ gamma_s, const float* __restrict__ beta_s, MfviView gs,
+               double* __restrict__ red_s, int G, int PPB) {
+  __shared__ float sm_scale[kMaxC], sm_shift[kMaxC], sm_mean[kMaxC], sm_invstd[kMaxC];
+  const int s = blockIdx.y;
+  load_bn_tables(sums_s, gamma_s, beta_s, s, Cs, 1.0 / ((double)H * W), sm_scale, sm_shift, sm_mean, sm_invstd);
+  __syncthreads();
+  const int group = threadIdx.x % G, slot = threadIdx.x / G;
+  const bool active = slot < PPB;
+  const int c0 = group * V;
+  float acc1[V], acc2[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) acc1[j] = acc2[j] = 0.f;
+  if (active) {
+    const int npix = H * W;
+    for (int p = blockIdx.x * PPB + slot; p < npix; p += gridDim.x * PPB) {
+      const int h = p / W, w = p % W;
+      Vec<V> d, yy;
+      d.load(dA.ptr + view_off(dA, s, h, w) + c0);
+      yy.load(ys.ptr + view_off(ys, s, h, w) + c0);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const float z = fmaf(yy.v[j], sm_scale[c0 + j], sm_shift[c0 + j]);
+        const float gg = z > 0.f ? d.v[j] : kLreluSlope * d.v[j];
+        const float xhat = (yy.v[j] - sm_mean[c0 + j]) * sm_invstd[c0 + j];
+        d.v[j] = gg;
+        acc1[j] += gg;
+        acc2[j] = fmaf(gg, xhat, acc2[j]);
+      }
+      d.store(gs.ptr + view_off(gs, s, h, w) + c0);
+    }
+  }
+  cta_reduce_2<V>(acc1, acc2, group, Cs, sm_scale, sm_shift, red_s + (size_t)s * Cs * 2, active);
+}
+
+// weight with which low-res index k enters hi-res index i (0 if not a tap)
+__device__ __forceinline__ float up_weight_of(int i, int k, int n, int mode) {
+  if (i < 0 || i >= 2 * n) return 0.f;
+  int i0, i1;
+  float w0, w1;
+  up_taps(i, n, mode, i0, i1, w0, w1);
+  float wgt = 0.f;
+  if (i0 == k) wgt += w0;
+  if (i1 == k) wgt += w1;
+  return wgt;
+}
+
+// B3b: deeper branch: gd = up2x^T(dA[:, Cs:]) * lrelu'(bn(yd)), red_d += …   (iterates low-res pixels)
+template <int V>
+__global__ void __launch_bounds__(kEwThreads)
+k_cat_bwd_up(MfviView dA, int H, int W, int mode, int Cs, MfviView yd, int Cd, const double* __restrict__ sums_d,
+             const float* __restrict__ gamma_d, const float* __restrict__ beta_d, MfviView gd,
+             double* __restrict__ red_d, int G, int PPB) {
+  __shared__ float sm_scale[kMaxC], sm_shift[kMaxC], sm_mean[kMaxC], sm_invstd[kMaxC];
+  const int s = blockIdx.y;
+  const int h2 = H / 2, w2 = W / 2;
+  load_bn_tables(sums_d, gamma_d, beta_d, s, Cd, 1.0 / ((double)h2 * w2), sm_scale, sm_shift, sm_mean, sm_invstd);
+  __syncthreads();
+  const int group = threadIdx.x % G, slot = threadIdx.x / G;
+  const bool active = slot < PPB;
+  const int c0 = group * V;
+  float acc1[V], acc2[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) acc1[j] = acc2[j] = 0.f;
+  if (active) {
+    const int npix = h2 * w2;
+    for (int p = blockIdx.x * PPB + slot; p < npix; p += gridDim.x * PPB) {
+      const int kh = p / w2, kw = p % w2;
+      Vec<V> a;
+#pragma unroll
+      for (int j = 0; j < V; ++j) a.v[j] = 0.f;
+      for (int dh = -1; dh <= 2; ++dh) {
+        const int ih = 2 * kh + dh;
+        const float wh = up_weight_of(ih, kh, h2, mode);
+        if (wh == 0.f) continue;
+        for (int dw = -1; dw <= 2; ++dw) {
+          const int iw = 2 * kw + dw;
+          const float ww = up_weight_of(iw, kw, w2, mode);
+          if (ww == 0.f) continue;
+          Vec<V> t;
+          t.load(dA.ptr + view_off(dA, s, ih, iw) + Cs + c0);
+#pragma unroll
+          for (int j = 0; j < V; ++j) a.v[j] = fmaf(wh * ww, t.v[j], a.v[j]);
+        }
+      }
+      Vec<V> yy;
+      yy.load(yd.ptr + view_off(yd, s, kh, kw) + c0);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const float z = fmaf(yy.v[j], sm_scale[c0 + j], sm_shift[c0 + j]);
+        const float gg = z > 0.f ? a.v[j] : kLreluSlope * a.v[j];
+        const float xhat = (yy.v[j] - sm_mean[c0 + j]) * sm_invstd[c0 + j];
+        a.v[j] = gg;
+        acc1[j] += gg;
+        acc2[j] = fmaf(gg, xhat, acc2[j]);
+      }
+      a.store(gd.ptr + view_off(gd, s, kh, kw) + c0);
+    }
+  }
+  cta_reduce_2<V>(acc1, acc2, group, Cd, sm_scale, sm_shift, red_d + (size_t)s * Cd * 2, active);
+}
+
+// running stats of all BatchNorms (one thread per channel)
+__global__ void k_bn_running(const double* __restrict__ arena, const int* __restrict__ ch_off,
+                             const long long* __restrict__ sums_off, const int* __restrict__ Cs,
+                             const int* __restrict__ count, int n_bn, int S, float momentum,
+                             float* __restrict__ running_mean, float* __restrict__ running_var) {
+  const int b = blockIdx.x;
+  if (b >= n_bn) return;
+  const int C = Cs[b];
+  const double n = (double)count[b];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float rm = running_mean[ch_off[b] + c], rv = running_var[ch_off[b] + c];
+    for (int s = 0; s < S; ++s) {
+      const double* sm = arena + sums_off[b] + ((size_t)s * C + c) * 2;
+      const double mean = sm[0] / n;
+      double var = sm[1] / n - mean * mean;
+      var = var < 0.0 ? 0.0 : var;
+      const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
+      rm = (1.f - momentum) * rm + momentum * (float)mean;
+      rv = (1.f - momentum) * rv + momentum * (float)unbiased;
+    }
+    running_mean[ch_off[b] + c] = rm;
+    running_var[ch_off[b] + c] = rv;
+  }
+}
+
+static inline int ew_grid(int npix, int PPB) {
+  int blocks = (npix + PPB - 1) / PPB;
+  const int cap = kNumSMs * 4;
+  if (blocks > cap) blocks = cap;
+  return blocks < 1 ? 1 : blocks;
+}
+
+}  // namespace mfvi
+
+using namespace mfvi;
+
+#define MFVI_EW_DISPATCH(GEOM, KERNEL, GRID, ...)                                              \
+  do {                                                                                         \
+    if ((GEOM).V == 4)                                                                         \
+      KERNEL<4><<<GRID, kEwThreads, 0, as_stream(st)>>>(__VA_ARGS__, (GEOM).G, (GEOM).PPB);    \
+    else                                                                                       \
+      KERNEL<1><<<GRID, kEwThreads, 0, as_stream(st)>>>(__VA_ARGS__, (GEOM).G, (GEOM).PPB);    \
+  } while (0)
+
+extern "C" {
+
+int mfvi_bn_act_pad_fwd(MfviView y, int S, int H, int W, int C, const double* sums, const float* gamma,
+                        const float* beta, int act, int pad, MfviView xp, mfvi_stream_t st) {
+  MFVI_REQUIRE(y.ptr && xp.ptr, "bn_act_pad_fwd: null pointer");
+  MFVI_REQUIRE(C >= 1 && C <= kMaxC, "bn_act_pad_fwd: C=%d out of range (1..%d)", C, kMaxC);
+  MFVI_REQUIRE(pad >= 0 && pad < H && pad < W, "bn_act_pad_fwd: pad must be smaller than the image");
+  const EwGeom ge = ew_geom(C, view_vec_ok(y) && view_vec_ok(xp));
+  MFVI_REQUIRE(ge.G <= kEwThreads, "bn_act_pad_fwd: too many channel groups");
+  dim3 grid(ew_grid((H + 2 * pad) * (W + 2 * pad), ge.PPB), S);
+  MFVI_EW_DISPATCH(ge, k_bn_act_pad_fwd, grid, y, H, W, C, sums, gamma, beta, act, pad, xp);
+  return check_launch("bn_act_pad_fwd");
+}
+
+int mfvi_cat_up_fwd(MfviView ys, int Cs, const double* sums_s, const float* gamma_s, const float* beta_s,
+                    MfviView yd, int Cd, const double* sums_d, const float* gamma_d, const float* beta_d,
+                    int S, int H, int W, int mode, MfviView A, double* sumsA, mfvi_stream_t st) {
+  MFVI_REQUIRE(yd.ptr && A.ptr && sumsA, "cat_up_fwd: null pointer");
+  MFVI_REQUIRE(Cs == 0 || ys.ptr, "cat_up_fwd: null skip branch");
+  MFVI_REQUIRE(H % 2 == 0 && W % 2 == 0, "cat_up_fwd: H,W must be even (centre-crop concat is not supported)");
+  MFVI_REQUIRE(Cs + Cd <= kMaxC && Cd >= 1, "cat_up_fwd: channel count out of range");
+  MFVI_REQUIRE(mode == 0 || mode == 1, "cat_up_fwd: mode must be 0 (bilinear) or 1 (nearest)");
+  const bool al = view_vec_ok(yd) && view_vec_ok(A) && (Cs == 0 || view_vec_ok(ys)) && Cs % 4 == 0 && Cd % 4 == 0;
+  const EwGeom ge = ew_geom(Cs + Cd, al);
+  MFVI_REQUIRE(ge.G <= kEwThreads, "cat_up_fwd: too many channel groups");
+  dim3 grid(ew_grid(H * W, ge.PPB), S);
+  MFVI_EW_DISPATCH(ge, k_cat_up_fwd, grid, ys, Cs, sums_s, gamma_s, beta_s, yd, Cd, sums_d, gamma_d, beta_d, H, W, mode,
+                   A, sumsA);
+  return check_launch("cat_up_fwd");
+}
+
+int mfvi_pad_act_bwd(MfviView dxp, int S, int H, int W, int C, int pad, MfviView y, const double* sums,
+                     const float* gamma, const float* beta, int act, MfviView g, double* red, mfvi_stream_t st) {
+  MFVI_REQUIRE(dxp.ptr && y.ptr && g.ptr && red && sums, "pad_act_bwd: null pointer");
+  MFVI_REQUIRE(C >= 1 && C <= kMaxC, "pad_act_bwd: C out of range");
+  MFVI_REQUIRE(pad >= 0 && pad < H && pad < W, "pad_act_bwd: pad must be smaller than the image");
+  const EwGeom ge = ew_geom(C, view_vec_ok(dxp) && view_vec_ok(y) && view_vec_ok(g));
+  MFVI_REQUIRE(ge.G <= kEwThreads, "pad_act_bwd: too many channel groups");
+  dim3 grid(ew_grid(H * W, ge.PPB), S);
+  MFVI_EW_DISPATCH(ge, k_pad_act_bwd, grid, dxp, H, W, C, pad, y, sums, gamma, beta, act, g, red);
+  return check_launch("pad_act_bwd");
+}
+
+int mfvi_bn_bwd_apply(MfviView g, MfviView y, int S, int H, int W, int C, const double* sums, const double* red,
+                      const float* gamma, MfviView dy, float* dgamma, float* dbeta, mfvi_stream_t st) {
+  MFVI_REQUIRE(g.ptr && y.ptr && dy.ptr && sums && red, "bn_bwd_apply: null pointer");
+  MFVI_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "bn_bwd_apply: dgamma/dbeta must both be set or NULL");
+  MFVI_REQUIRE(C >= 1 && C <= kMaxC, "bn_bwd_apply: C out of range");
+  const EwGeom ge = ew_geom(C, view_vec_ok(g) && view_vec_ok(y) && view_vec_ok(dy));
+  MFVI_REQUIRE(ge.G <= kEwThreads, "bn_bwd_apply: too many channel groups");
+  dim3 grid(ew_grid(H * W, ge.PPB), S);
+  MFVI_EW_DISPATCH(ge, k_bn_bwd_apply, grid, g, y, S, H, W, C, sums, red, gamma, dy, dgamma, dbeta);
+  return check_launch("bn_bwd_apply");
+}
+
+int mfvi_cat_up_bwd(MfviView dA, int S, int H, int W, int mode, MfviView ys, int Cs, const double* sums_s,
+                    const float* gamma_s, const float* beta_s, MfviView gs, double* red_s, MfviView yd, int Cd,
+                    const double* sums_d, const float* gamma_d, const float* beta_d, MfviView gd, double* red_d,
+                    mfvi_stream_t st) {
+  MFVI_REQUIRE(dA.ptr && yd.ptr && gd.ptr && red_d, "cat_up_bwd: null pointer");
+  MFVI_REQUIRE(H % 2 == 0 && W % 2 == 0, "cat_up_bwd: H,W must be even");
+  MFVI_REQUIRE(Cs + Cd <= kMaxC && Cd >= 1, "cat_up_bwd: channel count out of range");
+  if (Cs > 0) {
+    MFVI_REQUIRE(ys.ptr && gs.ptr && red_s, "cat_up_bwd: null skip branch");
+    const EwGeom ge = ew_geom(Cs, view_vec_ok(dA) && view_vec_ok(ys) && view_vec_ok(gs));
+    dim3 grid(ew_grid(H * W, ge.PPB), S);
+    MFVI_EW_DISPATCH(ge, k_cat_bwd_skip, grid, dA, H, W, ys, Cs, sums_s, gamma_s, beta_s, gs, red_s);
+    if (int rc = check_launch("cat_up_bwd(skip)")) return rc;
+  }
+  const EwGeom ge = ew_geom(Cd, view_vec_ok(dA) && view_vec_ok(yd) && view_vec_ok(gd) && Cs % 4 == 0);
+  MFVI_REQUIRE(ge.G <= kEwThreads, "cat_up_bwd: too many channel groups");
+  dim3 grid(ew_grid((H / 2) * (W / 2), ge.PPB), S);
+  MFVI_EW_DISPATCH(ge, k_cat_bwd_up, grid, dA, H, W, mode, Cs, yd, Cd, sums_d, gamma_d, beta_d, gd, red_d);
+  return check_launch("cat_up_bwd(up)");
+}
+
+int mfvi_bn_running_update(const double* arena, const int* ch_off, const long long* sums_off, const int* C,
+                           const int* count, int n_bn, int S, float momentum, float* running_mean,
+                           float* running_var, mfvi_stream_t st) {
+  MFVI_REQUIRE(arena && ch_off && sums_off && C && count && running_mean && running_var, "bn_running_update: null pointer");
+  if (n_bn == 0) return 0;
+  k_bn_running<<<n_bn, 128, 0, as_stream(st)>>>(arena, ch_off, sums_off, C, count, n_bn, S, momentum, running_mean,
+                                                 running_var);
+  return check_launch("bn_running_update");
+}
+
+}  // extern "C"

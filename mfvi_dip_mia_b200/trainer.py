@@ -1,0 +1,179 @@
+"""The MFVI-DIP training step on flat buffers: the fast path behind the runners.
+
+One `MfviDipTrainer.step()` is exactly the reference hot loop (bayesian_optimization.py:1361-1372, task variants
+:2182-2188, :3033-3038, :576-582):
+
+    zero_grad -> net_input = saved + N(0,1)*reg_noise_std -> out = net(net_input)   [S weight samples at once]
+    -> nll (task head) -> kl -> loss = mean_s nll_s + temp*kl -> backward -> [all-reduce] -> AdamW
+
+executed as a static list of libmfvidip kernels on one stream and replayed as a CUDA graph.  MC samples are
+sharded over ranks (rank r owns global samples [r*S/G, (r+1)*S/G)); eps is keyed by the GLOBAL sample id, so
+results do not depend on the number of GPUs beyond fp32 summation order; one NCCL all-reduce (average) of the
+flat gradient per step is the only communication.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+from .engine import KL, NLL, SkipEngine, SkipSpec
+
+
+class LossHead:
+    """Data term of the ELBO and its gradient w.r.t. the network output (engine.out -> engine.dout)."""
+
+    def __init__(self, eng: SkipEngine, task: str, *, target=None, mask=None, theta_deg=None, sino=None, sr_factor=4):
+        self.eng, self.task = eng, task
+        dev = eng.device
+        S, H, W, Cn = eng.out.shape
+        f = lambda t: None if t is None else torch.as_tensor(t).to(dev, torch.float32).contiguous()
+        if task in ("den", "sr"):
+            sub = 1 if task == "den" else int(sr_factor)
+            t = f(target).reshape(-1)
+            assert t.numel() == (H // sub) * (W // sub), "target must be (H/sub, W/sub)"
+            self.target, self.sub = t, sub
+            assert Cn >= 2
+        elif task == "inp":
+            t = f(target)
+            assert Cn == 4 and t.numel() == 3 * H * W
+            # reference layout (1,3,H,W) -> NHWC (H,W,3)
+            self.target = t.reshape(3, H, W).permute(1, 2, 0).contiguous()
+            self.mask = f(mask).reshape(H, W).contiguous()
+        elif task == "ct":
+            th = torch.as_tensor(theta_deg, dtype=torch.float64)
+            self.theta = torch.deg2rad(th).to(dev, torch.float32).contiguous()
+            self.T = self.theta.numel()
+            self.sino_t = f(sino).reshape(-1)
+            assert self.sino_t.numel() == Cn * self.T * W
+            self.sino = torch.empty(S, Cn, self.T, W, dtype=torch.float32, device=dev)
+            self.dsino = torch.empty_like(self.sino)
+        else:
+            raise ValueError(f"unknown task {task!r}")
+
+    def run(self):
+        e = self.eng
+        S, H, W, Cn = e.out.shape
+        loss_ptr = e._aptr(NLL)
+        if self.task in ("den", "sr"):
+            L.call("mfvi_gauss_nll_fwd_bwd", 0, L.view(e.out), S, H, W, Cn, self.sub, self.target.data_ptr(), None,
+                   loss_ptr, L.view(e.dout))
+        elif self.task == "inp":
+            L.call("mfvi_gauss_nll_fwd_bwd", 1, L.view(e.out), S, H, W, Cn, 1, self.target.data_ptr(),
+                   self.mask.data_ptr(), loss_ptr, L.view(e.dout))
+        else:
+            n = Cn * self.T * W
+            L.call("mfvi_radon_fwd", L.view(e.out), S, Cn, H, W, self.theta.data_ptr(), self.T, self.sino.data_ptr())
+            L.call("mfvi_mse_fwd_bwd", self.sino.data_ptr(), n, self.sino_t.data_ptr(), n, S, loss_ptr,
+                   self.dsino.data_ptr())
+            L.call("mfvi_radon_bwd", self.dsino.data_ptr(), S, Cn, H, W, self.theta.data_ptr(), self.T, L.view(e.dout))
+
+
+class MfviDipTrainer:
+    def __init__(self, spec: SkipSpec, task: str, net_input: torch.Tensor, *, temp: float, sigma: float, lr: float,
+                 mc_samples: int = 1, seed: int = 0, reg_noise_std: float = 0.1, device="cuda", math_mode: int = L.MATH_FP32,
+                 target=None, mask=None, theta_deg=None, sino=None, sr_factor: int = 4,
+                 rank: int = 0, world_size: int = 1, process_group=None, use_graph: bool = True,
+                 nan_guard: Optional[bool] = None, betas=(0.9, 0.999), adam_eps: float = 1e-8, weight_decay: float = 0.0,
+                 kl_type: str = "reverse", prior_mu: float = 0.0):
+        device = torch.device(device)
+        assert net_input.dim() == 4 and net_input.shape[0] == 1, "net_input must be (1,C,H,W) like the reference's"
+        _, Cin, H, W = net_input.shape
+        assert Cin == spec.num_input_channels
+        if mc_samples % world_size:
+            raise ValueError(f"mc_samples={mc_samples} must be divisible by world_size={world_size}")
+        self.S_global, self.S = mc_samples, mc_samples // world_size
+        self.rank, self.world_size, self.pg = rank, world_size, process_group
+        self.temp, self.sigma, self.lr = float(temp), float(sigma), float(lr)
+        self.prior_mu = float(prior_mu)
+        # prior scale: sqrt(temp)*sigma handed to VIModule, which adds 1e-6 (bayesian_optimization.py:1335-1336, module.py:38)
+        self.prior_sigma_plus_eps = math.sqrt(self.temp) * self.sigma + 1e-6
+        self.direction = 0 if kl_type == "reverse" else 1
+        self.betas, self.adam_eps, self.weight_decay = betas, adam_eps, weight_decay
+        self.reg_noise_std = float(reg_noise_std)
+        self.seed = int(seed)
+        self.eng = SkipEngine(spec, H, W, self.S, device, math=math_mode)
+        self.head = LossHead(self.eng, task, target=target, mask=mask, theta_deg=theta_deg, sino=sino, sr_factor=sr_factor)
+        self.nan_guard = (task == "ct") if nan_guard is None else nan_guard   # CT runner skips the update on NaN loss
+        e = self.eng
+        self.saved = net_input[0].to(device, torch.float32).permute(1, 2, 0).contiguous()   # NHWC (H,W,C)
+        self.noise = None                       # injected jitter normals (tests)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=device)     # device-side step counter
+        self.m = torch.zeros_like(e.theta)
+        self.v = torch.zeros_like(e.theta)
+        self.losses = torch.zeros(2, dtype=torch.float64, device=device)
+        self.init_parameters(self.seed)
+        self.use_graph = use_graph
+        self._graph = None
+        self._warm = 0
+
+    # ------------------------------------------------------------------
+    def init_parameters(self, seed: int, mu=(0.0, 0.1), rho=(-3.0, 0.1)):
+        """VIModule.reset_parameters (module.py:56-62): mu ~ N(0,0.1), rho ~ N(-3,0.1); BN gamma=1, beta=0.
+        Same seed on every rank => identical replicas without a broadcast."""
+        e = self.eng
+        g = torch.Generator(device=e.device).manual_seed(seed)
+        e.theta.zero_()
+        e.mu.normal_(mu[0], mu[1], generator=g)
+        e.rho.normal_(rho[0], rho[1], generator=g)
+        e.gamma.fill_(1.0)
+        e.running_mean.zero_()
+        e.running_var.fill_(1.0)
+        self.m.zero_()
+        self.v.zero_()
+        self.step_dev.zero_()
+
+    def _keys(self):
+        kw = L.key(self.seed, 0, self.rank * self.S, self.step_dev)
+        kj = L.key(self.seed, 0, 0, self.step_dev)
+        return kw, kj
+
+    def _step_eager(self):
+        e = self.eng
+        kw, kj = self._keys()
+        e.zero_accumulators()
+        e.set_input(self.saved, self.noise, self.reg_noise_std, kj)
+        e.sample_weights(kw)
+        e.forward()
+        self.head.run()
+        e.backward()
+        e.reparam_kl(kw, prior_mu=self.prior_mu, prior_sigma_plus_eps=self.prior_sigma_plus_eps, direction=self.direction,
+                     kscale=self.temp)
+        if self.world_size > 1:
+            torch.distributed.all_reduce(e.grad, op=torch.distributed.ReduceOp.AVG, group=self.pg)
+        e.update_running_stats()
+        L.call("mfvi_adamw_step", e.theta.data_ptr(), e.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+               e.n_theta_pad, self.lr, self.betas[0], self.betas[1], self.adam_eps, self.weight_decay, 1,
+               self.step_dev.data_ptr(), e._aptr(NLL) if self.nan_guard else None)
+        L.call("mfvi_counter_add", self.step_dev.data_ptr(), 1)
+
+    def step(self):
+        """One optimiser step, asynchronous on the current stream."""
+        if not self.use_graph:
+            return self._step_eager()
+        if self._graph is None:
+            if self._warm < 2:           # let lazy initialisation (func attributes, NCCL) happen outside the capture
+                self._warm += 1
+                return self._step_eager()
+            torch.cuda.synchronize()
+            before = L.launch_count
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step_eager()
+            self.launches_per_step = L.launch_count - before
+            self._graph = g
+            # the capture itself did not execute: fall through and replay once
+        self._graph.replay()
+
+    # ------------------------------------------------------------------
+    def loss_terms(self):
+        """(nll, kl, loss) of the last step as Python floats (synchronises)."""
+        a = self.eng.arena[:2].cpu()
+        kl, nll = float(a[KL]), float(a[NLL])
+        return nll, kl, nll + self.temp * kl
+
+    @property
+    def steps_done(self) -> int:
+        return int(self.step_dev.item())

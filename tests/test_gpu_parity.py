@@ -1,0 +1,358 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle / the golden fixtures generated from the
+imported reference (tests/golden/make_golden.py).  Tolerance: north_star's rtol 1e-3 in fp32, measured as the
+normalised max error max|a-b|/max|b| (tests/helpers.py); most checks are far tighter and say so.
+"""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mfvi_oracle as O
+from oracle import philox
+from tests.helpers import grad_errs, group, load_npz, rel_err
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-3
+
+SMALL = {
+    "den": O.SkipCfg(4, 2, (8, 16, 16), (8, 16, 16), (2, 2, 2), 3, 3, 1, True, False, "bilinear"),
+    "sr": O.SkipCfg(4, 2, (8, 16, 16), (8, 16, 16), (2, 2, 2), 3, 3, 1, True, False, "bilinear"),
+    "ct": O.SkipCfg(4, 1, (8, 16, 16), (8, 16, 16), (2, 2, 2), 3, 3, 1, True, False, "bilinear"),
+    "inp": O.SkipCfg(4, 4, (8, 16, 16), (8, 16, 16), (0, 0, 0), 5, 3, 1, False, False, "nearest"),
+}
+
+
+def spec_of(cfg):
+    from mfvi_dip_mia_b200 import SkipSpec
+    return SkipSpec(cfg.num_input_channels, cfg.num_output_channels, tuple(cfg.down), tuple(cfg.up), tuple(cfg.skip),
+                    cfg.filter_down, cfg.filter_up, cfg.filter_skip, cfg.need1x1_up, cfg.need_sigmoid, cfg.upsample_mode)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+# ----------------------------------------------------------------------------------------------- RNG
+def test_philox_bit_exact_and_normals(dev):
+    from mfvi_dip_mia_b200 import _lib as L
+    n = 4099
+    raw = torch.empty(n, dtype=torch.int32, device=dev)
+    L.call("mfvi_philox_raw_fill", raw.data_ptr(), n, L.key(0x1234567890ABCDEF, 7, 3), 5)
+    ref = philox.philox_raw(n, 0x1234567890ABCDEF, 5, 3, 7).reshape(-1)[:n]
+    assert np.array_equal(raw.cpu().numpy().view(np.uint32), ref)           # integer part: bit exact
+    z = torch.empty(n, dtype=torch.float32, device=dev)
+    L.call("mfvi_philox_normal_fill", z.data_ptr(), n, L.key(99, 1, 2), 0)
+    zr = philox.philox_normal(n, 99, 0, 2, 1)
+    assert np.abs(z.cpu().numpy() - zr).max() < 2e-5                         # fp32 log/sincos vs fp64
+    # device-side step counter adds to the step word
+    ctr = torch.tensor([4], dtype=torch.int32, device=dev)
+    z2 = torch.empty(n, dtype=torch.float32, device=dev)
+    L.call("mfvi_philox_normal_fill", z2.data_ptr(), n, L.key(99, 1, 2, ctr), 0)
+    assert np.abs(z2.cpu().numpy() - philox.philox_normal(n, 99, 0, 2, 5)).max() < 2e-5
+
+
+# ----------------------------------------------------------------------------------------------- layers
+@pytest.mark.parametrize("name", ["c1x1", "c3s1", "c3s2", "c5s2", "c5s1", "c3s1_odd"])
+def test_conv2drt_matches_reference(dev, name):
+    from mfvi_dip_mia_b200.BayTorch.modules import Conv2dRT
+    g = group(load_npz("layers.npz"), name + "/")
+    cin, cout, k, st, H, W = [int(v) for v in g["meta"]]
+    layer = Conv2dRT(cin, cout, k, stride=st, prior={"mu": 0.0, "sigma": 1e-8}).to(dev)
+    with torch.no_grad():
+        for pn in ["W_mu", "W_rho", "bias_mu", "bias_rho"]:
+            getattr(layer, pn).copy_(g[pn])
+    x = g["x"].to(dev).requires_grad_(True)
+    layer.inject_eps(g["eps_w"], g["eps_b"])
+    y = layer(x)
+    assert rel_err(y.cpu(), g["y"]) < 1e-5
+    y.backward(g["dy"].to(dev))
+    assert rel_err(x.grad.cpu(), g["dx"]) < 1e-5
+    for pn in ["W_mu", "W_rho", "bias_mu", "bias_rho"]:
+        assert rel_err(getattr(layer, pn).grad.cpu(), g["d" + pn]) < 2e-5, pn
+    layer.eval()
+    assert rel_err(layer(g["x"].to(dev)).cpu(), g["y_eval"]) < 1e-5
+
+
+def test_linearrt_matches_reference(dev):
+    from mfvi_dip_mia_b200.BayTorch.modules import LinearRT
+    g = group(load_npz("layers.npz"), "lin/")
+    layer = LinearRT(20, 12, prior={"mu": 0.0, "sigma": 1e-8}).to(dev)
+    with torch.no_grad():
+        for pn in ["W_mu", "W_rho", "bias_mu", "bias_rho"]:
+            getattr(layer, pn).copy_(g[pn])
+    x = g["x"].to(dev).requires_grad_(True)
+    layer.inject_eps(g["eps_w"], g["eps_b"])
+    y = layer(x)
+    assert rel_err(y.cpu(), g["y"]) < 1e-5
+    y.backward(g["dy"].to(dev))
+    assert rel_err(x.grad.cpu(), g["dx"]) < 1e-5
+    for pn in ["W_mu", "W_rho", "bias_mu", "bias_rho"]:
+        assert rel_err(getattr(layer, pn).grad.cpu(), g["d" + pn]) < 2e-5, pn
+
+
+@pytest.mark.parametrize("i", [0, 1, 2, 3])
+def test_layer_kl_matches_reference(dev, i):
+    from mfvi_dip_mia_b200.BayTorch.modules import Conv2dRT
+    g = group(load_npz("layers.npz"), f"kl{i}/")
+    temp, sigma, rev = [float(x) for x in g["meta"]]
+    layer = Conv2dRT(6, 5, 3, prior={"mu": 0.0, "sigma": np.sqrt(temp) * sigma},
+                     kl_type="reverse" if rev else "forward").to(dev)
+    with torch.no_grad():
+        for pn in ["W_mu", "W_rho", "bias_mu", "bias_rho"]:
+            getattr(layer, pn).copy_(g[pn])
+    kl = layer._kl
+    assert rel_err(kl.cpu(), g["kl"]) < 1e-5
+    kl.backward()
+    for pn in ["W_mu", "W_rho", "bias_mu", "bias_rho"]:
+        assert rel_err(getattr(layer, pn).grad.cpu(), g["d" + pn]) < 1e-4, pn
+
+
+def test_nll_matches_reference(dev):
+    from mfvi_dip_mia_b200.utils.bayesian_utils import gaussian_nll, gaussian_nll_inpainting
+    d = load_npz("layers.npz")
+    g = group(d, "nll/")
+    mu, s = g["mu"].to(dev).requires_grad_(True), g["s"].to(dev).requires_grad_(True)
+    v = gaussian_nll(mu, s, g["t"].to(dev))
+    assert rel_err(v.cpu(), g["v"]) < 1e-5
+    v.backward()
+    assert rel_err(mu.grad.cpu(), g["dmu"]) < 1e-5 and rel_err(s.grad.cpu(), g["ds"]) < 1e-5
+    assert rel_err(gaussian_nll(mu, s, g["t"].to(dev), reduction="sum").cpu(), g["v"] * mu.numel()) < 1e-5
+    g = group(d, "nlli/")
+    mu3, s1 = g["mu"].to(dev).requires_grad_(True), g["s"].to(dev).requires_grad_(True)
+    v = gaussian_nll_inpainting(mu3.sigmoid(), s1, g["t"].to(dev), g["m"].to(dev))
+    assert rel_err(v.cpu(), g["v"]) < 1e-5
+    v.backward()
+    assert rel_err(mu3.grad.cpu(), g["dmu"]) < 1e-5 and rel_err(s1.grad.cpu(), g["ds"]) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["r32", "r48", "r40c2"])
+def test_radon_matches_reference(dev, name):
+    from mfvi_dip_mia_b200.radon import FastRadonTransform
+    g = group(load_npz("layers.npz"), name + "/")
+    img = g["img"].to(dev).requires_grad_(True)
+    rad = FastRadonTransform(tuple(img.shape), g["theta"]).to(dev)
+    sino = rad(img)
+    assert tuple(sino.shape) == tuple(g["sino"].shape)
+    assert rel_err(sino.cpu(), g["sino"]) < 2e-5
+    sino.backward(g["dsino"].to(dev))
+    assert rel_err(img.grad.cpu(), g["dimg"]) < 2e-5
+
+
+# ----------------------------------------------------------------------------------------------- whole step
+def _fixture(task):
+    d = load_npz(f"skipnet_small_{task}.npz")
+    S = int(d["S"])
+    sd = group(d, "sd/")
+    eps = [group(d, f"eps{s}/") for s in range(S)]
+    ex = group(d, "extra/")
+    grads = group(d, "grad/")
+    return d, S, sd, eps, ex, grads
+
+
+def _head_kwargs(task, ex):
+    if task in ("den", "sr"):
+        return dict(target=ex["target"])
+    if task == "inp":
+        return dict(target=ex["target"], mask=ex["mask"])
+    return dict(theta_deg=ex["theta"], sino=ex["sino"])
+
+
+@pytest.mark.parametrize("task", ["den", "sr", "ct", "inp"])
+def test_engine_step_matches_reference(dev, task):
+    """Engine + loss head + reparam/KL kernel == S sequential reference forwards + loss.backward()."""
+    from mfvi_dip_mia_b200 import SkipEngine, _lib as L
+    from mfvi_dip_mia_b200.engine import KL, NLL
+    from mfvi_dip_mia_b200.trainer import LossHead
+    d, S, sd, eps, ex, grads = _fixture(task)
+    x = torch.from_numpy(d["net_input"])
+    eng = SkipEngine(spec_of(SMALL[task]), x.shape[2], x.shape[3], S, dev)
+    eng.load_params(sd, prefix="net.")
+    eng.pack_eps(eps, prefix="net.")
+    head = LossHead(eng, task, **_head_kwargs(task, ex))
+    temp, sigma = float(d["temp"]), float(d["sigma"])
+    eng.zero_accumulators()
+    eng.set_input(x[0].permute(1, 2, 0).contiguous().to(dev), None, 0.0, L.key(0))
+    eng.sample_weights(L.key(0))
+    eng.forward()
+    out = eng.out_nchw().cpu()
+    for s in range(S):
+        assert rel_err(out[s:s + 1], d[f"out{s}"]) < 1e-4, s
+    head.run()
+    eng.backward()
+    eng.reparam_kl(L.key(0), prior_mu=0.0, prior_sigma_plus_eps=O.prior_scale(temp, sigma), direction=0, kscale=temp)
+    a = eng.arena[:2].cpu()
+    assert rel_err(a[NLL], d["nll"]) < 1e-5
+    assert rel_err(a[KL], d["kl"]) < 1e-5
+    ours = {"net." + k: v.cpu() for k, v in eng.param_views("grad").items()}
+    errs = grad_errs({k: ours[k] for k in grads}, grads)
+    worst = max(errs, key=errs.get)
+    assert errs[worst] < RTOL, (worst, errs[worst])
+
+
+@pytest.mark.parametrize("task", ["den", "inp"])
+def test_meanfieldvi_dropin_matches_reference(dev, task):
+    """The reference's own call sequence (get_net/skip -> MeanFieldVI -> nll + temp*kl -> backward) on our classes."""
+    from mfvi_dip_mia_b200.BayTorch import MeanFieldVI
+    from mfvi_dip_mia_b200.models.skip import skip
+    from mfvi_dip_mia_b200.utils.bayesian_utils import gaussian_nll, gaussian_nll_inpainting
+    d, S, sd, eps, ex, grads = _fixture(task)
+    cfg = SMALL[task]
+    temp, sigma = float(d["temp"]), float(d["sigma"])
+    net = skip(cfg.num_input_channels, cfg.num_output_channels, num_channels_down=list(cfg.down),
+               num_channels_up=list(cfg.up), num_channels_skip=list(cfg.skip), filter_size_down=cfg.filter_down,
+               filter_size_up=cfg.filter_up, filter_skip_size=cfg.filter_skip, need_sigmoid=False, need_bias=True,
+               pad="reflection", upsample_mode=cfg.upsample_mode, need1x1_up=cfg.need1x1_up,
+               dropout_mode_down="None", dropout_mode_up="None", dropout_mode_skip="None", dropout_mode_output="None")
+    net = MeanFieldVI(net, prior={"mu": 0.0, "sigma": np.sqrt(temp) * sigma}, replace_layers="all", reparam="",
+                      device=dev, mc_samples=S)
+    assert set(net.state_dict().keys()) == set(json.loads(str(d["keys"])))
+    net.load_state_dict({k: v for k, v in sd.items()})
+    x = torch.from_numpy(d["net_input"]).to(dev)
+    net.prepare(x)
+    net.inject_eps(eps, prefix="net.")      # eps keys in the fixture carry the 'net.' prefix of MeanFieldVI.net
+    optimizer = torch.optim.AdamW(net.parameters(), lr=1e-3, weight_decay=0)
+    optimizer.zero_grad()
+    out = net(x)
+    assert tuple(out.shape) == (S, cfg.num_output_channels, x.shape[2], x.shape[3])
+    if task == "den":
+        nll = gaussian_nll(out[:, :1], out[:, 1:], ex["target"].to(dev))
+    else:
+        nll = gaussian_nll_inpainting(out[:, :3].sigmoid(), out[:, 3:], ex["target"].to(dev), ex["mask"].to(dev))
+    kl = net.kl()
+    assert tuple(kl.shape) == (1,)
+    loss = nll + temp * kl
+    loss.backward()
+    assert rel_err(nll.cpu(), d["nll"]) < 1e-5 and rel_err(kl.cpu(), d["kl"]) < 1e-5
+    assert rel_err(loss.cpu(), d["loss"]) < 1e-5
+    ours = {k: p.grad.cpu() for k, p in net.named_parameters()}
+    errs = grad_errs({k: ours[k] for k in grads}, grads)
+    worst = max(errs, key=errs.get)
+    assert errs[worst] < RTOL, (worst, errs[worst])
+    optimizer.step()      # the optimiser updates the flat storage through the views
+    assert torch.isfinite(net._engine.theta).all()
+
+
+def test_den256_full_size_matches_reference(dev):
+    """Metric-shape net (256^2, 26 convs), S=2, eps from OUR Philox stream definition regenerated by the oracle and
+    injected — compared with summaries of the imported reference's step (den256_summary.npz)."""
+    from mfvi_dip_mia_b200 import SkipEngine, SkipSpec, _lib as L
+    from mfvi_dip_mia_b200.engine import KL, NLL
+    from mfvi_dip_mia_b200.trainer import LossHead
+    from mfvi_dip_mia_b200.utils.phantoms import ellipse_phantom, noisy
+    d = load_npz("den256_summary.npz")
+    S, seed = int(d["S"]), int(d["philox_seed"])
+    temp, sigma = float(d["temp"]), float(d["sigma"])
+    eng = SkipEngine(SkipSpec(), 256, 256, S, dev)
+    # parameters: the reference net was built under torch.manual_seed(1) — re-create it through OUR classes, which
+    # draw the initial values from the same global RNG in the same order (VIModule.reset_parameters)
+    from mfvi_dip_mia_b200.BayTorch import MeanFieldVI
+    from mfvi_dip_mia_b200.models import get_net
+    torch.manual_seed(int(d["init_seed"]))
+    net = get_net(16, "skip", "reflection", skip_n33d=[16, 32, 64, 128, 128], skip_n33u=[16, 32, 64, 128, 128],
+                  skip_n11=4, num_scales=5, n_channels=2, upsample_mode="bilinear")
+    net = MeanFieldVI(net, prior={"mu": 0.0, "sigma": np.sqrt(temp) * sigma}, replace_layers="all", reparam="")
+    names = json.loads(str(d["grad_names"]))
+    pn = dict(net.named_parameters())
+    got_norms = np.array([float(pn[k].double().norm()) for k in names])
+    assert np.allclose(got_norms, d["param_norms"], rtol=1e-6), "initialisation order differs from the reference"
+    eng.load_params(net.net.state_dict())
+    eps = []
+    for s in range(S):
+        e = {}
+        for li, c in enumerate(eng.lay.convs):
+            e[c.key + ".W"] = torch.from_numpy(philox.philox_normal(c.w_numel, seed, 2 * li, s, 0)).reshape(c.cout, c.cin, c.k, c.k)
+            e[c.key + ".b"] = torch.from_numpy(philox.philox_normal(c.cout, seed, 2 * li + 1, s, 0))
+        eps.append(e)
+    eng.pack_eps(eps)
+    target = torch.from_numpy(noisy(ellipse_phantom(256), 0.1, 1))[None]
+    g = torch.Generator().manual_seed(int(d["input_seed"]))
+    net_input = torch.rand(1, 16, 256, 256, generator=g) * 0.1
+    head = LossHead(eng, "den", target=target)
+    eng.zero_accumulators()
+    eng.set_input(net_input[0].permute(1, 2, 0).contiguous().to(dev), None, 0.0, L.key(0))
+    eng.sample_weights(L.key(0))
+    eng.forward()
+    head.run()
+    eng.backward()
+    eng.reparam_kl(L.key(0), prior_mu=0.0, prior_sigma_plus_eps=O.prior_scale(temp, sigma), direction=0, kscale=temp)
+    out = eng.out_nchw().cpu()
+    for s in range(S):
+        assert rel_err(out[s:s + 1, :, ::8, ::8], d[f"out{s}_sub"]) < RTOL
+        assert np.allclose(out[s].double().mean(dim=(1, 2)).numpy(), d[f"out{s}_mean"], rtol=1e-3, atol=1e-5)
+    a = eng.arena[:2].cpu()
+    assert rel_err(a[NLL], d["nll"]) < 1e-4 and rel_err(a[KL], d["kl"]) < 1e-5
+    assert rel_err(a[NLL] + temp * a[KL], d["loss"]) < 1e-4
+    gv = {"net." + k: v.cpu() for k, v in eng.param_views("grad").items()}
+    norms = np.array([float(gv[k].double().norm()) for k in names])
+    big = d["grad_norms"] > 1e-3 * d["grad_norms"].max()
+    assert np.allclose(norms[big], d["grad_norms"][big], rtol=2e-3), np.abs(norms[big] / d["grad_norms"][big] - 1).max()
+    gref = group(d, "grad/")
+    for k, v in gref.items():
+        ours = gv[k].reshape(-1)[:4096]
+        den = max(float(v.abs().max()), 1e-3 * float(d["grad_absmax"].max()))
+        assert float((ours - v).abs().max()) / den < RTOL * 2, k
+
+
+# ----------------------------------------------------------------------------------------------- trainer
+def _oracle_eps_from_stream(eng, seed, step, S, sample0=0):
+    """eps the library's weight stream produces (flat storage index), mapped to reference-shaped tensors."""
+    out = []
+    for s in range(S):
+        flat = torch.from_numpy(philox.philox_normal(eng.lay.P, seed, 0, sample0 + s, step))
+        e = {}
+        for c in eng.lay.convs:
+            e["net." + c.key + ".W"] = flat[c.w_off:c.w_off + c.w_numel].view(c.k, c.k, c.cout, c.cin).permute(2, 3, 0, 1).contiguous()
+            e["net." + c.key + ".b"] = flat[c.b_off:c.b_off + c.cout].clone()
+        out.append(e)
+    return out
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_trainer_trajectory_matches_oracle(dev, use_graph):
+    """5 optimiser steps of MfviDipTrainer (in-kernel Philox eps + input jitter, AdamW) == the oracle fed with the
+    same streams regenerated on the CPU."""
+    from mfvi_dip_mia_b200 import MfviDipTrainer
+    task = "den"
+    d, S, sd, _, ex, _ = _fixture(task)
+    cfg = SMALL[task]
+    temp, sigma, lr, seed = float(d["temp"]), float(d["sigma"]), 1e-2, 4242
+    x = torch.from_numpy(d["net_input"])
+    tr = MfviDipTrainer(spec_of(cfg), task, x, temp=temp, sigma=sigma, lr=lr, mc_samples=S, seed=seed, device=dev,
+                        target=ex["target"], use_graph=use_graph)
+    tr.eng.load_params(sd, prefix="net.")
+    names = [k for k, v in sd.items() if v.is_floating_point() and "running" not in k]
+    p = {k: sd[k].clone().double() for k in names}
+    m = {k: torch.zeros_like(v) for k, v in p.items()}
+    v_ = {k: torch.zeros_like(v) for k, v in p.items()}
+    n_steps = 5
+    for it in range(n_steps):
+        tr.step()
+        nll_g, kl_g, loss_g = tr.loss_terms()
+        # ---- oracle step in float64 on the same streams
+        H, W, Cn = x.shape[2], x.shape[3], x.shape[1]
+        z = torch.from_numpy(philox.philox_normal(Cn * H * W, seed, 1, 0, it)).reshape(1, Cn, H, W).double()
+        xin = x.double() + 0.1 * z
+        leaves = {k: p[k].clone().requires_grad_(True) for k in names}
+        full = dict(sd)
+        full.update(leaves)
+        eps = [{k: e.double() for k, e in ed.items()} for ed in _oracle_eps_from_stream(tr.eng, seed, it, S)]
+        loss, nll, kl, _ = O.mfvi_loss(full, cfg, xin, eps, task=task, temp=temp,
+                                       prior_sigma_plus_eps=O.prior_scale(temp, sigma), target=ex["target"].double())
+        loss.backward()
+        assert rel_err(nll_g, nll) < 2e-4, (it, nll_g, float(nll))
+        assert rel_err(kl_g, kl) < 1e-5, it
+        for k in names:
+            p[k], m[k], v_[k] = O.adamw_step(p[k], leaves[k].grad, m[k], v_[k], it + 1, lr)
+    assert tr.steps_done == n_steps
+    ours = {"net." + k: t.cpu() for k, t in tr.eng.param_views("theta").items()}
+    # parameters moved by ~n_steps*lr; compare the UPDATE, not the value
+    worst = 0.0
+    for k in names:
+        upd_ref = (p[k] - sd[k].double())
+        upd = (ours[k].double() - sd[k].double())
+        worst = max(worst, float((upd - upd_ref).abs().max()) / (n_steps * lr))
+    assert worst < 0.02, worst       # AdamW's sign-like update amplifies tiny gradient noise near g~0
+    # running statistics followed S sequential forwards per step
+    assert torch.isfinite(tr.eng.running_var).all() and float(tr.eng.running_var.min()) >= 0
