@@ -173,7 +173,7 @@ class GaussianNllFn(torch.autograd.Function):
         else:
             t = target.to(mu.device, torch.float32).reshape(3, H, W).permute(1, 2, 0).contiguous()
             m = mask.to(mu.device, torch.float32).reshape(H, W).contiguous()
-            L.call("mfvi_gauss_nll_fwd_bwd", 1, L.view(out), N, H, W, 4, 1, t.data_ptr(), m.data_ptr(), acc.data_ptr(),
+            L.call("mfvi_gauss_nll_fwd_bwd", mode, L.view(out), N, H, W, 4, 1, t.data_ptr(), m.data_ptr(), acc.data_ptr(),
                    L.view(dout))
             count = N * H * W * 3
         scale = 1.0 if reduction == "mean" else float(count)

@@ -310,9 +310,11 @@ def _oracle_eps_from_stream(eng, seed, step, S, sample0=0):
 
 
 @pytest.mark.parametrize("use_graph", [False, True])
-def test_trainer_trajectory_matches_oracle(dev, use_graph):
-    """5 optimiser steps of MfviDipTrainer (in-kernel Philox eps + input jitter, AdamW) == the oracle fed with the
-    same streams regenerated on the CPU."""
+def test_trainer_steps_match_oracle(dev, use_graph):
+    """4 optimiser steps of MfviDipTrainer (in-kernel Philox eps + input jitter, AdamW), eager and as a CUDA graph.
+    AdamW's sign-like early updates amplify fp32 summation noise chaotically, so each step is checked on its own:
+    the oracle is evaluated at the GPU's parameters before the step on the same regenerated streams (loss terms,
+    every gradient), and the parameter update is checked against the oracle's AdamW applied to the GPU gradient."""
     from mfvi_dip_mia_b200 import MfviDipTrainer
     task = "den"
     d, S, sd, _, ex, _ = _fixture(task)
@@ -323,36 +325,29 @@ def test_trainer_trajectory_matches_oracle(dev, use_graph):
                         target=ex["target"], use_graph=use_graph)
     tr.eng.load_params(sd, prefix="net.")
     names = [k for k, v in sd.items() if v.is_floating_point() and "running" not in k]
-    p = {k: sd[k].clone().double() for k in names}
-    m = {k: torch.zeros_like(v) for k, v in p.items()}
-    v_ = {k: torch.zeros_like(v) for k, v in p.items()}
-    n_steps = 5
-    for it in range(n_steps):
+    H, W, Cn = x.shape[2], x.shape[3], x.shape[1]
+    rm0 = tr.eng.running_mean.clone()
+    for it in range(4):
+        theta0, m0, v0 = tr.eng.theta.clone().double().cpu(), tr.m.clone().double().cpu(), tr.v.clone().double().cpu()
+        p_old = {"net." + k: t.detach().clone().cpu() for k, t in tr.eng.param_views("theta").items()}
         tr.step()
         nll_g, kl_g, loss_g = tr.loss_terms()
-        # ---- oracle step in float64 on the same streams
-        H, W, Cn = x.shape[2], x.shape[3], x.shape[1]
-        z = torch.from_numpy(philox.philox_normal(Cn * H * W, seed, 1, 0, it)).reshape(1, Cn, H, W).double()
-        xin = x.double() + 0.1 * z
-        leaves = {k: p[k].clone().requires_grad_(True) for k in names}
+        z = torch.from_numpy(philox.philox_normal(Cn * H * W, seed, 1, 0, it)).reshape(1, Cn, H, W)
+        leaves = {k: p_old[k].clone().requires_grad_(True) for k in names}
         full = dict(sd)
         full.update(leaves)
-        eps = [{k: e.double() for k, e in ed.items()} for ed in _oracle_eps_from_stream(tr.eng, seed, it, S)]
-        loss, nll, kl, _ = O.mfvi_loss(full, cfg, xin, eps, task=task, temp=temp,
-                                       prior_sigma_plus_eps=O.prior_scale(temp, sigma), target=ex["target"].double())
+        eps = _oracle_eps_from_stream(tr.eng, seed, it, S)
+        loss, nll, kl, _ = O.mfvi_loss(full, cfg, x + 0.1 * z, eps, task=task, temp=temp,
+                                       prior_sigma_plus_eps=O.prior_scale(temp, sigma), target=ex["target"])
         loss.backward()
-        assert rel_err(nll_g, nll) < 2e-4, (it, nll_g, float(nll))
+        assert rel_err(nll_g, nll) < 1e-4, (it, nll_g, float(nll))
         assert rel_err(kl_g, kl) < 1e-5, it
-        for k in names:
-            p[k], m[k], v_[k] = O.adamw_step(p[k], leaves[k].grad, m[k], v_[k], it + 1, lr)
-    assert tr.steps_done == n_steps
-    ours = {"net." + k: t.cpu() for k, t in tr.eng.param_views("theta").items()}
-    # parameters moved by ~n_steps*lr; compare the UPDATE, not the value
-    worst = 0.0
-    for k in names:
-        upd_ref = (p[k] - sd[k].double())
-        upd = (ours[k].double() - sd[k].double())
-        worst = max(worst, float((upd - upd_ref).abs().max()) / (n_steps * lr))
-    assert worst < 0.02, worst       # AdamW's sign-like update amplifies tiny gradient noise near g~0
-    # running statistics followed S sequential forwards per step
-    assert torch.isfinite(tr.eng.running_var).all() and float(tr.eng.running_var.min()) >= 0
+        ours = {"net." + k: t.cpu() for k, t in tr.eng.param_views("grad").items()}
+        errs = grad_errs({k: ours[k] for k in names}, {k: leaves[k].grad for k in names})
+        worst = max(errs, key=errs.get)
+        assert errs[worst] < RTOL, (it, worst, errs[worst])
+        # AdamW kernel == torch.optim.AdamW arithmetic on the gradient the GPU produced
+        p_ref, _, _ = O.adamw_step(theta0, tr.eng.grad.double().cpu(), m0, v0, it + 1, lr)
+        assert float((tr.eng.theta.double().cpu() - p_ref).abs().max()) < 1e-6 + 1e-4 * lr, it
+    assert tr.steps_done == 4
+    assert torch.isfinite(tr.eng.running_var).all() and not torch.equal(tr.eng.running_mean, rm0)
