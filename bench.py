@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""MFVI-DIP ELBO steps/sec benchmark (BASELINE.json metric: 256x256 denoise net, MC=8).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mc 8] [--size 256]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one full optimiser step of the hot path (input jitter, S-sample forward, NLL, KL, backward,
+[all-reduce], AdamW) on synthetic data of the metric shape.  `value` = steps/s with everything resident in HBM
+(CUDA-graph replay, CUDA-event timing, max over ranks); `e2e` = the same through MfviDipTrainer.step_from_host with
+pinned HOST buffers (H2D of net input + target and D2H of the loss inside the timed region).  MC samples are split
+across GPUs (total work fixed => "strong" scaling).  `--impl reference` times the CPU restatement of the reference
+step (oracle/, PyTorch fp32 on all host threads; /root/reference itself does not exist on the GPU box).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TEMP, SIGMA, LR = 5.656911698337764e-07, 1.4616642493692077e-05, 1e-3   # test_configs/mfvi_den.json
+METRIC, UNIT = "mfvi_dip_elbo_steps_per_sec", "steps/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm": d["hbm_gbs"], "tensor_burst": d["bf16_tflops"], "tensor": d["bf16_tflops_sustained"], "src": "measured"}
+    return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synthetic_problem(size, seed=1):
+    import torch
+    from mfvi_dip_mia_b200.utils.phantoms import ellipse_phantom, noisy
+    target = torch.from_numpy(noisy(ellipse_phantom(size), 0.1, seed))[None]          # (1,1,H,W)
+    g = torch.Generator().manual_seed(seed)
+    net_input = torch.rand(1, 16, size, size, generator=g) * 0.1                      # get_noise('noise', 'u', 1/10)
+    return net_input, target
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import mfvi_oracle as O
+    from oracle.cpu_step import OracleStepper, time_steps
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    st = OracleStepper(O.SkipCfg(16, 2), args.size, args.size, mc_samples=args.mc, temp=TEMP, sigma=SIGMA, lr=LR, seed=1)
+    # bound the run: probe one sample-forward/backward, then choose how many MC samples a "step" evaluates
+    t0 = time.perf_counter()
+    st.step(1)
+    probe = time.perf_counter() - t0
+    budget = 240.0
+    total = args.steps + args.warmup
+    s_eval = max(1, min(args.mc, int(budget / max(probe * total, 1e-9))))
+    sec = time_steps(st, args.steps, args.warmup, s_eval)
+    # a full step evaluates args.mc samples; the sample evaluated s_eval of them (cost is linear in samples)
+    sec_full = sec * args.mc / s_eval
+    v = 1.0 / sec_full
+    sample = (f"{args.steps} steps x {s_eval} of {args.mc} MC samples per step (time scaled by {args.mc}/{s_eval}), "
+              f"{args.size}x{args.size}, oracle port of the reference step, torch {torch.__version__} CPU fp32")
+    line = {"metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec_full * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"mfvi_den {args.size}x{args.size} 5-scale skip net, MC={args.mc}, AdamW"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def kernel_breakdown(tr, iters=3):
+    """Per-kernel device time of one eager step (CUDA events around every C-ABI call)."""
+    import torch
+    from mfvi_dip_mia_b200 import _lib as L
+    agg = {}
+    for _ in range(iters):
+        L.timeline = []
+        tr._step_eager()
+        torch.cuda.synchronize()
+        tl, L.timeline = L.timeline, None
+        for name, e0, e1, meta in tl:
+            a = agg.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0})
+            a["ms"] += e0.elapsed_time(e1)
+            a["n"] += 1
+            if meta:
+                a["flops"] += meta.get("flops", 0.0)
+                a["bytes"] += meta.get("bytes", 0.0)
+    for a in agg.values():
+        for k in a:
+            a[k] /= iters
+    return agg
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mfvi_dip_mia_b200 import MfviDipTrainer, SkipSpec, _lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}"
+    net_input, target = synthetic_problem(args.size)
+    math_mode = L.MATH_TF32 if args.math == "tf32" else L.MATH_FP32
+    tr = MfviDipTrainer(SkipSpec(), "den", net_input, temp=TEMP, sigma=SIGMA, lr=LR, mc_samples=args.mc, seed=1,
+                        device=dev, target=target, rank=rank, world_size=world, math_mode=math_mode, use_graph=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):       # includes the 2 eager steps + graph capture
+        tr.step()
+    torch.cuda.synchronize()
+    with ClockSampler(local) as clk:
+        ms_total = timed(tr.step, args.steps)
+    clocks = clk.summary()
+    launches = tr.launches_per_step * args.steps
+    value = args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: host buffers in, loss out, through the public trainer call
+    h_in, h_tgt, h_res = tr.host_buffers()
+    h_in.copy_(tr.saved.cpu())
+    h_tgt.copy_(tr.head.target.cpu())
+    io = [0, 0]
+
+    def e2e_step():
+        io[0], io[1] = tr.step_from_host(h_in, h_tgt, h_res)
+        torch.cuda.current_stream().synchronize()      # the caller reads the loss every step
+    for _ in range(3):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e = {"value": args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": io[0], "d2h_bytes_per_step": io[1]}
+    nll, kl, loss = tr.loss_terms()
+
+    # ---- roofline of the dominant kernel (eager pass with events around every launch)
+    pk = peaks()
+    agg = kernel_breakdown(tr)
+    step_ms_eager = sum(a["ms"] for a in agg.values())
+    dom = max(agg, key=lambda k: agg[k]["ms"])
+    a = agg[dom]
+    if a["flops"] > 0:
+        ach = a["flops"] / (a["ms"] * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s",
+                "frac": ach / pk["tensor"], "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+                "launches_per_step": a["n"], "ms_per_step": a["ms"], "share_of_step": a["ms"] / step_ms_eager}
+    else:
+        ach = a["bytes"] / (a["ms"] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+                "traffic": None, "peak_source": pk["src"], "launches_per_step": a["n"], "ms_per_step": a["ms"],
+                "share_of_step": a["ms"] / step_ms_eager}
+    kernels = {}
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+        e = {"ms": round(v["ms"], 4), "n": v["n"], "share": round(v["ms"] / step_ms_eager, 4)}
+        if v["flops"]:
+            e["tflops"] = round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 3)
+        if v["bytes"]:
+            e["gbs"] = round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)
+        kernels[k] = e
+
+    if rank != 0:
+        return
+    # ---- CPU baseline on this box's host cores (bounded sample), N=1 only
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        from oracle import mfvi_oracle as O
+        from oracle.cpu_step import OracleStepper, time_steps
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        st = OracleStepper(O.SkipCfg(16, 2), args.size, args.size, mc_samples=args.mc, temp=TEMP, sigma=SIGMA, lr=LR)
+        t0 = time.perf_counter()
+        st.step(1)
+        probe = time.perf_counter() - t0
+        n_cpu = 3
+        s_eval = max(1, min(args.mc, int(20.0 / max(probe * (n_cpu + 1), 1e-9))))
+        sec = time_steps(st, n_cpu, 1, s_eval) * args.mc / s_eval
+        cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n_cpu} steps x {s_eval} of {args.mc} MC samples (time scaled by {args.mc}/{s_eval}), oracle "
+                         f"port of the reference step, torch CPU fp32"}
+    ws_mb = sum(t.numel() for t in tr.eng._bufs) * 4 / 2 ** 20
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "tf32" if args.math == "tf32" else "f32", "data": "synthetic",
+            "config": {"workload": f"mfvi_den {args.size}x{args.size} 5-scale skip net, MC={args.mc} split over {world} GPU(s), AdamW",
+                       "mc_per_gpu": tr.S, "l2": f"per-step activation working set {ws_mb:.0f} MiB > 126 MB L2 (no flush needed)",
+                       "cuda_graph": True, "last_loss": loss},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "kernels": kernels}
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mc", type=int, default=8)
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--math", default="fp32", choices=["fp32", "tf32"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+        rank = int(os.environ.get("RANK", "0"))
+        if rank != 0 and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -99,12 +99,22 @@ lib = _load()
 launch_count = 0   # number of kernel-launching C-ABI calls made by this process (bench.py reports it)
 
 
-def call(name: str, *args, stream=None):
+timeline = None     # when a list: every call appends (name, start_event, end_event, meta) — bench.py's per-kernel timing
+
+
+def call(name: str, *args, stream=None, meta=None):
     """Invoke `name(*args, stream)`; raises MfviError on a non-zero return code."""
     global launch_count
     if stream is None:
         stream = torch.cuda.current_stream().cuda_stream
-    rc = getattr(lib, name)(*args, stream)
+    if timeline is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args, stream)
+        e1.record()
+        timeline.append((name, e0, e1, meta))
+    else:
+        rc = getattr(lib, name)(*args, stream)
     launch_count += 1
     if rc != 0:
         raise MfviError(f"{name} failed (rc={rc}): {lib.mfvi_last_error().decode()}")

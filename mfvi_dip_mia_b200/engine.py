@@ -232,8 +232,8 @@ class SkipEngine:
         self.eps = None                      # [S][Pp] injected eps (allocated on demand)
         self.inject_eps = False
         self._bufs: List[torch.Tensor] = []
-        self.fwd_ops: List[Tuple[str, tuple]] = []
-        self.bwd_ops: List[Tuple[str, tuple]] = []
+        self.fwd_ops: List[Tuple[str, tuple, dict]] = []
+        self.bwd_ops: List[Tuple[str, tuple, dict]] = []
         self.need_input_grad = need_input_grad
         self._build_plan()
         # per-BN tables for the running-stat update
@@ -270,15 +270,28 @@ class SkipEngine:
             bn.count = Ho * Wo
         self.fwd_ops.append(("mfvi_conv2d_fwd", (
             C.byref(d), L.view(x), self.w.data_ptr() + 4 * c.w_off, self.w.data_ptr() + 4 * c.b_off, self.lay.P_pad,
-            L.view(y), None if bn is None else self._aptr(bn.sums_off))))
+            L.view(y), None if bn is None else self._aptr(bn.sums_off)), self._conv_meta(c, d, x, y)))
         self._keep.append(d)
         return y, d
+
+    def _conv_meta(self, c: ConvLayer, d, x, y):
+        """Algorithmic work of one conv launch (fwd, dgrad and wgrad all perform the same MACs):
+        flops = 2*S*Hout*Wout*Cout*Cin*KH*KW; bytes = input read once + sampled weights read once + output written once."""
+        flops = 2.0 * self.S * d.Hout * d.Wout * c.cout * c.cin * c.k * c.k
+        nbytes = 4.0 * (x.numel() + self.S * (c.w_numel + c.cout) + y.numel())
+        return {"flops": flops, "bytes": nbytes, "layer": c.key.rsplit(".", 1)[-1],
+                "shape": f"{c.cin}->{c.cout} k{c.k} s{c.stride} out{d.Hout}x{d.Wout}"}
+
+    @staticmethod
+    def _ew_meta(*tensors):
+        """Elementwise kernels: every operand tensor is read or written exactly once."""
+        return {"bytes": 4.0 * sum(t.numel() for t in tensors if t is not None)}
 
     def _bn_act_pad(self, y, bn: BnLayer, sums_ptr, gamma_ptr, beta_ptr, act, pad):
         S, H, W, Cn = y.shape
         xp = self._buf(H + 2 * pad, W + 2 * pad, Cn)
         self.fwd_ops.append(("mfvi_bn_act_pad_fwd", (L.view(y), S, H, W, Cn, sums_ptr, gamma_ptr, beta_ptr, act, pad,
-                                                     L.view(xp))))
+                                                     L.view(xp)), self._ew_meta(y, xp)))
         return xp
 
     # backward of  x = pad(act(bn(y)))  followed by the BN statistics backward:  dxp -> dy (returned)
@@ -287,20 +300,23 @@ class SkipEngine:
         sums, gamma, beta = self._bn_args(bn)
         red = self._aptr(bn.red_off)
         g = self._buf(H, W, Cn)
-        ops.append(("mfvi_pad_act_bwd", (L.view(dxp), S, H, W, Cn, pad, L.view(y), sums, gamma, beta, act, L.view(g), red)))
+        ops.append(("mfvi_pad_act_bwd", (L.view(dxp), S, H, W, Cn, pad, L.view(y), sums, gamma, beta, act, L.view(g), red),
+                    self._ew_meta(dxp, y, g)))
         ops.append(("mfvi_bn_bwd_apply", (L.view(g), L.view(y), S, H, W, Cn, sums, red, gamma, L.view(g),
-                                          self.g_gamma.data_ptr() + 4 * bn.ch_off, self.g_beta.data_ptr() + 4 * bn.ch_off)))
+                                          self.g_gamma.data_ptr() + 4 * bn.ch_off, self.g_beta.data_ptr() + 4 * bn.ch_off),
+                    self._ew_meta(g, y, g)))
         return g
 
     def _conv_bwd(self, ops, c: ConvLayer, d, x, dy, need_dx=True):
         """wgrad into dw[s] (+bias), dgrad into a fresh padded-input-sized buffer (returned)."""
+        meta = self._conv_meta(c, d, x, dy)
         ops.append(("mfvi_conv2d_wgrad", (C.byref(d), L.view(x), L.view(dy), self.dw.data_ptr() + 4 * c.w_off,
-                                          self.dw.data_ptr() + 4 * c.b_off, self.lay.P_pad)))
+                                          self.dw.data_ptr() + 4 * c.b_off, self.lay.P_pad), meta))
         if not need_dx:
             return None
         dx = self._buf(x.shape[1], x.shape[2], c.cin)
         ops.append(("mfvi_conv2d_dgrad", (C.byref(d), L.view(dy), self.w.data_ptr() + 4 * c.w_off, self.lay.P_pad,
-                                          L.view(dx), 0)))
+                                          L.view(dx), 0), meta))
         return dx
 
     # ---------------------------------------------------------------- plan
@@ -344,7 +360,8 @@ class SkipEngine:
             sb = self._bn_args(sc.skip_bn) if Cs else (None, None, None)
             zb = self._bn_args(z_bn)
             self.fwd_ops.append(("mfvi_cat_up_fwd", (L.view(ys) if Cs else null_view, Cs, *sb, L.view(z), Cd, *zb,
-                                                     S, Hs, Ws, mode, L.view(A), self._aptr(sc.cat_bn.sums_off))))
+                                                     S, Hs, Ws, mode, L.view(A), self._aptr(sc.cat_bn.sums_off)),
+                                 self._ew_meta(ys, z, A)))
             XA = self._bn_act_pad(A, sc.cat_bn, *self._bn_args(sc.cat_bn), 0, pu)
             yu, d_u = self._conv_fwd(sc.up, XA, sc.up_bn)
             if sc.up1 is not None:
@@ -368,15 +385,17 @@ class SkipEngine:
                 ops.append(("mfvi_cat_up_bwd", (
                     L.view(dA), S, Hs, Ws, mode, L.view(ys) if Cs else null_view, Cs, *sb,
                     L.view(gs) if Cs else null_view, self._aptr(sc.skip_bn.red_off) if Cs else None,
-                    L.view(z), Cd, *zb, L.view(gd), self._aptr(z_bn.red_off))))
+                    L.view(z), Cd, *zb, L.view(gd), self._aptr(z_bn.red_off)), self._ew_meta(dA, ys, z, gs, gd)))
                 # BN backward of the two branches (their LeakyReLU was folded into cat_up_bwd)
                 ops.append(("mfvi_bn_bwd_apply", (
                     L.view(gd), L.view(z), S, z.shape[1], z.shape[2], Cd, zb[0], self._aptr(z_bn.red_off), zb[1], L.view(gd),
-                    self.g_gamma.data_ptr() + 4 * z_bn.ch_off, self.g_beta.data_ptr() + 4 * z_bn.ch_off)))
+                    self.g_gamma.data_ptr() + 4 * z_bn.ch_off, self.g_beta.data_ptr() + 4 * z_bn.ch_off),
+                    self._ew_meta(gd, z, gd)))
                 if Cs:
                     ops.append(("mfvi_bn_bwd_apply", (
                         L.view(gs), L.view(ys), S, Hs, Ws, Cs, sb[0], self._aptr(sc.skip_bn.red_off), sb[1], L.view(gs),
-                        self.g_gamma.data_ptr() + 4 * sc.skip_bn.ch_off, self.g_beta.data_ptr() + 4 * sc.skip_bn.ch_off)))
+                        self.g_gamma.data_ptr() + 4 * sc.skip_bn.ch_off, self.g_beta.data_ptr() + 4 * sc.skip_bn.ch_off),
+                        self._ew_meta(gs, ys, gs)))
                 if inner_bwd is not None:
                     dTn = inner_bwd(ops, gd)
                     dy2 = self._bn_act_pad_bwd(ops, dTn, y2, sc.d2_bn, 1, Tn_pad)
@@ -390,19 +409,21 @@ class SkipEngine:
                     dT = self._buf(T.shape[1], T.shape[2], T.shape[3])
                     dT_d1 = self._interior(dT, Tpad - pd)
                     if Tpad != pd:
-                        ops.append(("mfvi_fill_f32", (dT.data_ptr(), dT.numel(), 0.0)))
+                        ops.append(("mfvi_fill_f32", (dT.data_ptr(), dT.numel(), 0.0), self._ew_meta(dT)))
+                m1 = self._conv_meta(sc.d1, d_1, x_d1, dy1)
                 ops.append(("mfvi_conv2d_wgrad", (C.byref(d_1), L.view(x_d1), L.view(dy1), self.dw.data_ptr() + 4 * sc.d1.w_off,
-                                                  self.dw.data_ptr() + 4 * sc.d1.b_off, lay.P_pad)))
+                                                  self.dw.data_ptr() + 4 * sc.d1.b_off, lay.P_pad), m1))
                 if need_dT:
                     ops.append(("mfvi_conv2d_dgrad", (C.byref(d_1), L.view(dy1), self.w.data_ptr() + 4 * sc.d1.w_off, lay.P_pad,
-                                                      L.view(dT_d1), 1 if Tpad != pd else 0)))
+                                                      L.view(dT_d1), 1 if Tpad != pd else 0), m1))
                 if Cs:
                     x_s = self._interior(T, Tpad - ps)
+                    ms = self._conv_meta(sc.skip_conv, d_s, x_s, gs)
                     ops.append(("mfvi_conv2d_wgrad", (C.byref(d_s), L.view(x_s), L.view(gs), self.dw.data_ptr() + 4 * sc.skip_conv.w_off,
-                                                      self.dw.data_ptr() + 4 * sc.skip_conv.b_off, lay.P_pad)))
+                                                      self.dw.data_ptr() + 4 * sc.skip_conv.b_off, lay.P_pad), ms))
                     if need_dT:
                         ops.append(("mfvi_conv2d_dgrad", (C.byref(d_s), L.view(gs), self.w.data_ptr() + 4 * sc.skip_conv.w_off,
-                                                          lay.P_pad, L.view(self._interior(dT, Tpad - ps)), 1)))
+                                                          lay.P_pad, L.view(self._interior(dT, Tpad - ps)), 1), ms))
                 return dT
 
             Tn_pad = in_pad(i + 1) if i < n - 1 else 0
@@ -419,7 +440,7 @@ class SkipEngine:
 
     # ---------------------------------------------------------------- execution
     def zero_accumulators(self):
-        L.call("mfvi_fill_f32", self.zbuf.data_ptr(), self.zbuf.numel(), 0.0)
+        L.call("mfvi_fill_f32", self.zbuf.data_ptr(), self.zbuf.numel(), 0.0, meta={"bytes": 4.0 * self.zbuf.numel()})
 
     def set_input(self, x_nhwc: torch.Tensor, noise: Optional[torch.Tensor], std: float, key: L.PhiloxKey):
         """x0 = reflect_pad(saved + std * N(0,1))  (reference bayesian_optimization.py:1363-1364).
@@ -436,20 +457,21 @@ class SkipEngine:
         """w_s = mu + softplus(rho) * eps_s for every layer at once (reference module.py:82-85)."""
         inj = self.inject_eps
         L.call("mfvi_sample_weights", self.mu.data_ptr(), self.rho.data_ptr(), self.lay.P, self.S,
-               self.eps.data_ptr() if inj else None, self.lay.P_pad, key, self.w.data_ptr(), self.lay.P_pad)
+               self.eps.data_ptr() if inj else None, self.lay.P_pad, key, self.w.data_ptr(), self.lay.P_pad,
+               meta={"bytes": 4.0 * self.lay.P * (2 + self.S)})
 
     def use_mean_weights(self):
         """Eval mode of RTLayer (reparam_layers.py:33-35): w = mu for every sample."""
         self.w[:, :self.lay.P].copy_(self.mu.unsqueeze(0).expand(self.S, -1))
 
     def forward(self):
-        for name, args in self.fwd_ops:
-            L.call(name, *args)
+        for name, args, meta in self.fwd_ops:
+            L.call(name, *args, meta=meta)
 
     def backward(self):
         """Consumes self.dout; fills dw[s], BN gamma/beta grads (and dx0 when requested)."""
-        for name, args in self.bwd_ops:
-            L.call(name, *args)
+        for name, args, meta in self.bwd_ops:
+            L.call(name, *args, meta=meta)
 
     def reparam_kl(self, key: L.PhiloxKey, *, prior_mu: float, prior_sigma_plus_eps: float, direction: int,
                    kscale: float, kscale_dev=None, data_term: bool = True, gscale: float = 1.0, accumulate: bool = False,
@@ -461,7 +483,8 @@ class SkipEngine:
                self.dw.data_ptr() if data_term else None, self.lay.P_pad, self.S if data_term else 0,
                self.eps.data_ptr() if inj else None, self.lay.P_pad, key, float(gscale),
                self._aptr(KL) if want_kl else None, self.g_mu.data_ptr() if want_grad else None,
-               self.g_rho.data_ptr() if want_grad else None, 1 if accumulate else 0)
+               self.g_rho.data_ptr() if want_grad else None, 1 if accumulate else 0,
+               meta={"bytes": 4.0 * self.lay.P * (2 + (self.S if data_term else 0) + (2 if want_grad else 0))})
 
     def update_running_stats(self, momentum: float = 0.1):
         L.call("mfvi_bn_running_update", self.arena.data_ptr(), self._bn_ch_off.data_ptr(), self._bn_sums_off.data_ptr(),

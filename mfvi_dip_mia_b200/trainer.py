@@ -59,16 +59,18 @@ class LossHead:
         loss_ptr = e._aptr(NLL)
         if self.task in ("den", "sr"):
             L.call("mfvi_gauss_nll_fwd_bwd", 0, L.view(e.out), S, H, W, Cn, self.sub, self.target.data_ptr(), None,
-                   loss_ptr, L.view(e.dout))
+                   loss_ptr, L.view(e.dout), meta={"bytes": 4.0 * (2 * e.out.numel() + self.target.numel())})
         elif self.task == "inp":
             L.call("mfvi_gauss_nll_fwd_bwd", 1, L.view(e.out), S, H, W, Cn, 1, self.target.data_ptr(),
-                   self.mask.data_ptr(), loss_ptr, L.view(e.dout))
+                   self.mask.data_ptr(), loss_ptr, L.view(e.dout),
+                   meta={"bytes": 4.0 * (2 * e.out.numel() + self.target.numel() + self.mask.numel())})
         else:
             n = Cn * self.T * W
-            L.call("mfvi_radon_fwd", L.view(e.out), S, Cn, H, W, self.theta.data_ptr(), self.T, self.sino.data_ptr())
+            rb = {"bytes": 4.0 * (e.out.numel() + self.sino.numel()), "samples": float(S * Cn * self.T * H * W)}
+            L.call("mfvi_radon_fwd", L.view(e.out), S, Cn, H, W, self.theta.data_ptr(), self.T, self.sino.data_ptr(), meta=rb)
             L.call("mfvi_mse_fwd_bwd", self.sino.data_ptr(), n, self.sino_t.data_ptr(), n, S, loss_ptr,
-                   self.dsino.data_ptr())
-            L.call("mfvi_radon_bwd", self.dsino.data_ptr(), S, Cn, H, W, self.theta.data_ptr(), self.T, L.view(e.dout))
+                   self.dsino.data_ptr(), meta={"bytes": 4.0 * (2 * self.sino.numel() + n)})
+            L.call("mfvi_radon_bwd", self.dsino.data_ptr(), S, Cn, H, W, self.theta.data_ptr(), self.T, L.view(e.dout), meta=rb)
 
 
 class MfviDipTrainer:
@@ -146,7 +148,7 @@ class MfviDipTrainer:
         e.update_running_stats()
         L.call("mfvi_adamw_step", e.theta.data_ptr(), e.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                e.n_theta_pad, self.lr, self.betas[0], self.betas[1], self.adam_eps, self.weight_decay, 1,
-               self.step_dev.data_ptr(), e._aptr(NLL) if self.nan_guard else None)
+               self.step_dev.data_ptr(), e._aptr(NLL) if self.nan_guard else None, meta={"bytes": 28.0 * e.n_theta_pad})
         L.call("mfvi_counter_add", self.step_dev.data_ptr(), 1)
 
     def step(self):
@@ -166,6 +168,27 @@ class MfviDipTrainer:
             self._graph = g
             # the capture itself did not execute: fall through and replay once
         self._graph.replay()
+
+    # ------------------------------------------------------------------ host-buffer entry (the e2e path of bench.py)
+    def host_buffers(self):
+        """Pinned host staging buffers: (net_input NHWC (H,W,C), target as the head stores it, result[2] doubles)."""
+        tgt = getattr(self.head, "target", None)
+        if tgt is None:
+            tgt = self.head.sino_t
+        return (torch.empty_like(self.saved, device="cpu").pin_memory(), torch.empty_like(tgt, device="cpu").pin_memory(),
+                torch.zeros(2, dtype=torch.float64).pin_memory())
+
+    def step_from_host(self, net_input_host, target_host, result_host):
+        """One step with HOST inputs: H2D copy of the fixed net input and the target, the step, D2H of [kl, nll].
+        Asynchronous; synchronise before reading result_host."""
+        tgt = getattr(self.head, "target", None)
+        if tgt is None:
+            tgt = self.head.sino_t
+        self.saved.copy_(net_input_host, non_blocking=True)
+        tgt.copy_(target_host, non_blocking=True)
+        self.step()
+        result_host.copy_(self.eng.arena[:2], non_blocking=True)
+        return self.saved.numel() * 4 + tgt.numel() * 4, 16
 
     # ------------------------------------------------------------------
     def loss_terms(self):
