@@ -1,0 +1,683 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (kind::tf32, fp32 accumulate in tensor memory).
+//
+// Every conv of the MFVI-DIP net is a "valid" convolution over a reflection-padded NHWC fp32 buffer, so tap (r,s) of
+// an output tile is just the same TMA box shifted by (r,s): no im2col buffer exists anywhere.
+//
+//   forward : D[128 pixels x Cout] += A_tap[128 x 32ch] * W_tap[Cout x 32ch]^T        A K-major, B K-major
+//   dgrad   : D[128 pixels x Cin ] += dY_tap[128 x 32co] * W_tap[32co x Cin]          A K-major, B MN-major
+//             (tap offsets negative; TMA zero-fills out-of-bounds coordinates)
+//   wgrad   : D[Cout x Cin] (per tap) += dY[pixels x Cout]^T * X_tap[pixels x Cin]    A MN-major, B MN-major, split-K
+//             over pixel chunks, fp32 atomics into dw
+//
+// CTA = 6 warps: warp 0 TMA producer, warp 1 TMEM allocator + single-thread MMA issuer, warps 2..5 epilogue
+// (TMEM -> registers -> shared staging -> coalesced global stores, fused bias and BatchNorm (sum, sumsq) statistics).
+// Operand tiles are 128-byte-swizzled rows of 32 fp32 (one swizzle atom), 3-4 stage mbarrier pipeline.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace mfvi {
+namespace tc {
+
+constexpr int kBM = 128;        // UMMA_M (cta_group::1)
+constexpr int kBK = 32;         // fp32 per k-chunk = one 128-byte swizzle row
+constexpr int kUmmaK = 8;       // kind::tf32
+constexpr int kThreads = 192;
+constexpr int kABytes = kBM * kBK * 4;   // 16 KB
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, 128-byte swizzle (sm_100 "version 1" descriptor).
+//   K-major : rows (M/N index) are 128 B apart, 8-row groups SBO = 1024 B apart; LBO unused.
+//   MN-major: rows (K index) are 128 B apart and hold 32 consecutive M/N elements; 8-row K groups SBO apart;
+//             32-element M/N blocks LBO apart.
+//   kind::tf32 MN-major operands must use the "128B swizzle with 32B atoms" layout (layout type 1; TMA swizzle
+//   128B_ATOM_32B): 32-byte chunks are XOR-swizzled with (row mod 4), K groups are 4 rows (SBO = 512 B).
+constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32 = 1;
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = kLayoutSw128) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;   // descriptor version (sm_100)
+  d |= static_cast<uint64_t>(layout) << 61;
+  return d;
+}
+// Instruction descriptor: D=f32, A=B=tf32, majors, N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ inline uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  uint32_t d = 0;
+  d |= 1u << 4;                       // c_format = F32
+  d |= 2u << 7;                       // a_format = TF32
+  d |= 2u << 10;                      // b_format = TF32
+  d |= static_cast<uint32_t>(a_mn_major & 1) << 15;
+  d |= static_cast<uint32_t>(b_mn_major & 1) << 16;
+  d |= static_cast<uint32_t>(N >> 3) << 17;
+  d |= static_cast<uint32_t>(M >> 4) << 24;
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------- fwd / dgrad
+struct TcConvArgs {
+  int Kc;             // contraction channels per tap (Cin fwd, Cout dgrad)
+  int N;              // valid output channels (Cout fwd, Cin dgrad)
+  int BN;             // UMMA N (multiple of 16; multiple of 32 when B is MN-major)
+  int KH, KW;
+  int Mh, Mw;         // output pixel space (Hout x Wout fwd, Hin x Win dgrad)
+  int TH, TW;         // pixel tile, TH*TW <= 128
+  int tiles_w;
+  int a_bcast, b_bcast;
+  int dgrad;          // tap offsets are negative, B is MN-major (original [tap][Cout][Cin] weights)
+  int stages;
+  uint32_t b_bytes;   // bytes of one B stage
+  uint32_t tmem_cols;
+  MfviView o;
+  const float* bias;  // [S][..] sampled bias (fwd only) or NULL
+  long long bias_sstride;
+  double* stats;      // [S][N][2] or NULL
+  int accumulate;
+  int vecO;
+};
+
+__global__ void __launch_bounds__(kThreads)
+k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcConvArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const uint32_t stage_bytes = kABytes + p.b_bytes;
+  uint8_t* ctrl = smem + static_cast<size_t>(p.stages) * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* tmem_full_bar = full_bar + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full_bar + 17);
+  int* row_off = reinterpret_cast<int*>(full_bar + 18);       // [128] element offset of each tile row, -1 = invalid
+  float* col_acc = reinterpret_cast<float*>(row_off + kBM);   // [BN][2]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int smp = blockIdx.z;
+  const int tile = blockIdx.x;
+  const int h0 = (tile / p.tiles_w) * p.TH, w0 = (tile % p.tiles_w) * p.TW;
+  const int n0 = blockIdx.y * p.BN;
+  const int chunks = (p.Kc + kBK - 1) / kBK;
+  const int n_iters = p.KH * p.KW * chunks;
+  const uint32_t a_box_bytes = static_cast<uint32_t>(p.TH * p.TW) * 128u;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(smem_u32(&full_bar[i]), 1);
+      mbar_init(smem_u32(&empty_bar[i]), 1);
+    }
+    mbar_init(smem_u32(tmem_full_bar), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer
+      for (int it = 0; it < n_iters; ++it) {
+        const int st = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(smem_u32(&empty_bar[st]), ph ^ 1);
+        const uint32_t fb = smem_u32(&full_bar[st]);
+        mbar_expect_tx(fb, a_box_bytes + p.b_bytes);
+        const int tap = it / chunks, kc = (it % chunks) * kBK;
+        const int r = tap / p.KW, s = tap % p.KW;
+        const uint32_t a_dst = smem_u32(smem + static_cast<size_t>(st) * stage_bytes);
+        const uint32_t b_dst = a_dst + kABytes;
+        const int hh = p.dgrad ? h0 - r : h0 + r, ww = p.dgrad ? w0 - s : w0 + s;
+        tma_load_4d(a_dst, &tmA, fb, kc, ww, hh, p.a_bcast ? 0 : smp);
+        const int bs = p.b_bcast ? 0 : smp;
+        if (!p.dgrad) {
+          tma_load_4d(b_dst, &tmB, fb, kc, n0, tap, bs);            // box (32 k, BN n)
+        } else {
+          for (int j = 0; j < p.BN / 32; ++j)                        // boxes (32 n, 32 k), 4 KB each
+            tma_load_4d(b_dst + j * 4096, &tmB, fb, n0 + 32 * j, kc, tap, bs);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread)
+    const uint32_t idesc = make_idesc(kBM, p.BN, 0, p.dgrad ? 1 : 0);
+    for (int it = 0; it < n_iters; ++it) {
+      const int st = it % p.stages;
+      const uint32_t ph = (it / p.stages) & 1;
+      mbar_wait(smem_u32(&full_bar[st]), ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(st) * stage_bytes);
+        const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+        for (int k = 0; k < kBK / kUmmaK; ++k) {
+          const uint64_t ad = make_desc(a_addr + k * (kUmmaK * 4), 16, 1024);
+          const uint64_t bd = p.dgrad ? make_desc(b_addr + k * 1024, 4096, 512, kLayoutSw128Base32)
+                                      : make_desc(b_addr + k * (kUmmaK * 4), 16, 1024);
+          tc_mma_tf32(tmem_base, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit(smem_u32(&empty_bar[st]));
+        if (it == n_iters - 1) tc_commit(smem_u32(tmem_full_bar));
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4
+    const int q = warp & 3;
+    const int m = q * 32 + lane;              // tile row == TMEM lane
+    const int et = threadIdx.x - 64;          // 0..127
+    {
+      const int hl = m / p.TW, wl = m % p.TW;
+      const bool ok = hl < p.TH && (h0 + hl) < p.Mh && (w0 + wl) < p.Mw;
+      row_off[m] = ok ? static_cast<int>(static_cast<long long>(h0 + hl) * p.o.hstride + static_cast<long long>(w0 + wl) * p.o.wstride) : -1;
+      for (int c = et; c < 2 * p.BN; c += 128) col_acc[c] = 0.f;
+    }
+    mbar_wait(smem_u32(tmem_full_bar), 0);
+    tc_fence_after();
+    float* stg = reinterpret_cast<float*>(smem);      // [128][BN+1], reuses the (drained) pipeline stages
+    const int ld = p.BN + 1;
+    const bool row_ok = row_off[m] >= 0;
+    const float* bias = (p.bias != nullptr) ? p.bias + static_cast<size_t>(smp) * p.bias_sstride + n0 : nullptr;
+    for (int c = 0; c < p.BN; c += 16) {
+      float v[16];
+      tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c), v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float x = v[j];
+        if (bias != nullptr && n0 + c + j < p.N) x += bias[c + j];
+        stg[m * ld + c + j] = (row_ok && n0 + c + j < p.N) ? x : 0.f;
+      }
+    }
+    tc_fence_before();
+    epi_barrier();
+    // ---- BatchNorm statistics of this tile (rows that are invalid hold zeros)
+    if (p.stats != nullptr) {
+      const int tpc = p.BN <= 128 ? 128 / p.BN : 1;          // threads per column
+      for (int col = et % p.BN, part = et / p.BN; col < p.BN && part < tpc; col += 128 * tpc) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int rr = part; rr < kBM; rr += tpc) {
+          const float x = stg[rr * ld + col];
+          s1 += x;
+          s2 = fmaf(x, x, s2);
+        }
+        atomicAdd(&col_acc[2 * col], s1);
+        atomicAdd(&col_acc[2 * col + 1], s2);
+        if (p.BN <= 128) break;
+      }
+      epi_barrier();
+      for (int col = et; col < p.BN; col += 128) {
+        if (n0 + col < p.N) {
+          double* dst = p.stats + (static_cast<size_t>(smp) * p.N + n0 + col) * 2;
+          atomicAdd(dst, static_cast<double>(col_acc[2 * col]));
+          atomicAdd(dst + 1, static_cast<double>(col_acc[2 * col + 1]));
+        }
+      }
+    }
+    // ---- coalesced store: BN/4 threads per row
+    float* obase = p.o.ptr + static_cast<size_t>(smp) * p.o.sstride + n0;
+    const int tpr = p.BN / 4;
+    for (int idx = et; idx < kBM * tpr; idx += 128) {
+      const int rr = idx / tpr, cq = (idx % tpr) * 4;
+      const int off = row_off[rr];
+      if (off < 0 || n0 + cq >= p.N) continue;
+      float* dst = obase + off + cq;
+      const float* src = stg + rr * ld + cq;
+      if (p.vecO && n0 + cq + 3 < p.N) {
+        float4 v = make_float4(src[0], src[1], src[2], src[3]);
+        if (p.accumulate) {
+          const float4 o = *reinterpret_cast<const float4*>(dst);
+          v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+        }
+        *reinterpret_cast<float4*>(dst) = v;
+      } else {
+        for (int j = 0; j < 4; ++j)
+          if (n0 + cq + j < p.N) dst[j] = p.accumulate ? dst[j] + src[j] : src[j];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- wgrad
+struct TcWgradArgs {
+  int Cout, Cin, KW;
+  int Ho, Wo;           // dy spatial size
+  int TH, TW, TP;       // pixel tile (K chunk) TP = TH*TW, multiple of 8
+  int tiles_w, n_tiles, tiles_per_cta;
+  int MB, NB;           // 32-channel blocks of dy (M) and x (N)
+  int x_bcast;
+  int stages;
+  uint32_t tmem_cols;
+  float* dw;            // [S][taps][Cout][Cin]
+  long long w_sstride;
+};
+
+__global__ void __launch_bounds__(kThreads)
+k_wgrad_tc(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, const TcWgradArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const uint32_t blk_bytes = static_cast<uint32_t>(p.TP) * 128u;          // one 32-channel block of TP pixel rows
+  const uint32_t a_bytes = 4u * blk_bytes;                                // M = 128 -> 4 blocks reserved
+  const uint32_t stage_bytes = a_bytes + static_cast<uint32_t>(p.NB) * blk_bytes;
+  uint8_t* ctrl = smem + static_cast<size_t>(p.stages) * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* tmem_full_bar = full_bar + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full_bar + 17);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int smp = blockIdx.z, tap = blockIdx.y;
+  const int r = tap / p.KW, s = tap % p.KW;
+  const int t_begin = blockIdx.x * p.tiles_per_cta;
+  const int t_end = min(t_begin + p.tiles_per_cta, p.n_tiles);
+  const int n_iters = t_end - t_begin;
+  const int BN = p.NB * 32;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDy);
+    tma_prefetch_desc(&tmX);
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(smem_u32(&full_bar[i]), 1);
+      mbar_init(smem_u32(&empty_bar[i]), 1);
+    }
+    mbar_init(smem_u32(tmem_full_bar), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (n_iters <= 0) {           // nothing to do (uniform per CTA)
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+    return;
+  }
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < n_iters; ++it) {
+        const int st = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(smem_u32(&empty_bar[st]), ph ^ 1);
+        const uint32_t fb = smem_u32(&full_bar[st]);
+        mbar_expect_tx(fb, static_cast<uint32_t>(p.MB + p.NB) * blk_bytes);
+        const int t = t_begin + it;
+        const int h0 = (t / p.tiles_w) * p.TH, w0 = (t % p.tiles_w) * p.TW;
+        const uint32_t a_dst = smem_u32(smem + static_cast<size_t>(st) * stage_bytes);
+        const uint32_t b_dst = a_dst + a_bytes;
+        for (int j = 0; j < p.MB; ++j) tma_load_4d(a_dst + j * blk_bytes, &tmDy, fb, 32 * j, w0, h0, smp);
+        for (int j = 0; j < p.NB; ++j) tma_load_4d(b_dst + j * blk_bytes, &tmX, fb, 32 * j, w0 + s, h0 + r, p.x_bcast ? 0 : smp);
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(kBM, BN, 1, 1);
+    const int ksteps = p.TP / kUmmaK;
+    for (int it = 0; it < n_iters; ++it) {
+      const int st = it % p.stages;
+      const uint32_t ph = (it / p.stages) & 1;
+      mbar_wait(smem_u32(&full_bar[st]), ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(st) * stage_bytes);
+        const uint32_t b_addr = a_addr + a_bytes;
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t ad = make_desc(a_addr + k * 1024, blk_bytes, 512, kLayoutSw128Base32);
+          const uint64_t bd = make_desc(b_addr + k * 1024, blk_bytes, 512, kLayoutSw128Base32);
+          tc_mma_tf32(tmem_base, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit(smem_u32(&empty_bar[st]));
+        if (it == n_iters - 1) tc_commit(smem_u32(tmem_full_bar));
+      }
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3;
+    const int co = q * 32 + lane;
+    mbar_wait(smem_u32(tmem_full_bar), 0);
+    tc_fence_after();
+    float* dst = p.dw + static_cast<size_t>(smp) * p.w_sstride + (static_cast<size_t>(tap) * p.Cout + co) * p.Cin;
+    for (int c = 0; c < BN; c += 16) {
+      float v[16];
+      tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c), v);
+      if (co < p.Cout) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          if (c + j + 3 < p.Cin) {
+            atomicAdd(reinterpret_cast<float4*>(dst + c + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+          } else {
+            for (int jj = j; jj < j + 4; ++jj)
+              if (c + jj < p.Cin) atomicAdd(dst + c + jj, v[jj]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// dbias[s][co] += sum over pixels of dy[s][.][.][co]   (one warp-row per pixel slice; HBM-bound column sum)
+__global__ void __launch_bounds__(256)
+k_bias_grad(MfviView dy, int H, int W, int C, float* __restrict__ dbias, long long sstride) {
+  extern __shared__ float sm_part[];                 // [C]
+  const int s = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) sm_part[c] = 0.f;
+  __syncthreads();
+  const int G = C / 4;                               // float4 groups per pixel (C % 4 == 0)
+  const int PPB = blockDim.x / G > 0 ? blockDim.x / G : 1;
+  const int g = threadIdx.x % G, slot = threadIdx.x / G;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (slot < PPB) {
+    const int npix = H * W;
+    for (int px = blockIdx.x * PPB + slot; px < npix; px += gridDim.x * PPB) {
+      const float4 v = *reinterpret_cast<const float4*>(dy.ptr + view_off(dy, s, px / W, px % W) + 4 * g);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    atomicAdd(&sm_part[4 * g + 0], acc.x);
+    atomicAdd(&sm_part[4 * g + 1], acc.y);
+    atomicAdd(&sm_part[4 * g + 2], acc.z);
+    atomicAdd(&sm_part[4 * g + 3], acc.w);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(dbias + static_cast<size_t>(s) * sstride + c, sm_part[c]);
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+static PFN_cuTensorMapEncodeTiled get_encode() {
+  static PFN_cuTensorMapEncodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+  });
+  return fn;
+}
+
+// 4-D fp32 tensor map, 128B swizzle, zero fill. dims/box innermost first; strides in bytes for dims 1..3.
+static bool encode_map(CUtensorMap* m, const void* base, const uint64_t dims[4], const uint64_t strides[3], const uint32_t box[4],
+                       const uint32_t estr[4], bool mn_major = false) {
+  PFN_cuTensorMapEncodeTiled enc = get_encode();
+  if (enc == nullptr) return false;
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+static bool view_tma_ok(const MfviView& v, int C) {
+  return (reinterpret_cast<uintptr_t>(v.ptr) % 16 == 0) && (C % 4 == 0) && (v.wstride % 4 == 0) && (v.hstride % 4 == 0) &&
+         (v.sstride % 4 == 0) && v.wstride >= C && v.hstride >= v.wstride;
+}
+
+static uint32_t pow2_cols(int n) {
+  uint32_t c = 32;
+  while (c < static_cast<uint32_t>(n)) c <<= 1;
+  return c;
+}
+
+static void pick_tile(int Mh, int Mw, int& TH, int& TW) {
+  TW = Mw >= 128 ? 128 : Mw;
+  TH = 128 / TW;
+  if (TH < 1) TH = 1;
+  if (TH > Mh) TH = Mh;
+}
+
+// a: activation view read through TMA (x for fwd, dy for dgrad), its channel count Ca and spatial size (Ha, Wa).
+static bool map_activation(CUtensorMap* m, const MfviView& a, int Ca, int Ha, int Wa, int S, int TH, int TW, bool& bcast,
+                           bool mn_major = false) {
+  bcast = (a.sstride == 0) || S == 1;
+  const uint64_t dims[4] = {static_cast<uint64_t>(Ca), static_cast<uint64_t>(Wa), static_cast<uint64_t>(Ha),
+                            static_cast<uint64_t>(bcast ? 1 : S)};
+  const uint64_t sbytes = bcast ? static_cast<uint64_t>(a.hstride) * Ha * 4 : static_cast<uint64_t>(a.sstride) * 4;
+  const uint64_t strides[3] = {static_cast<uint64_t>(a.wstride) * 4, static_cast<uint64_t>(a.hstride) * 4, sbytes};
+  const uint32_t box[4] = {static_cast<uint32_t>(kBK), static_cast<uint32_t>(TW), static_cast<uint32_t>(TH), 1};
+  const uint32_t estr[4] = {1, 1, 1, 1};
+  return encode_map(m, a.ptr, dims, strides, box, estr, mn_major);
+}
+
+static size_t conv_smem_bytes(int stages, uint32_t b_bytes, int BN) {
+  size_t pipe = static_cast<size_t>(stages) * (kABytes + b_bytes);
+  size_t stg = static_cast<size_t>(kBM) * (BN + 1) * 4;
+  if (stg > pipe) pipe = (stg + 1023) / 1024 * 1024;
+  return 1024 + pipe + 18 * 8 + kBM * 4 + static_cast<size_t>(BN) * 8 + 64;
+}
+
+}  // namespace tc
+}  // namespace mfvi
+
+using namespace mfvi;
+
+extern "C" {
+
+// Returns 0 on success, -1 when this shape is not taken by the tensor-core kernel (caller falls back), >0 on error.
+int mfvi_conv2d_fwd_tc(const MfviConvDesc* d, MfviView x, const float* w, const float* bias, long long w_sstride, MfviView y,
+                       double* stats, mfvi_stream_t st) {
+  using namespace mfvi::tc;
+  if (d->stride != 1 || !view_tma_ok(x, d->Cin) || (reinterpret_cast<uintptr_t>(w) % 16) || (w_sstride % 4) || d->Cout > 256) return -1;
+  TcConvArgs a{};
+  a.Kc = d->Cin; a.N = d->Cout; a.BN = (d->Cout + 15) / 16 * 16;
+  a.KH = d->KH; a.KW = d->KW; a.Mh = d->Hout; a.Mw = d->Wout;
+  pick_tile(a.Mh, a.Mw, a.TH, a.TW);
+  a.tiles_w = (a.Mw + a.TW - 1) / a.TW;
+  a.dgrad = 0;
+  a.b_bytes = static_cast<uint32_t>(a.BN) * 128u;
+  a.stages = a.BN >= 64 ? 3 : 4;
+  a.tmem_cols = pow2_cols(a.BN);
+  a.o = y; a.bias = bias; a.bias_sstride = w_sstride; a.stats = stats; a.accumulate = 0;
+  a.vecO = ((reinterpret_cast<uintptr_t>(y.ptr) % 16 == 0) && y.sstride % 4 == 0 && y.hstride % 4 == 0 && y.wstride % 4 == 0 && d->Cout % 4 == 0) ? 1 : 0;
+  CUtensorMap tmA, tmB;
+  bool ab = false;
+  if (!map_activation(&tmA, x, d->Cin, d->Hin, d->Win, d->S, a.TH, a.TW, ab)) return -1;
+  a.a_bcast = ab ? 1 : 0;
+  a.b_bcast = (w_sstride == 0 || d->S == 1) ? 1 : 0;
+  {
+    const uint64_t dims[4] = {static_cast<uint64_t>(d->Cin), static_cast<uint64_t>(d->Cout), static_cast<uint64_t>(d->KH * d->KW),
+                              static_cast<uint64_t>(a.b_bcast ? 1 : d->S)};
+    const uint64_t tap_bytes = static_cast<uint64_t>(d->Cout) * d->Cin * 4;
+    const uint64_t strides[3] = {static_cast<uint64_t>(d->Cin) * 4, tap_bytes,
+                                 a.b_bcast ? tap_bytes * d->KH * d->KW : static_cast<uint64_t>(w_sstride) * 4};
+    const uint32_t box[4] = {static_cast<uint32_t>(kBK), static_cast<uint32_t>(a.BN), 1, 1};
+    const uint32_t estr[4] = {1, 1, 1, 1};
+    if (!encode_map(&tmB, w, dims, strides, box, estr)) return -1;
+  }
+  const size_t smem = conv_smem_bytes(a.stages, a.b_bytes, a.BN);
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    MFVI_REQUIRE(e == cudaSuccess, "conv2d_fwd_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
+    attr = 200 * 1024;
+  }
+  const int tiles_h = (a.Mh + a.TH - 1) / a.TH;
+  dim3 grid(a.tiles_w * tiles_h, 1, d->S);
+  k_conv_tc<<<grid, kThreads, smem, as_stream(st)>>>(tmA, tmB, a);
+  return check_launch("conv2d_fwd_tc");
+}
+
+int mfvi_conv2d_dgrad_tc(const MfviConvDesc* d, MfviView dy, const float* w, long long w_sstride, MfviView dx, int accumulate,
+                         mfvi_stream_t st) {
+  using namespace mfvi::tc;
+  if (d->stride != 1 || !view_tma_ok(dy, d->Cout) || (reinterpret_cast<uintptr_t>(w) % 16) || (w_sstride % 4) || d->Cin % 4 ||
+      d->Cin > 256)
+    return -1;
+  TcConvArgs a{};
+  a.Kc = d->Cout; a.N = d->Cin; a.BN = (d->Cin + 31) / 32 * 32;
+  a.KH = d->KH; a.KW = d->KW; a.Mh = d->Hin; a.Mw = d->Win;
+  pick_tile(a.Mh, a.Mw, a.TH, a.TW);
+  a.tiles_w = (a.Mw + a.TW - 1) / a.TW;
+  a.dgrad = 1;
+  a.b_bytes = static_cast<uint32_t>(a.BN) * 128u;
+  a.stages = a.BN >= 64 ? 3 : 4;
+  a.tmem_cols = pow2_cols(a.BN);
+  a.o = dx; a.bias = nullptr; a.bias_sstride = 0; a.stats = nullptr; a.accumulate = accumulate;
+  a.vecO = ((reinterpret_cast<uintptr_t>(dx.ptr) % 16 == 0) && dx.sstride % 4 == 0 && dx.hstride % 4 == 0 && dx.wstride % 4 == 0) ? 1 : 0;
+  CUtensorMap tmA, tmB;
+  bool ab = false;
+  if (!map_activation(&tmA, dy, d->Cout, d->Hout, d->Wout, d->S, a.TH, a.TW, ab)) return -1;
+  a.a_bcast = ab ? 1 : 0;
+  a.b_bcast = (w_sstride == 0 || d->S == 1) ? 1 : 0;
+  {
+    // original weights [tap][Cout][Cin]: inner dim = Cin (the GEMM N), rows = Cout (the GEMM K): MN-major B
+    const uint64_t dims[4] = {static_cast<uint64_t>(d->Cin), static_cast<uint64_t>(d->Cout), static_cast<uint64_t>(d->KH * d->KW),
+                              static_cast<uint64_t>(a.b_bcast ? 1 : d->S)};
+    const uint64_t tap_bytes = static_cast<uint64_t>(d->Cout) * d->Cin * 4;
+    const uint64_t strides[3] = {static_cast<uint64_t>(d->Cin) * 4, tap_bytes,
+                                 a.b_bcast ? tap_bytes * d->KH * d->KW : static_cast<uint64_t>(w_sstride) * 4};
+    const uint32_t box[4] = {32, static_cast<uint32_t>(kBK), 1, 1};
+    const uint32_t estr[4] = {1, 1, 1, 1};
+    if (!encode_map(&tmB, w, dims, strides, box, estr, true)) return -1;
+  }
+  const size_t smem = conv_smem_bytes(a.stages, a.b_bytes, a.BN);
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    MFVI_REQUIRE(e == cudaSuccess, "conv2d_dgrad_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
+    attr = 200 * 1024;
+  }
+  const int tiles_h = (a.Mh + a.TH - 1) / a.TH;
+  dim3 grid(a.tiles_w * tiles_h, 1, d->S);
+  k_conv_tc<<<grid, kThreads, smem, as_stream(st)>>>(tmA, tmB, a);
+  return check_launch("conv2d_dgrad_tc");
+}
+
+int mfvi_conv2d_wgrad_tc(const MfviConvDesc* d, MfviView x, MfviView dy, float* dw, float* dbias, long long w_sstride,
+                         mfvi_stream_t st) {
+  using namespace mfvi::tc;
+  if (d->stride != 1 || !view_tma_ok(x, d->Cin) || !view_tma_ok(dy, d->Cout) || d->Cout > 128 || d->Cin > 256 ||
+      (reinterpret_cast<uintptr_t>(dw) % 16) || (w_sstride % 4))
+    return -1;
+  TcWgradArgs a{};
+  a.Cout = d->Cout; a.Cin = d->Cin; a.KW = d->KW; a.Ho = d->Hout; a.Wo = d->Wout;
+  a.MB = (d->Cout + 31) / 32; a.NB = (d->Cin + 31) / 32;
+  int TP = 128;
+  while (TP > 8 && static_cast<size_t>(4 + a.NB) * TP * 128 > 48 * 1024) TP >>= 1;
+  // the pixel tile must cover exactly TP rows (every K row enters the sum): TW | TP
+  int TW = d->Wout >= TP ? TP : d->Wout;
+  while (TW > 1 && TP % TW) --TW;
+  int TH = TP / TW;
+  if (TH > d->Hout) {        // tiny images: shrink the tile
+    TH = d->Hout;
+    TP = TH * TW;
+  }
+  if (TP % 8 || TW > 256 || TH > 256) return -1;
+  a.TH = TH; a.TW = TW; a.TP = TP;
+  a.tiles_w = (d->Wout + TW - 1) / TW;
+  a.n_tiles = a.tiles_w * ((d->Hout + TH - 1) / TH);
+  const int taps = d->KH * d->KW;
+  int chunks = (2 * kNumSMs + taps * d->S - 1) / (taps * d->S);
+  chunks = std::max(1, std::min(chunks, a.n_tiles));
+  a.tiles_per_cta = (a.n_tiles + chunks - 1) / chunks;
+  chunks = (a.n_tiles + a.tiles_per_cta - 1) / a.tiles_per_cta;
+  a.stages = 4;
+  a.tmem_cols = pow2_cols(a.NB * 32);
+  a.dw = dw; a.w_sstride = w_sstride;
+  CUtensorMap tmDy, tmX;
+  bool db = false, xb = false;
+  if (!map_activation(&tmDy, dy, d->Cout, d->Hout, d->Wout, d->S, TH, TW, db, true)) return -1;
+  if (db && d->S > 1) return -1;
+  if (!map_activation(&tmX, x, d->Cin, d->Hin, d->Win, d->S, TH, TW, xb, true)) return -1;
+  a.x_bcast = xb ? 1 : 0;
+  const size_t smem = 1024 + static_cast<size_t>(a.stages) * (4 + a.NB) * TP * 128 + 18 * 8 + 64;
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    MFVI_REQUIRE(e == cudaSuccess, "conv2d_wgrad_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
+    attr = 220 * 1024;
+  }
+  MFVI_REQUIRE(smem <= 220 * 1024, "conv2d_wgrad_tc: stage does not fit in shared memory");
+  dim3 grid(chunks, taps, d->S);
+  k_wgrad_tc<<<grid, kThreads, smem, as_stream(st)>>>(tmDy, tmX, a);
+  if (int rc = check_launch("conv2d_wgrad_tc")) return rc;
+  if (dbias != nullptr) {
+    int blocks = std::max(1, std::min(kNumSMs * 2, (d->Hout * d->Wout * (d->Cout / 4) + 255) / 256));
+    dim3 g2(blocks, d->S);
+    k_bias_grad<<<g2, 256, d->Cout * sizeof(float), as_stream(st)>>>(dy, d->Hout, d->Wout, d->Cout, dbias, w_sstride);
+    return check_launch("conv2d_wgrad_tc(bias)");
+  }
+  return 0;
+}
+
+}  // extern "C"

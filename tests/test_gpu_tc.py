@@ -1,0 +1,98 @@
+"""tcgen05 (kind::tf32, fp32 accumulate) convolution kernels against the exact-fp32 CUDA-core kernels of the same
+library, on the layer shapes of the MFVI-DIP nets.  TF32 keeps a 10-bit mantissa for the operands, so the bar here is
+the separately stated reduced-precision tolerance (north_star: "bf16 operands with fp32 accumulate stated
+separately"): normalised max error < 3e-3 (observed ~5e-4); the fp32 path is held to 1e-3 in test_gpu_parity.py."""
+import ctypes as C
+
+import pytest
+import torch
+
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+TF32_TOL = 3e-3
+
+# (cin, cout, k, H, W) — H, W = output size; stride 1; input is (H+k-1, W+k-1)
+SHAPES = [
+    (132, 128, 3, 16, 16), (36, 16, 3, 64, 64), (16, 4, 1, 32, 32), (128, 128, 1, 16, 16), (16, 2, 1, 64, 64),
+    (68, 32, 3, 32, 48), (16, 16, 5, 24, 24), (128, 128, 3, 8, 8), (64, 64, 3, 32, 32), (32, 32, 1, 128, 128),
+    (36, 16, 3, 256, 256),
+]
+
+
+def _run(shape, math, S=2, seed=0, broadcast_x=False):
+    from mfvi_dip_mia_b200 import _lib as L
+    cin, cout, k, H, W = shape
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(seed)
+    Hin, Win = H + k - 1, W + k - 1
+    x = torch.randn(1 if broadcast_x else S, Hin, Win, cin, device=dev, generator=g)
+    w = torch.randn(S, k * k * cout * cin + cout, device=dev, generator=g) * 0.1
+    dy = torch.randn(S, H, W, cout, device=dev, generator=g)
+    y = torch.zeros(S, H, W, cout, device=dev)
+    dx = torch.zeros(S, Hin, Win, cin, device=dev)
+    dw = torch.zeros_like(w)
+    stats = torch.zeros(S, cout, 2, dtype=torch.float64, device=dev)
+    d = L.ConvDesc(S, cin, cout, k, k, 1, Hin, Win, H, W, math)
+    P = w.shape[1]
+    boff = k * k * cout * cin
+    L.call("mfvi_conv2d_fwd", C.byref(d), L.view(x), w.data_ptr(), w.data_ptr() + 4 * boff, P, L.view(y), stats.data_ptr())
+    L.call("mfvi_conv2d_dgrad", C.byref(d), L.view(dy), w.data_ptr(), P, L.view(dx), 0)
+    L.call("mfvi_conv2d_wgrad", C.byref(d), L.view(x), L.view(dy), dw.data_ptr(), dw.data_ptr() + 4 * boff, P)
+    torch.cuda.synchronize()
+    return y, dx, dw, stats
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_tc_conv_matches_fp32_kernels(shape):
+    from mfvi_dip_mia_b200 import _lib as L
+    ref = _run(shape, L.MATH_FP32)
+    got = _run(shape, L.MATH_TF32)
+    names = ["y", "dx", "dw(+dbias)", "bn stats"]
+    for n, a, b in zip(names, got, ref):
+        assert torch.isfinite(a).all(), n
+        assert rel_err(a, b) < TF32_TOL, (shape, n, rel_err(a, b))
+
+
+def test_tc_conv_broadcast_input_and_accumulate():
+    from mfvi_dip_mia_b200 import _lib as L
+    shape = (16, 16, 3, 64, 64)
+    ref = _run(shape, L.MATH_FP32, broadcast_x=True)
+    got = _run(shape, L.MATH_TF32, broadcast_x=True)
+    assert rel_err(got[0], ref[0]) < TF32_TOL
+
+
+@pytest.mark.parametrize("task", ["den", "inp"])
+def test_tf32_engine_step_close_to_reference(task):
+    """Whole step in TF32 mode against the reference fixture: stated reduced-precision tolerance 2e-2 on gradients
+    (errors compound through 26 layers of forward and backward), 2e-3 on the loss terms."""
+    from mfvi_dip_mia_b200 import SkipEngine, _lib as L
+    from mfvi_dip_mia_b200.engine import KL, NLL
+    from mfvi_dip_mia_b200.trainer import LossHead
+    from oracle import mfvi_oracle as O
+    from tests.helpers import grad_errs
+    from tests.test_gpu_parity import SMALL, _fixture, _head_kwargs, spec_of
+    dev = torch.device("cuda:0")
+    d, S, sd, eps, ex, grads = _fixture(task)
+    x = torch.from_numpy(d["net_input"])
+    eng = SkipEngine(spec_of(SMALL[task]), x.shape[2], x.shape[3], S, dev, math=L.MATH_TF32)
+    eng.load_params(sd, prefix="net.")
+    eng.pack_eps(eps, prefix="net.")
+    head = LossHead(eng, task, **_head_kwargs(task, ex))
+    temp, sigma = float(d["temp"]), float(d["sigma"])
+    eng.zero_accumulators()
+    eng.set_input(x[0].permute(1, 2, 0).contiguous().to(dev), None, 0.0, L.key(0))
+    eng.sample_weights(L.key(0))
+    eng.forward()
+    head.run()
+    eng.backward()
+    eng.reparam_kl(L.key(0), prior_mu=0.0, prior_sigma_plus_eps=O.prior_scale(temp, sigma), direction=0, kscale=temp)
+    out = eng.out_nchw().cpu()
+    for s in range(S):
+        assert rel_err(out[s:s + 1], d[f"out{s}"]) < 1e-2, s
+    a = eng.arena[:2].cpu()
+    assert rel_err(a[NLL], d["nll"]) < 2e-3
+    ours = {"net." + k: v.cpu() for k, v in eng.param_views("grad").items()}
+    errs = grad_errs({k: ours[k] for k in grads}, grads)
+    worst = max(errs, key=errs.get)
+    assert errs[worst] < 2e-2, (worst, errs[worst])
