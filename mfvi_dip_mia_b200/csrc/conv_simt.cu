@@ -39,7 +39,7 @@ k_conv_igemm(const ConvArgs p) {
   constexpr int KPER = BK / KQ;      // k values per B loader thread
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
-  __shared__ float sm_stat[BN][2];
+  __shared__ double sm_stat[TY][BN][2];   // per-row-thread partial (sum, sumsq) of the BatchNorm statistics
 
   const MfviConvDesc& d = p.d;
   const int s = blockIdx.z;
@@ -144,7 +144,8 @@ k_conv_igemm(const ConvArgs p) {
     for (int j = 0; j < 4; ++j)
       if (nb + j < N) bv[j] = p.bias[(size_t)s * p.w_sstride + nb + j];
   }
-  float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};
+  // statistics in double: var = E[x^2] - mean^2 cancels badly when |mean| >> std, so no fp32 partial sums
+  double st1[4] = {0.0, 0.0, 0.0, 0.0}, st2[4] = {0.0, 0.0, 0.0, 0.0};
   float* o_base = p.o.ptr + (size_t)s * p.o.sstride;
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
@@ -168,24 +169,27 @@ k_conv_igemm(const ConvArgs p) {
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      st1[j] += v[j];
-      st2[j] = fmaf(v[j], v[j], st2[j]);
+      st1[j] += (double)v[j];
+      st2[j] += (double)v[j] * (double)v[j];
     }
   }
   if (!DGRAD && p.stats != nullptr) {
-    for (int c = tid; c < BN; c += 256) sm_stat[c][0] = sm_stat[c][1] = 0.f;
-    __syncthreads();
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      atomicAdd(&sm_stat[tx * 4 + j][0], st1[j]);
-      atomicAdd(&sm_stat[tx * 4 + j][1], st2[j]);
+      sm_stat[ty][tx * 4 + j][0] = st1[j];
+      sm_stat[ty][tx * 4 + j][1] = st2[j];
     }
     __syncthreads();
     for (int c = tid; c < BN; c += 256) {
       if (n0 + c < N) {
+        double a = 0.0, b = 0.0;
+        for (int r = 0; r < TY; ++r) {       // fixed order: deterministic per CTA
+          a += sm_stat[r][c][0];
+          b += sm_stat[r][c][1];
+        }
         double* dst = p.stats + ((size_t)s * N + n0 + c) * 2;
-        atomicAdd(dst + 0, (double)sm_stat[c][0]);
-        atomicAdd(dst + 1, (double)sm_stat[c][1]);
+        atomicAdd(dst + 0, a);
+        atomicAdd(dst + 1, b);
       }
     }
   }

@@ -59,6 +59,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -136,6 +142,10 @@ struct TcConvArgs {
   int tiles_w;
   int a_bcast, b_bcast;
   int dgrad;          // tap offsets are negative, B is MN-major (original [tap][Cout][Cin] weights)
+  int cstride;        // conv stride: fwd reads the input through a TMA map with elementStrides = cstride; dgrad with
+                      // cstride 2 runs one output-parity class per blockIdx.y (taps of matching parity only)
+  int Hfull, Wfull;   // dgrad: full dx size (Mh, Mw are per parity class)
+  int a_rows2;        // stride-2 forward: Hin/2 (row offset of one sample in the parity-split 5-D input map)
   int stages;
   uint32_t b_bytes;   // bytes of one B stage
   uint32_t tmem_cols;
@@ -158,15 +168,21 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   uint64_t* tmem_full_bar = full_bar + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full_bar + 17);
   int* row_off = reinterpret_cast<int*>(full_bar + 18);       // [128] element offset of each tile row, -1 = invalid
-  float* col_acc = reinterpret_cast<float*>(row_off + kBM);   // [BN][2]
+  double* col_acc = reinterpret_cast<double*>(row_off + kBM);  // [tpc][BN][2] partial BatchNorm statistics
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int smp = blockIdx.z;
   const int tile = blockIdx.x;
   const int h0 = (tile / p.tiles_w) * p.TH, w0 = (tile % p.tiles_w) * p.TW;
-  const int n0 = blockIdx.y * p.BN;
+  const int n0 = 0;
+  // tap subset: all taps, or (dgrad, stride 2) the taps whose parity matches this CTA's output-parity class
+  const bool par = p.dgrad && p.cstride == 2;
+  const int ph = par ? (blockIdx.y >> 1) : 0, pw = par ? (blockIdx.y & 1) : 0;
+  const int tstep = par ? 2 : 1;
+  const int nr = par ? (p.KH - ph + 1) / 2 : p.KH, ns = par ? (p.KW - pw + 1) / 2 : p.KW;
+  const int Mh = par ? (p.Hfull - ph + 1) / 2 : p.Mh, Mw = par ? (p.Wfull - pw + 1) / 2 : p.Mw;
   const int chunks = (p.Kc + kBK - 1) / kBK;
-  const int n_iters = p.KH * p.KW * chunks;
+  const int n_iters = nr * ns * chunks;
   const uint32_t a_box_bytes = static_cast<uint32_t>(p.TH * p.TW) * 128u;
 
   if (warp == 0 && lane == 0) {
@@ -190,16 +206,30 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       // ===== TMA producer
       for (int it = 0; it < n_iters; ++it) {
         const int st = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        mbar_wait(smem_u32(&empty_bar[st]), ph ^ 1);
+        const uint32_t phase = (it / p.stages) & 1;
+        mbar_wait(smem_u32(&empty_bar[st]), phase ^ 1);
         const uint32_t fb = smem_u32(&full_bar[st]);
         mbar_expect_tx(fb, a_box_bytes + p.b_bytes);
-        const int tap = it / chunks, kc = (it % chunks) * kBK;
-        const int r = tap / p.KW, s = tap % p.KW;
+        const int ti = it / chunks, kc = (it % chunks) * kBK;
+        const int r = ph + tstep * (ti / ns), s = pw + tstep * (ti % ns);
+        const int tap = r * p.KW + s;
         const uint32_t a_dst = smem_u32(smem + static_cast<size_t>(st) * stage_bytes);
         const uint32_t b_dst = a_dst + kABytes;
-        const int hh = p.dgrad ? h0 - r : h0 + r, ww = p.dgrad ? w0 - s : w0 + s;
-        tma_load_4d(a_dst, &tmA, fb, kc, ww, hh, p.a_bcast ? 0 : smp);
+        int hh, ww;
+        if (!p.dgrad) {
+          hh = h0 * p.cstride + r; ww = w0 * p.cstride + s;
+        } else if (!par) {
+          hh = h0 - r; ww = w0 - s;
+        } else {
+          hh = h0 + (ph - r) / 2; ww = w0 + (pw - s) / 2;       // (ph - r), (pw - s) are even
+        }
+        if (!p.dgrad && p.cstride == 2) {
+          // parity-split 5-D view (C, 2, W/2, 2, H/2 * S) of the padded input: pixel (2*w2 + pw, 2*h2 + ph)
+          const int rows = p.a_bcast ? 0 : smp * p.a_rows2;
+          tma_load_5d(a_dst, &tmA, fb, kc, s & 1, w0 + (s >> 1), r & 1, rows + h0 + (r >> 1));
+        } else {
+          tma_load_4d(a_dst, &tmA, fb, kc, ww, hh, p.a_bcast ? 0 : smp);
+        }
         const int bs = p.b_bcast ? 0 : smp;
         if (!p.dgrad) {
           tma_load_4d(b_dst, &tmB, fb, kc, n0, tap, bs);            // box (32 k, BN n)
@@ -214,8 +244,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const uint32_t idesc = make_idesc(kBM, p.BN, 0, p.dgrad ? 1 : 0);
     for (int it = 0; it < n_iters; ++it) {
       const int st = it % p.stages;
-      const uint32_t ph = (it / p.stages) & 1;
-      mbar_wait(smem_u32(&full_bar[st]), ph);
+      const uint32_t phase = (it / p.stages) & 1;
+      mbar_wait(smem_u32(&full_bar[st]), phase);
       tc_fence_after();
       if (lane == 0) {
         const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(st) * stage_bytes);
@@ -239,19 +269,26 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int et = threadIdx.x - 64;          // 0..127
     {
       const int hl = m / p.TW, wl = m % p.TW;
-      const bool ok = hl < p.TH && (h0 + hl) < p.Mh && (w0 + wl) < p.Mw;
-      row_off[m] = ok ? static_cast<int>(static_cast<long long>(h0 + hl) * p.o.hstride + static_cast<long long>(w0 + wl) * p.o.wstride) : -1;
-      for (int c = et; c < 2 * p.BN; c += 128) col_acc[c] = 0.f;
+      const bool ok = hl < p.TH && (h0 + hl) < Mh && (w0 + wl) < Mw;
+      const long long oh = static_cast<long long>(h0 + hl) * tstep + ph, ow = static_cast<long long>(w0 + wl) * tstep + pw;
+      row_off[m] = ok ? static_cast<int>(oh * p.o.hstride + ow * p.o.wstride) : -1;
     }
-    mbar_wait(smem_u32(tmem_full_bar), 0);
-    tc_fence_after();
+    if (n_iters > 0) {
+      mbar_wait(smem_u32(tmem_full_bar), 0);
+      tc_fence_after();
+    }
     float* stg = reinterpret_cast<float*>(smem);      // [128][BN+1], reuses the (drained) pipeline stages
     const int ld = p.BN + 1;
     const bool row_ok = row_off[m] >= 0;
     const float* bias = (p.bias != nullptr) ? p.bias + static_cast<size_t>(smp) * p.bias_sstride + n0 : nullptr;
     for (int c = 0; c < p.BN; c += 16) {
       float v[16];
-      tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c), v);
+      if (n_iters > 0) {
+        tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c), v);
+      } else {                                   // parity class without taps (e.g. 1x1 stride 2): dx = 0 there
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+      }
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         float x = v[j];
@@ -263,24 +300,30 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     epi_barrier();
     // ---- BatchNorm statistics of this tile (rows that are invalid hold zeros)
     if (p.stats != nullptr) {
+      // column sums in double (var = E[x^2] - mean^2 cancels when |mean| >> std), fixed summation order
       const int tpc = p.BN <= 128 ? 128 / p.BN : 1;          // threads per column
-      for (int col = et % p.BN, part = et / p.BN; col < p.BN && part < tpc; col += 128 * tpc) {
-        float s1 = 0.f, s2 = 0.f;
+      for (int col = et % p.BN, part = et / p.BN; col < p.BN && part < tpc; col += 128) {
+        double s1 = 0.0, s2 = 0.0;
         for (int rr = part; rr < kBM; rr += tpc) {
-          const float x = stg[rr * ld + col];
+          const double x = static_cast<double>(stg[rr * ld + col]);
           s1 += x;
-          s2 = fmaf(x, x, s2);
+          s2 += x * x;
         }
-        atomicAdd(&col_acc[2 * col], s1);
-        atomicAdd(&col_acc[2 * col + 1], s2);
+        col_acc[(part * p.BN + col) * 2] = s1;
+        col_acc[(part * p.BN + col) * 2 + 1] = s2;
         if (p.BN <= 128) break;
       }
       epi_barrier();
       for (int col = et; col < p.BN; col += 128) {
         if (n0 + col < p.N) {
+          double s1 = 0.0, s2 = 0.0;
+          for (int part = 0; part < tpc; ++part) {
+            s1 += col_acc[(part * p.BN + col) * 2];
+            s2 += col_acc[(part * p.BN + col) * 2 + 1];
+          }
           double* dst = p.stats + (static_cast<size_t>(smp) * p.N + n0 + col) * 2;
-          atomicAdd(dst, static_cast<double>(col_acc[2 * col]));
-          atomicAdd(dst + 1, static_cast<double>(col_acc[2 * col + 1]));
+          atomicAdd(dst, s1);
+          atomicAdd(dst + 1, s2);
         }
       }
     }
@@ -321,6 +364,8 @@ struct TcWgradArgs {
   int TH, TW, TP;       // pixel tile (K chunk) TP = TH*TW, multiple of 8
   int tiles_w, n_tiles, tiles_per_cta;
   int MB, NB;           // 32-channel blocks of dy (M) and x (N)
+  int cstride;          // conv stride; 2 = x is read through the parity-split 5-D map
+  int x_rows2;          // Hin/2
   int x_bcast;
   int stages;
   uint32_t tmem_cols;
@@ -383,7 +428,13 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUt
         const uint32_t a_dst = smem_u32(smem + static_cast<size_t>(st) * stage_bytes);
         const uint32_t b_dst = a_dst + a_bytes;
         for (int j = 0; j < p.MB; ++j) tma_load_4d(a_dst + j * blk_bytes, &tmDy, fb, 32 * j, w0, h0, smp);
-        for (int j = 0; j < p.NB; ++j) tma_load_4d(b_dst + j * blk_bytes, &tmX, fb, 32 * j, w0 + s, h0 + r, p.x_bcast ? 0 : smp);
+        if (p.cstride == 2) {
+          const int rows = p.x_bcast ? 0 : smp * p.x_rows2;
+          for (int j = 0; j < p.NB; ++j)
+            tma_load_5d(b_dst + j * blk_bytes, &tmX, fb, 32 * j, s & 1, w0 + (s >> 1), r & 1, rows + h0 + (r >> 1));
+        } else {
+          for (int j = 0; j < p.NB; ++j) tma_load_4d(b_dst + j * blk_bytes, &tmX, fb, 32 * j, w0 + s, h0 + r, p.x_bcast ? 0 : smp);
+        }
       }
     }
   } else if (warp == 1) {
@@ -477,15 +528,22 @@ static PFN_cuTensorMapEncodeTiled get_encode() {
 }
 
 // 4-D fp32 tensor map, 128B swizzle, zero fill. dims/box innermost first; strides in bytes for dims 1..3.
-static bool encode_map(CUtensorMap* m, const void* base, const uint64_t dims[4], const uint64_t strides[3], const uint32_t box[4],
-                       const uint32_t estr[4], bool mn_major = false) {
+static bool encode_map(CUtensorMap* m, const void* base, const uint64_t* dims, const uint64_t* strides, const uint32_t* box,
+                       const uint32_t* estr, bool mn_major = false, int rank = 4) {
   PFN_cuTensorMapEncodeTiled enc = get_encode();
   if (enc == nullptr) return false;
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
+}
+
+// Stride 1 and 2 are taken (stride 2: parity-split 5-D input maps for fwd/wgrad, one output-parity class per
+// blockIdx.y for dgrad).  MFVI_TC_STRIDE2=0 sends stride-2 layers back to the fp32 CUDA-core kernels (debug switch).
+static bool tc_stride_ok(int stride) {
+  static const bool s2 = [] { const char* e = getenv("MFVI_TC_STRIDE2"); return e == nullptr || e[0] != '0'; }();
+  return stride == 1 || (stride == 2 && s2);
 }
 
 static bool view_tma_ok(const MfviView& v, int C) {
@@ -508,14 +566,28 @@ static void pick_tile(int Mh, int Mw, int& TH, int& TW) {
 
 // a: activation view read through TMA (x for fwd, dy for dgrad), its channel count Ca and spatial size (Ha, Wa).
 static bool map_activation(CUtensorMap* m, const MfviView& a, int Ca, int Ha, int Wa, int S, int TH, int TW, bool& bcast,
-                           bool mn_major = false) {
+                           bool mn_major = false, int cstride = 1) {
   bcast = (a.sstride == 0) || S == 1;
+  if (cstride == 2) {
+    // parity-split view: dims (C, 2, W/2, 2, H/2 * S); the sample axis is folded into the row axis, which needs
+    // densely stacked samples.  (TMA elementStrides are avoided on purpose.)
+    if ((Ha & 1) || (Wa & 1) || (!bcast && a.sstride != static_cast<long long>(Ha) * a.hstride)) return false;
+    const uint64_t dims[5] = {static_cast<uint64_t>(Ca), 2, static_cast<uint64_t>(Wa / 2), 2,
+                              static_cast<uint64_t>(Ha / 2) * (bcast ? 1 : S)};
+    const uint64_t strides[4] = {static_cast<uint64_t>(a.wstride) * 4, static_cast<uint64_t>(a.wstride) * 8,
+                                 static_cast<uint64_t>(a.hstride) * 4, static_cast<uint64_t>(a.hstride) * 8};
+    const uint32_t box[5] = {static_cast<uint32_t>(kBK), 1, static_cast<uint32_t>(TW), 1, static_cast<uint32_t>(TH)};
+    const uint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (TW > 256 || TH > 256) return false;
+    return encode_map(m, a.ptr, dims, strides, box, estr, mn_major, 5);
+  }
   const uint64_t dims[4] = {static_cast<uint64_t>(Ca), static_cast<uint64_t>(Wa), static_cast<uint64_t>(Ha),
                             static_cast<uint64_t>(bcast ? 1 : S)};
   const uint64_t sbytes = bcast ? static_cast<uint64_t>(a.hstride) * Ha * 4 : static_cast<uint64_t>(a.sstride) * 4;
   const uint64_t strides[3] = {static_cast<uint64_t>(a.wstride) * 4, static_cast<uint64_t>(a.hstride) * 4, sbytes};
   const uint32_t box[4] = {static_cast<uint32_t>(kBK), static_cast<uint32_t>(TW), static_cast<uint32_t>(TH), 1};
   const uint32_t estr[4] = {1, 1, 1, 1};
+  if (TW > 256 || TH > 256) return false;
   return encode_map(m, a.ptr, dims, strides, box, estr, mn_major);
 }
 
@@ -523,7 +595,7 @@ static size_t conv_smem_bytes(int stages, uint32_t b_bytes, int BN) {
   size_t pipe = static_cast<size_t>(stages) * (kABytes + b_bytes);
   size_t stg = static_cast<size_t>(kBM) * (BN + 1) * 4;
   if (stg > pipe) pipe = (stg + 1023) / 1024 * 1024;
-  return 1024 + pipe + 18 * 8 + kBM * 4 + static_cast<size_t>(BN) * 8 + 64;
+  return 1024 + pipe + 18 * 8 + kBM * 4 + static_cast<size_t>(BN > 128 ? BN : 128) * 16 + 64;
 }
 
 }  // namespace tc
@@ -537,21 +609,22 @@ extern "C" {
 int mfvi_conv2d_fwd_tc(const MfviConvDesc* d, MfviView x, const float* w, const float* bias, long long w_sstride, MfviView y,
                        double* stats, mfvi_stream_t st) {
   using namespace mfvi::tc;
-  if (d->stride != 1 || !view_tma_ok(x, d->Cin) || (reinterpret_cast<uintptr_t>(w) % 16) || (w_sstride % 4) || d->Cout > 256) return -1;
+  if (!tc_stride_ok(d->stride) || !view_tma_ok(x, d->Cin) || (reinterpret_cast<uintptr_t>(w) % 16) || (w_sstride % 4) || d->Cout > 256) return -1;
   TcConvArgs a{};
   a.Kc = d->Cin; a.N = d->Cout; a.BN = (d->Cout + 15) / 16 * 16;
   a.KH = d->KH; a.KW = d->KW; a.Mh = d->Hout; a.Mw = d->Wout;
   pick_tile(a.Mh, a.Mw, a.TH, a.TW);
   a.tiles_w = (a.Mw + a.TW - 1) / a.TW;
-  a.dgrad = 0;
+  a.dgrad = 0; a.cstride = d->stride; a.Hfull = a.Mh; a.Wfull = a.Mw; a.a_rows2 = d->Hin / 2;
   a.b_bytes = static_cast<uint32_t>(a.BN) * 128u;
   a.stages = a.BN >= 64 ? 3 : 4;
+  if (const char* e = getenv("MFVI_TC_STAGES")) a.stages = atoi(e);
   a.tmem_cols = pow2_cols(a.BN);
   a.o = y; a.bias = bias; a.bias_sstride = w_sstride; a.stats = stats; a.accumulate = 0;
   a.vecO = ((reinterpret_cast<uintptr_t>(y.ptr) % 16 == 0) && y.sstride % 4 == 0 && y.hstride % 4 == 0 && y.wstride % 4 == 0 && d->Cout % 4 == 0) ? 1 : 0;
   CUtensorMap tmA, tmB;
   bool ab = false;
-  if (!map_activation(&tmA, x, d->Cin, d->Hin, d->Win, d->S, a.TH, a.TW, ab)) return -1;
+  if (!map_activation(&tmA, x, d->Cin, d->Hin, d->Win, d->S, a.TH, a.TW, ab, false, d->stride)) return -1;
   a.a_bcast = ab ? 1 : 0;
   a.b_bcast = (w_sstride == 0 || d->S == 1) ? 1 : 0;
   {
@@ -580,12 +653,14 @@ int mfvi_conv2d_fwd_tc(const MfviConvDesc* d, MfviView x, const float* w, const 
 int mfvi_conv2d_dgrad_tc(const MfviConvDesc* d, MfviView dy, const float* w, long long w_sstride, MfviView dx, int accumulate,
                          mfvi_stream_t st) {
   using namespace mfvi::tc;
-  if (d->stride != 1 || !view_tma_ok(dy, d->Cout) || (reinterpret_cast<uintptr_t>(w) % 16) || (w_sstride % 4) || d->Cin % 4 ||
+  if (!tc_stride_ok(d->stride) || !view_tma_ok(dy, d->Cout) || (reinterpret_cast<uintptr_t>(w) % 16) || (w_sstride % 4) || d->Cin % 4 ||
       d->Cin > 256)
     return -1;
   TcConvArgs a{};
   a.Kc = d->Cout; a.N = d->Cin; a.BN = (d->Cin + 31) / 32 * 32;
-  a.KH = d->KH; a.KW = d->KW; a.Mh = d->Hin; a.Mw = d->Win;
+  a.KH = d->KH; a.KW = d->KW;
+  a.cstride = d->stride; a.Hfull = d->Hin; a.Wfull = d->Win;
+  a.Mh = (d->Hin + d->stride - 1) / d->stride; a.Mw = (d->Win + d->stride - 1) / d->stride;   // largest parity class
   pick_tile(a.Mh, a.Mw, a.TH, a.TW);
   a.tiles_w = (a.Mw + a.TW - 1) / a.TW;
   a.dgrad = 1;
@@ -618,7 +693,7 @@ int mfvi_conv2d_dgrad_tc(const MfviConvDesc* d, MfviView dy, const float* w, lon
     attr = 200 * 1024;
   }
   const int tiles_h = (a.Mh + a.TH - 1) / a.TH;
-  dim3 grid(a.tiles_w * tiles_h, 1, d->S);
+  dim3 grid(a.tiles_w * tiles_h, d->stride == 2 ? 4 : 1, d->S);
   k_conv_tc<<<grid, kThreads, smem, as_stream(st)>>>(tmA, tmB, a);
   return check_launch("conv2d_dgrad_tc");
 }
@@ -626,12 +701,12 @@ int mfvi_conv2d_dgrad_tc(const MfviConvDesc* d, MfviView dy, const float* w, lon
 int mfvi_conv2d_wgrad_tc(const MfviConvDesc* d, MfviView x, MfviView dy, float* dw, float* dbias, long long w_sstride,
                          mfvi_stream_t st) {
   using namespace mfvi::tc;
-  if (d->stride != 1 || !view_tma_ok(x, d->Cin) || !view_tma_ok(dy, d->Cout) || d->Cout > 128 || d->Cin > 256 ||
+  if (!tc_stride_ok(d->stride) || !view_tma_ok(x, d->Cin) || !view_tma_ok(dy, d->Cout) || d->Cout > 128 || d->Cin > 256 ||
       (reinterpret_cast<uintptr_t>(dw) % 16) || (w_sstride % 4))
     return -1;
   TcWgradArgs a{};
   a.Cout = d->Cout; a.Cin = d->Cin; a.KW = d->KW; a.Ho = d->Hout; a.Wo = d->Wout;
-  a.MB = (d->Cout + 31) / 32; a.NB = (d->Cin + 31) / 32;
+  a.MB = (d->Cout + 31) / 32; a.NB = (d->Cin + 31) / 32; a.cstride = d->stride; a.x_rows2 = d->Hin / 2;
   int TP = 128;
   while (TP > 8 && static_cast<size_t>(4 + a.NB) * TP * 128 > 48 * 1024) TP >>= 1;
   // the pixel tile must cover exactly TP rows (every K row enters the sum): TW | TP
@@ -658,7 +733,7 @@ int mfvi_conv2d_wgrad_tc(const MfviConvDesc* d, MfviView x, MfviView dy, float* 
   bool db = false, xb = false;
   if (!map_activation(&tmDy, dy, d->Cout, d->Hout, d->Wout, d->S, TH, TW, db, true)) return -1;
   if (db && d->S > 1) return -1;
-  if (!map_activation(&tmX, x, d->Cin, d->Hin, d->Win, d->S, TH, TW, xb, true)) return -1;
+  if (!map_activation(&tmX, x, d->Cin, d->Hin, d->Win, d->S, TH, TW, xb, true, d->stride)) return -1;
   a.x_bcast = xb ? 1 : 0;
   const size_t smem = 1024 + static_cast<size_t>(a.stages) * (4 + a.NB) * TP * 128 + 18 * 8 + 64;
   static size_t attr = 0;

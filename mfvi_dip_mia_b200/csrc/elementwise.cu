@@ -66,31 +66,34 @@ __device__ __forceinline__ void load_bn_tables(const double* __restrict__ sums, 
   }
 }
 
-// CTA-level reduction of per-thread partial sums for a fixed channel (threads [slot][group] layout),
-// then one double atomicAdd per channel into dst[c*2 + {0,1}].
+// CTA-level reduction of per-thread partial sums for a fixed channel (threads [slot][group] layout) without
+// shared-memory atomics: every thread parks its V partial sums in a [slot][C] table, thread c then adds the column
+// of channel c over the slots, and issues one double atomicAdd per channel per CTA into dst[c*2 + {0,1}].
+// `scratch` must hold 2 * kEwThreads * 4 doubles.  Partial sums are carried in double: a CTA now covers thousands of
+// pixels and the BatchNorm backward subtracts these means from values of the same size (cancellation).
 template <int V>
-__device__ __forceinline__ void cta_reduce_2(float (&a)[V], float (&b)[V], int group, int C, float* sm_a, float* sm_b,
-                                             double* __restrict__ dst, bool active) {
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    sm_a[c] = 0.f;
-    sm_b[c] = 0.f;
-  }
+__device__ __forceinline__ void cta_reduce_2(double (&a)[V], double (&b)[V], int group, int slot, int G, int PPB, int C,
+                                             double* scratch, double* __restrict__ dst, bool active) {
+  double* ta = scratch;
+  double* tb = scratch + kEwThreads * 4;
+  const int ld = G * V;                       // >= C
   __syncthreads();
   if (active) {
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      const int c = group * V + j;
-      if (c < C) {
-        atomicAdd(&sm_a[c], a[j]);
-        atomicAdd(&sm_b[c], b[j]);
-      }
+      ta[slot * ld + group * V + j] = a[j];
+      tb[slot * ld + group * V + j] = b[j];
     }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    atomicAdd(&dst[(size_t)c * 2 + 0], (double)sm_a[c]);
-    atomicAdd(&dst[(size_t)c * 2 + 1], (double)sm_b[c]);
+    double sa = 0.0, sb = 0.0;
+    for (int sl = 0; sl < PPB; ++sl) {
+      sa += ta[sl * ld + c];
+      sb += tb[sl * ld + c];
+    }
+    atomicAdd(&dst[(size_t)c * 2 + 0], sa);
+    atomicAdd(&dst[(size_t)c * 2 + 1], sb);
   }
 }
 
@@ -146,7 +149,8 @@ k_cat_up_fwd(MfviView ys, int Cs, const double* __restrict__ sums_s, const float
              const float* __restrict__ beta_s, MfviView yd, int Cd, const double* __restrict__ sums_d,
              const float* __restrict__ gamma_d, const float* __restrict__ beta_d, int H, int W, int mode, MfviView A,
              double* __restrict__ sumsA, int G, int PPB) {
-  __shared__ float sm_scale[kMaxC], sm_shift[kMaxC], sm_a[kMaxC], sm_b[kMaxC];
+  __shared__ float sm_scale[kMaxC], sm_shift[kMaxC];
+  __shared__ double sm_red[2 * kEwThreads * 4];
   const int s = blockIdx.y;
   const int C = Cs + Cd;
   const int h2 = H / 2, w2 = W / 2;
@@ -156,9 +160,9 @@ k_cat_up_fwd(MfviView ys, int Cs, const double* __restrict__ sums_s, const float
   const int group = threadIdx.x % G, slot = threadIdx.x / G;
   const bool active = slot < PPB;
   const int c0 = group * V;
-  float acc1[V], acc2[V];
+  double acc1[V], acc2[V];
 #pragma unroll
-  for (int j = 0; j < V; ++j) acc1[j] = acc2[j] = 0.f;
+  for (int j = 0; j < V; ++j) acc1[j] = acc2[j] = 0.0;
   if (active) {
     const int npix = H * W;
     for (int p = blockIdx.x * PPB + slot; p < npix; p += gridDim.x * PPB) {
@@ -197,12 +201,12 @@ k_cat_up_fwd(MfviView ys, int Cs, const double* __restrict__ sums_s, const float
       o.store(A.ptr + view_off(A, s, h, w) + c0);
 #pragma unroll
       for (int j = 0; j < V; ++j) {
-        acc1[j] += o.v[j];
-        acc2[j] = fmaf(o.v[j], o.v[j], acc2[j]);
+        acc1[j] += (double)o.v[j];
+        acc2[j] += (double)o.v[j] * (double)o.v[j];
       }
     }
   }
-  cta_reduce_2<V>(acc1, acc2, group, C, sm_a, sm_b, sumsA + (size_t)s * C * 2, active);
+  cta_reduce_2<V>(acc1, acc2, group, slot, G, PPB, C, sm_red, sumsA + (size_t)s * C * 2, active);
 }
 
 // number of padded positions (per dimension) that reflect onto source index h: fills q[0..n)
@@ -221,15 +225,16 @@ k_pad_act_bwd(MfviView dxp, int H, int W, int C, int pad, MfviView y, const doub
               const float* __restrict__ gamma, const float* __restrict__ beta, int act, MfviView g,
               double* __restrict__ red, int G, int PPB) {
   __shared__ float sm_scale[kMaxC], sm_shift[kMaxC], sm_mean[kMaxC], sm_invstd[kMaxC];
+  __shared__ double sm_red[2 * kEwThreads * 4];
   const int s = blockIdx.y;
   load_bn_tables(sums, gamma, beta, s, C, 1.0 / ((double)H * W), sm_scale, sm_shift, sm_mean, sm_invstd);
   __syncthreads();
   const int group = threadIdx.x % G, slot = threadIdx.x / G;
   const bool active = slot < PPB;
   const int c0 = group * V;
-  float acc1[V], acc2[V];
+  double acc1[V], acc2[V];
 #pragma unroll
-  for (int j = 0; j < V; ++j) acc1[j] = acc2[j] = 0.f;
+  for (int j = 0; j < V; ++j) acc1[j] = acc2[j] = 0.0;
   if (active) {
     const int npix = H * W;
     for (int p = blockIdx.x * PPB + slot; p < npix; p += gridDim.x * PPB) {
@@ -256,13 +261,13 @@ k_pad_act_bwd(MfviView dxp, int H, int W, int C, int pad, MfviView y, const doub
         if (act && z <= 0.f) gg *= kLreluSlope;
         const float xhat = (yy.v[j] - sm_mean[c0 + j]) * sm_invstd[c0 + j];
         a.v[j] = gg;
-        acc1[j] += gg;
-        acc2[j] = fmaf(gg, xhat, acc2[j]);
+        acc1[j] += (double)gg;
+        acc2[j] += (double)gg * (double)xhat;
       }
       a.store(g.ptr + view_off(g, s, h, w) + c0);
     }
   }
-  cta_reduce_2<V>(acc1, acc2, group, C, sm_scale, sm_shift, red + (size_t)s * C * 2, active);
+  cta_reduce_2<V>(acc1, acc2, group, slot, G, PPB, C, sm_red, red + (size_t)s * C * 2, active);
 }
 
 // B2: dy = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)); block (0,0) also writes dgamma/dbeta.
@@ -318,15 +323,16 @@ k_cat_bwd_skip(MfviView dA, int H, int W, MfviView ys, int Cs, const double* __r
                const float* __restrict__ gamma_s, const float* __restrict__ beta_s, MfviView gs,
                double* __restrict__ red_s, int G, int PPB) {
   __shared__ float sm_scale[kMaxC], sm_shift[kMaxC], sm_mean[kMaxC], sm_invstd[kMaxC];
+  __shared__ double sm_red[2 * kEwThreads * 4];
   const int s = blockIdx.y;
   load_bn_tables(sums_s, gamma_s, beta_s, s, Cs, 1.0 / ((double)H * W), sm_scale, sm_shift, sm_mean, sm_invstd);
   __syncthreads();
   const int group = threadIdx.x % G, slot = threadIdx.x / G;
   const bool active = slot < PPB;
   const int c0 = group * V;
-  float acc1[V], acc2[V];
+  double acc1[V], acc2[V];
 #pragma unroll
-  for (int j = 0; j < V; ++j) acc1[j] = acc2[j] = 0.f;
+  for (int j = 0; j < V; ++j) acc1[j] = acc2[j] = 0.0;
   if (active) {
     const int npix = H * W;
     for (int p = blockIdx.x * PPB + slot; p < npix; p += gridDim.x * PPB) {
@@ -340,13 +346,13 @@ k_cat_bwd_skip(MfviView dA, int H, int W, MfviView ys, int Cs, const double* __r
         const float gg = z > 0.f ? d.v[j] : kLreluSlope * d.v[j];
         const float xhat = (yy.v[j] - sm_mean[c0 + j]) * sm_invstd[c0 + j];
         d.v[j] = gg;
-        acc1[j] += gg;
-        acc2[j] = fmaf(gg, xhat, acc2[j]);
+        acc1[j] += (double)gg;
+        acc2[j] += (double)gg * (double)xhat;
       }
       d.store(gs.ptr + view_off(gs, s, h, w) + c0);
     }
   }
-  cta_reduce_2<V>(acc1, acc2, group, Cs, sm_scale, sm_shift, red_s + (size_t)s * Cs * 2, active);
+  cta_reduce_2<V>(acc1, acc2, group, slot, G, PPB, Cs, sm_red, red_s + (size_t)s * Cs * 2, active);
 }
 
 // weight with which low-res index k enters hi-res index i (0 if not a tap)
@@ -368,6 +374,7 @@ k_cat_bwd_up(MfviView dA, int H, int W, int mode, int Cs, MfviView yd, int Cd, c
              const float* __restrict__ gamma_d, const float* __restrict__ beta_d, MfviView gd,
              double* __restrict__ red_d, int G, int PPB) {
   __shared__ float sm_scale[kMaxC], sm_shift[kMaxC], sm_mean[kMaxC], sm_invstd[kMaxC];
+  __shared__ double sm_red[2 * kEwThreads * 4];
   const int s = blockIdx.y;
   const int h2 = H / 2, w2 = W / 2;
   load_bn_tables(sums_d, gamma_d, beta_d, s, Cd, 1.0 / ((double)h2 * w2), sm_scale, sm_shift, sm_mean, sm_invstd);
@@ -375,9 +382,9 @@ k_cat_bwd_up(MfviView dA, int H, int W, int mode, int Cs, MfviView yd, int Cd, c
   const int group = threadIdx.x % G, slot = threadIdx.x / G;
   const bool active = slot < PPB;
   const int c0 = group * V;
-  float acc1[V], acc2[V];
+  double acc1[V], acc2[V];
 #pragma unroll
-  for (int j = 0; j < V; ++j) acc1[j] = acc2[j] = 0.f;
+  for (int j = 0; j < V; ++j) acc1[j] = acc2[j] = 0.0;
   if (active) {
     const int npix = h2 * w2;
     for (int p = blockIdx.x * PPB + slot; p < npix; p += gridDim.x * PPB) {
@@ -407,13 +414,13 @@ k_cat_bwd_up(MfviView dA, int H, int W, int mode, int Cs, MfviView yd, int Cd, c
         const float gg = z > 0.f ? a.v[j] : kLreluSlope * a.v[j];
         const float xhat = (yy.v[j] - sm_mean[c0 + j]) * sm_invstd[c0 + j];
         a.v[j] = gg;
-        acc1[j] += gg;
-        acc2[j] = fmaf(gg, xhat, acc2[j]);
+        acc1[j] += (double)gg;
+        acc2[j] += (double)gg * (double)xhat;
       }
       a.store(gd.ptr + view_off(gd, s, kh, kw) + c0);
     }
   }
-  cta_reduce_2<V>(acc1, acc2, group, Cd, sm_scale, sm_shift, red_d + (size_t)s * Cd * 2, active);
+  cta_reduce_2<V>(acc1, acc2, group, slot, G, PPB, Cd, sm_red, red_d + (size_t)s * Cd * 2, active);
 }
 
 // running stats of all BatchNorms (one thread per channel)
@@ -441,9 +448,13 @@ __global__ void k_bn_running(const double* __restrict__ arena, const int* __rest
   }
 }
 
-static inline int ew_grid(int npix, int PPB) {
+// chunks per sample: the whole launch (all S samples) gets about kCtasPerSM resident CTAs per SM, so that the
+// per-CTA prologue (BN tables) and epilogue (reductions, double atomics) are amortised over many pixels
+constexpr int kCtasPerSM = 6;
+static inline int ew_grid(int npix, int PPB, int S) {
   int blocks = (npix + PPB - 1) / PPB;
-  const int cap = kNumSMs * 4;
+  int cap = (kNumSMs * kCtasPerSM + S - 1) / S;
+  if (cap < 1) cap = 1;
   if (blocks > cap) blocks = cap;
   return blocks < 1 ? 1 : blocks;
 }
@@ -469,7 +480,7 @@ int mfvi_bn_act_pad_fwd(MfviView y, int S, int H, int W, int C, const double* su
   MFVI_REQUIRE(pad >= 0 && pad < H && pad < W, "bn_act_pad_fwd: pad must be smaller than the image");
   const EwGeom ge = ew_geom(C, view_vec_ok(y) && view_vec_ok(xp));
   MFVI_REQUIRE(ge.G <= kEwThreads, "bn_act_pad_fwd: too many channel groups");
-  dim3 grid(ew_grid((H + 2 * pad) * (W + 2 * pad), ge.PPB), S);
+  dim3 grid(ew_grid((H + 2 * pad) * (W + 2 * pad), ge.PPB, S), S);
   MFVI_EW_DISPATCH(ge, k_bn_act_pad_fwd, grid, y, H, W, C, sums, gamma, beta, act, pad, xp);
   return check_launch("bn_act_pad_fwd");
 }
@@ -485,7 +496,7 @@ int mfvi_cat_up_fwd(MfviView ys, int Cs, const double* sums_s, const float* gamm
   const bool al = view_vec_ok(yd) && view_vec_ok(A) && (Cs == 0 || view_vec_ok(ys)) && Cs % 4 == 0 && Cd % 4 == 0;
   const EwGeom ge = ew_geom(Cs + Cd, al);
   MFVI_REQUIRE(ge.G <= kEwThreads, "cat_up_fwd: too many channel groups");
-  dim3 grid(ew_grid(H * W, ge.PPB), S);
+  dim3 grid(ew_grid(H * W, ge.PPB, S), S);
   MFVI_EW_DISPATCH(ge, k_cat_up_fwd, grid, ys, Cs, sums_s, gamma_s, beta_s, yd, Cd, sums_d, gamma_d, beta_d, H, W, mode,
                    A, sumsA);
   return check_launch("cat_up_fwd");
@@ -498,7 +509,7 @@ int mfvi_pad_act_bwd(MfviView dxp, int S, int H, int W, int C, int pad, MfviView
   MFVI_REQUIRE(pad >= 0 && pad < H && pad < W, "pad_act_bwd: pad must be smaller than the image");
   const EwGeom ge = ew_geom(C, view_vec_ok(dxp) && view_vec_ok(y) && view_vec_ok(g));
   MFVI_REQUIRE(ge.G <= kEwThreads, "pad_act_bwd: too many channel groups");
-  dim3 grid(ew_grid(H * W, ge.PPB), S);
+  dim3 grid(ew_grid(H * W, ge.PPB, S), S);
   MFVI_EW_DISPATCH(ge, k_pad_act_bwd, grid, dxp, H, W, C, pad, y, sums, gamma, beta, act, g, red);
   return check_launch("pad_act_bwd");
 }
@@ -510,7 +521,7 @@ int mfvi_bn_bwd_apply(MfviView g, MfviView y, int S, int H, int W, int C, const 
   MFVI_REQUIRE(C >= 1 && C <= kMaxC, "bn_bwd_apply: C out of range");
   const EwGeom ge = ew_geom(C, view_vec_ok(g) && view_vec_ok(y) && view_vec_ok(dy));
   MFVI_REQUIRE(ge.G <= kEwThreads, "bn_bwd_apply: too many channel groups");
-  dim3 grid(ew_grid(H * W, ge.PPB), S);
+  dim3 grid(ew_grid(H * W, ge.PPB, S), S);
   MFVI_EW_DISPATCH(ge, k_bn_bwd_apply, grid, g, y, S, H, W, C, sums, red, gamma, dy, dgamma, dbeta);
   return check_launch("bn_bwd_apply");
 }
@@ -525,13 +536,13 @@ int mfvi_cat_up_bwd(MfviView dA, int S, int H, int W, int mode, MfviView ys, int
   if (Cs > 0) {
     MFVI_REQUIRE(ys.ptr && gs.ptr && red_s, "cat_up_bwd: null skip branch");
     const EwGeom ge = ew_geom(Cs, view_vec_ok(dA) && view_vec_ok(ys) && view_vec_ok(gs));
-    dim3 grid(ew_grid(H * W, ge.PPB), S);
+    dim3 grid(ew_grid(H * W, ge.PPB, S), S);
     MFVI_EW_DISPATCH(ge, k_cat_bwd_skip, grid, dA, H, W, ys, Cs, sums_s, gamma_s, beta_s, gs, red_s);
     if (int rc = check_launch("cat_up_bwd(skip)")) return rc;
   }
   const EwGeom ge = ew_geom(Cd, view_vec_ok(dA) && view_vec_ok(yd) && view_vec_ok(gd) && Cs % 4 == 0);
   MFVI_REQUIRE(ge.G <= kEwThreads, "cat_up_bwd: too many channel groups");
-  dim3 grid(ew_grid((H / 2) * (W / 2), ge.PPB), S);
+  dim3 grid(ew_grid((H / 2) * (W / 2), ge.PPB, S), S);
   MFVI_EW_DISPATCH(ge, k_cat_bwd_up, grid, dA, H, W, mode, Cs, yd, Cd, sums_d, gamma_d, beta_d, gd, red_d);
   return check_launch("cat_up_bwd(up)");
 }

@@ -21,7 +21,7 @@ for sh in shapes:
     for n, a, b in zip(["y", "dx", "dw", "stats"], got, ref):
         summarize(n, a, b)
     # per-tap error of dw
-    cin, cout, k, H, W = sh
+    cin, cout, k, H, W = sh[:5]
     dwa = got[2][:, :k*k*cout*cin].reshape(-1, k*k, cout, cin); dwb = ref[2][:, :k*k*cout*cin].reshape(-1, k*k, cout, cin)
     print("   dw per tap:", [f"{float((dwa[:,t]-dwb[:,t]).abs().max()/dwb.abs().max()):.1e}" for t in range(k*k)])
     dxa, dxb = got[1], ref[1]
