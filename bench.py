@@ -276,7 +276,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mc", type=int, default=8)
     ap.add_argument("--size", type=int, default=256)
-    ap.add_argument("--math", default="fp32", choices=["fp32", "tf32"])
+    ap.add_argument("--math", default="tf32", choices=["fp32", "tf32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -20,6 +20,7 @@ import torch
 
 from . import _lib as L
 from .engine import KL, NLL, SkipEngine, SkipSpec
+from .sharding import allreduce_mean_, shard_samples
 
 
 class LossHead:
@@ -84,9 +85,8 @@ class MfviDipTrainer:
         assert net_input.dim() == 4 and net_input.shape[0] == 1, "net_input must be (1,C,H,W) like the reference's"
         _, Cin, H, W = net_input.shape
         assert Cin == spec.num_input_channels
-        if mc_samples % world_size:
-            raise ValueError(f"mc_samples={mc_samples} must be divisible by world_size={world_size}")
-        self.S_global, self.S = mc_samples, mc_samples // world_size
+        self.S_global = mc_samples
+        self.S, self.sample0 = shard_samples(mc_samples, rank, world_size)
         self.rank, self.world_size, self.pg = rank, world_size, process_group
         self.temp, self.sigma, self.lr = float(temp), float(sigma), float(lr)
         self.prior_mu = float(prior_mu)
@@ -128,7 +128,7 @@ class MfviDipTrainer:
         self.step_dev.zero_()
 
     def _keys(self):
-        kw = L.key(self.seed, 0, self.rank * self.S, self.step_dev)
+        kw = L.key(self.seed, 0, self.sample0, self.step_dev)
         kj = L.key(self.seed, 0, 0, self.step_dev)
         return kw, kj
 
@@ -144,7 +144,7 @@ class MfviDipTrainer:
         e.reparam_kl(kw, prior_mu=self.prior_mu, prior_sigma_plus_eps=self.prior_sigma_plus_eps, direction=self.direction,
                      kscale=self.temp)
         if self.world_size > 1:
-            torch.distributed.all_reduce(e.grad, op=torch.distributed.ReduceOp.AVG, group=self.pg)
+            allreduce_mean_(e.grad, self.pg)
         e.update_running_stats()
         L.call("mfvi_adamw_step", e.theta.data_ptr(), e.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                e.n_theta_pad, self.lr, self.betas[0], self.betas[1], self.adam_eps, self.weight_decay, 1,

@@ -1,0 +1,167 @@
+"""CPU-only checks (no GPU, no compute calls into the library): the C-ABI library loads and exports every symbol
+include/mfvi_dip.h declares, the host-side mirror of the reference interface builds the reference's module tree /
+state-dict keys, the plugin surface refuses to run without CUDA (no silent fallback), and the N>1 sharding maths holds
+under a world_size-2 gloo group."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import GOLDEN
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from mfvi_dip_mia_b200 import _lib
+    with open(os.path.join(ROOT, "include", "mfvi_dip.h")) as f:
+        hdr = f.read()
+    declared = set(re.findall(r"\b(mfvi_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    for sym in sorted(declared):
+        assert hasattr(_lib.lib, sym), f"libmfvidip.so lacks {sym}"
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    assert _lib.lib.mfvi_abi_version() == _lib.ABI_VERSION
+    # the struct mirrors must match the C layout (x86-64 SysV)
+    import ctypes as C
+    assert C.sizeof(_lib.View) == 24 and C.sizeof(_lib.ConvDesc) == 44 and C.sizeof(_lib.PhiloxKey) == 24
+
+
+def _ref_keys():
+    with open(os.path.join(GOLDEN, "full_net_keys.json")) as f:
+        return json.load(f)
+
+
+def _build(task):
+    from mfvi_dip_mia_b200.models import get_net
+    from mfvi_dip_mia_b200.models.skip import skip
+    if task == "inp":      # bayesian_optimization.py:2970-2998 of the reference
+        return skip(16, 4, num_channels_down=[16, 32, 64, 128, 128, 128], num_channels_up=[16, 32, 64, 128, 128, 128],
+                    num_channels_skip=[0] * 6, filter_size_down=5, filter_size_up=3, filter_skip_size=1,
+                    need_sigmoid=False, need_bias=True, pad="reflection", upsample_mode="nearest", need1x1_up=False,
+                    dropout_mode_down="None", dropout_mode_up="None", dropout_mode_skip="None", dropout_mode_output="None")
+    depth, out = {"den": (16, 2), "sr": (32, 2), "ct": (16, 1)}[task]
+    return get_net(depth, "skip", "reflection", skip_n33d=[16, 32, 64, 128, 128], skip_n33u=[16, 32, 64, 128, 128],
+                   skip_n11=4, num_scales=5, n_channels=out, upsample_mode="bilinear")
+
+
+@pytest.mark.parametrize("task", ["den", "sr", "ct", "inp"])
+def test_meanfieldvi_state_dict_matches_reference(task):
+    from mfvi_dip_mia_b200 import build_layout
+    from mfvi_dip_mia_b200.BayTorch import MeanFieldVI
+    ref = _ref_keys()[task]
+    torch.manual_seed(1)
+    net = MeanFieldVI(_build(task), prior={"mu": 0.0, "sigma": 1e-8}, replace_layers="all", reparam="")
+    sd = net.state_dict()
+    assert list(sd.keys()) == ref["keys"]                       # same keys in the same order
+    assert [list(v.shape) for v in sd.values()] == ref["shapes"]
+    assert sum(p.numel() for p in net.parameters()) == ref["n_params"]
+    # identical RNG consumption => identical initial values (reference built under torch.manual_seed(1))
+    assert abs(float(sum(p.double().sum() for p in net.parameters())) - ref["param_sum"]) < 1e-6 * ref["param_abs_sum"]
+    lay = build_layout(net.net._skip_spec)
+    assert 2 * lay.P + 2 * lay.Q == ref["n_params"]
+    assert {f"net.{c.key}.W_mu" for c in lay.convs} <= set(ref["keys"])
+    assert {f"net.{b.key}.weight" for b in lay.bns} <= set(ref["keys"])
+
+
+def test_replace_layers_substring_semantics():
+    """freq_to_bayes.py:55: the key of the LEAF module must contain `replace_layers` ('up' -> 11 of 26)."""
+    from mfvi_dip_mia_b200.BayTorch import MeanFieldVI
+    from mfvi_dip_mia_b200.BayTorch.modules import Conv2dRT
+    counts = {}
+    for mode in ["all", "up", "down", "none"]:
+        net = MeanFieldVI(_build("den"), prior={"mu": 0.0, "sigma": 0.1}, replace_layers=mode, reparam="")
+        counts[mode] = sum(isinstance(m, Conv2dRT) for m in net.modules())
+    assert counts == {"all": 26, "up": 11, "down": 0, "none": 0}
+    with pytest.raises(NotImplementedError):
+        MeanFieldVI(_build("den"), reparam="local")
+
+
+def test_no_cpu_fallback():
+    from mfvi_dip_mia_b200 import MfviDipTrainer, SkipSpec, _lib
+    from mfvi_dip_mia_b200.BayTorch import MeanFieldVI
+    from mfvi_dip_mia_b200.BayTorch.modules import Conv2dRT
+    from mfvi_dip_mia_b200.radon import FastRadonTransform
+    from mfvi_dip_mia_b200.utils.bayesian_utils import gaussian_nll
+    net = MeanFieldVI(_build("den"), prior={"mu": 0.0, "sigma": 0.1}, replace_layers="all", reparam="")
+    with pytest.raises(_lib.MfviError):
+        net(torch.zeros(1, 16, 32, 32))
+    with pytest.raises(_lib.MfviError):
+        Conv2dRT(4, 4, 3)(torch.zeros(1, 4, 8, 8))
+    with pytest.raises(_lib.MfviError):
+        gaussian_nll(torch.zeros(1, 1, 8, 8), torch.zeros(1, 1, 8, 8), torch.zeros(1, 1, 8, 8))
+    with pytest.raises(_lib.MfviError):
+        FastRadonTransform((1, 1, 8, 8), torch.arange(0., 180., 45.))(torch.zeros(1, 1, 8, 8))
+    with pytest.raises(_lib.MfviError):
+        MfviDipTrainer(SkipSpec(), "den", torch.zeros(1, 16, 32, 32), temp=1e-6, sigma=1e-4, lr=1e-3, device="cpu",
+                       target=torch.zeros(1, 1, 32, 32))
+
+
+def test_shard_samples():
+    from mfvi_dip_mia_b200.sharding import shard_samples
+    assert [shard_samples(8, r, 4) for r in range(4)] == [(2, 0), (2, 2), (2, 4), (2, 6)]
+    assert shard_samples(8, 0, 1) == (8, 0)
+    with pytest.raises(ValueError):
+        shard_samples(8, 0, 3)
+    with pytest.raises(ValueError):
+        shard_samples(8, 4, 4)
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as dist
+from oracle import mfvi_oracle as O
+from mfvi_dip_mia_b200.sharding import allreduce_mean_, shard_samples
+from tests.helpers import group, load_npz
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+d = load_npz("skipnet_small_den.npz")
+cfg = O.SkipCfg(4, 2, (8, 16, 16), (8, 16, 16), (2, 2, 2), 3, 3, 1, True, False, "bilinear")
+S = int(d["S"]); temp, sigma = float(d["temp"]), float(d["sigma"])
+sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in group(d, "sd/").items()}
+s_local, s0 = shard_samples(S, rank, world)
+eps = [group(d, f"eps{s}/") for s in range(s0, s0 + s_local)]          # eps keyed by GLOBAL sample id
+loss, nll, kl, _ = O.mfvi_loss(sd, cfg, torch.from_numpy(d["net_input"]), eps, task="den", temp=temp,
+                               prior_sigma_plus_eps=O.prior_scale(temp, sigma), target=group(d, "extra/")["target"])
+loss.backward()                                                          # local: mean over OWN samples + T*KL
+names = sorted(group(d, "grad/").keys())
+flat = torch.cat([sd[k].grad.reshape(-1) for k in names])
+allreduce_mean_(flat)                                                    # the step's only collective
+ref = torch.cat([group(d, "grad/")[k].reshape(-1) for k in names])
+err = float((flat - ref).abs().max() / ref.abs().max())
+print(f"rank {rank} err {err:.3e}")
+assert err < 1e-4, err
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_gloo_sharded_gradient_equals_single_process(tmp_path):
+    """world_size 2 on CPU (gloo): each rank evaluates its own MC-sample shard with the oracle, the gradients are
+    averaged with the trainer's collective helper, and every rank ends with the single-process S=2 reference gradient."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = 29500 + os.getpid() % 2000
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(script), ROOT]
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=280, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "rank 0 err" in r.stdout and "rank 1 err" in r.stdout
+
+
+def test_bench_reference_arm_prints_contract_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--size", "64", "--mc", "2"], capture_output=True, text=True, timeout=280, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ["metric", "value", "unit", "impl", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"]:
+        assert k in line, k
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]
