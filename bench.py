@@ -264,8 +264,6 @@ def run_ours(args):
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def main():
@@ -283,11 +281,18 @@ def main():
         run_reference(args)
     else:
         run_ours(args)
-        rank = int(os.environ.get("RANK", "0"))
-        if rank != 0 and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            # Captured CUDA graphs hold NCCL kernels: tearing the communicator down under them can hang at exit.
+            # All ranks rendezvous once more, then leave without running the NCCL/CUDA destructors.
+            import torch
             import torch.distributed as dist
+            torch.cuda.synchronize()
             if dist.is_initialized():
-                dist.destroy_process_group()
+                dist.barrier()
+                torch.cuda.synchronize()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
 
 
 if __name__ == "__main__":

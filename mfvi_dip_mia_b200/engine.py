@@ -235,6 +235,10 @@ class SkipEngine:
         self.fwd_ops: List[Tuple[str, tuple, dict]] = []
         self.bwd_ops: List[Tuple[str, tuple, dict]] = []
         self.need_input_grad = need_input_grad
+        # weight-gradient kernels only feed dw (consumed after the whole backward), so they run on a side stream
+        # concurrently with the dgrad / elementwise chain (fork-join by events; becomes a parallel branch of the graph)
+        self.overlap_wgrad = True
+        self._side = torch.cuda.Stream(device=device)
         self._build_plan()
         # per-BN tables for the running-stat update
         self._bn_ch_off = torch.tensor([b.ch_off for b in lay.bns], dtype=torch.int32, device=device)
@@ -470,8 +474,22 @@ class SkipEngine:
 
     def backward(self):
         """Consumes self.dout; fills dw[s], BN gamma/beta grads (and dx0 when requested)."""
+        overlap = self.overlap_wgrad and L.timeline is None
+        main = torch.cuda.current_stream(self.device)
+        side, forked = self._side, False
         for name, args, meta in self.bwd_ops:
-            L.call(name, *args, meta=meta)
+            if overlap and name == "mfvi_conv2d_wgrad":
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                L.call(name, *args, stream=side.cuda_stream, meta=meta)
+                forked = True
+            else:
+                L.call(name, *args, meta=meta)
+        if forked:
+            ev = torch.cuda.Event()
+            ev.record(side)
+            main.wait_event(ev)
 
     def reparam_kl(self, key: L.PhiloxKey, *, prior_mu: float, prior_sigma_plus_eps: float, direction: int,
                    kscale: float, kscale_dev=None, data_term: bool = True, gscale: float = 1.0, accumulate: bool = False,
