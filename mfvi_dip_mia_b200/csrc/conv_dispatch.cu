@@ -9,11 +9,15 @@ int mfvi_conv2d_wgrad_simt(const MfviConvDesc*, MfviView, MfviView, float*, floa
 int mfvi_conv2d_fwd_tc(const MfviConvDesc*, MfviView, const float*, const float*, long long, MfviView, double*, mfvi_stream_t);
 int mfvi_conv2d_dgrad_tc(const MfviConvDesc*, MfviView, const float*, long long, MfviView, int, mfvi_stream_t);
 int mfvi_conv2d_wgrad_tc(const MfviConvDesc*, MfviView, MfviView, float*, float*, long long, mfvi_stream_t);
+int mfvi_conv2d_fwd_tc2(const MfviConvDesc*, MfviView, const float*, const float*, long long, MfviView, double*, mfvi_stream_t);
+int mfvi_conv2d_dgrad_tc2(const MfviConvDesc*, MfviView, const float*, long long, MfviView, int, mfvi_stream_t);
 
 int mfvi_conv2d_fwd(const MfviConvDesc* d, MfviView x, const float* w, const float* bias, long long w_sstride,
                     MfviView y, double* stats, mfvi_stream_t st) {
   if (d != nullptr && d->math == MFVI_MATH_TF32) {
-    const int rc = mfvi_conv2d_fwd_tc(d, x, w, bias, w_sstride, y, stats, st);
+    int rc = mfvi_conv2d_fwd_tc2(d, x, w, bias, w_sstride, y, stats, st);
+    if (rc >= 0) return rc;
+    rc = mfvi_conv2d_fwd_tc(d, x, w, bias, w_sstride, y, stats, st);
     if (rc >= 0) return rc;
   }
   return mfvi_conv2d_fwd_simt(d, x, w, bias, w_sstride, y, stats, st);
@@ -22,7 +26,9 @@ int mfvi_conv2d_fwd(const MfviConvDesc* d, MfviView x, const float* w, const flo
 int mfvi_conv2d_dgrad(const MfviConvDesc* d, MfviView dy, const float* w, long long w_sstride, MfviView dx,
                       int accumulate, mfvi_stream_t st) {
   if (d != nullptr && d->math == MFVI_MATH_TF32) {
-    const int rc = mfvi_conv2d_dgrad_tc(d, dy, w, w_sstride, dx, accumulate, st);
+    int rc = mfvi_conv2d_dgrad_tc2(d, dy, w, w_sstride, dx, accumulate, st);
+    if (rc >= 0) return rc;
+    rc = mfvi_conv2d_dgrad_tc(d, dy, w, w_sstride, dx, accumulate, st);
     if (rc >= 0) return rc;
   }
   return mfvi_conv2d_dgrad_simt(d, dy, w, w_sstride, dx, accumulate, st);

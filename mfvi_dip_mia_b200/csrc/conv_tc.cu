@@ -19,6 +19,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace mfvi {
 namespace tc {
@@ -28,108 +29,6 @@ constexpr int kBK = 32;         // fp32 per k-chunk = one 128-byte swizzle row
 constexpr int kUmmaK = 8;       // kind::tf32
 constexpr int kThreads = 192;
 constexpr int kABytes = kBM * kBK * 4;   // 16 KB
-
-// ---------------------------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-
-// Shared-memory matrix descriptor, 128-byte swizzle (sm_100 "version 1" descriptor).
-//   K-major : rows (M/N index) are 128 B apart, 8-row groups SBO = 1024 B apart; LBO unused.
-//   MN-major: rows (K index) are 128 B apart and hold 32 consecutive M/N elements; 8-row K groups SBO apart;
-//             32-element M/N blocks LBO apart.
-//   kind::tf32 MN-major operands must use the "128B swizzle with 32B atoms" layout (layout type 1; TMA swizzle
-//   128B_ATOM_32B): 32-byte chunks are XOR-swizzled with (row mod 4), K groups are 4 rows (SBO = 512 B).
-constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32 = 1;
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = kLayoutSw128) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= static_cast<uint64_t>(1) << 46;   // descriptor version (sm_100)
-  d |= static_cast<uint64_t>(layout) << 61;
-  return d;
-}
-// Instruction descriptor: D=f32, A=B=tf32, majors, N>>3 at [17,23), M>>4 at [24,29).
-__host__ __device__ inline uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
-  uint32_t d = 0;
-  d |= 1u << 4;                       // c_format = F32
-  d |= 2u << 7;                       // a_format = TF32
-  d |= 2u << 10;                      // b_format = TF32
-  d |= static_cast<uint32_t>(a_mn_major & 1) << 15;
-  d |= static_cast<uint32_t>(b_mn_major & 1) << 16;
-  d |= static_cast<uint32_t>(N >> 3) << 17;
-  d |= static_cast<uint32_t>(M >> 4) << 24;
-  return d;
-}
 
 // ---------------------------------------------------------------------------------------------- fwd / dgrad
 struct TcConvArgs {
@@ -170,7 +69,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   int* row_off = reinterpret_cast<int*>(full_bar + 18);       // [128] element offset of each tile row, -1 = invalid
   double* col_acc = reinterpret_cast<double*>(row_off + kBM);  // [tpc][BN][2] partial BatchNorm statistics
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for ptxas
   const int smp = blockIdx.z;
   const int tile = blockIdx.x;
   const int h0 = (tile / p.tiles_w) * p.TH, w0 = (tile % p.tiles_w) * p.TW;
@@ -247,7 +146,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const uint32_t phase = (it / p.stages) & 1;
       mbar_wait(smem_u32(&full_bar[st]), phase);
       tc_fence_after();
-      if (lane == 0) {
+      {
         const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(st) * stage_bytes);
         const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
@@ -255,12 +154,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           const uint64_t ad = make_desc(a_addr + k * (kUmmaK * 4), 16, 1024);
           const uint64_t bd = p.dgrad ? make_desc(b_addr + k * 1024, 4096, 512, kLayoutSw128Base32)
                                       : make_desc(b_addr + k * (kUmmaK * 4), 16, 1024);
-          tc_mma_tf32(tmem_base, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          tc_mma_tf32_elect(tmem_base, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
         }
-        tc_commit(smem_u32(&empty_bar[st]));
-        if (it == n_iters - 1) tc_commit(smem_u32(tmem_full_bar));
+        tc_commit_elect(smem_u32(&empty_bar[st]));
+        if (it == n_iters - 1) tc_commit_elect(smem_u32(tmem_full_bar));
       }
-      __syncwarp();
     }
   } else {
     // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4
@@ -386,7 +284,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUt
   uint64_t* tmem_full_bar = full_bar + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full_bar + 17);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for ptxas
   const int smp = blockIdx.z, tap = blockIdx.y;
   const int r = tap / p.KW, s = tap % p.KW;
   const int t_begin = blockIdx.x * p.tiles_per_cta;
@@ -445,18 +343,17 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUt
       const uint32_t ph = (it / p.stages) & 1;
       mbar_wait(smem_u32(&full_bar[st]), ph);
       tc_fence_after();
-      if (lane == 0) {
+      {
         const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(st) * stage_bytes);
         const uint32_t b_addr = a_addr + a_bytes;
         for (int k = 0; k < ksteps; ++k) {
           const uint64_t ad = make_desc(a_addr + k * 1024, blk_bytes, 512, kLayoutSw128Base32);
           const uint64_t bd = make_desc(b_addr + k * 1024, blk_bytes, 512, kLayoutSw128Base32);
-          tc_mma_tf32(tmem_base, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          tc_mma_tf32_elect(tmem_base, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
         }
-        tc_commit(smem_u32(&empty_bar[st]));
-        if (it == n_iters - 1) tc_commit(smem_u32(tmem_full_bar));
+        tc_commit_elect(smem_u32(&empty_bar[st]));
+        if (it == n_iters - 1) tc_commit_elect(smem_u32(tmem_full_bar));
       }
-      __syncwarp();
     }
   } else {
     const int q = warp & 3;

@@ -1,0 +1,528 @@
+// "Halo" implicit-GEMM convolution on tcgen05 / TMEM / TMA for sm_100a (kind::tf32, fp32 accumulate in tensor memory):
+// forward and data-gradient of the stride-1 sampled-weight convolutions.
+//
+// conv_tc.cu loads one TMA box per filter tap, so a 3x3 layer streams its input nine times from L2 into shared memory and
+// the 16..32-channel full-resolution layers (most of the step's bytes) are bound by that traffic and by per-CTA latency.
+// Here a CTA loads the (TH+KH-1) x (TW+KW-1) input halo of a TH x TW output tile ONCE per 32-channel chunk, as one dense
+// box whose rows are pixels (pitch Pw = TW+KW-1 pixels) and whose 128/64/32-byte rows are channels.  In that "flat" pixel
+// space output position q = hl*Pw + wl reads, for tap (r,s), halo row q + r*Pw + s: every tap is the SAME operand shifted
+// by a constant number of rows, and a UMMA shared-memory descriptor may start at any row because the hardware swizzle is a
+// function of the absolute address (probe: scripts/umma_shift_test.cu, profiles/r01_umma_row_shift_probe.txt).  The
+// 128-row M tiles therefore tile the flat space; the KW-1 junk positions at the end of each tile row are computed and dropped.
+//
+//   forward : D[q][co] += sum_tap  X[q + r*Pw + s][ci-chunk] * W[tap][co][ci-chunk]^T        A K-major, B K-major
+//   dgrad   : D[q][ci] += sum_tap dY[q + (KH-1-r)*Pw + (KW-1-s)][co-chunk] * W[tap][co-chunk][ci]   A K-major, B MN-major
+//             (the halo box starts at (h0-KH+1, w0-KW+1); TMA zero-fills outside dY)
+//
+// Channel chunks are 32 fp32 (SWIZZLE_128B) plus one narrower tail chunk of 8 or 16 (SWIZZLE_32B / 64B), so Cin = 36 costs
+// 40 channels of traffic, not 64.  Persistent CTAs walk a static tile list; 7 warps: 0 = activation TMA producer,
+// 1 = TMEM owner + single-thread MMA issuer, 2 = weight TMA producer, 3..6 = epilogue (TMEM -> registers -> global,
+// fused bias and per-sample BatchNorm (sum, sumsq) in double).  Accumulators are double-buffered in TMEM when they fit, so
+// the epilogue of tile i overlaps the loads and MMAs of tile i+1.
+#include <algorithm>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace mfvi {
+namespace tc2 {
+using namespace mfvi::tc;
+
+constexpr int kThreads = 224;
+constexpr int kMaxChunks = 9;
+constexpr int kMaxStages = 4;
+constexpr int kTrLd = 17;
+
+struct Args {
+  int n_chunks;
+  int ck0[kMaxChunks], cw[kMaxChunks];   // first channel and width (8/16/32) of every contraction chunk
+  int N, BN, n_nb;                       // valid output channels, UMMA N per CTA, number of N blocks
+  int KH, KW, taps, g, n_groups;         // g = taps per weight stage
+  int Mh, Mw, TH, TW, Pw, tiles_h, tiles_w;
+  int n_mt, total_tiles, tiles_per_sample;
+  int box_rows;                          // (TH+KH-1) * Pw
+  int dgrad, a_bcast, b_bcast;
+  int n_a, n_b, acc_stages;
+  uint32_t a_stage_bytes, b_stage_bytes, tmem_cols;
+  MfviView o;
+  const float* bias;
+  long long bias_sstride;
+  double* stats;
+  int accumulate, vecO;
+  long long* dbg;     // optional timeline of CTA 0 (clock64 stamps), 8 slots per tile
+};
+
+#define TC2_STAMP(slot) do { if (p.dbg != nullptr && blockIdx.x == 0) p.dbg[(tile_i) * 8 + (slot)] = clock64(); } while (0)
+
+struct TileCoord {
+  int smp, nb, th, tw;
+};
+__device__ __forceinline__ TileCoord decode_tile(const Args& p, int t) {
+  TileCoord c;
+  c.smp = t / p.tiles_per_sample;
+  int r = t - c.smp * p.tiles_per_sample;
+  const int per_nb = p.tiles_h * p.tiles_w;
+  c.nb = r / per_nb;
+  r -= c.nb * per_nb;
+  c.th = r / p.tiles_w;
+  c.tw = r - c.th * p.tiles_w;
+  return c;
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAt,
+            const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBt, const Args p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* a_stages = smem;
+  uint8_t* b_stages = a_stages + static_cast<size_t>(p.n_a) * p.a_stage_bytes;
+  uint8_t* ctrl = b_stages + static_cast<size_t>(p.n_b) * p.b_stage_bytes;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(ctrl);
+  uint64_t* a_empty = a_full + kMaxStages;
+  uint64_t* b_full = a_empty + kMaxStages;
+  uint64_t* b_empty = b_full + kMaxStages;
+  uint64_t* acc_full = b_empty + kMaxStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* tr_all = reinterpret_cast<float*>(ctrl + 256);      // [4 warps][32][kTrLd]
+
+  // warp index through a shuffle: ptxas then treats it (and every role branch on it) as warp-uniform and keeps the UMMA /
+  // TMA operands in uniform registers instead of R2UR-ing them before every instruction
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmAt);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmBt);
+    for (int i = 0; i < kMaxStages; ++i) {
+      mbar_init(smem_u32(&a_full[i]), 1);
+      mbar_init(smem_u32(&a_empty[i]), 1);
+      mbar_init(smem_u32(&b_full[i]), 1);
+      mbar_init(smem_u32(&b_empty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&acc_full[i]), 1);
+      mbar_init(smem_u32(&acc_empty[i]), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc_cols = static_cast<uint32_t>(p.n_mt * p.BN);
+
+  if (warp == 0) {
+    // ===== activation producer: one halo box per (tile, chunk)
+    if (lane == 0) {
+      uint32_t ia = 0;
+      int tile_i = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_i) {
+        const TileCoord tc = decode_tile(p, t);
+        const int h0 = tc.th * p.TH - (p.dgrad ? p.KH - 1 : 0);
+        const int w0 = tc.tw * p.TW - (p.dgrad ? p.KW - 1 : 0);
+        for (int c = 0; c < p.n_chunks; ++c, ++ia) {
+          const uint32_t st = ia % p.n_a, ph = (ia / p.n_a) & 1;
+          mbar_wait(smem_u32(&a_empty[st]), ph ^ 1);
+          if (c == 0) TC2_STAMP(0);
+          const uint32_t fb = smem_u32(&a_full[st]);
+          mbar_expect_tx(fb, static_cast<uint32_t>(p.box_rows) * p.cw[c] * 4u);
+          tma_load_4d(smem_u32(a_stages + static_cast<size_t>(st) * p.a_stage_bytes), p.cw[c] == 32 ? &tmA : &tmAt, fb, p.ck0[c],
+                      w0, h0, p.a_bcast ? 0 : tc.smp);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===== weight producer: g taps of one chunk per stage
+    if (lane == 0) {
+      uint32_t ib = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        const int bs = p.b_bcast ? 0 : tc.smp;
+        const int n0 = tc.nb * p.BN;
+        for (int c = 0; c < p.n_chunks; ++c) {
+          const CUtensorMap* map = p.cw[c] == 32 ? &tmB : &tmBt;
+          for (int grp = 0; grp < p.n_groups; ++grp, ++ib) {
+            const uint32_t st = ib % p.n_b, ph = (ib / p.n_b) & 1;
+            mbar_wait(smem_u32(&b_empty[st]), ph ^ 1);
+            const uint32_t fb = smem_u32(&b_full[st]);
+            const uint32_t dst = smem_u32(b_stages + static_cast<size_t>(st) * p.b_stage_bytes);
+            if (!p.dgrad) {
+              mbar_expect_tx(fb, static_cast<uint32_t>(p.g * p.BN * p.cw[c]) * 4u);
+              tma_load_4d(dst, map, fb, p.ck0[c], n0, grp * p.g, bs);                      // box (w k, BN n, g taps)
+            } else {
+              const uint32_t blk = static_cast<uint32_t>(p.g * p.cw[c]) * 128u;            // one 32-wide n block
+              mbar_expect_tx(fb, blk * static_cast<uint32_t>(p.BN / 32));
+              for (int j = 0; j < p.BN / 32; ++j)
+                tma_load_4d(dst + j * blk, map, fb, n0 + 32 * j, p.ck0[c], grp * p.g, bs);  // box (32 n, w k, g taps)
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer
+    const uint32_t idesc = make_idesc(128, p.BN, 0, p.dgrad ? 1 : 0);
+    uint32_t ia = 0, ib = 0, it = 0;
+    int tile_i = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it, ++tile_i) {
+      const uint32_t as = it % p.acc_stages, aph = (it / p.acc_stages) & 1;
+      mbar_wait(smem_u32(&acc_empty[as]), aph ^ 1);
+      tc_fence_after();
+      if (lane == 0) TC2_STAMP(1);
+      const uint32_t d_base = tmem_base + as * acc_cols;
+      for (int c = 0; c < p.n_chunks; ++c, ++ia) {
+        const uint32_t sa = ia % p.n_a;
+        mbar_wait(smem_u32(&a_full[sa]), (ia / p.n_a) & 1);
+        tc_fence_after();
+        if (lane == 0 && c == 0) TC2_STAMP(2);
+        const int w = p.cw[c];
+        const uint32_t rb = static_cast<uint32_t>(w) * 4u, sbo = 8u * rb, layout = kmajor_layout(w);
+        const int ksteps = w / 8;
+        const uint32_t a_base = smem_u32(a_stages + static_cast<size_t>(sa) * p.a_stage_bytes);
+        for (int grp = 0; grp < p.n_groups; ++grp, ++ib) {
+          const uint32_t sb = ib % p.n_b;
+          mbar_wait(smem_u32(&b_full[sb]), (ib / p.n_b) & 1);
+          tc_fence_after();
+          {
+            const uint32_t b_base = smem_u32(b_stages + static_cast<size_t>(sb) * p.b_stage_bytes);
+            for (int tt = 0; tt < p.g; ++tt) {
+              const int tap = grp * p.g + tt;
+              if (tap >= p.taps) break;
+              const int r = tap / p.KW, s = tap - r * p.KW;
+              const int off_rows = p.dgrad ? (p.KH - 1 - r) * p.Pw + (p.KW - 1 - s) : r * p.Pw + s;
+              for (int j = 0; j < p.n_mt; ++j) {
+                const uint32_t a_row = a_base + static_cast<uint32_t>(j * 128 + off_rows) * rb;
+                for (int k = 0; k < ksteps; ++k) {
+                  const uint64_t ad = make_desc(a_row + k * 32, 16, sbo, layout);
+                  const uint64_t bd = p.dgrad
+                      ? make_desc(b_base + static_cast<uint32_t>(tt * w) * 128u + k * 1024, static_cast<uint32_t>(p.g * w) * 128u, 512,
+                                  kLayoutSw128Base32)
+                      : make_desc(b_base + static_cast<uint32_t>(tt * p.BN) * rb + k * 32, 16, sbo, layout);
+                  tc_mma_tf32_elect(d_base + j * p.BN, ad, bd, idesc, (c > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                }
+              }
+            }
+            tc_commit_elect(smem_u32(&b_empty[sb]));
+          }
+        }
+        tc_commit_elect(smem_u32(&a_empty[sa]));
+      }
+      tc_commit_elect(smem_u32(&acc_full[as]));
+      if (lane == 0) TC2_STAMP(3);
+    }
+  } else {
+    // ===== epilogue warps 3..6: TMEM lane quarter = warp % 4.  Lane l owns flat position (j*128 + q*32 + l) of M tile j.
+    const int q = warp & 3;
+    uint32_t it = 0;
+    int tile_i = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it, ++tile_i) {
+      const TileCoord tc = decode_tile(p, t);
+      const uint32_t as = it % p.acc_stages;
+      if (warp == 3 && lane == 0) TC2_STAMP(4);
+      mbar_wait(smem_u32(&acc_full[as]), (it / p.acc_stages) & 1);
+      tc_fence_after();
+      if (warp == 3 && lane == 0) TC2_STAMP(5);
+      const int n0 = tc.nb * p.BN;
+      const float* bias = p.bias != nullptr ? p.bias + static_cast<size_t>(tc.smp) * p.bias_sstride + n0 : nullptr;
+      float* obase = p.o.ptr + static_cast<size_t>(tc.smp) * p.o.sstride + n0;
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * acc_cols;
+#pragma unroll 1
+      for (int c = 0; c < p.BN; c += 16) {
+        float b[16], s1[16], s2[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          b[i] = (bias != nullptr && n0 + c + i < p.N) ? __ldg(bias + c + i) : 0.f;
+          s1[i] = 0.f;
+          s2[i] = 0.f;
+        }
+        const bool full16 = n0 + c + 15 < p.N;
+#pragma unroll 1
+        for (int j = 0; j < p.n_mt; ++j) {
+          const int pos = j * 128 + q * 32 + lane;
+          const int hl = pos / p.Pw, wl = pos - hl * p.Pw;
+          const int gh = tc.th * p.TH + hl, gw = tc.tw * p.TW + wl;
+          const bool valid = hl < p.TH && wl < p.TW && gh < p.Mh && gw < p.Mw;
+          float v[16];
+          tmem_ld16(tbase + static_cast<uint32_t>(j * p.BN + c), v);
+          if (valid) {
+            float* optr = obase + static_cast<size_t>(gh) * p.o.hstride + static_cast<size_t>(gw) * p.o.wstride + c;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              v[i] += b[i];
+              s1[i] += v[i];
+              s2[i] = fmaf(v[i], v[i], s2[i]);
+            }
+            if (p.vecO && full16) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                float4 o4 = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                float4* dst = reinterpret_cast<float4*>(optr + i);
+                if (p.accumulate) {
+                  const float4 old = *dst;
+                  o4.x += old.x; o4.y += old.y; o4.z += old.z; o4.w += old.w;
+                }
+                *dst = o4;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (n0 + c + i < p.N) optr[i] = p.accumulate ? optr[i] + v[i] : v[i];
+            }
+          }
+        }
+        if (p.stats != nullptr) {
+          // (sum, sumsq) of 16 channels: per-lane fp32 partials over <= n_mt rows, then a transposing butterfly across the
+          // 32 lanes in double (fixed order).  Lane l ends up with the total of cell l: l < 16 -> sum of channel c+l,
+          // l >= 16 -> sum of squares of channel c+l-16.
+          double d[16];
+          {
+            const bool hi = lane & 16;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const double keep = hi ? static_cast<double>(s2[i]) : static_cast<double>(s1[i]);
+              const double send = hi ? static_cast<double>(s1[i]) : static_cast<double>(s2[i]);
+              d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+          }
+#pragma unroll
+          for (int off = 8; off >= 1; off >>= 1) {
+            const bool hi = lane & off;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+              const double keep = hi ? d[i + off] : d[i];
+              const double send = hi ? d[i] : d[i + off];
+              d[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+          }
+          const int col = n0 + c + (lane & 15);
+          if (col < p.N) atomicAdd(p.stats + (static_cast<size_t>(tc.smp) * p.N + col) * 2 + (lane >> 4), d[0]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (warp == 3 && lane == 0) TC2_STAMP(6);
+      if (lane == 0) mbar_arrive(smem_u32(&acc_empty[as]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline int rup(int a, int b) { return cdiv(a, b) * b; }
+
+static bool view_ok(const MfviView& v, int C) {
+  return (reinterpret_cast<uintptr_t>(v.ptr) % 16 == 0) && (C % 4 == 0) && (v.wstride % 4 == 0) && (v.hstride % 4 == 0) &&
+         (v.sstride % 4 == 0) && v.wstride >= C && v.hstride >= v.wstride;
+}
+
+static CUtensorMapSwizzle swz_of(int width) {
+  return width == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : (width == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+struct Plan {
+  bool ok = false;
+  int TH, TW, Pw, tiles_h, tiles_w, n_mt, BN, n_nb, g, n_groups, n_a, n_b, acc_stages, box_rows, grid;
+  uint32_t a_stage, b_stage, tmem_cols;
+  size_t smem;
+  double cost;
+};
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e != nullptr ? atoi(e) : dflt;
+}
+
+static Plan make_plan(int S, int Mh, int Mw, int KH, int KW, int n_chunks, const int* cw, int Nvalid, bool dgrad) {
+  Plan best;
+  best.cost = 1e30;
+  int kw_total = 0, rb_max = 0;
+  for (int i = 0; i < n_chunks; ++i) {
+    kw_total += cw[i];
+    rb_max = std::max(rb_max, cw[i] * 4);
+  }
+  const int taps = KH * KW;
+  const int nq = dgrad ? 32 : 16;
+  const int BN_full = rup(Nvalid, nq);
+  const int force_th = env_int("MFVI_TC2_TH", 0), force_strips = env_int("MFVI_TC2_STRIPS", 0), force_bn = env_int("MFVI_TC2_BN", 0);
+  for (int split = 1; split <= 8; split *= 2) {
+    if (BN_full % split) break;
+    const int BN = BN_full / split;
+    if (BN % nq || BN > 256) continue;
+    if (force_bn && BN != force_bn) continue;
+    for (int strips = 1; strips <= 4; ++strips) {
+      if (force_strips && strips != force_strips) continue;
+      const int TW = cdiv(Mw, strips);
+      const int Pw = TW + KW - 1;
+      if (Pw > 256) continue;
+      if (strips > 1 && cdiv(Mw, TW) != strips) continue;
+      for (int TH = 1; TH <= std::min(Mh, 64); ++TH) {
+        if (force_th && TH != force_th) continue;
+        if (TH + KH - 1 > 256) break;
+        Plan pl;
+        pl.TH = TH; pl.TW = TW; pl.Pw = Pw; pl.BN = BN; pl.n_nb = split;
+        pl.tiles_h = cdiv(Mh, TH); pl.tiles_w = strips;
+        pl.box_rows = (TH + KH - 1) * Pw;
+        pl.n_mt = cdiv((TH - 1) * Pw + TW, 128);
+        const int acc_cols = pl.n_mt * BN;
+        if (acc_cols > 512) break;
+        pl.acc_stages = 2 * acc_cols <= 512 ? 2 : 1;
+        uint32_t cols = 32;
+        while (cols < static_cast<uint32_t>(pl.acc_stages * acc_cols)) cols <<= 1;
+        pl.tmem_cols = cols;
+        const int a_rows = std::max(pl.box_rows, pl.n_mt * 128 + (KH - 1) * Pw + KW - 1);
+        pl.a_stage = static_cast<uint32_t>(rup(a_rows * rb_max, 1024));
+        int g = taps;
+        while (g > 1 && g * BN * rb_max > 32 * 1024) --g;
+        while (taps % g) --g;           // equal groups
+        pl.g = g; pl.n_groups = taps / g;
+        pl.b_stage = static_cast<uint32_t>(rup(g * BN * rb_max, 1024));
+        pl.n_a = 2;
+        pl.n_b = (pl.n_groups * n_chunks > 1) ? 3 : 2;
+        pl.smem = 1024 + static_cast<size_t>(pl.n_a) * pl.a_stage + static_cast<size_t>(pl.n_b) * pl.b_stage + 256 + 4 * 32 * kTrLd * 4 +
+                  4 * BN * 16 + 64;
+        if (pl.smem > 200 * 1024) break;
+        const int tiles = S * split * pl.tiles_h * pl.tiles_w;
+        const int cpsm = (pl.smem <= 100 * 1024 && cols <= 256) ? 2 : 1;
+        const int slots = kNumSMs * cpsm;
+        const int waves = cdiv(tiles, slots);
+        const double t_load = (static_cast<double>(pl.box_rows) * kw_total * 4 + static_cast<double>(taps) * BN * kw_total * 4) / 40.0 * cpsm;
+        const double t_mma = static_cast<double>(pl.n_mt) * taps * (kw_total / 8) * std::max(BN / 2, 16) * cpsm;
+        const double t_epi = static_cast<double>(pl.n_mt) * (BN / 16) * 120.0;
+        const double t_tile = std::max(t_load, std::max(t_mma, t_epi)) + 500.0;
+        pl.cost = 5000.0 + waves * t_tile + std::min(t_load, 4000.0);
+        pl.grid = std::min(tiles, slots);
+        pl.ok = true;
+        if (pl.cost < best.cost) best = pl;
+      }
+    }
+  }
+  return best;
+}
+
+static int split_chunks(int Kc, int* ck0, int* cw) {
+  int n = 0, k = 0;
+  while (Kc - k >= 32 && n < kMaxChunks) {
+    ck0[n] = k; cw[n] = 32; ++n; k += 32;
+  }
+  if (Kc - k >= 32) return -1;
+  const int rem = Kc - k;
+  if (rem > 0) {
+    if (n >= kMaxChunks) return -1;
+    ck0[n] = k;
+    cw[n] = rem <= 8 ? 8 : (rem <= 16 ? 16 : 32);
+    ++n;
+  }
+  return n;
+}
+
+// a: the activation read through TMA (x for forward, dy for dgrad); Ca channels, (Ha, Wa) pixels.
+static int launch(const MfviConvDesc* d, bool dgrad, MfviView a, int Ca, int Ha, int Wa, const float* w, long long w_sstride,
+                  MfviView o, int Mh, int Mw, int Nvalid, const float* bias, double* stats, int accumulate, mfvi_stream_t st,
+                  const char* what) {
+  Args p{};
+  p.n_chunks = split_chunks(Ca, p.ck0, p.cw);
+  if (p.n_chunks <= 0) return -1;
+  const Plan pl = make_plan(d->S, Mh, Mw, d->KH, d->KW, p.n_chunks, p.cw, Nvalid, dgrad);
+  if (!pl.ok) return -1;
+  p.N = Nvalid; p.BN = pl.BN; p.n_nb = pl.n_nb;
+  p.KH = d->KH; p.KW = d->KW; p.taps = d->KH * d->KW; p.g = pl.g; p.n_groups = pl.n_groups;
+  p.Mh = Mh; p.Mw = Mw; p.TH = pl.TH; p.TW = pl.TW; p.Pw = pl.Pw; p.tiles_h = pl.tiles_h; p.tiles_w = pl.tiles_w;
+  p.n_mt = pl.n_mt;
+  p.tiles_per_sample = pl.n_nb * pl.tiles_h * pl.tiles_w;
+  p.total_tiles = d->S * p.tiles_per_sample;
+  p.box_rows = pl.box_rows;
+  p.dgrad = dgrad ? 1 : 0;
+  p.a_bcast = (a.sstride == 0 || d->S == 1) ? 1 : 0;
+  p.b_bcast = (w_sstride == 0 || d->S == 1) ? 1 : 0;
+  p.n_a = pl.n_a; p.n_b = pl.n_b; p.acc_stages = pl.acc_stages;
+  p.a_stage_bytes = pl.a_stage; p.b_stage_bytes = pl.b_stage; p.tmem_cols = pl.tmem_cols;
+  p.o = o; p.bias = bias; p.bias_sstride = w_sstride; p.stats = stats; p.accumulate = accumulate;
+  p.vecO = ((reinterpret_cast<uintptr_t>(o.ptr) % 16 == 0) && o.sstride % 4 == 0 && o.hstride % 4 == 0 && o.wstride % 4 == 0) ? 1 : 0;
+  if (const char* e = getenv("MFVI_TC2_DBG")) p.dbg = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));   // device pointer (debug)
+
+  // ---- tensor maps: wide (32-channel) and tail chunk variants
+  int tail_w = 0;
+  bool has32 = false;
+  for (int i = 0; i < p.n_chunks; ++i) {
+    if (p.cw[i] == 32) has32 = true; else tail_w = p.cw[i];
+  }
+  CUtensorMap tmA, tmAt, tmB, tmBt;
+  auto enc_a = [&](CUtensorMap* m, int width) {
+    const uint64_t dims[4] = {static_cast<uint64_t>(Ca), static_cast<uint64_t>(Wa), static_cast<uint64_t>(Ha),
+                              static_cast<uint64_t>(p.a_bcast ? 1 : d->S)};
+    const uint64_t sbytes = p.a_bcast ? static_cast<uint64_t>(a.hstride) * Ha * 4 : static_cast<uint64_t>(a.sstride) * 4;
+    const uint64_t strides[3] = {static_cast<uint64_t>(a.wstride) * 4, static_cast<uint64_t>(a.hstride) * 4, sbytes};
+    const uint32_t box[4] = {static_cast<uint32_t>(width), static_cast<uint32_t>(pl.Pw), static_cast<uint32_t>(pl.TH + d->KH - 1), 1};
+    return tma_encode(m, a.ptr, 4, dims, strides, box, swz_of(width));
+  };
+  auto enc_b = [&](CUtensorMap* m, int width) {
+    const uint64_t dims[4] = {static_cast<uint64_t>(d->Cin), static_cast<uint64_t>(d->Cout), static_cast<uint64_t>(p.taps),
+                              static_cast<uint64_t>(p.b_bcast ? 1 : d->S)};
+    const uint64_t tap_bytes = static_cast<uint64_t>(d->Cout) * d->Cin * 4;
+    const uint64_t strides[3] = {static_cast<uint64_t>(d->Cin) * 4, tap_bytes,
+                                 p.b_bcast ? tap_bytes * p.taps : static_cast<uint64_t>(w_sstride) * 4};
+    if (!dgrad) {
+      const uint32_t box[4] = {static_cast<uint32_t>(width), static_cast<uint32_t>(pl.BN), static_cast<uint32_t>(pl.g), 1};
+      return tma_encode(m, w, 4, dims, strides, box, swz_of(width));
+    }
+    const uint32_t box[4] = {32, static_cast<uint32_t>(width), static_cast<uint32_t>(pl.g), 1};
+    return tma_encode(m, w, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  };
+  const int wide = has32 ? 32 : tail_w, narrow = tail_w ? tail_w : 32;
+  if (!enc_a(&tmA, wide) || !enc_a(&tmAt, narrow) || !enc_b(&tmB, wide) || !enc_b(&tmBt, narrow)) return -1;
+  if (!has32) {          // only a narrow chunk exists: the kernel picks the *t maps for width != 32
+    tmA = tmAt;
+    tmB = tmBt;
+  }
+  static size_t attr = 0;
+  if (pl.smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(k_conv_halo, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    MFVI_REQUIRE(e == cudaSuccess, "%s: cannot raise dynamic shared memory: %s", what, cudaGetErrorString(e));
+    attr = 200 * 1024;
+  }
+  if (env_int("MFVI_TC2_VERBOSE", 0))
+    fprintf(stderr, "[tc2] %s Kc=%d N=%d k%d M=%dx%d S=%d: TH=%d TW=%d Pw=%d n_mt=%d BN=%d nb=%d g=%d acc_stages=%d smem=%zu grid=%d tiles=%d\n",
+            what, Ca, Nvalid, d->KH, Mh, Mw, d->S, pl.TH, pl.TW, pl.Pw, pl.n_mt, pl.BN, pl.n_nb, pl.g, pl.acc_stages, pl.smem, pl.grid,
+            p.total_tiles);
+  k_conv_halo<<<pl.grid, kThreads, pl.smem, as_stream(st)>>>(tmA, tmAt, tmB, tmBt, p);
+  return check_launch(what);
+}
+
+}  // namespace tc2
+}  // namespace mfvi
+
+using namespace mfvi;
+
+extern "C" {
+
+// Return 0 on success, -1 when the shape is not taken (caller falls back to conv_tc.cu / conv_simt.cu), >0 on error.
+int mfvi_conv2d_fwd_tc2(const MfviConvDesc* d, MfviView x, const float* w, const float* bias, long long w_sstride, MfviView y,
+                        double* stats, mfvi_stream_t st) {
+  static const bool on = tc2::env_int("MFVI_TC2", 1) != 0;
+  if (!on || d->stride != 1 || !tc2::view_ok(x, d->Cin) || (reinterpret_cast<uintptr_t>(w) % 16) || (w_sstride % 4) || d->Cin % 4 ||
+      d->Cout > 256)
+    return -1;
+  return tc2::launch(d, false, x, d->Cin, d->Hin, d->Win, w, w_sstride, y, d->Hout, d->Wout, d->Cout, bias, stats, 0, st,
+                     "conv2d_fwd_tc2");
+}
+
+int mfvi_conv2d_dgrad_tc2(const MfviConvDesc* d, MfviView dy, const float* w, long long w_sstride, MfviView dx, int accumulate,
+                          mfvi_stream_t st) {
+  static const bool on = tc2::env_int("MFVI_TC2", 1) != 0;
+  if (!on || d->stride != 1 || !tc2::view_ok(dy, d->Cout) || (reinterpret_cast<uintptr_t>(w) % 16) || (w_sstride % 4) || d->Cin % 4 ||
+      d->Cin > 256)
+    return -1;
+  return tc2::launch(d, true, dy, d->Cout, d->Hout, d->Wout, w, w_sstride, dx, d->Hin, d->Win, d->Cin, nullptr, nullptr, accumulate, st,
+                     "conv2d_dgrad_tc2");
+}
+
+}  // extern "C"

@@ -16,7 +16,8 @@ TF32_TOL = 3e-3
 SHAPES = [
     (132, 128, 3, 16, 16), (36, 16, 3, 64, 64), (16, 4, 1, 32, 32), (128, 128, 1, 16, 16), (16, 2, 1, 64, 64),
     (68, 32, 3, 32, 48), (16, 16, 5, 24, 24), (128, 128, 3, 8, 8), (64, 64, 3, 32, 32), (32, 32, 1, 128, 128),
-    (36, 16, 3, 256, 256),
+    (36, 16, 3, 256, 256), (68, 32, 3, 128, 128), (16, 16, 1, 256, 256), (132, 64, 3, 64, 64), (128, 4, 1, 16, 16),
+    (16, 4, 1, 256, 256), (132, 128, 3, 32, 32), (64, 64, 1, 64, 64), (20, 24, 3, 37, 29), (16, 16, 5, 130, 70),
     (16, 16, 3, 128, 128, 2), (64, 128, 3, 16, 16, 2), (128, 128, 3, 8, 8, 2), (16, 16, 5, 32, 32, 2), (32, 64, 3, 31, 33, 2),
     (16, 32, 1, 16, 16, 2),
 ]
