@@ -11,6 +11,8 @@ int mfvi_conv2d_dgrad_tc(const MfviConvDesc*, MfviView, const float*, long long,
 int mfvi_conv2d_wgrad_tc(const MfviConvDesc*, MfviView, MfviView, float*, float*, long long, mfvi_stream_t);
 int mfvi_conv2d_fwd_tc2(const MfviConvDesc*, MfviView, const float*, const float*, long long, MfviView, double*, mfvi_stream_t);
 int mfvi_conv2d_dgrad_tc2(const MfviConvDesc*, MfviView, const float*, long long, MfviView, int, mfvi_stream_t);
+int mfvi_conv2d_wgrad_tc2(const MfviConvDesc*, MfviView, MfviView, float*, long long, mfvi_stream_t);
+int mfvi_conv2d_bias_grad_tc(const MfviConvDesc*, MfviView, float*, long long, mfvi_stream_t);
 
 int mfvi_conv2d_fwd(const MfviConvDesc* d, MfviView x, const float* w, const float* bias, long long w_sstride,
                     MfviView y, double* stats, mfvi_stream_t st) {
@@ -37,7 +39,10 @@ int mfvi_conv2d_dgrad(const MfviConvDesc* d, MfviView dy, const float* w, long l
 int mfvi_conv2d_wgrad(const MfviConvDesc* d, MfviView x, MfviView dy, float* dw, float* dbias, long long w_sstride,
                       mfvi_stream_t st) {
   if (d != nullptr && d->math == MFVI_MATH_TF32) {
-    const int rc = mfvi_conv2d_wgrad_tc(d, x, dy, dw, dbias, w_sstride, st);
+    int rc = mfvi_conv2d_wgrad_tc2(d, x, dy, dw, w_sstride, st);
+    if (rc == 0 && dbias != nullptr) rc = mfvi_conv2d_bias_grad_tc(d, dy, dbias, w_sstride, st);
+    if (rc >= 0) return rc;
+    rc = mfvi_conv2d_wgrad_tc(d, x, dy, dw, dbias, w_sstride, st);
     if (rc >= 0) return rc;
   }
   return mfvi_conv2d_wgrad_simt(d, x, dy, dw, dbias, w_sstride, st);

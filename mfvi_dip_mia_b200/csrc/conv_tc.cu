@@ -149,13 +149,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       {
         const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(st) * stage_bytes);
         const uint32_t b_addr = a_addr + kABytes;
+        const uint32_t a_lo = desc_lo(a_addr, 16), a_hi = desc_hi(1024, kLayoutSw128);
+        const uint32_t b_lo = p.dgrad ? desc_lo(b_addr, 4096) : desc_lo(b_addr, 16);
+        const uint32_t b_hi = p.dgrad ? desc_hi(512, kLayoutSw128Base32) : a_hi;
+        const uint32_t b_k = p.dgrad ? 64u : 2u;
 #pragma unroll
-        for (int k = 0; k < kBK / kUmmaK; ++k) {
-          const uint64_t ad = make_desc(a_addr + k * (kUmmaK * 4), 16, 1024);
-          const uint64_t bd = p.dgrad ? make_desc(b_addr + k * 1024, 4096, 512, kLayoutSw128Base32)
-                                      : make_desc(b_addr + k * (kUmmaK * 4), 16, 1024);
-          tc_mma_tf32_elect(tmem_base, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
-        }
+        for (int k = 0; k < kBK / kUmmaK; ++k)
+          tc_mma_tf32_elect(tmem_base, desc_pack(a_lo + 2u * k, a_hi), desc_pack(b_lo + b_k * k, b_hi), idesc, (it > 0 || k > 0) ? 1u : 0u);
         tc_commit_elect(smem_u32(&empty_bar[st]));
         if (it == n_iters - 1) tc_commit_elect(smem_u32(tmem_full_bar));
       }
@@ -346,11 +346,10 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUt
       {
         const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(st) * stage_bytes);
         const uint32_t b_addr = a_addr + a_bytes;
-        for (int k = 0; k < ksteps; ++k) {
-          const uint64_t ad = make_desc(a_addr + k * 1024, blk_bytes, 512, kLayoutSw128Base32);
-          const uint64_t bd = make_desc(b_addr + k * 1024, blk_bytes, 512, kLayoutSw128Base32);
-          tc_mma_tf32_elect(tmem_base, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
-        }
+        const uint32_t hi = desc_hi(512, kLayoutSw128Base32);
+        uint32_t a_lo = desc_lo(a_addr, blk_bytes), b_lo = desc_lo(b_addr, blk_bytes);
+        for (int k = 0; k < ksteps; ++k, a_lo += 64u, b_lo += 64u)
+          tc_mma_tf32_elect(tmem_base, desc_pack(a_lo, hi), desc_pack(b_lo, hi), idesc, (it > 0 || k > 0) ? 1u : 0u);
         tc_commit_elect(smem_u32(&empty_bar[st]));
         if (it == n_iters - 1) tc_commit_elect(smem_u32(tmem_full_bar));
       }
@@ -595,6 +594,15 @@ int mfvi_conv2d_dgrad_tc(const MfviConvDesc* d, MfviView dy, const float* w, lon
   return check_launch("conv2d_dgrad_tc");
 }
 
+// dbias[s][co] += sum over pixels of dy (requires Cout % 4 == 0 and 16-byte aligned rows: the same conditions as the TMA paths)
+int mfvi_conv2d_bias_grad_tc(const MfviConvDesc* d, MfviView dy, float* dbias, long long w_sstride, mfvi_stream_t st) {
+  using namespace mfvi::tc;
+  int blocks = std::max(1, std::min(kNumSMs * 2, (d->Hout * d->Wout * (d->Cout / 4) + 255) / 256));
+  dim3 g2(blocks, d->S);
+  k_bias_grad<<<g2, 256, d->Cout * sizeof(float), as_stream(st)>>>(dy, d->Hout, d->Wout, d->Cout, dbias, w_sstride);
+  return check_launch("conv2d_bias_grad_tc");
+}
+
 int mfvi_conv2d_wgrad_tc(const MfviConvDesc* d, MfviView x, MfviView dy, float* dw, float* dbias, long long w_sstride,
                          mfvi_stream_t st) {
   using namespace mfvi::tc;
@@ -643,12 +651,7 @@ int mfvi_conv2d_wgrad_tc(const MfviConvDesc* d, MfviView x, MfviView dy, float* 
   dim3 grid(chunks, taps, d->S);
   k_wgrad_tc<<<grid, kThreads, smem, as_stream(st)>>>(tmDy, tmX, a);
   if (int rc = check_launch("conv2d_wgrad_tc")) return rc;
-  if (dbias != nullptr) {
-    int blocks = std::max(1, std::min(kNumSMs * 2, (d->Hout * d->Wout * (d->Cout / 4) + 255) / 256));
-    dim3 g2(blocks, d->S);
-    k_bias_grad<<<g2, 256, d->Cout * sizeof(float), as_stream(st)>>>(dy, d->Hout, d->Wout, d->Cout, dbias, w_sstride);
-    return check_launch("conv2d_wgrad_tc(bias)");
-  }
+  if (dbias != nullptr) return mfvi_conv2d_bias_grad_tc(d, dy, dbias, w_sstride, st);
   return 0;
 }
 

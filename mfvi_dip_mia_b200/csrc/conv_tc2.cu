@@ -167,6 +167,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const uint32_t idesc = make_idesc(128, p.BN, 0, p.dgrad ? 1 : 0);
     uint32_t ia = 0, ib = 0, it = 0;
     int tile_i = 0;
+    long long cyc_wait_a = 0, cyc_wait_b = 0, cyc_issue = 0, n_mma = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it, ++tile_i) {
       const uint32_t as = it % p.acc_stages, aph = (it / p.acc_stages) & 1;
       mbar_wait(smem_u32(&acc_empty[as]), aph ^ 1);
@@ -175,8 +176,10 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t d_base = tmem_base + as * acc_cols;
       for (int c = 0; c < p.n_chunks; ++c, ++ia) {
         const uint32_t sa = ia % p.n_a;
+        long long tw0 = p.dbg ? clock64() : 0;
         mbar_wait(smem_u32(&a_full[sa]), (ia / p.n_a) & 1);
         tc_fence_after();
+        if (p.dbg) cyc_wait_a += clock64() - tw0;
         if (lane == 0 && c == 0) TC2_STAMP(2);
         const int w = p.cw[c];
         const uint32_t rb = static_cast<uint32_t>(w) * 4u, sbo = 8u * rb, layout = kmajor_layout(w);
@@ -184,34 +187,49 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const uint32_t a_base = smem_u32(a_stages + static_cast<size_t>(sa) * p.a_stage_bytes);
         for (int grp = 0; grp < p.n_groups; ++grp, ++ib) {
           const uint32_t sb = ib % p.n_b;
+          long long tb0 = p.dbg ? clock64() : 0;
           mbar_wait(smem_u32(&b_full[sb]), (ib / p.n_b) & 1);
           tc_fence_after();
+          long long ti0 = p.dbg ? clock64() : 0;
+          if (p.dbg) cyc_wait_b += ti0 - tb0;
           {
             const uint32_t b_base = smem_u32(b_stages + static_cast<size_t>(sb) * p.b_stage_bytes);
-            for (int tt = 0; tt < p.g; ++tt) {
-              const int tap = grp * p.g + tt;
-              if (tap >= p.taps) break;
-              const int r = tap / p.KW, s = tap - r * p.KW;
-              const int off_rows = p.dgrad ? (p.KH - 1 - r) * p.Pw + (p.KW - 1 - s) : r * p.Pw + s;
-              for (int j = 0; j < p.n_mt; ++j) {
-                const uint32_t a_row = a_base + static_cast<uint32_t>(j * 128 + off_rows) * rb;
-                for (int k = 0; k < ksteps; ++k) {
-                  const uint64_t ad = make_desc(a_row + k * 32, 16, sbo, layout);
-                  const uint64_t bd = p.dgrad
-                      ? make_desc(b_base + static_cast<uint32_t>(tt * w) * 128u + k * 1024, static_cast<uint32_t>(p.g * w) * 128u, 512,
-                                  kLayoutSw128Base32)
-                      : make_desc(b_base + static_cast<uint32_t>(tt * p.BN) * rb + k * 32, 16, sbo, layout);
-                  tc_mma_tf32_elect(d_base + j * p.BN, ad, bd, idesc, (c > 0 || tap > 0 || k > 0) ? 1u : 0u);
-                }
+            // descriptors: hi words fixed per chunk, lo words advance by (bytes >> 4)
+            const uint32_t a_hi = desc_hi(sbo, layout);
+            const uint32_t b_hi = p.dgrad ? desc_hi(512, kLayoutSw128Base32) : a_hi;
+            const uint32_t b_lo0 = p.dgrad ? desc_lo(b_base, static_cast<uint32_t>(p.g * w) * 128u) : desc_lo(b_base, 16);
+            const uint32_t b_tap = p.dgrad ? static_cast<uint32_t>(w) * 8u : (static_cast<uint32_t>(p.BN) * rb) >> 4;   // per tap
+            const uint32_t b_k = p.dgrad ? 64u : 2u;                                                                    // per k-step
+            const uint32_t a_lo0 = desc_lo(a_base, 16);
+            const uint32_t a_mt = (128u * rb) >> 4, rb16 = rb >> 4;
+            const int tap0 = grp * p.g;
+            int r = tap0 / p.KW, sx = tap0 - r * p.KW;
+            const int ntap = min(p.g, p.taps - tap0);
+            for (int tt = 0; tt < ntap; ++tt) {
+              const int off_rows = p.dgrad ? (p.KH - 1 - r) * p.Pw + (p.KW - 1 - sx) : r * p.Pw + sx;
+              const uint32_t a_t = a_lo0 + static_cast<uint32_t>(off_rows) * rb16;
+              const uint32_t b_t = b_lo0 + static_cast<uint32_t>(tt) * b_tap;
+              const bool first_tap = (c == 0 && tap0 + tt == 0);
+              uint32_t d_col = d_base;
+              for (int j = 0; j < p.n_mt; ++j, d_col += p.BN) {
+                const uint32_t a_j = a_t + static_cast<uint32_t>(j) * a_mt;
+                for (int k = 0; k < ksteps; ++k)
+                  tc_mma_tf32_elect(d_col, desc_pack(a_j + 2u * k, a_hi), desc_pack(b_t + b_k * k, b_hi), idesc,
+                                    (first_tap && k == 0) ? 0u : 1u);
               }
+              if (++sx == p.KW) { sx = 0; ++r; }
             }
             tc_commit_elect(smem_u32(&b_empty[sb]));
+            if (p.dbg) { cyc_issue += clock64() - ti0; n_mma += static_cast<long long>(p.g) * p.n_mt * ksteps; }
           }
         }
         tc_commit_elect(smem_u32(&a_empty[sa]));
       }
       tc_commit_elect(smem_u32(&acc_full[as]));
       if (lane == 0) TC2_STAMP(3);
+    }
+    if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0) {
+      p.dbg[63 * 8 + 0] = cyc_wait_a; p.dbg[63 * 8 + 1] = cyc_wait_b; p.dbg[63 * 8 + 2] = cyc_issue; p.dbg[63 * 8 + 3] = n_mma;
     }
   } else {
     // ===== epilogue warps 3..6: TMEM lane quarter = warp % 4.  Lane l owns flat position (j*128 + q*32 + l) of M tile j.

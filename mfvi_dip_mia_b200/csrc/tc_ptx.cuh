@@ -119,6 +119,20 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= static_cast<uint64_t>(layout) << 61;
   return d;
 }
+// The two 32-bit halves of a shared-memory descriptor.  lo = start address (>>4) | LBO (>>4) << 16 : advancing the operand by
+// `bytes` is `lo + (bytes >> 4)`, so inner loops only add to `lo` and keep `hi` (SBO, version, layout) fixed.
+__host__ __device__ inline uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__host__ __device__ inline uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
+}
+__device__ __forceinline__ uint64_t desc_pack(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+
 // Instruction descriptor: D=f32, A=B=tf32, majors, N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ inline uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
   uint32_t d = 0;

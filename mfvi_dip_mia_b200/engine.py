@@ -311,11 +311,18 @@ class SkipEngine:
                     self._ew_meta(g, y, g)))
         return g
 
-    def _conv_bwd(self, ops, c: ConvLayer, d, x, dy, need_dx=True):
+    def _dbias_ptr(self, c: ConvLayer, bn_follows: bool):
+        """A conv bias that feeds a train-mode BatchNorm has an identically zero data gradient (BN subtracts the
+        per-sample channel mean, so sum_pixels dL/dy = gamma*invstd*(sum g - sum g - mean(g*xhat)*sum xhat) = 0; the
+        reference's autograd returns rounding noise ~1e-9 there).  The engine leaves dw[s][bias] at its zero fill for those
+        layers instead of reducing dy again; only the final conv (no BN behind it) computes a bias gradient."""
+        return None if bn_follows else self.dw.data_ptr() + 4 * c.b_off
+
+    def _conv_bwd(self, ops, c: ConvLayer, d, x, dy, need_dx=True, bn_follows=True):
         """wgrad into dw[s] (+bias), dgrad into a fresh padded-input-sized buffer (returned)."""
         meta = self._conv_meta(c, d, x, dy)
         ops.append(("mfvi_conv2d_wgrad", (C.byref(d), L.view(x), L.view(dy), self.dw.data_ptr() + 4 * c.w_off,
-                                          self.dw.data_ptr() + 4 * c.b_off, self.lay.P_pad), meta))
+                                          self._dbias_ptr(c, bn_follows), self.lay.P_pad), meta))
         if not need_dx:
             return None
         dx = self._buf(x.shape[1], x.shape[2], c.cin)
@@ -416,7 +423,7 @@ class SkipEngine:
                         ops.append(("mfvi_fill_f32", (dT.data_ptr(), dT.numel(), 0.0), self._ew_meta(dT)))
                 m1 = self._conv_meta(sc.d1, d_1, x_d1, dy1)
                 ops.append(("mfvi_conv2d_wgrad", (C.byref(d_1), L.view(x_d1), L.view(dy1), self.dw.data_ptr() + 4 * sc.d1.w_off,
-                                                  self.dw.data_ptr() + 4 * sc.d1.b_off, lay.P_pad), m1))
+                                                  self._dbias_ptr(sc.d1, True), lay.P_pad), m1))
                 if need_dT:
                     ops.append(("mfvi_conv2d_dgrad", (C.byref(d_1), L.view(dy1), self.w.data_ptr() + 4 * sc.d1.w_off, lay.P_pad,
                                                       L.view(dT_d1), 1 if Tpad != pd else 0), m1))
@@ -424,7 +431,7 @@ class SkipEngine:
                     x_s = self._interior(T, Tpad - ps)
                     ms = self._conv_meta(sc.skip_conv, d_s, x_s, gs)
                     ops.append(("mfvi_conv2d_wgrad", (C.byref(d_s), L.view(x_s), L.view(gs), self.dw.data_ptr() + 4 * sc.skip_conv.w_off,
-                                                      self.dw.data_ptr() + 4 * sc.skip_conv.b_off, lay.P_pad), ms))
+                                                      self._dbias_ptr(sc.skip_conv, True), lay.P_pad), ms))
                     if need_dT:
                         ops.append(("mfvi_conv2d_dgrad", (C.byref(d_s), L.view(gs), self.w.data_ptr() + 4 * sc.skip_conv.w_off,
                                                           lay.P_pad, L.view(self._interior(dT, Tpad - ps)), 1), ms))
@@ -438,7 +445,7 @@ class SkipEngine:
         self.out, d_f = self._conv_fwd(lay.final, XF, None)
         self.dout = torch.zeros_like(self.out)
         ops = self.bwd_ops
-        dXF = self._conv_bwd(ops, lay.final, d_f, XF, self.dout)
+        dXF = self._conv_bwd(ops, lay.final, d_f, XF, self.dout, bn_follows=False)
         dz0 = self._bn_act_pad_bwd(ops, dXF, z0, z0_bn, 1, 0)
         self.dx0 = bwd0(ops, dz0)
 

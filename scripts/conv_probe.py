@@ -32,7 +32,7 @@ flush = torch.empty(256 * 2 ** 20 // 4, device=dev)
 ops = {
     "fwd": lambda: L.call("mfvi_conv2d_fwd", C.byref(d), L.view(x), w.data_ptr(), w.data_ptr() + 4 * boff, P, L.view(y), stats.data_ptr()),
     "dgrad": lambda: L.call("mfvi_conv2d_dgrad", C.byref(d), L.view(dy), w.data_ptr(), P, L.view(dx), 0),
-    "wgrad": lambda: L.call("mfvi_conv2d_wgrad", C.byref(d), L.view(x), L.view(dy), dw.data_ptr(), dw.data_ptr() + 4 * boff, P),
+    "wgrad": lambda: L.call("mfvi_conv2d_wgrad", C.byref(d), L.view(x), L.view(dy), dw.data_ptr(), None if os.environ.get("PROBE_NOBIAS") else dw.data_ptr() + 4 * boff, P),
 }
 flops = 2.0 * S * H * W * cout * cin * k * k
 for name, fn in ops.items():
@@ -69,3 +69,4 @@ if os.environ.get("TC2_TIMELINE"):
         if int(t[i, 0]) == 0:
             break
         print(i, [int(v) - t0 if int(v) else None for v in t[i]])
+    print("mma warp totals: wait_a %d  wait_b %d  issue %d cycles for %d MMAs" % tuple(int(v) for v in t[63, :4]))

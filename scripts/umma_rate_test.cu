@@ -1,0 +1,65 @@
+// Probe: cycles per tcgen05.mma.kind::tf32 instruction (SS mode, operands in shared memory) as a function of M and N.
+// Issues `n_iss` back-to-back MMAs on the same operands from one elected lane and waits for the commit.
+#include <cstdio>
+#include <cstdlib>
+#include "../mfvi_dip_mia_b200/csrc/tc_ptx.cuh"
+using namespace mfvi::tc;
+
+__global__ void __launch_bounds__(128) k_rate(int M, int N, int n_iss, int mn_major, int distinct_acc, int a_mode, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 96 * 1024);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 0.f;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(bar), 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(smem_u32(slot), 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+  if (warp == 0) {
+    const uint32_t idesc = make_idesc(M, N, mn_major, mn_major);
+    const uint32_t a = smem_u32(smem), b = smem_u32(smem + 48 * 1024);
+    const long long t0 = clock64();
+    for (int i = 0; i < n_iss; ++i) {
+      const uint32_t k = (i & 3);
+      // a_mode 0: same rows always; 1: new row window every 4 MMAs (k cycles inside); 2: new row window every MMA; 3: window shifts by 1 row every 4 MMAs
+      uint32_t a_off = 0;
+      if (a_mode == 1) a_off = ((i >> 2) * 37u % 200u) * 128u;
+      if (a_mode == 2) a_off = (i * 37u % 200u) * 128u;
+      if (a_mode == 3) a_off = ((i >> 2) % 200u) * 128u;
+      const uint64_t ad = mn_major ? make_desc(a + a_off + k * 1024, 4096, 512, kLayoutSw128Base32) : make_desc(a + a_off + k * 32, 16, 1024);
+      const uint64_t bd = mn_major ? make_desc(b + k * 1024, 4096, 512, kLayoutSw128Base32) : make_desc(b + k * 32, 16, 1024);
+      const uint32_t d = tmem + (distinct_acc ? ((i & 1) * 256u) : 0u);
+      tc_mma_tf32_elect(d, ad, bd, idesc, 1u);
+    }
+    const long long t1 = clock64();
+    tc_commit_elect(smem_u32(bar));
+    mbar_wait(smem_u32(bar), 0);
+    const long long t2 = clock64();
+    if ((threadIdx.x & 31) == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+int main() {
+  long long* d; cudaMalloc(&d, 16);
+  cudaFuncSetAttribute(k_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  const int n_iss = 512;
+  for (int mn = 0; mn < 1; ++mn)
+    for (int M : {128})
+      for (int N : {16, 64, 128, 256})
+        for (int dist : {0, 1, 2, 3}) {
+          k_rate<<<1, 128, 100 * 1024>>>(M, N, n_iss, mn, 0, dist, d);
+          cudaError_t e = cudaDeviceSynchronize();
+          if (e != cudaSuccess) { printf("error %s (M=%d N=%d)\n", cudaGetErrorString(e), M, N); return 1; }
+          long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+          printf("%s M=%3d N=%3d %s: issue %6.1f cyc/MMA, complete %6.1f cyc/MMA\n", mn ? "MN-major" : "K-major ", M, N,
+                 dist == 0 ? "A fixed         " : dist == 1 ? "A new per 4 MMAs" : dist == 2 ? "A new per MMA   " : "A +1 row per 4  ", (double)h[0] / n_iss, (double)h[1] / n_iss);
+        }
+  return 0;
+}

@@ -56,12 +56,12 @@ __global__ void __launch_bounds__(128) k_probe(const __grid_constant__ CUtensorM
     mbar_init(smem_u32(mma_bar), 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(smem_u32(slot), 32);
+  if (warp == 0) tmem_alloc(smem_u32(slot), 128);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *slot;
-  const int N = mode == 0 ? 16 : 32;
+  const int N = mode == 0 ? 16 : (mode == 2 ? 96 : 32);
   if (threadIdx.x == 0) {
     const uint32_t small_bytes = mode == 0 ? 16 * 128 : 4 * 128 * 128;
     mbar_expect_tx(smem_u32(bar), R * 128 + small_bytes);
@@ -80,6 +80,14 @@ __global__ void __launch_bounds__(128) k_probe(const __grid_constant__ CUtensorM
         uint64_t ad = make_desc(a_addr, 16, 1024);
         if (use_bo) ad |= static_cast<uint64_t>((a_addr >> 7) & 7) << 49;
         const uint64_t bd = make_desc(smem_u32(small) + k * 32, 16, 1024);
+        tc_mma_tf32(tmem, ad, bd, idesc, k > 0);
+      }
+    } else if (mode == 2) {
+      // aliasing: M blocks = A shifted by pitch_rows rows each (LBO = pitch_rows*128), N blocks = B shifted by 1 row each (LBO = 128)
+      const uint32_t idesc = make_idesc(128, 96, 1, 1);
+      for (int k = 0; k < 8; ++k) {
+        const uint64_t ad = make_desc(smem_u32(small) + (shift + 8 * k) * 128, pitch_rows * 128, 512, kLayoutSw128Base32);
+        const uint64_t bd = make_desc(smem_u32(big) + (8 * k) * 128, 128, 512, kLayoutSw128Base32);
         tc_mma_tf32(tmem, ad, bd, idesc, k > 0);
       }
     } else {
@@ -105,7 +113,7 @@ __global__ void __launch_bounds__(128) k_probe(const __grid_constant__ CUtensorM
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 32); }
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 128); }
 }
 
 int main() {
@@ -115,7 +123,7 @@ int main() {
   for (int i = 0; i < 4 * 128 * 32; ++i) smallMN[i] = static_cast<float>((i * 13 + (i >> 5) * 3) % 11) - 5.f;
   float *dBig, *dK, *dMN, *dOut;
   cudaMalloc(&dBig, big.size() * 4); cudaMalloc(&dK, smallK.size() * 4); cudaMalloc(&dMN, smallMN.size() * 4);
-  cudaMalloc(&dOut, 128 * 32 * 4);
+  cudaMalloc(&dOut, 128 * 96 * 4);
   cudaMemcpy(dBig, big.data(), big.size() * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(dK, smallK.data(), smallK.size() * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(dMN, smallMN.data(), smallMN.size() * 4, cudaMemcpyHostToDevice);
@@ -148,6 +156,33 @@ int main() {
             if (err > maxerr) maxerr = err;
           }
         printf("mode %s base_offset_mode %d shift %3d : max abs err %g %s\n", mode == 0 ? "K-major " : "MN-major", bo, shift, maxerr,
+               maxerr < 1e-3 ? "OK" : "MISMATCH");
+      }
+    }
+  }
+  {
+    CUtensorMap tmBig = map2d(dBig, R, 256, true);
+    CUtensorMap tmSmall = map2d(dMN, 4 * 128, 128, true);
+    const int pitches[] = {10, 13, 66, 130};
+    for (int pitch : pitches) {
+      for (int shift : {0, 3}) {
+        cudaMemset(dOut, 0, 128 * 96 * 4);
+        k_probe<<<1, 128, smem>>>(tmBig, tmSmall, 2, shift, 0, pitch, dOut);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("alias pitch %d: CUDA error %s\n", pitch, cudaGetErrorString(e)); return 1; }
+        std::vector<float> out(128 * 96);
+        cudaMemcpy(out.data(), dOut, out.size() * 4, cudaMemcpyDeviceToHost);
+        double maxerr = 0;
+        // A rows: smallMN viewed as 512 consecutive rows of 32 (TMA loaded 4 boxes of 128 rows back to back)
+        for (int m = 0; m < 128; ++m)
+          for (int n = 0; n < 96; ++n) {
+            double ref = 0;
+            for (int k = 0; k < 64; ++k)
+              ref += (double)smallMN[(shift + k + (m / 32) * pitch) * 32 + (m % 32)] * big[(k + n / 32) * 32 + (n % 32)];
+            const double err = fabs(ref - out[m * 96 + n]);
+            if (err > maxerr) maxerr = err;
+          }
+        printf("alias MN-major: M blocks shifted by %3d rows, N blocks by 1 row, start shift %d : max abs err %g %s\n", pitch, shift, maxerr,
                maxerr < 1e-3 ? "OK" : "MISMATCH");
       }
     }
