@@ -55,7 +55,9 @@ class _FusedForward(torch.autograd.Function):
             raise L.MfviError("MeanFieldVI: backward in eval mode is not supported by the fused engine")
         d = dout.to(torch.float32).contiguous()
         S, Cn, H, W = d.shape
-        L.call("mfvi_nchw_to_nhwc", d.data_ptr(), eng.dout.data_ptr(), S, Cn, H, W)
+        dn = torch.empty(S, H, W, Cn, dtype=torch.float32, device=d.device)
+        L.call("mfvi_nchw_to_nhwc", d.data_ptr(), dn.data_ptr(), S, Cn, H, W)
+        eng.dout.copy_(dn)                      # dout keeps a 4-float channel pitch
         owner._attach_grads()
         Pp, Q = eng.lay.P_pad, eng.lay.Q
         bn_before = eng.grad[2 * Pp:2 * Pp + 2 * Q].clone()

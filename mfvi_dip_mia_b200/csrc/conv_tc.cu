@@ -384,27 +384,33 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUt
   }
 }
 
-// dbias[s][co] += sum over pixels of dy[s][.][.][co]   (one warp-row per pixel slice; HBM-bound column sum)
+// dbias[s][co] += sum over pixels of dy[s][.][.][co]   (HBM-bound column sum; V = 4 when C % 4 == 0, else scalar)
+template <int V>
 __global__ void __launch_bounds__(256)
 k_bias_grad(MfviView dy, int H, int W, int C, float* __restrict__ dbias, long long sstride) {
   extern __shared__ float sm_part[];                 // [C]
   const int s = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += blockDim.x) sm_part[c] = 0.f;
   __syncthreads();
-  const int G = C / 4;                               // float4 groups per pixel (C % 4 == 0)
+  const int G = C / V;                               // channel groups per pixel
   const int PPB = blockDim.x / G > 0 ? blockDim.x / G : 1;
   const int g = threadIdx.x % G, slot = threadIdx.x / G;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float acc[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) acc[j] = 0.f;
   if (slot < PPB) {
     const int npix = H * W;
     for (int px = blockIdx.x * PPB + slot; px < npix; px += gridDim.x * PPB) {
-      const float4 v = *reinterpret_cast<const float4*>(dy.ptr + view_off(dy, s, px / W, px % W) + 4 * g);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      const float* src = dy.ptr + view_off(dy, s, px / W, px % W) + V * g;
+      if (V == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(src);
+        acc[0] += v.x; acc[1 % V] += v.y; acc[2 % V] += v.z; acc[3 % V] += v.w;
+      } else {
+        acc[0] += src[0];
+      }
     }
-    atomicAdd(&sm_part[4 * g + 0], acc.x);
-    atomicAdd(&sm_part[4 * g + 1], acc.y);
-    atomicAdd(&sm_part[4 * g + 2], acc.z);
-    atomicAdd(&sm_part[4 * g + 3], acc.w);
+#pragma unroll
+    for (int j = 0; j < V; ++j) atomicAdd(&sm_part[V * g + j], acc[j]);
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(dbias + static_cast<size_t>(s) * sstride + c, sm_part[c]);
@@ -597,9 +603,16 @@ int mfvi_conv2d_dgrad_tc(const MfviConvDesc* d, MfviView dy, const float* w, lon
 // dbias[s][co] += sum over pixels of dy (requires Cout % 4 == 0 and 16-byte aligned rows: the same conditions as the TMA paths)
 int mfvi_conv2d_bias_grad_tc(const MfviConvDesc* d, MfviView dy, float* dbias, long long w_sstride, mfvi_stream_t st) {
   using namespace mfvi::tc;
-  int blocks = std::max(1, std::min(kNumSMs * 2, (d->Hout * d->Wout * (d->Cout / 4) + 255) / 256));
+  const bool vec = d->Cout % 4 == 0 && (reinterpret_cast<uintptr_t>(dy.ptr) % 16 == 0) && dy.sstride % 4 == 0 && dy.hstride % 4 == 0 &&
+                   dy.wstride % 4 == 0;
+  const int groups = vec ? d->Cout / 4 : d->Cout;
+  if (groups > 256) return -1;
+  int blocks = std::max(1, std::min(kNumSMs * 2, (d->Hout * d->Wout * groups + 255) / 256));
   dim3 g2(blocks, d->S);
-  k_bias_grad<<<g2, 256, d->Cout * sizeof(float), as_stream(st)>>>(dy, d->Hout, d->Wout, d->Cout, dbias, w_sstride);
+  if (vec)
+    k_bias_grad<4><<<g2, 256, d->Cout * sizeof(float), as_stream(st)>>>(dy, d->Hout, d->Wout, d->Cout, dbias, w_sstride);
+  else
+    k_bias_grad<1><<<g2, 256, d->Cout * sizeof(float), as_stream(st)>>>(dy, d->Hout, d->Wout, d->Cout, dbias, w_sstride);
   return check_launch("conv2d_bias_grad_tc");
 }
 

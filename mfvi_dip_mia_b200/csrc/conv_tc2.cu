@@ -338,7 +338,8 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int rup(int a, int b) { return cdiv(a, b) * b; }
 
 static bool view_ok(const MfviView& v, int C) {
-  return (reinterpret_cast<uintptr_t>(v.ptr) % 16 == 0) && (C % 4 == 0) && (v.wstride % 4 == 0) && (v.hstride % 4 == 0) &&
+  // TMA needs a 16-byte aligned base and 16-byte multiples for every stride; the channel count itself is free
+  return (reinterpret_cast<uintptr_t>(v.ptr) % 16 == 0) && C >= 1 && (v.wstride % 4 == 0) && (v.hstride % 4 == 0) &&
          (v.sstride % 4 == 0) && v.wstride >= C && v.hstride >= v.wstride;
 }
 
@@ -413,6 +414,7 @@ static Plan make_plan(int S, int Mh, int Mw, int KH, int KW, int n_chunks, const
         const int slots = kNumSMs * cpsm;
         const int waves = cdiv(tiles, slots);
         const double t_load = (static_cast<double>(pl.box_rows) * kw_total * 4 + static_cast<double>(taps) * BN * kw_total * 4) / 40.0 * cpsm;
+        // (a tcgen05.mma costs ~100 issue cycles whatever its N, but charging that here picks worse tiles in practice: measured)
         const double t_mma = static_cast<double>(pl.n_mt) * taps * (kw_total / 8) * std::max(BN / 2, 16) * cpsm;
         const double t_epi = static_cast<double>(pl.n_mt) * (BN / 16) * 120.0;
         const double t_tile = std::max(t_load, std::max(t_mma, t_epi)) + 500.0;

@@ -180,7 +180,8 @@ static int env_int(const char* name, int dflt) {
 }
 
 static bool view_ok(const MfviView& v, int C) {
-  return (reinterpret_cast<uintptr_t>(v.ptr) % 16 == 0) && (C % 4 == 0) && (v.wstride % 4 == 0) && (v.hstride % 4 == 0) &&
+  // TMA needs a 16-byte aligned base and 16-byte multiples for every stride; the channel count itself is free
+  return (reinterpret_cast<uintptr_t>(v.ptr) % 16 == 0) && C >= 1 && (v.wstride % 4 == 0) && (v.hstride % 4 == 0) &&
          (v.sstride % 4 == 0) && v.wstride >= C && v.hstride >= v.wstride;
 }
 

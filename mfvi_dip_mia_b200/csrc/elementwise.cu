@@ -98,32 +98,125 @@ __device__ __forceinline__ void cta_reduce_2(double (&a)[V], double (&b)[V], int
 }
 
 // ---------------------------------------------------------------------------------------------
+// Common iteration scheme of the kernels below.  grid = (chunks, S).  A CTA owns a CONTIGUOUS range of the pixel space
+// [p0, p1); thread (slot, group) owns channel quad `group` and walks pixels p0+slot, p0+slot+PPB, ... keeping (h, w)
+// incrementally (no division in the loop).  The BatchNorm constants of the thread's channels live in registers, and the
+// per-channel reductions are carried in fp32 for kFlush pixels at a time before they are added to double accumulators.
+constexpr int kFlush = 8;
+
+struct PixIter {
+  int p, npix, h, w, W, step, dh, dw;
+  // grid-stride over pixels (all CTAs sweep the image together, which keeps DRAM pages hot); (h, w) advance incrementally
+  __device__ __forceinline__ PixIter(int npix_, int Wd, int PPB, int slot) {
+    npix = npix_;
+    p = blockIdx.x * PPB + slot;
+    W = Wd;
+    step = gridDim.x * PPB;
+    dh = step / Wd;
+    dw = step - dh * Wd;
+    h = p / Wd;
+    w = p - h * Wd;
+  }
+  __device__ __forceinline__ bool valid() const { return p < npix; }
+  __device__ __forceinline__ void next() {
+    p += step;
+    w += dw;
+    h += dh;
+    if (w >= W) {
+      w -= W;
+      ++h;
+    }
+  }
+};
+
+// BatchNorm constants of one sample: computed once per CTA (one thread per channel, double rsqrt) into shared memory,
+// then every thread keeps the V channels it owns in registers.  z = y*sc + sh ; xhat = (y - mean)*invstd
+struct BnTable {
+  float sc[kMaxC], sh[kMaxC], mean[kMaxC], invstd[kMaxC];
+  __device__ __forceinline__ void fill(const double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       int s, int C, double inv_count, int dst0 = 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float m = 0.f, is = 1.f;
+      if (sums != nullptr) bn_mean_invstd(sums + ((size_t)s * C + c) * 2, inv_count, m, is);
+      const float g = gamma != nullptr ? gamma[c] : 1.f;
+      const float b = beta != nullptr ? beta[c] : 0.f;
+      sc[dst0 + c] = g * is;
+      sh[dst0 + c] = b - m * g * is;
+      mean[dst0 + c] = m;
+      invstd[dst0 + c] = is;
+    }
+  }
+};
+
+template <int V>
+struct BnRegs {
+  float sc[V], sh[V], mean[V], invstd[V];
+  __device__ __forceinline__ void load(const BnTable& t, int c0, int C) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const bool ok = c0 + j < C;
+      sc[j] = ok ? t.sc[c0 + j] : 0.f;
+      sh[j] = ok ? t.sh[c0 + j] : 0.f;
+      mean[j] = ok ? t.mean[c0 + j] : 0.f;
+      invstd[j] = ok ? t.invstd[c0 + j] : 1.f;
+    }
+  }
+};
+
+template <int V>
+struct Acc2 {
+  float fa[V], fb[V];
+  double da[V], db[V];
+  int n;
+  __device__ __forceinline__ Acc2() : n(0) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      fa[j] = fb[j] = 0.f;
+      da[j] = db[j] = 0.0;
+    }
+  }
+  __device__ __forceinline__ void flush() {
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      da[j] += (double)fa[j];
+      db[j] += (double)fb[j];
+      fa[j] = fb[j] = 0.f;
+    }
+    n = 0;
+  }
+  __device__ __forceinline__ void tick() {
+    if (++n == kFlush) flush();
+  }
+};
+
 // F1: xp = reflect_pad(act(bn(y)))            grid = (chunks, S)
 template <int V>
 __global__ void __launch_bounds__(kEwThreads)
 k_bn_act_pad_fwd(MfviView y, int H, int W, int C, const double* __restrict__ sums, const float* __restrict__ gamma,
                  const float* __restrict__ beta, int act, int pad, MfviView xp, int G, int PPB) {
-  __shared__ float sm_scale[kMaxC], sm_shift[kMaxC];
+  __shared__ BnTable tab;
   const int s = blockIdx.y;
-  load_bn_tables(sums, gamma, beta, s, C, 1.0 / ((double)H * W), sm_scale, sm_shift, nullptr, nullptr);
+  tab.fill(sums, gamma, beta, s, C, 1.0 / ((double)H * W));
   __syncthreads();
   const int group = threadIdx.x % G, slot = threadIdx.x / G;
   if (slot >= PPB) return;
-  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
-  const int npix = Hp * Wp;
   const int c0 = group * V;
-  for (int p = blockIdx.x * PPB + slot; p < npix; p += gridDim.x * PPB) {
-    const int hp = p / Wp, wp = p % Wp;
-    const int h = reflect_idx(hp - pad, H), w = reflect_idx(wp - pad, W);
+  BnRegs<V> bn;
+  bn.load(tab, c0, C);
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  const float* ybase = y.ptr + (size_t)s * y.sstride + c0;
+  float* xbase = xp.ptr + (size_t)s * xp.sstride + c0;
+  for (PixIter it(Hp * Wp, Wp, PPB, slot); it.valid(); it.next()) {
+    const int h = reflect_idx(it.h - pad, H), w = reflect_idx(it.w - pad, W);
     Vec<V> t;
-    t.load(y.ptr + view_off(y, s, h, w) + c0);
+    t.load(ybase + (size_t)h * y.hstride + (size_t)w * y.wstride);
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      float z = fmaf(t.v[j], sm_scale[c0 + j], sm_shift[c0 + j]);
+      float z = fmaf(t.v[j], bn.sc[j], bn.sh[j]);
       if (act) z = z > 0.f ? z : kLreluSlope * z;
       t.v[j] = z;
     }
-    t.store(xp.ptr + view_off(xp, s, hp, wp) + c0);
+    t.store(xbase + (size_t)it.h * xp.hstride + (size_t)it.w * xp.wstride);
   }
 }
 
@@ -149,46 +242,48 @@ k_cat_up_fwd(MfviView ys, int Cs, const double* __restrict__ sums_s, const float
              const float* __restrict__ beta_s, MfviView yd, int Cd, const double* __restrict__ sums_d,
              const float* __restrict__ gamma_d, const float* __restrict__ beta_d, int H, int W, int mode, MfviView A,
              double* __restrict__ sumsA, int G, int PPB) {
-  __shared__ float sm_scale[kMaxC], sm_shift[kMaxC];
   __shared__ double sm_red[2 * kEwThreads * 4];
+  __shared__ BnTable tab;
   const int s = blockIdx.y;
   const int C = Cs + Cd;
   const int h2 = H / 2, w2 = W / 2;
-  if (Cs > 0) load_bn_tables(sums_s, gamma_s, beta_s, s, Cs, 1.0 / ((double)H * W), sm_scale, sm_shift, nullptr, nullptr);
-  load_bn_tables(sums_d, gamma_d, beta_d, s, Cd, 1.0 / ((double)h2 * w2), sm_scale + Cs, sm_shift + Cs, nullptr, nullptr);
+  if (Cs > 0) tab.fill(sums_s, gamma_s, beta_s, s, Cs, 1.0 / ((double)H * W));
+  tab.fill(sums_d, gamma_d, beta_d, s, Cd, 1.0 / ((double)h2 * w2), Cs);
   __syncthreads();
   const int group = threadIdx.x % G, slot = threadIdx.x / G;
   const bool active = slot < PPB;
   const int c0 = group * V;
-  double acc1[V], acc2[V];
-#pragma unroll
-  for (int j = 0; j < V; ++j) acc1[j] = acc2[j] = 0.0;
+  const bool skip = c0 < Cs;          // Cs % V == 0 is guaranteed by the host (V falls back to 1 otherwise)
+  Acc2<V> acc;
   if (active) {
-    const int npix = H * W;
-    for (int p = blockIdx.x * PPB + slot; p < npix; p += gridDim.x * PPB) {
-      const int h = p / W, w = p % W;
+    BnRegs<V> bn;
+    bn.load(tab, c0, C);
+    const float* sbase = skip ? ys.ptr + (size_t)s * ys.sstride + c0 : nullptr;
+    const float* dbase = yd.ptr + (size_t)s * yd.sstride + (c0 - Cs);
+    float* abase = A.ptr + (size_t)s * A.sstride + c0;
+    for (PixIter it(H * W, W, PPB, slot); it.valid(); it.next()) {
+      const int h = it.h, w = it.w;
       Vec<V> o;
-      if (c0 < Cs) {  // Cs % V == 0 is guaranteed by the host (V falls back to 1 otherwise)
-        o.load(ys.ptr + view_off(ys, s, h, w) + c0);
+      if (skip) {
+        o.load(sbase + (size_t)h * ys.hstride + (size_t)w * ys.wstride);
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-          const float z = fmaf(o.v[j], sm_scale[c0 + j], sm_shift[c0 + j]);
+          const float z = fmaf(o.v[j], bn.sc[j], bn.sh[j]);
           o.v[j] = z > 0.f ? z : kLreluSlope * z;
         }
       } else {
-        const int cd = c0 - Cs;
         int ha, hb, wa, wb;
         float wha, whb, wwa, wwb;
         up_taps(h, h2, mode, ha, hb, wha, whb);
         up_taps(w, w2, mode, wa, wb, wwa, wwb);
         Vec<V> t00, t01, t10, t11;
-        t00.load(yd.ptr + view_off(yd, s, ha, wa) + cd);
-        t01.load(yd.ptr + view_off(yd, s, ha, wb) + cd);
-        t10.load(yd.ptr + view_off(yd, s, hb, wa) + cd);
-        t11.load(yd.ptr + view_off(yd, s, hb, wb) + cd);
+        t00.load(dbase + (size_t)ha * yd.hstride + (size_t)wa * yd.wstride);
+        t01.load(dbase + (size_t)ha * yd.hstride + (size_t)wb * yd.wstride);
+        t10.load(dbase + (size_t)hb * yd.hstride + (size_t)wa * yd.wstride);
+        t11.load(dbase + (size_t)hb * yd.hstride + (size_t)wb * yd.wstride);
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-          const float sc = sm_scale[c0 + j], sh = sm_shift[c0 + j];
+          const float sc = bn.sc[j], sh = bn.sh[j];
           float z00 = fmaf(t00.v[j], sc, sh), z01 = fmaf(t01.v[j], sc, sh);
           float z10 = fmaf(t10.v[j], sc, sh), z11 = fmaf(t11.v[j], sc, sh);
           z00 = z00 > 0.f ? z00 : kLreluSlope * z00;
@@ -198,15 +293,17 @@ k_cat_up_fwd(MfviView ys, int Cs, const double* __restrict__ sums_s, const float
           o.v[j] = wha * (wwa * z00 + wwb * z01) + whb * (wwa * z10 + wwb * z11);
         }
       }
-      o.store(A.ptr + view_off(A, s, h, w) + c0);
+      o.store(abase + (size_t)h * A.hstride + (size_t)w * A.wstride);
 #pragma unroll
       for (int j = 0; j < V; ++j) {
-        acc1[j] += (double)o.v[j];
-        acc2[j] += (double)o.v[j] * (double)o.v[j];
+        acc.fa[j] += o.v[j];
+        acc.fb[j] = fmaf(o.v[j], o.v[j], acc.fb[j]);
       }
+      acc.tick();
     }
+    acc.flush();
   }
-  cta_reduce_2<V>(acc1, acc2, group, slot, G, PPB, C, sm_red, sumsA + (size_t)s * C * 2, active);
+  cta_reduce_2<V>(acc.da, acc.db, group, slot, G, PPB, C, sm_red, sumsA + (size_t)s * C * 2, active);
 }
 
 // number of padded positions (per dimension) that reflect onto source index h: fills q[0..n)
@@ -224,50 +321,56 @@ __global__ void __launch_bounds__(kEwThreads)
 k_pad_act_bwd(MfviView dxp, int H, int W, int C, int pad, MfviView y, const double* __restrict__ sums,
               const float* __restrict__ gamma, const float* __restrict__ beta, int act, MfviView g,
               double* __restrict__ red, int G, int PPB) {
-  __shared__ float sm_scale[kMaxC], sm_shift[kMaxC], sm_mean[kMaxC], sm_invstd[kMaxC];
   __shared__ double sm_red[2 * kEwThreads * 4];
   const int s = blockIdx.y;
-  load_bn_tables(sums, gamma, beta, s, C, 1.0 / ((double)H * W), sm_scale, sm_shift, sm_mean, sm_invstd);
-  __syncthreads();
   const int group = threadIdx.x % G, slot = threadIdx.x / G;
   const bool active = slot < PPB;
   const int c0 = group * V;
-  double acc1[V], acc2[V];
-#pragma unroll
-  for (int j = 0; j < V; ++j) acc1[j] = acc2[j] = 0.0;
+  Acc2<V> acc;
+  __shared__ BnTable tab;
+  tab.fill(sums, gamma, beta, s, C, 1.0 / ((double)H * W));
+  __syncthreads();
   if (active) {
-    const int npix = H * W;
-    for (int p = blockIdx.x * PPB + slot; p < npix; p += gridDim.x * PPB) {
-      const int h = p / W, w = p % W;
-      int qh[3], qw[3];
-      const int nh = pad > 0 ? fold_sources(h, H, pad, qh) : (qh[0] = h, 1);
-      const int nw = pad > 0 ? fold_sources(w, W, pad, qw) : (qw[0] = w, 1);
+    BnRegs<V> bn;
+    bn.load(tab, c0, C);
+    const float* dbase = dxp.ptr + (size_t)s * dxp.sstride + c0;
+    const float* ybase = y.ptr + (size_t)s * y.sstride + c0;
+    float* gbase = g.ptr + (size_t)s * g.sstride + c0;
+    for (PixIter it(H * W, W, PPB, slot); it.valid(); it.next()) {
+      const int h = it.h, w = it.w;
       Vec<V> a;
+      a.load(dbase + (size_t)(h + pad) * dxp.hstride + (size_t)(w + pad) * dxp.wstride);
+      const bool edge = pad > 0 && (h <= pad || w <= pad || h >= H - 1 - pad || w >= W - 1 - pad);
+      if (edge) {          // reflected border positions fold back onto this pixel
+        int qh[3], qw[3];
+        const int nh = fold_sources(h, H, pad, qh), nw = fold_sources(w, W, pad, qw);
+        for (int ih = 0; ih < nh; ++ih)
+          for (int iw = 0; iw < nw; ++iw) {
+            if (ih == 0 && iw == 0) continue;
+            Vec<V> t;
+            t.load(dbase + (size_t)qh[ih] * dxp.hstride + (size_t)qw[iw] * dxp.wstride);
 #pragma unroll
-      for (int j = 0; j < V; ++j) a.v[j] = 0.f;
-      for (int ih = 0; ih < nh; ++ih)
-        for (int iw = 0; iw < nw; ++iw) {
-          Vec<V> t;
-          t.load(dxp.ptr + view_off(dxp, s, qh[ih], qw[iw]) + c0);
-#pragma unroll
-          for (int j = 0; j < V; ++j) a.v[j] += t.v[j];
-        }
+            for (int j = 0; j < V; ++j) a.v[j] += t.v[j];
+          }
+      }
       Vec<V> yy;
-      yy.load(y.ptr + view_off(y, s, h, w) + c0);
+      yy.load(ybase + (size_t)h * y.hstride + (size_t)w * y.wstride);
 #pragma unroll
       for (int j = 0; j < V; ++j) {
-        const float z = fmaf(yy.v[j], sm_scale[c0 + j], sm_shift[c0 + j]);
+        const float z = fmaf(yy.v[j], bn.sc[j], bn.sh[j]);
         float gg = a.v[j];
         if (act && z <= 0.f) gg *= kLreluSlope;
-        const float xhat = (yy.v[j] - sm_mean[c0 + j]) * sm_invstd[c0 + j];
+        const float xhat = (yy.v[j] - bn.mean[j]) * bn.invstd[j];
         a.v[j] = gg;
-        acc1[j] += (double)gg;
-        acc2[j] += (double)gg * (double)xhat;
+        acc.fa[j] += gg;
+        acc.fb[j] = fmaf(gg, xhat, acc.fb[j]);
       }
-      a.store(g.ptr + view_off(g, s, h, w) + c0);
+      a.store(gbase + (size_t)h * g.hstride + (size_t)w * g.wstride);
+      acc.tick();
     }
+    acc.flush();
   }
-  cta_reduce_2<V>(acc1, acc2, group, slot, G, PPB, C, sm_red, red + (size_t)s * C * 2, active);
+  cta_reduce_2<V>(acc.da, acc.db, group, slot, G, PPB, C, sm_red, red + (size_t)s * C * 2, active);
 }
 
 // B2: dy = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)); block (0,0) also writes dgamma/dbeta.
@@ -276,18 +379,10 @@ __global__ void __launch_bounds__(kEwThreads)
 k_bn_bwd_apply(MfviView g, MfviView y, int S, int H, int W, int C, const double* __restrict__ sums,
                const double* __restrict__ red, const float* __restrict__ gamma, MfviView dy,
                float* __restrict__ dgamma, float* __restrict__ dbeta, int G, int PPB) {
-  __shared__ float sm_k[kMaxC], sm_mean[kMaxC], sm_invstd[kMaxC], sm_m1[kMaxC], sm_m2[kMaxC];
   const int s = blockIdx.y;
   const double inv_count = 1.0 / ((double)H * W);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float mean, invstd;
-    bn_mean_invstd(sums + ((size_t)s * C + c) * 2, inv_count, mean, invstd);
-    sm_mean[c] = mean;
-    sm_invstd[c] = invstd;
-    sm_k[c] = (gamma != nullptr ? gamma[c] : 1.f) * invstd;
-    sm_m1[c] = (float)(red[((size_t)s * C + c) * 2 + 0] * inv_count);
-    sm_m2[c] = (float)(red[((size_t)s * C + c) * 2 + 1] * inv_count);
-    if (blockIdx.x == 0 && blockIdx.y == 0 && dgamma != nullptr) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && dgamma != nullptr) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
       double dg = 0.0, db = 0.0;
       for (int ss = 0; ss < S; ++ss) {
         db += red[((size_t)ss * C + c) * 2 + 0];
@@ -297,22 +392,44 @@ k_bn_bwd_apply(MfviView g, MfviView y, int S, int H, int W, int C, const double*
       dbeta[c] = (float)db;
     }
   }
+  __shared__ float sm_k[kMaxC], sm_mean[kMaxC], sm_invstd[kMaxC], sm_m1[kMaxC], sm_m2[kMaxC];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean_c, invstd_c;
+    bn_mean_invstd(sums + ((size_t)s * C + c) * 2, inv_count, mean_c, invstd_c);
+    sm_mean[c] = mean_c;
+    sm_invstd[c] = invstd_c;
+    sm_k[c] = (gamma != nullptr ? gamma[c] : 1.f) * invstd_c;
+    sm_m1[c] = (float)(red[((size_t)s * C + c) * 2 + 0] * inv_count);
+    sm_m2[c] = (float)(red[((size_t)s * C + c) * 2 + 1] * inv_count);
+  }
   __syncthreads();
   const int group = threadIdx.x % G, slot = threadIdx.x / G;
   if (slot >= PPB) return;
   const int c0 = group * V;
-  const int npix = H * W;
-  for (int p = blockIdx.x * PPB + slot; p < npix; p += gridDim.x * PPB) {
-    const int h = p / W, w = p % W;
+  float k[V], mean[V], invstd[V], m1[V], m2[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const bool ok = c0 + j < C;
+    mean[j] = ok ? sm_mean[c0 + j] : 0.f;
+    invstd[j] = ok ? sm_invstd[c0 + j] : 1.f;
+    k[j] = ok ? sm_k[c0 + j] : 0.f;
+    m1[j] = ok ? sm_m1[c0 + j] : 0.f;
+    m2[j] = ok ? sm_m2[c0 + j] : 0.f;
+  }
+  const float* gbase = g.ptr + (size_t)s * g.sstride + c0;
+  const float* ybase = y.ptr + (size_t)s * y.sstride + c0;
+  float* obase = dy.ptr + (size_t)s * dy.sstride + c0;
+  for (PixIter it(H * W, W, PPB, slot); it.valid(); it.next()) {
+    const int h = it.h, w = it.w;
     Vec<V> gg, yy;
-    gg.load(g.ptr + view_off(g, s, h, w) + c0);
-    yy.load(y.ptr + view_off(y, s, h, w) + c0);
+    gg.load(gbase + (size_t)h * g.hstride + (size_t)w * g.wstride);
+    yy.load(ybase + (size_t)h * y.hstride + (size_t)w * y.wstride);
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      const float xhat = (yy.v[j] - sm_mean[c0 + j]) * sm_invstd[c0 + j];
-      gg.v[j] = sm_k[c0 + j] * (gg.v[j] - sm_m1[c0 + j] - xhat * sm_m2[c0 + j]);
+      const float xhat = (yy.v[j] - mean[j]) * invstd[j];
+      gg.v[j] = k[j] * (gg.v[j] - m1[j] - xhat * m2[j]);
     }
-    gg.store(dy.ptr + view_off(dy, s, h, w) + c0);
+    gg.store(obase + (size_t)h * dy.hstride + (size_t)w * dy.wstride);
   }
 }
 
@@ -322,37 +439,41 @@ __global__ void __launch_bounds__(kEwThreads)
 k_cat_bwd_skip(MfviView dA, int H, int W, MfviView ys, int Cs, const double* __restrict__ sums_s,
                const float* __restrict__ gamma_s, const float* __restrict__ beta_s, MfviView gs,
                double* __restrict__ red_s, int G, int PPB) {
-  __shared__ float sm_scale[kMaxC], sm_shift[kMaxC], sm_mean[kMaxC], sm_invstd[kMaxC];
   __shared__ double sm_red[2 * kEwThreads * 4];
   const int s = blockIdx.y;
-  load_bn_tables(sums_s, gamma_s, beta_s, s, Cs, 1.0 / ((double)H * W), sm_scale, sm_shift, sm_mean, sm_invstd);
-  __syncthreads();
   const int group = threadIdx.x % G, slot = threadIdx.x / G;
   const bool active = slot < PPB;
   const int c0 = group * V;
-  double acc1[V], acc2[V];
-#pragma unroll
-  for (int j = 0; j < V; ++j) acc1[j] = acc2[j] = 0.0;
+  Acc2<V> acc;
+  __shared__ BnTable tab;
+  tab.fill(sums_s, gamma_s, beta_s, s, Cs, 1.0 / ((double)H * W));
+  __syncthreads();
   if (active) {
-    const int npix = H * W;
-    for (int p = blockIdx.x * PPB + slot; p < npix; p += gridDim.x * PPB) {
-      const int h = p / W, w = p % W;
+    BnRegs<V> bn;
+    bn.load(tab, c0, Cs);
+    const float* dbase = dA.ptr + (size_t)s * dA.sstride + c0;
+    const float* ybase = ys.ptr + (size_t)s * ys.sstride + c0;
+    float* gbase = gs.ptr + (size_t)s * gs.sstride + c0;
+    for (PixIter it(H * W, W, PPB, slot); it.valid(); it.next()) {
+      const int h = it.h, w = it.w;
       Vec<V> d, yy;
-      d.load(dA.ptr + view_off(dA, s, h, w) + c0);
-      yy.load(ys.ptr + view_off(ys, s, h, w) + c0);
+      d.load(dbase + (size_t)h * dA.hstride + (size_t)w * dA.wstride);
+      yy.load(ybase + (size_t)h * ys.hstride + (size_t)w * ys.wstride);
 #pragma unroll
       for (int j = 0; j < V; ++j) {
-        const float z = fmaf(yy.v[j], sm_scale[c0 + j], sm_shift[c0 + j]);
+        const float z = fmaf(yy.v[j], bn.sc[j], bn.sh[j]);
         const float gg = z > 0.f ? d.v[j] : kLreluSlope * d.v[j];
-        const float xhat = (yy.v[j] - sm_mean[c0 + j]) * sm_invstd[c0 + j];
+        const float xhat = (yy.v[j] - bn.mean[j]) * bn.invstd[j];
         d.v[j] = gg;
-        acc1[j] += (double)gg;
-        acc2[j] += (double)gg * (double)xhat;
+        acc.fa[j] += gg;
+        acc.fb[j] = fmaf(gg, xhat, acc.fb[j]);
       }
-      d.store(gs.ptr + view_off(gs, s, h, w) + c0);
+      d.store(gbase + (size_t)h * gs.hstride + (size_t)w * gs.wstride);
+      acc.tick();
     }
+    acc.flush();
   }
-  cta_reduce_2<V>(acc1, acc2, group, slot, G, PPB, Cs, sm_red, red_s + (size_t)s * Cs * 2, active);
+  cta_reduce_2<V>(acc.da, acc.db, group, slot, G, PPB, Cs, sm_red, red_s + (size_t)s * Cs * 2, active);
 }
 
 // weight with which low-res index k enters hi-res index i (0 if not a tap)
@@ -373,54 +494,65 @@ __global__ void __launch_bounds__(kEwThreads)
 k_cat_bwd_up(MfviView dA, int H, int W, int mode, int Cs, MfviView yd, int Cd, const double* __restrict__ sums_d,
              const float* __restrict__ gamma_d, const float* __restrict__ beta_d, MfviView gd,
              double* __restrict__ red_d, int G, int PPB) {
-  __shared__ float sm_scale[kMaxC], sm_shift[kMaxC], sm_mean[kMaxC], sm_invstd[kMaxC];
   __shared__ double sm_red[2 * kEwThreads * 4];
   const int s = blockIdx.y;
   const int h2 = H / 2, w2 = W / 2;
-  load_bn_tables(sums_d, gamma_d, beta_d, s, Cd, 1.0 / ((double)h2 * w2), sm_scale, sm_shift, sm_mean, sm_invstd);
-  __syncthreads();
   const int group = threadIdx.x % G, slot = threadIdx.x / G;
   const bool active = slot < PPB;
   const int c0 = group * V;
-  double acc1[V], acc2[V];
-#pragma unroll
-  for (int j = 0; j < V; ++j) acc1[j] = acc2[j] = 0.0;
+  Acc2<V> acc;
+  __shared__ BnTable tab;
+  tab.fill(sums_d, gamma_d, beta_d, s, Cd, 1.0 / ((double)h2 * w2));
+  __syncthreads();
   if (active) {
-    const int npix = h2 * w2;
-    for (int p = blockIdx.x * PPB + slot; p < npix; p += gridDim.x * PPB) {
-      const int kh = p / w2, kw = p % w2;
+    BnRegs<V> bn;
+    bn.load(tab, c0, Cd);
+    const float* dbase = dA.ptr + (size_t)s * dA.sstride + Cs + c0;
+    const float* ybase = yd.ptr + (size_t)s * yd.sstride + c0;
+    float* gbase = gd.ptr + (size_t)s * gd.sstride + c0;
+    for (PixIter it(h2 * w2, w2, PPB, slot); it.valid(); it.next()) {
+      const int kh = it.h, kw = it.w;
+      // hi-res rows 2kh-1 .. 2kh+2 receive low-res row kh with these weights (0 outside the image / when not a tap)
+      float wh[4], ww[4];
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        wh[d] = up_weight_of(2 * kh + d - 1, kh, h2, mode);
+        ww[d] = up_weight_of(2 * kw + d - 1, kw, w2, mode);
+      }
       Vec<V> a;
 #pragma unroll
       for (int j = 0; j < V; ++j) a.v[j] = 0.f;
-      for (int dh = -1; dh <= 2; ++dh) {
-        const int ih = 2 * kh + dh;
-        const float wh = up_weight_of(ih, kh, h2, mode);
-        if (wh == 0.f) continue;
-        for (int dw = -1; dw <= 2; ++dw) {
-          const int iw = 2 * kw + dw;
-          const float ww = up_weight_of(iw, kw, w2, mode);
-          if (ww == 0.f) continue;
-          Vec<V> t;
-          t.load(dA.ptr + view_off(dA, s, ih, iw) + Cs + c0);
 #pragma unroll
-          for (int j = 0; j < V; ++j) a.v[j] = fmaf(wh * ww, t.v[j], a.v[j]);
+      for (int dh = 0; dh < 4; ++dh) {
+        if (wh[dh] == 0.f) continue;
+        const float* row = dbase + (size_t)(2 * kh + dh - 1) * dA.hstride;
+#pragma unroll
+        for (int dw = 0; dw < 4; ++dw) {
+          if (ww[dw] == 0.f) continue;
+          Vec<V> t;
+          t.load(row + (size_t)(2 * kw + dw - 1) * dA.wstride);
+          const float wgt = wh[dh] * ww[dw];
+#pragma unroll
+          for (int j = 0; j < V; ++j) a.v[j] = fmaf(wgt, t.v[j], a.v[j]);
         }
       }
       Vec<V> yy;
-      yy.load(yd.ptr + view_off(yd, s, kh, kw) + c0);
+      yy.load(ybase + (size_t)kh * yd.hstride + (size_t)kw * yd.wstride);
 #pragma unroll
       for (int j = 0; j < V; ++j) {
-        const float z = fmaf(yy.v[j], sm_scale[c0 + j], sm_shift[c0 + j]);
+        const float z = fmaf(yy.v[j], bn.sc[j], bn.sh[j]);
         const float gg = z > 0.f ? a.v[j] : kLreluSlope * a.v[j];
-        const float xhat = (yy.v[j] - sm_mean[c0 + j]) * sm_invstd[c0 + j];
+        const float xhat = (yy.v[j] - bn.mean[j]) * bn.invstd[j];
         a.v[j] = gg;
-        acc1[j] += (double)gg;
-        acc2[j] += (double)gg * (double)xhat;
+        acc.fa[j] += gg;
+        acc.fb[j] = fmaf(gg, xhat, acc.fb[j]);
       }
-      a.store(gd.ptr + view_off(gd, s, kh, kw) + c0);
+      a.store(gbase + (size_t)kh * gd.hstride + (size_t)kw * gd.wstride);
+      acc.tick();
     }
+    acc.flush();
   }
-  cta_reduce_2<V>(acc1, acc2, group, slot, G, PPB, Cd, sm_red, red_d + (size_t)s * Cd * 2, active);
+  cta_reduce_2<V>(acc.da, acc.db, group, slot, G, PPB, Cd, sm_red, red_d + (size_t)s * Cd * 2, active);
 }
 
 // running stats of all BatchNorms (one thread per channel)

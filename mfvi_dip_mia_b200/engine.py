@@ -269,7 +269,9 @@ class SkipEngine:
     def _conv_fwd(self, c: ConvLayer, x: torch.Tensor, bn: Optional[BnLayer]):
         """x: padded input view (S or 1, Hin, Win, cin) -> raw conv output y (S,Ho,Wo,cout)."""
         d, Ho, Wo = self._desc(c, x.shape[1], x.shape[2])
-        y = self._buf(Ho, Wo, c.cout)
+        # channel pitch rounded up to 4 floats: a 2-channel output keeps 16-byte aligned pixels, so TMA can read its
+        # gradient (dgrad / wgrad of the final conv run on the tensor-core kernels too)
+        y = self._buf(Ho, Wo, (c.cout + 3) // 4 * 4)[..., :c.cout]
         if bn is not None:
             bn.count = Ho * Wo
         self.fwd_ops.append(("mfvi_conv2d_fwd", (
@@ -443,7 +445,8 @@ class SkipEngine:
         z0, z0_bn, bwd0 = run_scale(0, self.x0, self.pad0)
         XF = self._bn_act_pad(z0, z0_bn, *self._bn_args(z0_bn), 1, 0)
         self.out, d_f = self._conv_fwd(lay.final, XF, None)
-        self.dout = torch.zeros_like(self.out)
+        self.dout = torch.zeros(self.out.shape[:3] + ((lay.final.cout + 3) // 4 * 4,), dtype=torch.float32,
+                                device=self.device)[..., :lay.final.cout]
         ops = self.bwd_ops
         dXF = self._conv_bwd(ops, lay.final, d_f, XF, self.dout, bn_follows=False)
         dz0 = self._bn_act_pad_bwd(ops, dXF, z0, z0_bn, 1, 0)
@@ -557,5 +560,5 @@ class SkipEngine:
     def out_nchw(self) -> torch.Tensor:
         S, H, W, Cn = self.out.shape
         o = torch.empty(S, Cn, H, W, dtype=torch.float32, device=self.device)
-        L.call("mfvi_nhwc_to_nchw", self.out.data_ptr(), o.data_ptr(), S, Cn, H, W)
+        L.call("mfvi_nhwc_to_nchw", self.out.contiguous().data_ptr(), o.data_ptr(), S, Cn, H, W)
         return o
