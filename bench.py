@@ -209,21 +209,31 @@ def run_ours(args):
     e2e = {"value": args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": io[0], "d2h_bytes_per_step": io[1]}
     nll, kl, loss = tr.loss_terms()
 
-    # ---- roofline of the dominant kernel (eager pass with events around every launch)
+    # ---- roofline of the dominant kernel family (eager pass with CUDA events around every C-ABI launch)
     pk = peaks()
     agg = kernel_breakdown(tr)
     step_ms_eager = sum(a["ms"] for a in agg.values())
     dom = max(agg, key=lambda k: agg[k]["ms"])
     a = agg[dom]
+    # measured DRAM bytes per step of every family (ncu dram__bytes_read+write, profiles/r01_dram_traffic.json)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
+    if os.path.exists(tp) and args.size == 256 and args.mc == 8 and world == 1:
+        with open(tp) as f:
+            traffic = json.load(f).get("bytes_per_step", {}).get(dom)
     if a["flops"] > 0:
+        # the convolutions run tcgen05 kind::tf32: half the dense bf16 rate MEASURED_PEAKS.json reports
+        peak = pk["tensor"] / 2.0 if args.math == "tf32" else 75.0
         ach = a["flops"] / (a["ms"] * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s",
-                "frac": ach / pk["tensor"], "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+        roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach / peak, "traffic": traffic,
+                "peak_source": pk["src"] + " bf16 sustained / 2 (kind::tf32)" if args.math == "tf32" else "fp32 CUDA-core nominal",
+                "algorithmic_gbs": a["bytes"] / (a["ms"] * 1e-3) / 1e9, "hbm_peak_gbs": pk["hbm"],
                 "launches_per_step": a["n"], "ms_per_step": a["ms"], "share_of_step": a["ms"] / step_ms_eager}
     else:
         ach = a["bytes"] / (a["ms"] * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
-                "traffic": None, "peak_source": pk["src"], "launches_per_step": a["n"], "ms_per_step": a["ms"],
+                "traffic": traffic, "peak_source": pk["src"], "launches_per_step": a["n"], "ms_per_step": a["ms"],
                 "share_of_step": a["ms"] / step_ms_eager}
     kernels = {}
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
