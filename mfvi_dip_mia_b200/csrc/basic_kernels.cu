@@ -2,6 +2,7 @@
 // losses, AdamW, input jitter.  All HBM-bound: vectorised (float4) coalesced access, grid sized in multiples
 // of the SM count, warp-shuffle reductions, one double atomic per CTA.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -14,6 +15,11 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("MFVI_PDL"); return e == nullptr || e[0] != '0'; }();
+  return on;
 }
 
 int check_launch(const char* what) {
@@ -65,6 +71,8 @@ __global__ void k_philox_normal(float* __restrict__ out, size_t n, MfviPhiloxKey
 __global__ void k_sample_weights(const float* __restrict__ mu, const float* __restrict__ rho, size_t n, int S,
                                  const float* __restrict__ eps, long long eps_sstride, MfviPhiloxKey key,
                                  float* __restrict__ w_out, long long w_sstride) {
+  pdl_trigger();
+  pdl_wait();
   const size_t nb = (n + 3) / 4;
   const uint32_t step = eff_step(key);
   const bool vec = (n % 4 == 0) && (w_sstride % 4 == 0) && (eps == nullptr || eps_sstride % 4 == 0);
@@ -117,6 +125,8 @@ k_kl_reparam(const float* __restrict__ mu, const float* __restrict__ rho, size_t
              float kscale, const float* __restrict__ kscale_dev, const float* __restrict__ dw, long long dw_sstride, int S, const float* __restrict__ eps,
              long long eps_sstride, MfviPhiloxKey key, float gscale, double* __restrict__ kl_out,
              float* __restrict__ grad_mu, float* __restrict__ grad_rho, int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   const size_t nb = (n + 3) / 4;
   const uint32_t step = eff_step(key);
   if (kscale_dev != nullptr) kscale *= *kscale_dev;
@@ -202,6 +212,8 @@ k_kl_reparam(const float* __restrict__ mu, const float* __restrict__ rho, size_t
 __global__ void __launch_bounds__(256)
 k_nll(int mode, MfviView out, int S, int H, int W, int C, int sub, const float* __restrict__ target,
       const float* __restrict__ mask, double* __restrict__ loss_out, MfviView dout, float inv_count) {
+  pdl_trigger();
+  pdl_wait();
   const int Hs = H / sub, Ws = W / sub;
   const size_t per_s = (size_t)H * W;
   const size_t total = per_s * S;
@@ -261,6 +273,8 @@ k_nll(int mode, MfviView out, int S, int H, int W, int C, int sub, const float* 
 __global__ void __launch_bounds__(256)
 k_mse(const float* __restrict__ a, long long a_sstride, const float* __restrict__ b, size_t n, int S,
       double* __restrict__ loss_out, float* __restrict__ da, float inv_count) {
+  pdl_trigger();
+  pdl_wait();
   double acc = 0.0;
   const size_t total = n * S;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -286,6 +300,8 @@ __global__ void __launch_bounds__(256)
 k_adamw(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n,
         float lr, float b1, float b2, float eps, float wd, int step, const uint32_t* __restrict__ step_dev,
         const double* __restrict__ skip_if_nonfinite) {
+  pdl_trigger();
+  pdl_wait();
   if (skip_if_nonfinite != nullptr) {
     const double l = *skip_if_nonfinite;
     if (!(l == l) || l > 1.7e308 || l < -1.7e308) return;
@@ -331,6 +347,8 @@ k_adamw(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ 
 __global__ void __launch_bounds__(256)
 k_input_jitter_pad(const float* __restrict__ saved, const float* __restrict__ noise, int H, int W, int C, float stdv,
                    int pad, MfviPhiloxKey key, MfviView xp) {
+  pdl_trigger();
+  pdl_wait();
   const int Hp = H + 2 * pad, Wp = W + 2 * pad;
   const size_t total = (size_t)Hp * Wp * C;
   const uint32_t step = eff_step(key);
@@ -353,9 +371,15 @@ k_input_jitter_pad(const float* __restrict__ saved, const float* __restrict__ no
   }
 }
 
-__global__ void k_counter_add(uint32_t* ctr, uint32_t inc) { *ctr += inc; }
+__global__ void k_counter_add(uint32_t* ctr, uint32_t inc) {
+  pdl_trigger();
+  pdl_wait();
+  *ctr += inc;
+}
 
 __global__ void k_fill(float* __restrict__ p, size_t n, float v) {
+  pdl_trigger();
+  pdl_wait();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
@@ -411,7 +435,7 @@ int mfvi_sample_weights(const float* mu, const float* rho, size_t n, int S, cons
   MFVI_REQUIRE(mu && rho && w_out, "sample_weights: null pointer");
   MFVI_REQUIRE(S >= 1, "sample_weights: S must be >= 1");
   if (n == 0) return 0;
-  k_sample_weights<<<grid_for((n + 3) / 4, 256), 256, 0, as_stream(st)>>>(mu, rho, n, S, eps, eps_sstride, key, w_out,
+  launch_k(k_sample_weights, grid_for((n + 3) / 4, 256), 256, 0, as_stream(st), mu, rho, n, S, eps, eps_sstride, key, w_out,
                                                                           w_sstride);
   return check_launch("sample_weights");
 }
@@ -427,7 +451,7 @@ int mfvi_kl_reparam_fwd_bwd(const float* mu, const float* rho, size_t n, float p
   MFVI_REQUIRE(direction == 0 || direction == 1, "kl_reparam: direction must be 0 (reverse) or 1 (forward)");
   if (n == 0) return 0;
   if (S <= 0) dw = nullptr;
-  k_kl_reparam<<<grid_for((n + 3) / 4, 256, 4), 256, 0, as_stream(st)>>>(
+  launch_k(k_kl_reparam, grid_for((n + 3) / 4, 256, 4), 256, 0, as_stream(st), 
       mu, rho, n, prior_mu, (float)prior_sigma_plus_eps, direction, kscale, kscale_dev, dw, dw_sstride, S, eps, eps_sstride, key,
       gscale, kl_out, grad_mu, grad_rho, accumulate);
   return check_launch("kl_reparam");
@@ -440,7 +464,7 @@ int mfvi_gauss_nll_fwd_bwd(int mode, MfviView out, int S, int H, int W, int C, i
   MFVI_REQUIRE(sub >= 1 && H % sub == 0 && W % sub == 0, "gauss_nll: H,W must be multiples of sub");
   MFVI_REQUIRE(mode == 0 ? C >= 2 : (C == 4 && mask != nullptr && sub == 1), "gauss_nll: bad channel count / mask");
   const double count = mode == 0 ? (double)(H / sub) * (W / sub) * S : (double)H * W * 3 * S;
-  k_nll<<<grid_for((size_t)H * W * S, 256), 256, 0, as_stream(st)>>>(mode, out, S, H, W, C, sub, target, mask, loss_out,
+  launch_k(k_nll, grid_for((size_t)H * W * S, 256), 256, 0, as_stream(st), mode, out, S, H, W, C, sub, target, mask, loss_out,
                                                                     dout, (float)(1.0 / count));
   return check_launch("gauss_nll");
 }
@@ -448,7 +472,7 @@ int mfvi_gauss_nll_fwd_bwd(int mode, MfviView out, int S, int H, int W, int C, i
 int mfvi_mse_fwd_bwd(const float* a, long long a_sstride, const float* b, size_t n, int S, double* loss_out, float* da,
                      mfvi_stream_t st) {
   MFVI_REQUIRE(a && b, "mse: null pointer");
-  k_mse<<<grid_for(n * S, 256), 256, 0, as_stream(st)>>>(a, a_sstride, b, n, S, loss_out, da,
+  launch_k(k_mse, grid_for(n * S, 256), 256, 0, as_stream(st), a, a_sstride, b, n, S, loss_out, da,
                                                          (float)(1.0 / ((double)n * S)));
   return check_launch("mse");
 }
@@ -460,14 +484,14 @@ int mfvi_adamw_step(float* p, const float* g, float* m, float* v, size_t n, floa
   MFVI_REQUIRE(step >= 1 || (step >= 0 && step_dev != nullptr), "adamw: step counts from 1");
   MFVI_REQUIRE((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                 reinterpret_cast<uintptr_t>(v)) % 16 == 0, "adamw: buffers must be 16-byte aligned");
-  k_adamw<<<grid_for(n / 4 + 1, 256), 256, 0, as_stream(st)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
+  launch_k(k_adamw, grid_for(n / 4 + 1, 256), 256, 0, as_stream(st), p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
                                                                 step, step_dev, skip_if_nonfinite);
   return check_launch("adamw");
 }
 
 int mfvi_counter_add(uint32_t* ctr, uint32_t inc, mfvi_stream_t st) {
   MFVI_REQUIRE(ctr != nullptr, "counter_add: null pointer");
-  k_counter_add<<<1, 1, 0, as_stream(st)>>>(ctr, inc);
+  launch_k(k_counter_add, 1, 1, 0, as_stream(st), ctr, inc);
   return check_launch("counter_add");
 }
 
@@ -475,7 +499,7 @@ int mfvi_input_jitter_pad(const float* saved, const float* noise, int H, int W, 
                           MfviPhiloxKey key, MfviView xp, mfvi_stream_t st) {
   MFVI_REQUIRE(saved && xp.ptr, "input_jitter_pad: null pointer");
   MFVI_REQUIRE(pad >= 0 && pad < H && pad < W, "input_jitter_pad: pad must be smaller than the image");
-  k_input_jitter_pad<<<grid_for((size_t)(H + 2 * pad) * (W + 2 * pad) * C, 256), 256, 0, as_stream(st)>>>(
+  launch_k(k_input_jitter_pad, grid_for((size_t)(H + 2 * pad) * (W + 2 * pad) * C, 256), 256, 0, as_stream(st), 
       saved, noise, H, W, C, stdv, pad, key, xp);
   return check_launch("input_jitter_pad");
 }
@@ -483,7 +507,7 @@ int mfvi_input_jitter_pad(const float* saved, const float* noise, int H, int W, 
 int mfvi_fill_f32(float* p, size_t n, float v, mfvi_stream_t st) {
   if (n == 0) return 0;
   MFVI_REQUIRE(p, "fill: null pointer");
-  k_fill<<<grid_for(n, 256), 256, 0, as_stream(st)>>>(p, n, v);
+  launch_k(k_fill, grid_for(n, 256), 256, 0, as_stream(st), p, n, v);
   return check_launch("fill");
 }
 

@@ -22,6 +22,32 @@ int check_launch(const char* what);
 
 static inline cudaStream_t as_stream(mfvi_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Programmatic dependent launch: every hot-path kernel is launched with programmatic stream serialisation, calls
+// pdl_trigger() first thing (the next kernel of the stream may start its prologue: block scheduling, barrier init, TMEM
+// allocation, shared-memory zero fill) and pdl_wait() before it touches global memory (returns once the preceding kernel
+// has completed and flushed).  A step is ~170 short kernels, so hiding launch latency / prologues matters.  MFVI_PDL=0
+// switches the attribute off (the device-side instructions are then no-ops).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+bool pdl_enabled();
+
+template <typename... P, typename... A>
+static inline cudaError_t launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+
 constexpr int kNumSMs = 148;  // B200
 constexpr float kBnEps = 1e-5f;
 constexpr float kLreluSlope = 0.2f;

@@ -58,6 +58,7 @@ struct TcConvArgs {
 
 __global__ void __launch_bounds__(kThreads)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcConvArgs p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const uint32_t stage_bytes = kABytes + p.b_bytes;
@@ -99,6 +100,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -273,6 +275,7 @@ struct TcWgradArgs {
 
 __global__ void __launch_bounds__(kThreads)
 k_wgrad_tc(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, const TcWgradArgs p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const uint32_t blk_bytes = static_cast<uint32_t>(p.TP) * 128u;          // one 32-channel block of TP pixel rows
@@ -307,6 +310,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
   if (n_iters <= 0) {           // nothing to do (uniform per CTA)
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
@@ -388,6 +392,8 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUt
 template <int V>
 __global__ void __launch_bounds__(256)
 k_bias_grad(MfviView dy, int H, int W, int C, float* __restrict__ dbias, long long sstride) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm_part[];                 // [C]
   const int s = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += blockDim.x) sm_part[c] = 0.f;
@@ -548,7 +554,7 @@ int mfvi_conv2d_fwd_tc(const MfviConvDesc* d, MfviView x, const float* w, const 
   }
   const int tiles_h = (a.Mh + a.TH - 1) / a.TH;
   dim3 grid(a.tiles_w * tiles_h, 1, d->S);
-  k_conv_tc<<<grid, kThreads, smem, as_stream(st)>>>(tmA, tmB, a);
+  launch_k(k_conv_tc, grid, kThreads, smem, as_stream(st), tmA, tmB, a);
   return check_launch("conv2d_fwd_tc");
 }
 
@@ -596,7 +602,7 @@ int mfvi_conv2d_dgrad_tc(const MfviConvDesc* d, MfviView dy, const float* w, lon
   }
   const int tiles_h = (a.Mh + a.TH - 1) / a.TH;
   dim3 grid(a.tiles_w * tiles_h, d->stride == 2 ? 4 : 1, d->S);
-  k_conv_tc<<<grid, kThreads, smem, as_stream(st)>>>(tmA, tmB, a);
+  launch_k(k_conv_tc, grid, kThreads, smem, as_stream(st), tmA, tmB, a);
   return check_launch("conv2d_dgrad_tc");
 }
 
@@ -610,9 +616,9 @@ int mfvi_conv2d_bias_grad_tc(const MfviConvDesc* d, MfviView dy, float* dbias, l
   int blocks = std::max(1, std::min(kNumSMs * 2, (d->Hout * d->Wout * groups + 255) / 256));
   dim3 g2(blocks, d->S);
   if (vec)
-    k_bias_grad<4><<<g2, 256, d->Cout * sizeof(float), as_stream(st)>>>(dy, d->Hout, d->Wout, d->Cout, dbias, w_sstride);
+    launch_k(k_bias_grad<4>, g2, 256, d->Cout * sizeof(float), as_stream(st), dy, d->Hout, d->Wout, d->Cout, dbias, w_sstride);
   else
-    k_bias_grad<1><<<g2, 256, d->Cout * sizeof(float), as_stream(st)>>>(dy, d->Hout, d->Wout, d->Cout, dbias, w_sstride);
+    launch_k(k_bias_grad<1>, g2, 256, d->Cout * sizeof(float), as_stream(st), dy, d->Hout, d->Wout, d->Cout, dbias, w_sstride);
   return check_launch("conv2d_bias_grad_tc");
 }
 
@@ -662,7 +668,7 @@ int mfvi_conv2d_wgrad_tc(const MfviConvDesc* d, MfviView x, MfviView dy, float* 
   }
   MFVI_REQUIRE(smem <= 220 * 1024, "conv2d_wgrad_tc: stage does not fit in shared memory");
   dim3 grid(chunks, taps, d->S);
-  k_wgrad_tc<<<grid, kThreads, smem, as_stream(st)>>>(tmDy, tmX, a);
+  launch_k(k_wgrad_tc, grid, kThreads, smem, as_stream(st), tmDy, tmX, a);
   if (int rc = check_launch("conv2d_wgrad_tc")) return rc;
   if (dbias != nullptr) return mfvi_conv2d_bias_grad_tc(d, dy, dbias, w_sstride, st);
   return 0;

@@ -72,6 +72,7 @@ __device__ __forceinline__ TileCoord decode_tile(const Args& p, int t) {
 __global__ void __launch_bounds__(kThreads, 2)
 k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAt,
             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBt, const Args p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* a_stages = smem;
@@ -113,6 +114,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t acc_cols = static_cast<uint32_t>(p.n_mt * p.BN);
+  pdl_wait();          // prologue above overlapped the previous kernel; global memory is touched only from here on
 
   if (warp == 0) {
     // ===== activation producer: one halo box per (tile, chunk)
@@ -513,7 +515,7 @@ static int launch(const MfviConvDesc* d, bool dgrad, MfviView a, int Ca, int Ha,
     fprintf(stderr, "[tc2] %s Kc=%d N=%d k%d M=%dx%d S=%d: TH=%d TW=%d Pw=%d n_mt=%d BN=%d nb=%d g=%d acc_stages=%d smem=%zu grid=%d tiles=%d\n",
             what, Ca, Nvalid, d->KH, Mh, Mw, d->S, pl.TH, pl.TW, pl.Pw, pl.n_mt, pl.BN, pl.n_nb, pl.g, pl.acc_stages, pl.smem, pl.grid,
             p.total_tiles);
-  k_conv_halo<<<pl.grid, kThreads, pl.smem, as_stream(st)>>>(tmA, tmAt, tmB, tmBt, p);
+  launch_k(k_conv_halo, pl.grid, kThreads, pl.smem, as_stream(st), tmA, tmAt, tmB, tmBt, p);
   return check_launch(what);
 }
 

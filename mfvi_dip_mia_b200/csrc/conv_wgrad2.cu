@@ -46,6 +46,7 @@ struct WArgs {
 
 __global__ void __launch_bounds__(kThreads, 1)
 k_wgrad_alias(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, const WArgs p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* ctrl = smem + static_cast<size_t>(p.n_stages) * p.stage_bytes;
@@ -83,6 +84,7 @@ k_wgrad_alias(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();          // the zero fill / barrier / TMEM prologue overlapped the previous kernel
   const uint32_t dy_bytes = static_cast<uint32_t>(p.dy_rows) * 128u, x_bytes = static_cast<uint32_t>(p.x_rows) * 128u;
   const int BN = p.K3 ? 96 : 128;
 
@@ -282,7 +284,7 @@ int mfvi_conv2d_wgrad_tc2(const MfviConvDesc* d, MfviView x, MfviView dy, float*
   if (env_int("MFVI_TC2_VERBOSE", 0))
     fprintf(stderr, "[wgrad2] %d->%d k%d %dx%d S=%d: TH=%d TW=%d Pw=%d n_k=%d cblk=%d stage=%u grid=%d tiles/cta=%d\n", d->Cin, d->Cout, d->KH,
             d->Hout, d->Wout, d->S, a.TH, a.TW, a.Pw, a.n_k, a.n_cblk, a.stage_bytes, d->S * a.ctas_per_sample, a.tiles_per_cta);
-  k_wgrad_alias<<<d->S * a.ctas_per_sample, kThreads, smem, as_stream(st)>>>(tmDy, tmX, a);
+  launch_k(k_wgrad_alias, d->S * a.ctas_per_sample, kThreads, smem, as_stream(st), tmDy, tmX, a);
   return check_launch("conv2d_wgrad_tc2");
 }
 

@@ -194,6 +194,8 @@ template <int V>
 __global__ void __launch_bounds__(kEwThreads)
 k_bn_act_pad_fwd(MfviView y, int H, int W, int C, const double* __restrict__ sums, const float* __restrict__ gamma,
                  const float* __restrict__ beta, int act, int pad, MfviView xp, int G, int PPB) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ BnTable tab;
   const int s = blockIdx.y;
   tab.fill(sums, gamma, beta, s, C, 1.0 / ((double)H * W));
@@ -242,6 +244,8 @@ k_cat_up_fwd(MfviView ys, int Cs, const double* __restrict__ sums_s, const float
              const float* __restrict__ beta_s, MfviView yd, int Cd, const double* __restrict__ sums_d,
              const float* __restrict__ gamma_d, const float* __restrict__ beta_d, int H, int W, int mode, MfviView A,
              double* __restrict__ sumsA, int G, int PPB) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double sm_red[2 * kEwThreads * 4];
   __shared__ BnTable tab;
   const int s = blockIdx.y;
@@ -321,6 +325,8 @@ __global__ void __launch_bounds__(kEwThreads)
 k_pad_act_bwd(MfviView dxp, int H, int W, int C, int pad, MfviView y, const double* __restrict__ sums,
               const float* __restrict__ gamma, const float* __restrict__ beta, int act, MfviView g,
               double* __restrict__ red, int G, int PPB) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double sm_red[2 * kEwThreads * 4];
   const int s = blockIdx.y;
   const int group = threadIdx.x % G, slot = threadIdx.x / G;
@@ -379,6 +385,8 @@ __global__ void __launch_bounds__(kEwThreads)
 k_bn_bwd_apply(MfviView g, MfviView y, int S, int H, int W, int C, const double* __restrict__ sums,
                const double* __restrict__ red, const float* __restrict__ gamma, MfviView dy,
                float* __restrict__ dgamma, float* __restrict__ dbeta, int G, int PPB) {
+  pdl_trigger();
+  pdl_wait();
   const int s = blockIdx.y;
   const double inv_count = 1.0 / ((double)H * W);
   if (blockIdx.x == 0 && blockIdx.y == 0 && dgamma != nullptr) {
@@ -439,6 +447,8 @@ __global__ void __launch_bounds__(kEwThreads)
 k_cat_bwd_skip(MfviView dA, int H, int W, MfviView ys, int Cs, const double* __restrict__ sums_s,
                const float* __restrict__ gamma_s, const float* __restrict__ beta_s, MfviView gs,
                double* __restrict__ red_s, int G, int PPB) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double sm_red[2 * kEwThreads * 4];
   const int s = blockIdx.y;
   const int group = threadIdx.x % G, slot = threadIdx.x / G;
@@ -494,6 +504,8 @@ __global__ void __launch_bounds__(kEwThreads)
 k_cat_bwd_up(MfviView dA, int H, int W, int mode, int Cs, MfviView yd, int Cd, const double* __restrict__ sums_d,
              const float* __restrict__ gamma_d, const float* __restrict__ beta_d, MfviView gd,
              double* __restrict__ red_d, int G, int PPB) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double sm_red[2 * kEwThreads * 4];
   const int s = blockIdx.y;
   const int h2 = H / 2, w2 = W / 2;
@@ -560,6 +572,8 @@ __global__ void k_bn_running(const double* __restrict__ arena, const int* __rest
                              const long long* __restrict__ sums_off, const int* __restrict__ Cs,
                              const int* __restrict__ count, int n_bn, int S, float momentum,
                              float* __restrict__ running_mean, float* __restrict__ running_var) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x;
   if (b >= n_bn) return;
   const int C = Cs[b];
@@ -598,9 +612,9 @@ using namespace mfvi;
 #define MFVI_EW_DISPATCH(GEOM, KERNEL, GRID, ...)                                              \
   do {                                                                                         \
     if ((GEOM).V == 4)                                                                         \
-      KERNEL<4><<<GRID, kEwThreads, 0, as_stream(st)>>>(__VA_ARGS__, (GEOM).G, (GEOM).PPB);    \
+      launch_k(KERNEL<4>, GRID, kEwThreads, 0, as_stream(st), __VA_ARGS__, (GEOM).G, (GEOM).PPB);  \
     else                                                                                       \
-      KERNEL<1><<<GRID, kEwThreads, 0, as_stream(st)>>>(__VA_ARGS__, (GEOM).G, (GEOM).PPB);    \
+      launch_k(KERNEL<1>, GRID, kEwThreads, 0, as_stream(st), __VA_ARGS__, (GEOM).G, (GEOM).PPB);  \
   } while (0)
 
 extern "C" {
@@ -684,7 +698,7 @@ int mfvi_bn_running_update(const double* arena, const int* ch_off, const long lo
                            float* running_var, mfvi_stream_t st) {
   MFVI_REQUIRE(arena && ch_off && sums_off && C && count && running_mean && running_var, "bn_running_update: null pointer");
   if (n_bn == 0) return 0;
-  k_bn_running<<<n_bn, 128, 0, as_stream(st)>>>(arena, ch_off, sums_off, C, count, n_bn, S, momentum, running_mean,
+  launch_k(k_bn_running, n_bn, 128, 0, as_stream(st), arena, ch_off, sums_off, C, count, n_bn, S, momentum, running_mean,
                                                  running_var);
   return check_launch("bn_running_update");
 }
