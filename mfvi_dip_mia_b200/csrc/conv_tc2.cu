@@ -50,6 +50,7 @@ struct Args {
   double* stats;
   int accumulate, vecO;
   long long* dbg;     // optional timeline of CTA 0 (clock64 stamps), 8 slots per tile
+  int dbg_mode;       // timing experiments only (results are garbage): 1 = no epilogue work, 2 = no TMA after the first stages, 3 = both
 };
 
 #define TC2_STAMP(slot) do { if (p.dbg != nullptr && blockIdx.x == 0) p.dbg[(tile_i) * 8 + (slot)] = clock64(); } while (0)
@@ -69,6 +70,7 @@ __device__ __forceinline__ TileCoord decode_tile(const Args& p, int t) {
   return c;
 }
 
+template <bool DGRAD>
 __global__ void __launch_bounds__(kThreads, 2)
 k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAt,
             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBt, const Args p) {
@@ -123,13 +125,14 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int tile_i = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_i) {
         const TileCoord tc = decode_tile(p, t);
-        const int h0 = tc.th * p.TH - (p.dgrad ? p.KH - 1 : 0);
-        const int w0 = tc.tw * p.TW - (p.dgrad ? p.KW - 1 : 0);
+        const int h0 = tc.th * p.TH - (DGRAD ? p.KH - 1 : 0);
+        const int w0 = tc.tw * p.TW - (DGRAD ? p.KW - 1 : 0);
         for (int c = 0; c < p.n_chunks; ++c, ++ia) {
           const uint32_t st = ia % p.n_a, ph = (ia / p.n_a) & 1;
           mbar_wait(smem_u32(&a_empty[st]), ph ^ 1);
           if (c == 0) TC2_STAMP(0);
           const uint32_t fb = smem_u32(&a_full[st]);
+          if ((p.dbg_mode & 2) && ia >= static_cast<uint32_t>(p.n_a)) { mbar_arrive(fb); continue; }
           mbar_expect_tx(fb, static_cast<uint32_t>(p.box_rows) * p.cw[c] * 4u);
           tma_load_4d(smem_u32(a_stages + static_cast<size_t>(st) * p.a_stage_bytes), p.cw[c] == 32 ? &tmA : &tmAt, fb, p.ck0[c],
                       w0, h0, p.a_bcast ? 0 : tc.smp);
@@ -151,7 +154,8 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             mbar_wait(smem_u32(&b_empty[st]), ph ^ 1);
             const uint32_t fb = smem_u32(&b_full[st]);
             const uint32_t dst = smem_u32(b_stages + static_cast<size_t>(st) * p.b_stage_bytes);
-            if (!p.dgrad) {
+            if ((p.dbg_mode & 2) && ib >= static_cast<uint32_t>(p.n_b)) { mbar_arrive(fb); continue; }
+            if (!DGRAD) {
               mbar_expect_tx(fb, static_cast<uint32_t>(p.g * p.BN * p.cw[c]) * 4u);
               tma_load_4d(dst, map, fb, p.ck0[c], n0, grp * p.g, bs);                      // box (w k, BN n, g taps)
             } else {
@@ -166,7 +170,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ===== MMA issuer
-    const uint32_t idesc = make_idesc(128, p.BN, 0, p.dgrad ? 1 : 0);
+    const uint32_t idesc = make_idesc(128, p.BN, 0, DGRAD ? 1 : 0);
     uint32_t ia = 0, ib = 0, it = 0;
     int tile_i = 0;
     long long cyc_wait_a = 0, cyc_wait_b = 0, cyc_issue = 0, n_mma = 0;
@@ -198,26 +202,50 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint32_t b_base = smem_u32(b_stages + static_cast<size_t>(sb) * p.b_stage_bytes);
             // descriptors: hi words fixed per chunk, lo words advance by (bytes >> 4)
             const uint32_t a_hi = desc_hi(sbo, layout);
-            const uint32_t b_hi = p.dgrad ? desc_hi(512, kLayoutSw128Base32) : a_hi;
-            const uint32_t b_lo0 = p.dgrad ? desc_lo(b_base, static_cast<uint32_t>(p.g * w) * 128u) : desc_lo(b_base, 16);
-            const uint32_t b_tap = p.dgrad ? static_cast<uint32_t>(w) * 8u : (static_cast<uint32_t>(p.BN) * rb) >> 4;   // per tap
-            const uint32_t b_k = p.dgrad ? 64u : 2u;                                                                    // per k-step
+            const uint32_t b_hi = DGRAD ? desc_hi(512, kLayoutSw128Base32) : a_hi;
+            const uint32_t b_lo0 = DGRAD ? desc_lo(b_base, static_cast<uint32_t>(p.g * w) * 128u) : desc_lo(b_base, 16);
+            const uint32_t b_tap = DGRAD ? static_cast<uint32_t>(w) * 8u : (static_cast<uint32_t>(p.BN) * rb) >> 4;   // per tap
+            constexpr uint32_t b_k = DGRAD ? 64u : 2u;                                                                // per k-step
             const uint32_t a_lo0 = desc_lo(a_base, 16);
             const uint32_t a_mt = (128u * rb) >> 4, rb16 = rb >> 4;
             const int tap0 = grp * p.g;
             int r = tap0 / p.KW, sx = tap0 - r * p.KW;
             const int ntap = min(p.g, p.taps - tap0);
             for (int tt = 0; tt < ntap; ++tt) {
-              const int off_rows = p.dgrad ? (p.KH - 1 - r) * p.Pw + (p.KW - 1 - sx) : r * p.Pw + sx;
+              const int off_rows = DGRAD ? (p.KH - 1 - r) * p.Pw + (p.KW - 1 - sx) : r * p.Pw + sx;
               const uint32_t a_t = a_lo0 + static_cast<uint32_t>(off_rows) * rb16;
               const uint32_t b_t = b_lo0 + static_cast<uint32_t>(tt) * b_tap;
-              const bool first_tap = (c == 0 && tap0 + tt == 0);
+              const uint32_t acc0 = (c == 0 && tap0 + tt == 0) ? 0u : 1u;
               uint32_t d_col = d_base;
-              for (int j = 0; j < p.n_mt; ++j, d_col += p.BN) {
-                const uint32_t a_j = a_t + static_cast<uint32_t>(j) * a_mt;
-                for (int k = 0; k < ksteps; ++k)
-                  tc_mma_tf32_elect(d_col, desc_pack(a_j + 2u * k, a_hi), desc_pack(b_t + b_k * k, b_hi), idesc,
-                                    (first_tap && k == 0) ? 0u : 1u);
+              if (ksteps == 4) {
+                // four k-steps of a 32-channel chunk: the eight descriptor low words stay live across the M tiles, so one
+                // MMA costs ~2 uniform-datapath instructions (each ~10 cycles) instead of ~8
+                uint32_t al0 = a_t, al1 = a_t + 2u, al2 = a_t + 4u, al3 = a_t + 6u;
+                const uint32_t bl0 = b_t, bl1 = b_t + b_k, bl2 = b_t + 2u * b_k, bl3 = b_t + 3u * b_k;
+                for (int j = 0; j < p.n_mt; ++j) {
+                  tc_mma_tf32_elect(d_col, desc_pack(al0, a_hi), desc_pack(bl0, b_hi), idesc, acc0);
+                  tc_mma_tf32_elect(d_col, desc_pack(al1, a_hi), desc_pack(bl1, b_hi), idesc, 1u);
+                  tc_mma_tf32_elect(d_col, desc_pack(al2, a_hi), desc_pack(bl2, b_hi), idesc, 1u);
+                  tc_mma_tf32_elect(d_col, desc_pack(al3, a_hi), desc_pack(bl3, b_hi), idesc, 1u);
+                  al0 += a_mt; al1 += a_mt; al2 += a_mt; al3 += a_mt;
+                  d_col += p.BN;
+                }
+              } else if (ksteps == 2) {
+                uint32_t al0 = a_t, al1 = a_t + 2u;
+                const uint32_t bl1 = b_t + b_k;
+                for (int j = 0; j < p.n_mt; ++j) {
+                  tc_mma_tf32_elect(d_col, desc_pack(al0, a_hi), desc_pack(b_t, b_hi), idesc, acc0);
+                  tc_mma_tf32_elect(d_col, desc_pack(al1, a_hi), desc_pack(bl1, b_hi), idesc, 1u);
+                  al0 += a_mt; al1 += a_mt;
+                  d_col += p.BN;
+                }
+              } else {
+                uint32_t al0 = a_t;
+                for (int j = 0; j < p.n_mt; ++j) {
+                  tc_mma_tf32_elect(d_col, desc_pack(al0, a_hi), desc_pack(b_t, b_hi), idesc, acc0);
+                  al0 += a_mt;
+                  d_col += p.BN;
+                }
               }
               if (++sx == p.KW) { sx = 0; ++r; }
             }
@@ -250,7 +278,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       float* obase = p.o.ptr + static_cast<size_t>(tc.smp) * p.o.sstride + n0;
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * acc_cols;
 #pragma unroll 1
-      for (int c = 0; c < p.BN; c += 16) {
+      for (int c = 0; c < ((p.dbg_mode & 1) ? 0 : p.BN); c += 16) {
         float b[16], s1[16], s2[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -470,6 +498,7 @@ static int launch(const MfviConvDesc* d, bool dgrad, MfviView a, int Ca, int Ha,
   p.o = o; p.bias = bias; p.bias_sstride = w_sstride; p.stats = stats; p.accumulate = accumulate;
   p.vecO = ((reinterpret_cast<uintptr_t>(o.ptr) % 16 == 0) && o.sstride % 4 == 0 && o.hstride % 4 == 0 && o.wstride % 4 == 0) ? 1 : 0;
   if (const char* e = getenv("MFVI_TC2_DBG")) p.dbg = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));   // device pointer (debug)
+  p.dbg_mode = env_int("MFVI_TC2_DBGMODE", 0);
 
   // ---- tensor maps: wide (32-channel) and tail chunk variants
   int tail_w = 0;
@@ -507,7 +536,8 @@ static int launch(const MfviConvDesc* d, bool dgrad, MfviView a, int Ca, int Ha,
   }
   static size_t attr = 0;
   if (pl.smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_halo, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_conv_halo<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     MFVI_REQUIRE(e == cudaSuccess, "%s: cannot raise dynamic shared memory: %s", what, cudaGetErrorString(e));
     attr = 200 * 1024;
   }
@@ -515,7 +545,10 @@ static int launch(const MfviConvDesc* d, bool dgrad, MfviView a, int Ca, int Ha,
     fprintf(stderr, "[tc2] %s Kc=%d N=%d k%d M=%dx%d S=%d: TH=%d TW=%d Pw=%d n_mt=%d BN=%d nb=%d g=%d acc_stages=%d smem=%zu grid=%d tiles=%d\n",
             what, Ca, Nvalid, d->KH, Mh, Mw, d->S, pl.TH, pl.TW, pl.Pw, pl.n_mt, pl.BN, pl.n_nb, pl.g, pl.acc_stages, pl.smem, pl.grid,
             p.total_tiles);
-  launch_k(k_conv_halo, pl.grid, kThreads, pl.smem, as_stream(st), tmA, tmAt, tmB, tmBt, p);
+  if (dgrad)
+    launch_k(k_conv_halo<true>, pl.grid, kThreads, pl.smem, as_stream(st), tmA, tmAt, tmB, tmBt, p);
+  else
+    launch_k(k_conv_halo<false>, pl.grid, kThreads, pl.smem, as_stream(st), tmA, tmAt, tmB, tmBt, p);
   return check_launch(what);
 }
 

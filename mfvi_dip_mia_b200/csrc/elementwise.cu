@@ -166,20 +166,23 @@ struct BnRegs {
 template <int V>
 struct Acc2 {
   float fa[V], fb[V];
-  double da[V], db[V];
+  double* cell;        // thread-private doubles in shared memory, laid out [2V][kEwThreads] (bank-conflict free); keeps 4V
+                       // registers free -> higher occupancy
   int n;
-  __device__ __forceinline__ Acc2() : n(0) {
+  __device__ __forceinline__ explicit Acc2(double* scratch) : n(0) {
+    cell = scratch + threadIdx.x;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       fa[j] = fb[j] = 0.f;
-      da[j] = db[j] = 0.0;
+      cell[j * kEwThreads] = 0.0;
+      cell[(V + j) * kEwThreads] = 0.0;
     }
   }
   __device__ __forceinline__ void flush() {
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      da[j] += (double)fa[j];
-      db[j] += (double)fb[j];
+      cell[j * kEwThreads] += (double)fa[j];
+      cell[(V + j) * kEwThreads] += (double)fb[j];
       fa[j] = fb[j] = 0.f;
     }
     n = 0;
@@ -188,6 +191,24 @@ struct Acc2 {
     if (++n == kFlush) flush();
   }
 };
+
+// CTA-level reduction of the thread-private (sum a, sum b) cells ([2V][thread] doubles, threads laid out [slot][group]):
+// thread c adds the cells of channel c over the pixel slots and issues one double atomicAdd per channel into dst[c*2+{0,1}].
+template <int V>
+__device__ __forceinline__ void cta_reduce_cells(const double* cells, int G, int PPB, int C, double* __restrict__ dst) {
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int group = c / V, j = c - group * V;
+    double sa = 0.0, sb = 0.0;
+    for (int sl = 0; sl < PPB; ++sl) {
+      const double* cell = cells + (sl * G + group);
+      sa += cell[j * kEwThreads];
+      sb += cell[(V + j) * kEwThreads];
+    }
+    atomicAdd(&dst[(size_t)c * 2 + 0], sa);
+    atomicAdd(&dst[(size_t)c * 2 + 1], sb);
+  }
+}
 
 // F1: xp = reflect_pad(act(bn(y)))            grid = (chunks, S)
 template <int V>
@@ -239,7 +260,7 @@ __device__ __forceinline__ void up_taps(int i, int n, int mode, int& i0, int& i1
 
 // F2: A = cat(lrelu(bn(ys)), up2x(lrelu(bn(yd)))), sumsA += (sum, sumsq)      grid = (chunks, S)
 template <int V>
-__global__ void __launch_bounds__(kEwThreads)
+__global__ void __launch_bounds__(kEwThreads, 4)
 k_cat_up_fwd(MfviView ys, int Cs, const double* __restrict__ sums_s, const float* __restrict__ gamma_s,
              const float* __restrict__ beta_s, MfviView yd, int Cd, const double* __restrict__ sums_d,
              const float* __restrict__ gamma_d, const float* __restrict__ beta_d, int H, int W, int mode, MfviView A,
@@ -258,7 +279,7 @@ k_cat_up_fwd(MfviView ys, int Cs, const double* __restrict__ sums_s, const float
   const bool active = slot < PPB;
   const int c0 = group * V;
   const bool skip = c0 < Cs;          // Cs % V == 0 is guaranteed by the host (V falls back to 1 otherwise)
-  Acc2<V> acc;
+  Acc2<V> acc(sm_red);
   if (active) {
     BnRegs<V> bn;
     bn.load(tab, c0, C);
@@ -307,7 +328,7 @@ k_cat_up_fwd(MfviView ys, int Cs, const double* __restrict__ sums_s, const float
     }
     acc.flush();
   }
-  cta_reduce_2<V>(acc.da, acc.db, group, slot, G, PPB, C, sm_red, sumsA + (size_t)s * C * 2, active);
+  cta_reduce_cells<V>(sm_red, G, PPB, C, sumsA + (size_t)s * C * 2);
 }
 
 // number of padded positions (per dimension) that reflect onto source index h: fills q[0..n)
@@ -321,7 +342,7 @@ __device__ __forceinline__ int fold_sources(int h, int n, int pad, int (&q)[3]) 
 
 // B1: g = fold_reflect(dxp) * act'(bn(y)), red += (sum g, sum g*xhat)      grid = (chunks, S)
 template <int V>
-__global__ void __launch_bounds__(kEwThreads)
+__global__ void __launch_bounds__(kEwThreads, 4)
 k_pad_act_bwd(MfviView dxp, int H, int W, int C, int pad, MfviView y, const double* __restrict__ sums,
               const float* __restrict__ gamma, const float* __restrict__ beta, int act, MfviView g,
               double* __restrict__ red, int G, int PPB) {
@@ -332,7 +353,7 @@ k_pad_act_bwd(MfviView dxp, int H, int W, int C, int pad, MfviView y, const doub
   const int group = threadIdx.x % G, slot = threadIdx.x / G;
   const bool active = slot < PPB;
   const int c0 = group * V;
-  Acc2<V> acc;
+  Acc2<V> acc(sm_red);
   __shared__ BnTable tab;
   tab.fill(sums, gamma, beta, s, C, 1.0 / ((double)H * W));
   __syncthreads();
@@ -376,7 +397,7 @@ k_pad_act_bwd(MfviView dxp, int H, int W, int C, int pad, MfviView y, const doub
     }
     acc.flush();
   }
-  cta_reduce_2<V>(acc.da, acc.db, group, slot, G, PPB, C, sm_red, red + (size_t)s * C * 2, active);
+  cta_reduce_cells<V>(sm_red, G, PPB, C, red + (size_t)s * C * 2);
 }
 
 // B2: dy = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)); block (0,0) also writes dgamma/dbeta.
@@ -443,7 +464,7 @@ k_bn_bwd_apply(MfviView g, MfviView y, int S, int H, int W, int C, const double*
 
 // B3a: skip branch of the concat: gs = dA[:, :Cs] * lrelu'(bn(ys)), red_s += …
 template <int V>
-__global__ void __launch_bounds__(kEwThreads)
+__global__ void __launch_bounds__(kEwThreads, 4)
 k_cat_bwd_skip(MfviView dA, int H, int W, MfviView ys, int Cs, const double* __restrict__ sums_s,
                const float* __restrict__ gamma_s, const float* __restrict__ beta_s, MfviView gs,
                double* __restrict__ red_s, int G, int PPB) {
@@ -454,7 +475,7 @@ k_cat_bwd_skip(MfviView dA, int H, int W, MfviView ys, int Cs, const double* __r
   const int group = threadIdx.x % G, slot = threadIdx.x / G;
   const bool active = slot < PPB;
   const int c0 = group * V;
-  Acc2<V> acc;
+  Acc2<V> acc(sm_red);
   __shared__ BnTable tab;
   tab.fill(sums_s, gamma_s, beta_s, s, Cs, 1.0 / ((double)H * W));
   __syncthreads();
@@ -483,7 +504,7 @@ k_cat_bwd_skip(MfviView dA, int H, int W, MfviView ys, int Cs, const double* __r
     }
     acc.flush();
   }
-  cta_reduce_2<V>(acc.da, acc.db, group, slot, G, PPB, Cs, sm_red, red_s + (size_t)s * Cs * 2, active);
+  cta_reduce_cells<V>(sm_red, G, PPB, Cs, red_s + (size_t)s * Cs * 2);
 }
 
 // weight with which low-res index k enters hi-res index i (0 if not a tap)
@@ -500,7 +521,7 @@ __device__ __forceinline__ float up_weight_of(int i, int k, int n, int mode) {
 
 // B3b: deeper branch: gd = up2x^T(dA[:, Cs:]) * lrelu'(bn(yd)), red_d += …   (iterates low-res pixels)
 template <int V>
-__global__ void __launch_bounds__(kEwThreads)
+__global__ void __launch_bounds__(kEwThreads, 4)
 k_cat_bwd_up(MfviView dA, int H, int W, int mode, int Cs, MfviView yd, int Cd, const double* __restrict__ sums_d,
              const float* __restrict__ gamma_d, const float* __restrict__ beta_d, MfviView gd,
              double* __restrict__ red_d, int G, int PPB) {
@@ -512,7 +533,7 @@ k_cat_bwd_up(MfviView dA, int H, int W, int mode, int Cs, MfviView yd, int Cd, c
   const int group = threadIdx.x % G, slot = threadIdx.x / G;
   const bool active = slot < PPB;
   const int c0 = group * V;
-  Acc2<V> acc;
+  Acc2<V> acc(sm_red);
   __shared__ BnTable tab;
   tab.fill(sums_d, gamma_d, beta_d, s, Cd, 1.0 / ((double)h2 * w2));
   __syncthreads();
@@ -564,7 +585,7 @@ k_cat_bwd_up(MfviView dA, int H, int W, int mode, int Cs, MfviView yd, int Cd, c
     }
     acc.flush();
   }
-  cta_reduce_2<V>(acc.da, acc.db, group, slot, G, PPB, Cd, sm_red, red_d + (size_t)s * Cd * 2, active);
+  cta_reduce_cells<V>(sm_red, G, PPB, Cd, red_d + (size_t)s * Cd * 2);
 }
 
 // running stats of all BatchNorms (one thread per channel)
