@@ -40,8 +40,16 @@ struct Args {
   int KH, KW, taps, g, n_groups;         // g = taps per weight stage
   int Mh, Mw, TH, TW, Pw, tiles_h, tiles_w;
   int n_mt, total_tiles, tiles_per_sample;
-  int box_rows;                          // (TH+KH-1) * Pw
+  int box_rows;                          // (TH+hh) * Pw : rows of one halo box
   int dgrad, a_bcast, b_bcast;
+  int cstride;                           // conv stride (1 or 2)
+  int hh, hw;                            // halo rows / columns of the box beyond the TH x TW tile
+  int org_h, org_w;                      // the box starts at (tile origin - org): dgrad reaches up / left
+  int planes, plane_rows;                // stride-2 forward: the input is read as 4 parity planes (row, col parity), each a halo
+                                         // box of its own, plane_rows shared-memory rows apart
+  int a_rows2;                           // stride-2 forward: Hin/2 (rows of one sample in the parity-split 5-D map)
+  int n_cls;                             // stride-2 dgrad: 4 output-parity classes, each a stride-1 problem over a tap subset
+  int tap_off[4][25];                    // [class][tap] -> operand row offset of the tap inside the A stage, -1 = tap not in class
   int n_a, n_b, acc_stages;
   uint32_t a_stage_bytes, b_stage_bytes, tmem_cols;
   MfviView o;
@@ -56,15 +64,17 @@ struct Args {
 #define TC2_STAMP(slot) do { if (p.dbg != nullptr && blockIdx.x == 0) p.dbg[(tile_i) * 8 + (slot)] = clock64(); } while (0)
 
 struct TileCoord {
-  int smp, nb, th, tw;
+  int smp, nb, cls, th, tw;
 };
 __device__ __forceinline__ TileCoord decode_tile(const Args& p, int t) {
   TileCoord c;
   c.smp = t / p.tiles_per_sample;
   int r = t - c.smp * p.tiles_per_sample;
-  const int per_nb = p.tiles_h * p.tiles_w;
+  const int per_cls = p.tiles_h * p.tiles_w, per_nb = per_cls * p.n_cls;
   c.nb = r / per_nb;
   r -= c.nb * per_nb;
+  c.cls = r / per_cls;
+  r -= c.cls * per_cls;
   c.th = r / p.tiles_w;
   c.tw = r - c.th * p.tiles_w;
   return c;
@@ -125,17 +135,27 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int tile_i = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_i) {
         const TileCoord tc = decode_tile(p, t);
-        const int h0 = tc.th * p.TH - (DGRAD ? p.KH - 1 : 0);
-        const int w0 = tc.tw * p.TW - (DGRAD ? p.KW - 1 : 0);
+        const int h0 = tc.th * p.TH - p.org_h;
+        const int w0 = tc.tw * p.TW - p.org_w;
         for (int c = 0; c < p.n_chunks; ++c, ++ia) {
           const uint32_t st = ia % p.n_a, ph = (ia / p.n_a) & 1;
           mbar_wait(smem_u32(&a_empty[st]), ph ^ 1);
           if (c == 0) TC2_STAMP(0);
           const uint32_t fb = smem_u32(&a_full[st]);
           if ((p.dbg_mode & 2) && ia >= static_cast<uint32_t>(p.n_a)) { mbar_arrive(fb); continue; }
-          mbar_expect_tx(fb, static_cast<uint32_t>(p.box_rows) * p.cw[c] * 4u);
-          tma_load_4d(smem_u32(a_stages + static_cast<size_t>(st) * p.a_stage_bytes), p.cw[c] == 32 ? &tmA : &tmAt, fb, p.ck0[c],
-                      w0, h0, p.a_bcast ? 0 : tc.smp);
+          const uint32_t box_bytes = static_cast<uint32_t>(p.box_rows) * p.cw[c] * 4u;
+          const uint32_t dst = smem_u32(a_stages + static_cast<size_t>(st) * p.a_stage_bytes);
+          const CUtensorMap* map = p.cw[c] == 32 ? &tmA : &tmAt;
+          if (p.planes == 1) {
+            mbar_expect_tx(fb, box_bytes);
+            tma_load_4d(dst, map, fb, p.ck0[c], w0, h0, p.a_bcast ? 0 : tc.smp);
+          } else {
+            // parity-split 5-D view (C, 2, W/2, 2, H/2 * S): plane (pr, ps) holds pixels (2i + pr, 2j + ps)
+            mbar_expect_tx(fb, 4u * box_bytes);
+            const int rows = (p.a_bcast ? 0 : tc.smp * p.a_rows2) + h0;
+            const uint32_t pl_bytes = static_cast<uint32_t>(p.plane_rows) * p.cw[c] * 4u;
+            for (int pl = 0; pl < 4; ++pl) tma_load_5d(dst + pl * pl_bytes, map, fb, p.ck0[c], pl & 1, w0, pl >> 1, rows);
+          }
         }
       }
     }
@@ -180,6 +200,8 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tc_fence_after();
       if (lane == 0) TC2_STAMP(1);
       const uint32_t d_base = tmem_base + as * acc_cols;
+      const int tcls = decode_tile(p, t).cls;
+      bool started = false;                            // the first MMA of every accumulator overwrites, the rest accumulate
       for (int c = 0; c < p.n_chunks; ++c, ++ia) {
         const uint32_t sa = ia % p.n_a;
         long long tw0 = p.dbg ? clock64() : 0;
@@ -209,13 +231,14 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint32_t a_lo0 = desc_lo(a_base, 16);
             const uint32_t a_mt = (128u * rb) >> 4, rb16 = rb >> 4;
             const int tap0 = grp * p.g;
-            int r = tap0 / p.KW, sx = tap0 - r * p.KW;
             const int ntap = min(p.g, p.taps - tap0);
             for (int tt = 0; tt < ntap; ++tt) {
-              const int off_rows = DGRAD ? (p.KH - 1 - r) * p.Pw + (p.KW - 1 - sx) : r * p.Pw + sx;
+              const int off_rows = p.tap_off[tcls][tap0 + tt];
+              if (off_rows < 0) continue;            // tap belongs to another output-parity class (stride-2 dgrad)
               const uint32_t a_t = a_lo0 + static_cast<uint32_t>(off_rows) * rb16;
               const uint32_t b_t = b_lo0 + static_cast<uint32_t>(tt) * b_tap;
-              const uint32_t acc0 = (c == 0 && tap0 + tt == 0) ? 0u : 1u;
+              const uint32_t acc0 = started ? 1u : 0u;
+              started = true;
               uint32_t d_col = d_base;
               if (ksteps == 4) {
                 // four k-steps of a 32-channel chunk: the eight descriptor low words stay live across the M tiles, so one
@@ -247,7 +270,6 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                   d_col += p.BN;
                 }
               }
-              if (++sx == p.KW) { sx = 0; ++r; }
             }
             tc_commit_elect(smem_u32(&b_empty[sb]));
             if (p.dbg) { cyc_issue += clock64() - ti0; n_mma += static_cast<long long>(p.g) * p.n_mt * ksteps; }
@@ -277,6 +299,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const float* bias = p.bias != nullptr ? p.bias + static_cast<size_t>(tc.smp) * p.bias_sstride + n0 : nullptr;
       float* obase = p.o.ptr + static_cast<size_t>(tc.smp) * p.o.sstride + n0;
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * acc_cols;
+      const int ostr = p.n_cls == 4 ? 2 : 1;
 #pragma unroll 1
       for (int c = 0; c < ((p.dbg_mode & 1) ? 0 : p.BN); c += 16) {
         float b[16], s1[16], s2[16];
@@ -291,7 +314,8 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int j = 0; j < p.n_mt; ++j) {
           const int pos = j * 128 + q * 32 + lane;
           const int hl = pos / p.Pw, wl = pos - hl * p.Pw;
-          const int gh = tc.th * p.TH + hl, gw = tc.tw * p.TW + wl;
+          // stride-2 dgrad: this tile is output-parity class (cls >> 1, cls & 1) of dx, written with pixel stride 2
+          const int gh = (tc.th * p.TH + hl) * ostr + (tc.cls >> 1), gw = (tc.tw * p.TW + wl) * ostr + (tc.cls & 1);
           const bool valid = hl < p.TH && wl < p.TW && gh < p.Mh && gw < p.Mw;
           float v[16];
           tmem_ld16(tbase + static_cast<uint32_t>(j * p.BN + c), v);
@@ -379,7 +403,7 @@ static CUtensorMapSwizzle swz_of(int width) {
 
 struct Plan {
   bool ok = false;
-  int TH, TW, Pw, tiles_h, tiles_w, n_mt, BN, n_nb, g, n_groups, n_a, n_b, acc_stages, box_rows, grid;
+  int TH, TW, Pw, tiles_h, tiles_w, n_mt, BN, n_nb, g, n_groups, n_a, n_b, acc_stages, box_rows, plane_rows, grid;
   uint32_t a_stage, b_stage, tmem_cols;
   size_t smem;
   double cost;
@@ -390,7 +414,10 @@ static int env_int(const char* name, int dflt) {
   return e != nullptr ? atoi(e) : dflt;
 }
 
-static Plan make_plan(int S, int Mh, int Mw, int KH, int KW, int n_chunks, const int* cw, int Nvalid, bool dgrad) {
+// (Mh, Mw): the pixel space the M tiles cover (output pixels; for stride-2 dgrad one output-parity class);  (hh, hw): halo
+// of the box;  planes: 4 parity planes per stage for the stride-2 forward;  n_cls: 4 parity classes for the stride-2 dgrad
+static Plan make_plan(int S, int Mh, int Mw, int hh, int hw, int taps, int planes, int n_cls, int n_chunks, const int* cw,
+                      int Nvalid, bool dgrad) {
   Plan best;
   best.cost = 1e30;
   int kw_total = 0, rb_max = 0;
@@ -398,7 +425,6 @@ static Plan make_plan(int S, int Mh, int Mw, int KH, int KW, int n_chunks, const
     kw_total += cw[i];
     rb_max = std::max(rb_max, cw[i] * 4);
   }
-  const int taps = KH * KW;
   const int nq = dgrad ? 32 : 16;
   const int BN_full = rup(Nvalid, nq);
   const int force_th = env_int("MFVI_TC2_TH", 0), force_strips = env_int("MFVI_TC2_STRIPS", 0), force_bn = env_int("MFVI_TC2_BN", 0);
@@ -410,16 +436,16 @@ static Plan make_plan(int S, int Mh, int Mw, int KH, int KW, int n_chunks, const
     for (int strips = 1; strips <= 4; ++strips) {
       if (force_strips && strips != force_strips) continue;
       const int TW = cdiv(Mw, strips);
-      const int Pw = TW + KW - 1;
+      const int Pw = TW + hw;
       if (Pw > 256) continue;
       if (strips > 1 && cdiv(Mw, TW) != strips) continue;
       for (int TH = 1; TH <= std::min(Mh, 64); ++TH) {
         if (force_th && TH != force_th) continue;
-        if (TH + KH - 1 > 256) break;
+        if (TH + hh > 256) break;
         Plan pl;
         pl.TH = TH; pl.TW = TW; pl.Pw = Pw; pl.BN = BN; pl.n_nb = split;
         pl.tiles_h = cdiv(Mh, TH); pl.tiles_w = strips;
-        pl.box_rows = (TH + KH - 1) * Pw;
+        pl.box_rows = (TH + hh) * Pw;
         pl.n_mt = cdiv((TH - 1) * Pw + TW, 128);
         const int acc_cols = pl.n_mt * BN;
         if (acc_cols > 512) break;
@@ -427,8 +453,8 @@ static Plan make_plan(int S, int Mh, int Mw, int KH, int KW, int n_chunks, const
         uint32_t cols = 32;
         while (cols < static_cast<uint32_t>(pl.acc_stages * acc_cols)) cols <<= 1;
         pl.tmem_cols = cols;
-        const int a_rows = std::max(pl.box_rows, pl.n_mt * 128 + (KH - 1) * Pw + KW - 1);
-        pl.a_stage = static_cast<uint32_t>(rup(a_rows * rb_max, 1024));
+        pl.plane_rows = rup(std::max(pl.box_rows, pl.n_mt * 128 + hh * Pw + hw), 8);
+        pl.a_stage = static_cast<uint32_t>(rup(planes * pl.plane_rows * rb_max, 1024));
         int g = taps;
         while (g > 1 && g * BN * rb_max > 32 * 1024) --g;
         while (taps % g) --g;           // equal groups
@@ -439,11 +465,11 @@ static Plan make_plan(int S, int Mh, int Mw, int KH, int KW, int n_chunks, const
         pl.smem = 1024 + static_cast<size_t>(pl.n_a) * pl.a_stage + static_cast<size_t>(pl.n_b) * pl.b_stage + 256 + 4 * 32 * kTrLd * 4 +
                   4 * BN * 16 + 64;
         if (pl.smem > 200 * 1024) break;
-        const int tiles = S * split * pl.tiles_h * pl.tiles_w;
+        const int tiles = S * split * n_cls * pl.tiles_h * pl.tiles_w;
         const int cpsm = (pl.smem <= 100 * 1024 && cols <= 256) ? 2 : 1;
         const int slots = kNumSMs * cpsm;
         const int waves = cdiv(tiles, slots);
-        const double t_load = (static_cast<double>(pl.box_rows) * kw_total * 4 + static_cast<double>(taps) * BN * kw_total * 4) / 40.0 * cpsm;
+        const double t_load = (static_cast<double>(planes) * pl.box_rows * kw_total * 4 + static_cast<double>(taps) * BN * kw_total * 4) / 40.0 * cpsm;
         // (a tcgen05.mma costs ~100 issue cycles whatever its N, but charging that here picks worse tiles in practice: measured)
         const double t_mma = static_cast<double>(pl.n_mt) * taps * (kw_total / 8) * std::max(BN / 2, 16) * cpsm;
         const double t_epi = static_cast<double>(pl.n_mt) * (BN / 16) * 120.0;
@@ -481,17 +507,55 @@ static int launch(const MfviConvDesc* d, bool dgrad, MfviView a, int Ca, int Ha,
   Args p{};
   p.n_chunks = split_chunks(Ca, p.ck0, p.cw);
   if (p.n_chunks <= 0) return -1;
-  const Plan pl = make_plan(d->S, Mh, Mw, d->KH, d->KW, p.n_chunks, p.cw, Nvalid, dgrad);
+  const int taps = d->KH * d->KW;
+  if (taps > 25) return -1;
+  const bool s2 = d->stride == 2;
+  const bool a_bcast = (a.sstride == 0 || d->S == 1);
+  int hh, hw, planes = 1, n_cls = 1, Th_space = Mh, Tw_space = Mw;
+  if (!s2) {
+    hh = d->KH - 1; hw = d->KW - 1;
+  } else {
+    if (d->KH < 2 || d->KW < 2) return -1;                 // 1x1 stride 2: parity classes without taps; left to conv_tc.cu
+    hh = (d->KH - 1) >> 1; hw = (d->KW - 1) >> 1;
+    if (!dgrad) {
+      // forward reads 4 parity planes through a 5-D view that folds the sample axis into the row axis
+      if ((Ha & 1) || (Wa & 1) || (!a_bcast && a.sstride != static_cast<long long>(Ha) * a.hstride)) return -1;
+      planes = 4;
+    } else {
+      n_cls = 4;
+      Th_space = (Mh + 1) / 2; Tw_space = (Mw + 1) / 2;    // largest parity class of dx
+    }
+  }
+  const Plan pl = make_plan(d->S, Th_space, Tw_space, hh, hw, taps, planes, n_cls, p.n_chunks, p.cw, Nvalid, dgrad);
   if (!pl.ok) return -1;
+  p.cstride = d->stride; p.hh = hh; p.hw = hw; p.planes = planes; p.plane_rows = pl.plane_rows; p.n_cls = n_cls;
+  p.org_h = dgrad ? hh : 0; p.org_w = dgrad ? hw : 0;
+  p.a_rows2 = Ha / 2;
+  for (int cls = 0; cls < 4; ++cls)
+    for (int tap = 0; tap < 25; ++tap) {
+      int off = -1;
+      if (tap < taps && cls < n_cls) {
+        const int r = tap / d->KW, sx = tap % d->KW;
+        if (!s2) {
+          off = dgrad ? (d->KH - 1 - r) * pl.Pw + (d->KW - 1 - sx) : r * pl.Pw + sx;
+        } else if (!dgrad) {
+          off = ((r & 1) * 2 + (sx & 1)) * pl.plane_rows + (r >> 1) * pl.Pw + (sx >> 1);
+        } else {
+          const int ph = cls >> 1, pw = cls & 1;
+          if ((r & 1) == ph && (sx & 1) == pw) off = (hh + (ph - r) / 2) * pl.Pw + (hw + (pw - sx) / 2);
+        }
+      }
+      p.tap_off[cls][tap] = off;
+    }
   p.N = Nvalid; p.BN = pl.BN; p.n_nb = pl.n_nb;
   p.KH = d->KH; p.KW = d->KW; p.taps = d->KH * d->KW; p.g = pl.g; p.n_groups = pl.n_groups;
   p.Mh = Mh; p.Mw = Mw; p.TH = pl.TH; p.TW = pl.TW; p.Pw = pl.Pw; p.tiles_h = pl.tiles_h; p.tiles_w = pl.tiles_w;
   p.n_mt = pl.n_mt;
-  p.tiles_per_sample = pl.n_nb * pl.tiles_h * pl.tiles_w;
+  p.tiles_per_sample = pl.n_nb * n_cls * pl.tiles_h * pl.tiles_w;
   p.total_tiles = d->S * p.tiles_per_sample;
   p.box_rows = pl.box_rows;
   p.dgrad = dgrad ? 1 : 0;
-  p.a_bcast = (a.sstride == 0 || d->S == 1) ? 1 : 0;
+  p.a_bcast = a_bcast ? 1 : 0;
   p.b_bcast = (w_sstride == 0 || d->S == 1) ? 1 : 0;
   p.n_a = pl.n_a; p.n_b = pl.n_b; p.acc_stages = pl.acc_stages;
   p.a_stage_bytes = pl.a_stage; p.b_stage_bytes = pl.b_stage; p.tmem_cols = pl.tmem_cols;
@@ -508,11 +572,19 @@ static int launch(const MfviConvDesc* d, bool dgrad, MfviView a, int Ca, int Ha,
   }
   CUtensorMap tmA, tmAt, tmB, tmBt;
   auto enc_a = [&](CUtensorMap* m, int width) {
+    if (planes == 4) {
+      const uint64_t dims[5] = {static_cast<uint64_t>(Ca), 2, static_cast<uint64_t>(Wa / 2), 2,
+                                static_cast<uint64_t>(Ha / 2) * (a_bcast ? 1 : d->S)};
+      const uint64_t strides[4] = {static_cast<uint64_t>(a.wstride) * 4, static_cast<uint64_t>(a.wstride) * 8,
+                                   static_cast<uint64_t>(a.hstride) * 4, static_cast<uint64_t>(a.hstride) * 8};
+      const uint32_t box[5] = {static_cast<uint32_t>(width), 1, static_cast<uint32_t>(pl.Pw), 1, static_cast<uint32_t>(pl.TH + hh)};
+      return tma_encode(m, a.ptr, 5, dims, strides, box, swz_of(width));
+    }
     const uint64_t dims[4] = {static_cast<uint64_t>(Ca), static_cast<uint64_t>(Wa), static_cast<uint64_t>(Ha),
                               static_cast<uint64_t>(p.a_bcast ? 1 : d->S)};
     const uint64_t sbytes = p.a_bcast ? static_cast<uint64_t>(a.hstride) * Ha * 4 : static_cast<uint64_t>(a.sstride) * 4;
     const uint64_t strides[3] = {static_cast<uint64_t>(a.wstride) * 4, static_cast<uint64_t>(a.hstride) * 4, sbytes};
-    const uint32_t box[4] = {static_cast<uint32_t>(width), static_cast<uint32_t>(pl.Pw), static_cast<uint32_t>(pl.TH + d->KH - 1), 1};
+    const uint32_t box[4] = {static_cast<uint32_t>(width), static_cast<uint32_t>(pl.Pw), static_cast<uint32_t>(pl.TH + hh), 1};
     return tma_encode(m, a.ptr, 4, dims, strides, box, swz_of(width));
   };
   auto enc_b = [&](CUtensorMap* m, int width) {
@@ -563,7 +635,8 @@ extern "C" {
 int mfvi_conv2d_fwd_tc2(const MfviConvDesc* d, MfviView x, const float* w, const float* bias, long long w_sstride, MfviView y,
                         double* stats, mfvi_stream_t st) {
   static const bool on = tc2::env_int("MFVI_TC2", 1) != 0;
-  if (!on || d->stride != 1 || !tc2::view_ok(x, d->Cin) || (reinterpret_cast<uintptr_t>(w) % 16) || (w_sstride % 4) || d->Cin % 4 ||
+  static const bool on2 = tc2::env_int("MFVI_TC2_S2", 1) != 0;
+  if (!on || !(d->stride == 1 || (d->stride == 2 && on2)) || !tc2::view_ok(x, d->Cin) || (reinterpret_cast<uintptr_t>(w) % 16) || (w_sstride % 4) || d->Cin % 4 ||
       d->Cout > 256)
     return -1;
   return tc2::launch(d, false, x, d->Cin, d->Hin, d->Win, w, w_sstride, y, d->Hout, d->Wout, d->Cout, bias, stats, 0, st,
@@ -573,7 +646,8 @@ int mfvi_conv2d_fwd_tc2(const MfviConvDesc* d, MfviView x, const float* w, const
 int mfvi_conv2d_dgrad_tc2(const MfviConvDesc* d, MfviView dy, const float* w, long long w_sstride, MfviView dx, int accumulate,
                           mfvi_stream_t st) {
   static const bool on = tc2::env_int("MFVI_TC2", 1) != 0;
-  if (!on || d->stride != 1 || !tc2::view_ok(dy, d->Cout) || (reinterpret_cast<uintptr_t>(w) % 16) || (w_sstride % 4) || d->Cin % 4 ||
+  static const bool on2 = tc2::env_int("MFVI_TC2_S2", 1) != 0;
+  if (!on || !(d->stride == 1 || (d->stride == 2 && on2)) || !tc2::view_ok(dy, d->Cout) || (reinterpret_cast<uintptr_t>(w) % 16) || (w_sstride % 4) || d->Cin % 4 ||
       d->Cin > 256)
     return -1;
   return tc2::launch(d, true, dy, d->Cout, d->Hout, d->Wout, w, w_sstride, dx, d->Hin, d->Win, d->Cin, nullptr, nullptr, accumulate, st,
