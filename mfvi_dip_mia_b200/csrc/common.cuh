@@ -72,7 +72,9 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& z0, float& z1) {
   const float u1 = (static_cast<float>(xa >> 8) + 0.5f) * 5.9604644775390625e-08f;  // 2^-24
   const float u2 = (static_cast<float>(xb >> 8) + 0.5f) * 5.9604644775390625e-08f;
-  const float r = sqrtf(-2.0f * __logf(u1));
+  // logf, not __logf: the fast intrinsic's absolute error (~4e-7 near u1 = 1) becomes a ~2e-5 error of eps, which is 100x
+  // the fp32 rounding of the sampled weights and makes long trajectories drift away from the reference faster than necessary
+  const float r = sqrtf(-2.0f * logf(u1));
   float sn, cs;
   sincospif(2.0f * u2, &sn, &cs);
   z0 = r * cs;

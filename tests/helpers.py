@@ -56,3 +56,14 @@ def grad_errs(ours, ref, floor_frac=1e-3, bias_frac=0.05):
                 den = max(den, bias_frac * float(torch.as_tensor(ref[wk]).abs().max()))
         out[k] = float((a - b).abs().max()) / den
     return out
+
+
+def fake_trial(temp, sigma, device, offset=0.0):
+    """Stand-in for a trial runner in the CPU test of the trial fan-out: objective = a smooth function of the candidate;
+    one candidate diverges (NaN) and one crashes."""
+    import math
+    if temp == 3.0:
+        return float("nan")
+    if temp == 4.0:
+        raise RuntimeError("boom")
+    return offset + math.log10(temp) - 2.0 * math.log10(sigma) + (0.0 if device == "cpu:0" else 0.5)

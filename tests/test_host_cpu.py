@@ -165,3 +165,18 @@ def test_bench_reference_arm_prints_contract_line():
         assert k in line, k
     assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]
+
+
+def test_trial_fanout_round_robin_and_nan_filter():
+    """eval_trials: one process per candidate, devices round-robin, NaN / crashed trials dropped
+    (reference bayesian_optimization.py:3756-3781)."""
+    from mfvi_dip_mia_b200.runners import eval_trials, log_grid
+    from tests.helpers import fake_trial
+    cands = [(1.0, 0.1), (2.0, 0.1), (3.0, 0.1), (4.0, 0.1), (5.0, 0.01)]
+    X, Y = eval_trials(cands, ["cpu:0", "cpu:1"], fake_trial, {"offset": 1.0}, start_method="fork")
+    assert X == [(1.0, 0.1), (2.0, 0.1), (5.0, 0.01)]
+    import math
+    exp = [1.0 + math.log10(t) - 2 * math.log10(s) + (0.0 if i % 2 == 0 else 0.5) for i, (t, s) in zip([0, 1, 4], X)]
+    assert all(abs(a - b) < 1e-12 for a, b in zip(Y, exp))
+    g = log_grid([[-10, 0], [-10, 0]], 8)
+    assert len(g) == 64 and abs(g[0][0] - 1e-10) < 1e-20 and abs(g[-1][1] - 1.0) < 1e-12
