@@ -181,6 +181,39 @@ int mfvi_adamw_step(float* p, const float* g, float* m, float* v, size_t n, floa
  * (effective AdamW step = step + *step_dev). */
 int mfvi_counter_add(uint32_t* ctr, uint32_t inc, mfvi_stream_t st);
 
+/* ---- f1: per-iteration bookkeeping of the runners (bayesian_optimization.py:1374-1416) ----------------------
+ * One launch per iteration, no host synchronisation, CUDA-graph capturable.  it = iter_offset + *iter_dev.
+ *   cur = (mean_s out[s,.,0], mean_s exp(-out[s,.,1]));  out_avg[2][H][W] = it==0 ? cur : out_avg*w + cur*(1-w);
+ *   ring_epi[it % ring] = clip01(cur_mean), ring_ale[it % ring] = clip01(cur_var)   (ring may be 0);
+ *   acc[0] += sum (noisy - clip(mean))^2     acc[1] += sum (gt - clip(mean))^2    acc[2] += sum (gt - clip(avg_mean))^2
+ *   acc[3] += sum (noisy - avg_mean)^2       acc[4] += sum (gt - avg_mean)^2      (caller zeroes acc; gt/noisy optional)
+ * PSNR = 10*log10(H*W/acc[k])  (utils/common_utils.py:297-305). */
+int mfvi_bookkeep_step(MfviView out, int S, int H, int W, float exp_weight, const float* gt, const float* noisy,
+                       float* out_avg, float* ring_epi, float* ring_ale, int ring, const uint32_t* iter_dev,
+                       int iter_offset, double* acc, mfvi_stream_t st);
+/* out_sum[0] += sum over pixels of the SSIM map of (a, b) — 11x11 Gaussian window sigma 1.5, zero padding
+ * (utils/common_utils.py:308-353); clip_b != 0 clips b to [0,1] first.  SSIM = out_sum/(H*W). */
+int mfvi_ssim(const float* a, const float* b, int H, int W, int clip_b, double* out_sum, mfvi_stream_t st);
+/* epi = unbiased variance over the first n ring entries, ale = their mean variance (bayesian_optimization.py:1410-1411),
+ * err2 (optional, needs gt) = mean_n (ring_epi - gt)^2 for the UCE calibration curve (eval_denoising.ipynb:467-482). */
+int mfvi_ring_uncertainty(const float* ring_epi, const float* ring_ale, int n, int H, int W, const float* gt, float* epi,
+                          float* ale, float* err2, mfvi_stream_t st);
+
+/* ---- f3: local-reparameterisation layers (BayTorch/modules/reparam_layers.py:39-72) ------------------------------
+ * LRTLayer.forward = conv(x, W_mu, b_mu) + sqrt(1e-16 + conv(x^2, softplus(W_rho)^2, softplus(b_rho)^2)) * eps.  The two
+ * convolutions are mfvi_conv2d_{fwd,dgrad,wgrad} with one weight set for the whole batch (w_sstride 0); these are the
+ * flat elementwise pieces and their backward chains (n contiguous floats each):
+ *   softplus_sq_fwd : sigma2 = softplus(rho)^2           softplus_sq_bwd : drho (+)= dsigma2 * 2*softplus(rho)*sigmoid(rho)
+ *   square_fwd      : x2 = x*x                           square_bwd      : dx   (+)= dx2 * 2*x
+ *   lrt_noise_fwd   : out = act_mu + sqrt(1e-16+act_var)*eps
+ *   lrt_noise_bwd   : dvar = dout * eps / (2*sqrt(1e-16+act_var))           (d act_mu = dout) */
+int mfvi_softplus_sq_fwd(const float* rho, size_t n, float* sigma2, mfvi_stream_t st);
+int mfvi_softplus_sq_bwd(const float* rho, const float* dsigma2, size_t n, float* drho, int accumulate, mfvi_stream_t st);
+int mfvi_square_fwd(const float* x, size_t n, float* x2, mfvi_stream_t st);
+int mfvi_square_bwd(const float* x, const float* dx2, size_t n, float* dx, int accumulate, mfvi_stream_t st);
+int mfvi_lrt_noise_fwd(const float* act_mu, const float* act_var, const float* eps, size_t n, float* out, mfvi_stream_t st);
+int mfvi_lrt_noise_bwd(const float* dout, const float* act_var, const float* eps, size_t n, float* dvar, mfvi_stream_t st);
+
 /* small utilities used by the host side */
 int mfvi_fill_f32(float* p, size_t n, float v, mfvi_stream_t st);
 int mfvi_nchw_to_nhwc(const float* src, float* dst, int N, int C, int H, int W, mfvi_stream_t st);

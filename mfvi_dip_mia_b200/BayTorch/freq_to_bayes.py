@@ -19,7 +19,7 @@ import torch.nn as nn
 
 from .. import _lib as L
 from ..engine import SkipEngine
-from .modules import Conv2dRT, LinearRT
+from .modules import Conv2dLRT, Conv2dRT, LinearLRT, LinearRT, VIModule
 
 
 class _FusedForward(torch.autograd.Function):
@@ -97,11 +97,11 @@ class MeanFieldVI(nn.Module):
         super().__init__()
         self.net = net
         self.device = torch.device(device)
-        if reparam == 'local':
-            raise NotImplementedError(
-                "reparam='local' (Conv2dLRT/LinearLRT) is not part of the MFVI-DIP hot path: every runner passes "
-                "reparam='' (reference bayesian_optimization.py:1342). Pass reparam=''.")
-        self._conv2d, self._linear = Conv2dRT, LinearRT
+        # reparam='local' (the reference's default, freq_to_bayes.py:22-25) builds local-reparameterisation layers; they
+        # run module by module on the library's kernels.  The fused whole-network engine serves reparam='' (weight-space
+        # sampling), which is what every MFVI runner passes (bayesian_optimization.py:1342).
+        self._local = reparam == 'local'
+        self._conv2d, self._linear = (Conv2dLRT, LinearLRT) if self._local else (Conv2dRT, LinearRT)
         assert replace_layers in ['up', 'down', 'all', 'none']
         self._replace_layers = '' if replace_layers == 'all' else replace_layers
         self.mc_samples, self.sample0, self.math = int(mc_samples), int(sample0), math
@@ -110,8 +110,8 @@ class MeanFieldVI(nn.Module):
         self._replace_deterministic_modules(self.net, prior, posteriors, kl_type)
         self.net = net.to(self.device)
         n_left = sum(isinstance(m, (nn.Conv2d, nn.Linear)) for m in net.modules())
-        vi = [m for m in net.modules() if isinstance(m, (Conv2dRT, LinearRT))]
-        self._spec = getattr(net, "_skip_spec", None) if (n_left == 0 and n_conv_before > 0) else None
+        vi = [m for m in net.modules() if isinstance(m, VIModule)]
+        self._spec = getattr(net, "_skip_spec", None) if (n_left == 0 and n_conv_before > 0 and not self._local) else None
         if vi:
             self._prior_mu, self._prior_scale = vi[0].prior_loc, vi[0].prior_scale
             self._direction = 0 if vi[0].kl_type == 'reverse' else 1
@@ -215,6 +215,6 @@ class MeanFieldVI(nn.Module):
             return _FusedKl.apply(self._anchor, self)
         kl = torch.zeros(1, dtype=torch.float32, device=self.device)
         for layer in self.modules():
-            if isinstance(layer, (Conv2dRT, LinearRT)):
+            if isinstance(layer, VIModule):
                 kl = kl + layer._kl
         return kl

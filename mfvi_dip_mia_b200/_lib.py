@@ -69,6 +69,15 @@ _SIGS = {
     "mfvi_input_jitter_pad": [_P, _P, _I, _I, _I, _F, _I, PhiloxKey, View],
     "mfvi_adamw_step": [_P, _P, _P, _P, _SZ, _F, _F, _F, _F, _F, _I, _P, _P],
     "mfvi_counter_add": [_P, _U32],
+    "mfvi_bookkeep_step": [View, _I, _I, _I, _F, _P, _P, _P, _P, _P, _I, _P, _I, _P],
+    "mfvi_ssim": [_P, _P, _I, _I, _I, _P],
+    "mfvi_ring_uncertainty": [_P, _P, _I, _I, _I, _P, _P, _P, _P],
+    "mfvi_softplus_sq_fwd": [_P, _SZ, _P],
+    "mfvi_softplus_sq_bwd": [_P, _P, _SZ, _P, _I],
+    "mfvi_square_fwd": [_P, _SZ, _P],
+    "mfvi_square_bwd": [_P, _P, _SZ, _P, _I],
+    "mfvi_lrt_noise_fwd": [_P, _P, _P, _SZ, _P],
+    "mfvi_lrt_noise_bwd": [_P, _P, _P, _SZ, _P],
     "mfvi_fill_f32": [_P, _SZ, _F],
     "mfvi_nchw_to_nhwc": [_P, _P, _I, _I, _I, _I],
     "mfvi_nhwc_to_nchw": [_P, _P, _I, _I, _I, _I],

@@ -75,12 +75,16 @@ __global__ void k_sample_weights(const float* __restrict__ mu, const float* __re
   pdl_wait();
   const size_t nb = (n + 3) / 4;
   const uint32_t step = eff_step(key);
-  const bool vec = (n % 4 == 0) && (w_sstride % 4 == 0) && (eps == nullptr || eps_sstride % 4 == 0);
+  // vector path per 4-element block: strides keep 16-byte alignment; only the last (partial) block of n goes scalar
+  const bool vec_ok = (w_sstride % 4 == 0) && (eps == nullptr || eps_sstride % 4 == 0) &&
+                      ((reinterpret_cast<uintptr_t>(mu) | reinterpret_cast<uintptr_t>(rho) | reinterpret_cast<uintptr_t>(w_out) |
+                        reinterpret_cast<uintptr_t>(eps)) % 16 == 0);
   for (size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x; b < nb; b += (size_t)gridDim.x * blockDim.x) {
+    const bool vec = vec_ok && (b * 4 + 4 <= n);
     float m[4], sg[4];
     if (vec) {
-      const float4 m4 = reinterpret_cast<const float4*>(mu)[b];
-      const float4 r4 = reinterpret_cast<const float4*>(rho)[b];
+      const float4 m4 = __ldg(reinterpret_cast<const float4*>(mu) + b);
+      const float4 r4 = __ldg(reinterpret_cast<const float4*>(rho) + b);
       m[0] = m4.x; m[1] = m4.y; m[2] = m4.z; m[3] = m4.w;
       sg[0] = softplus_f(r4.x); sg[1] = softplus_f(r4.y); sg[2] = softplus_f(r4.z); sg[3] = softplus_f(r4.w);
     } else {
@@ -93,9 +97,14 @@ __global__ void k_sample_weights(const float* __restrict__ mu, const float* __re
     for (int s = 0; s < S; ++s) {
       float e[4];
       if (eps != nullptr) {
-        for (int j = 0; j < 4; ++j) {
-          const size_t i = b * 4 + j;
-          e[j] = i < n ? eps[(size_t)s * eps_sstride + i] : 0.f;
+        if (vec) {
+          const float4 e4 = __ldg(reinterpret_cast<const float4*>(eps + (size_t)s * eps_sstride) + b);
+          e[0] = e4.x; e[1] = e4.y; e[2] = e4.z; e[3] = e4.w;
+        } else {
+          for (int j = 0; j < 4; ++j) {
+            const size_t i = b * 4 + j;
+            e[j] = i < n ? eps[(size_t)s * eps_sstride + i] : 0.f;
+          }
         }
       } else {
         const float4 z = philox_normal4((uint32_t)b, MFVI_STREAM_WEIGHTS, key.sample0 + s, step, key.seed);
@@ -131,33 +140,84 @@ k_kl_reparam(const float* __restrict__ mu, const float* __restrict__ rho, size_t
   const uint32_t step = eff_step(key);
   if (kscale_dev != nullptr) kscale *= *kscale_dev;
   double kl_acc = 0.0;
+  const bool vec_ok = (dw == nullptr || dw_sstride % 4 == 0) && (eps == nullptr || eps_sstride % 4 == 0) &&
+                      ((reinterpret_cast<uintptr_t>(mu) | reinterpret_cast<uintptr_t>(rho) | reinterpret_cast<uintptr_t>(dw) |
+                        reinterpret_cast<uintptr_t>(eps) | reinterpret_cast<uintptr_t>(grad_mu) |
+                        reinterpret_cast<uintptr_t>(grad_rho)) % 16 == 0);
   for (size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x; b < nb; b += (size_t)gridDim.x * blockDim.x) {
+    const bool vec = vec_ok && (b * 4 + 4 <= n);
     float gm[4] = {0.f, 0.f, 0.f, 0.f}, ge[4] = {0.f, 0.f, 0.f, 0.f};
-    if (dw != nullptr) {
-      for (int s = 0; s < S; ++s) {
-        float e[4];
-        if (eps == nullptr) {
-          const float4 z = philox_normal4((uint32_t)b, MFVI_STREAM_WEIGHTS, key.sample0 + s, step, key.seed);
-          e[0] = z.x; e[1] = z.y; e[2] = z.z; e[3] = z.w;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const size_t i = b * 4 + j;
-          if (i < n) {
-            const float d = dw[(size_t)s * dw_sstride + i];
-            const float ee = eps != nullptr ? eps[(size_t)s * eps_sstride + i] : e[j];
-            gm[j] += d;
-            ge[j] = fmaf(d, ee, ge[j]);
+    float mr[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    float gold[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    if (vec) {
+      const float4 m4 = __ldg(reinterpret_cast<const float4*>(mu) + b), r4 = __ldg(reinterpret_cast<const float4*>(rho) + b);
+      mr[0][0] = m4.x; mr[0][1] = m4.y; mr[0][2] = m4.z; mr[0][3] = m4.w;
+      mr[1][0] = r4.x; mr[1][1] = r4.y; mr[1][2] = r4.z; mr[1][3] = r4.w;
+      if (accumulate && grad_mu != nullptr) {
+        const float4 a4 = reinterpret_cast<const float4*>(grad_mu)[b], c4 = reinterpret_cast<const float4*>(grad_rho)[b];
+        gold[0][0] = a4.x; gold[0][1] = a4.y; gold[0][2] = a4.z; gold[0][3] = a4.w;
+        gold[1][0] = c4.x; gold[1][1] = c4.y; gold[1][2] = c4.z; gold[1][3] = c4.w;
+      }
+    } else {
+      for (int j = 0; j < 4; ++j) {
+        const size_t i = b * 4 + j;
+        if (i < n) {
+          mr[0][j] = mu[i];
+          mr[1][j] = rho[i];
+          if (accumulate && grad_mu != nullptr) {
+            gold[0][j] = grad_mu[i];
+            gold[1][j] = grad_rho[i];
           }
         }
       }
     }
+    if (dw != nullptr) {
+      if (vec) {
+        // the S gradient rows are independent streams: issue the loads of a group of 4 samples before the Philox work
+        for (int s0 = 0; s0 < S; s0 += 4) {
+          float4 d4[4], e4[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int s = s0 + u < S ? s0 + u : S - 1;
+            d4[u] = __ldg(reinterpret_cast<const float4*>(dw + (size_t)s * dw_sstride) + b);
+            if (eps != nullptr) e4[u] = __ldg(reinterpret_cast<const float4*>(eps + (size_t)s * eps_sstride) + b);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (s0 + u >= S) break;
+            if (eps == nullptr) e4[u] = philox_normal4((uint32_t)b, MFVI_STREAM_WEIGHTS, key.sample0 + s0 + u, step, key.seed);
+            gm[0] += d4[u].x; gm[1] += d4[u].y; gm[2] += d4[u].z; gm[3] += d4[u].w;
+            ge[0] = fmaf(d4[u].x, e4[u].x, ge[0]); ge[1] = fmaf(d4[u].y, e4[u].y, ge[1]);
+            ge[2] = fmaf(d4[u].z, e4[u].z, ge[2]); ge[3] = fmaf(d4[u].w, e4[u].w, ge[3]);
+          }
+        }
+      } else {
+        for (int s = 0; s < S; ++s) {
+          float e[4];
+          if (eps == nullptr) {
+            const float4 z = philox_normal4((uint32_t)b, MFVI_STREAM_WEIGHTS, key.sample0 + s, step, key.seed);
+            e[0] = z.x; e[1] = z.y; e[2] = z.z; e[3] = z.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const size_t i = b * 4 + j;
+            if (i < n) {
+              const float d = dw[(size_t)s * dw_sstride + i];
+              const float ee = eps != nullptr ? eps[(size_t)s * eps_sstride + i] : e[j];
+              gm[j] += d;
+              ge[j] = fmaf(d, ee, ge[j]);
+            }
+          }
+        }
+      }
+    }
+    float ga[4], gc[4];
     float kl_local = 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const size_t i = b * 4 + j;
       if (i >= n) continue;
-      const float m = mu[i], r = rho[i];
+      const float m = mr[0][j], r = mr[1][j];
       const float sig = softplus_f(r);
       const float sgm = sigmoid_f(r);
       const float dm = m - mp;
@@ -178,16 +238,16 @@ k_kl_reparam(const float* __restrict__ mu, const float* __restrict__ rho, size_t
         dkl_dsig = sig * inv * inv - 1.f / sig;
       }
       kl_local += kl;
-      if (grad_mu != nullptr) {
-        float a = gscale * gm[j] + kscale * dkl_dmu;
-        float c = (gscale * ge[j] + kscale * dkl_dsig) * sgm;
-        if (accumulate) {
-          a += grad_mu[i];
-          c += grad_rho[i];
-        }
-        grad_mu[i] = a;
-        grad_rho[i] = c;
+      ga[j] = gscale * gm[j] + kscale * dkl_dmu + gold[0][j];
+      gc[j] = (gscale * ge[j] + kscale * dkl_dsig) * sgm + gold[1][j];
+      if (grad_mu != nullptr && !vec) {
+        grad_mu[i] = ga[j];
+        grad_rho[i] = gc[j];
       }
+    }
+    if (grad_mu != nullptr && vec) {
+      reinterpret_cast<float4*>(grad_mu)[b] = make_float4(ga[0], ga[1], ga[2], ga[3]);
+      reinterpret_cast<float4*>(grad_rho)[b] = make_float4(gc[0], gc[1], gc[2], gc[3]);
     }
     kl_acc += (double)kl_local;
   }
@@ -344,6 +404,46 @@ k_adamw(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ 
 }
 
 // xp[hp][wp][c] = saved[h][w][c] + std * z(c,h,w);  (h,w) = reflect(hp-pad, wp-pad)
+// padded positions whose reflection is source index h (per dimension): fills q[0..cnt)
+__device__ __forceinline__ int jitter_targets(int h, int n, int pad, int (&q)[3]) {
+  int cnt = 0;
+  q[cnt++] = h + pad;
+  if (h >= 1 && h <= pad) q[cnt++] = pad - h;
+  if (h <= n - 2 && h >= n - 1 - pad) q[cnt++] = 2 * (n - 1) - h + pad;
+  return cnt;
+}
+
+// One thread per (h, 4 consecutive w, c): ONE Philox block yields the four normals of NCHW flat indices (c,h,w..w+3)
+// (W % 4 == 0), each written to its interior position and to the border positions that reflect onto it.
+__global__ void __launch_bounds__(256)
+k_input_jitter_pad4(const float* __restrict__ saved, int H, int W, int C, float stdv, int pad, MfviPhiloxKey key, MfviView xp) {
+  pdl_trigger();
+  pdl_wait();
+  const int W4 = W >> 2;
+  const int total = H * W4 * C;
+  const uint32_t step = eff_step(key);
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int c = idx % C;
+    const int g = idx / C;
+    const int w0 = (g % W4) << 2, h = g / W4;
+    const uint32_t flat = (static_cast<uint32_t>(c) * H + h) * W + w0;
+    const float4 z4 = philox_normal4(flat >> 2, MFVI_STREAM_INPUT_JITTER, key.sample0, step, key.seed);
+    const float z[4] = {z4.x, z4.y, z4.z, z4.w};
+    int qh[3];
+    const int nh = jitter_targets(h, H, pad, qh);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int w = w0 + j;
+      const float v = fmaf(stdv, z[j], __ldg(saved + (static_cast<size_t>(h) * W + w) * C + c));
+      int qw[3];
+      const int nw = jitter_targets(w, W, pad, qw);
+      for (int a = 0; a < nh; ++a)
+        for (int b = 0; b < nw; ++b)
+          xp.ptr[static_cast<size_t>(qh[a]) * xp.hstride + static_cast<size_t>(qw[b]) * xp.wstride + c] = v;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_input_jitter_pad(const float* __restrict__ saved, const float* __restrict__ noise, int H, int W, int C, float stdv,
                    int pad, MfviPhiloxKey key, MfviView xp) {
@@ -451,7 +551,7 @@ int mfvi_kl_reparam_fwd_bwd(const float* mu, const float* rho, size_t n, float p
   MFVI_REQUIRE(direction == 0 || direction == 1, "kl_reparam: direction must be 0 (reverse) or 1 (forward)");
   if (n == 0) return 0;
   if (S <= 0) dw = nullptr;
-  launch_k(k_kl_reparam, grid_for((n + 3) / 4, 256, 4), 256, 0, as_stream(st), 
+  launch_k(k_kl_reparam, grid_for((n + 3) / 4, 256, 8), 256, 0, as_stream(st), 
       mu, rho, n, prior_mu, (float)prior_sigma_plus_eps, direction, kscale, kscale_dev, dw, dw_sstride, S, eps, eps_sstride, key,
       gscale, kl_out, grad_mu, grad_rho, accumulate);
   return check_launch("kl_reparam");
@@ -499,8 +599,11 @@ int mfvi_input_jitter_pad(const float* saved, const float* noise, int H, int W, 
                           MfviPhiloxKey key, MfviView xp, mfvi_stream_t st) {
   MFVI_REQUIRE(saved && xp.ptr, "input_jitter_pad: null pointer");
   MFVI_REQUIRE(pad >= 0 && pad < H && pad < W, "input_jitter_pad: pad must be smaller than the image");
-  launch_k(k_input_jitter_pad, grid_for((size_t)(H + 2 * pad) * (W + 2 * pad) * C, 256), 256, 0, as_stream(st), 
-      saved, noise, H, W, C, stdv, pad, key, xp);
+  if (noise == nullptr && W % 4 == 0 && 2 * pad < H && 2 * pad < W && (size_t)H * W * C < (1u << 31))
+    launch_k(k_input_jitter_pad4, grid_for((size_t)H * (W / 4) * C, 256), 256, 0, as_stream(st), saved, H, W, C, stdv, pad, key, xp);
+  else
+    launch_k(k_input_jitter_pad, grid_for((size_t)(H + 2 * pad) * (W + 2 * pad) * C, 256), 256, 0, as_stream(st),
+             saved, noise, H, W, C, stdv, pad, key, xp);
   return check_launch("input_jitter_pad");
 }
 

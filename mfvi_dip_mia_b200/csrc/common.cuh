@@ -72,11 +72,15 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& z0, float& z1) {
   const float u1 = (static_cast<float>(xa >> 8) + 0.5f) * 5.9604644775390625e-08f;  // 2^-24
   const float u2 = (static_cast<float>(xb >> 8) + 0.5f) * 5.9604644775390625e-08f;
-  // logf, not __logf: the fast intrinsic's absolute error (~4e-7 near u1 = 1) becomes a ~2e-5 error of eps, which is 100x
-  // the fp32 rounding of the sampled weights and makes long trajectories drift away from the reference faster than necessary
-  const float r = sqrtf(-2.0f * logf(u1));
+  // MUFU-based log / sin / cos: drawing the S*P normals of a step is otherwise instruction-bound (~30 us per pass with
+  // logf / sincospif vs the ~8 us its HBM traffic takes).  The angle is shifted into [-pi, pi), where the fast sine and
+  // cosine are accurate to ~4e-7 absolute: cos(2 pi u) = -cos(2 pi u - pi).  |z - z_fp64| stays below ~1e-5
+  // (tests/test_gpu_parity.py::test_philox_bit_exact_and_normals); the uniform bits themselves are bit-exact.
+  const float r = sqrtf(-2.0f * __logf(u1));
   float sn, cs;
-  sincospif(2.0f * u2, &sn, &cs);
+  __sincosf(fmaf(u2, 6.283185307179586f, -3.141592653589793f), &sn, &cs);
+  sn = -sn;
+  cs = -cs;
   z0 = r * cs;
   z1 = r * sn;
 }

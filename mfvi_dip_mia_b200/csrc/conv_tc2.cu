@@ -309,23 +309,26 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           s1[i] = 0.f;
           s2[i] = 0.f;
         }
+        if (n0 + c >= p.N) break;          // column groups beyond the valid channels (N padded up to the UMMA granule)
         const bool full16 = n0 + c + 15 < p.N;
-#pragma unroll 1
-        for (int j = 0; j < p.n_mt; ++j) {
+        // one M tile: bias, BatchNorm partials, store.  The TMEM load of the NEXT M tile is in flight meanwhile.
+        auto consume = [&](const uint32_t (&r)[16], int j) {
           const int pos = j * 128 + q * 32 + lane;
           const int hl = pos / p.Pw, wl = pos - hl * p.Pw;
           // stride-2 dgrad: this tile is output-parity class (cls >> 1, cls & 1) of dx, written with pixel stride 2
           const int gh = (tc.th * p.TH + hl) * ostr + (tc.cls >> 1), gw = (tc.tw * p.TW + wl) * ostr + (tc.cls & 1);
           const bool valid = hl < p.TH && wl < p.TW && gh < p.Mh && gw < p.Mw;
-          float v[16];
-          tmem_ld16(tbase + static_cast<uint32_t>(j * p.BN + c), v);
           if (valid) {
+            float v[16];
             float* optr = obase + static_cast<size_t>(gh) * p.o.hstride + static_cast<size_t>(gw) * p.o.wstride + c;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              v[i] += b[i];
-              s1[i] += v[i];
-              s2[i] = fmaf(v[i], v[i], s2[i]);
+              v[i] = __uint_as_float(r[i]);
+              if (!DGRAD) {                      // bias and BatchNorm partials exist in the forward only
+                v[i] += b[i];
+                s1[i] += v[i];
+                s2[i] = fmaf(v[i], v[i], s2[i]);
+              }
             }
             if (p.vecO && full16) {
 #pragma unroll
@@ -344,8 +347,21 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 if (n0 + c + i < p.N) optr[i] = p.accumulate ? optr[i] + v[i] : v[i];
             }
           }
+        };
+        uint32_t ra[16], rb[16];
+        tmem_ld16_issue(tbase + static_cast<uint32_t>(c), ra);
+#pragma unroll 1
+        for (int j = 0; j < p.n_mt; j += 2) {
+          tmem_ld16_wait(ra);
+          if (j + 1 < p.n_mt) tmem_ld16_issue(tbase + static_cast<uint32_t>((j + 1) * p.BN + c), rb);
+          consume(ra, j);
+          if (j + 1 < p.n_mt) {
+            tmem_ld16_wait(rb);
+            if (j + 2 < p.n_mt) tmem_ld16_issue(tbase + static_cast<uint32_t>((j + 2) * p.BN + c), ra);
+            consume(rb, j + 1);
+          }
         }
-        if (p.stats != nullptr) {
+        if (!DGRAD && p.stats != nullptr) {
           // (sum, sumsq) of 16 channels: per-lane fp32 partials over <= n_mt rows, then a transposing butterfly across the
           // 32 lanes in double (fixed order).  Lane l ends up with the total of cell l: l < 16 -> sum of channel c+l,
           // l >= 16 -> sum of squares of channel c+l-16.
@@ -470,10 +486,14 @@ static Plan make_plan(int S, int Mh, int Mw, int hh, int hw, int taps, int plane
         const int slots = kNumSMs * cpsm;
         const int waves = cdiv(tiles, slots);
         const double t_load = (static_cast<double>(planes) * pl.box_rows * kw_total * 4 + static_cast<double>(taps) * BN * kw_total * 4) / 40.0 * cpsm;
-        // (a tcgen05.mma costs ~100 issue cycles whatever its N, but charging that here picks worse tiles in practice: measured)
-        const double t_mma = static_cast<double>(pl.n_mt) * taps * (kw_total / 8) * std::max(BN / 2, 16) * cpsm;
-        const double t_epi = static_cast<double>(pl.n_mt) * (BN / 16) * 120.0;
-        const double t_tile = std::max(t_load, std::max(t_mma, t_epi)) + 500.0;
+        // measured (profiles/r01_umma_rate_probe.txt, conv timelines): a kind::tf32 M=128 MMA issues every ~39 cycles up to
+        // N=48 and ~N/2 beyond, plus ~6 cycles of loop overhead; an epilogue unit (128 rows x 16 columns) costs ~300 cycles
+        const double mma_cyc = std::max(39.0 + 0.2 * (BN - 16), 0.5 * BN) + 6.0;
+        const double t_mma = static_cast<double>(pl.n_mt) * taps * (kw_total / 8) * mma_cyc * cpsm;
+        const int n_units = cdiv(std::min(Nvalid, BN), 16);
+        const double t_epi = static_cast<double>(pl.n_mt) * n_units * 300.0;
+        // with a single accumulator stage the epilogue of tile i cannot overlap the MMAs of tile i+1
+        const double t_tile = (pl.acc_stages == 2 ? std::max(t_load, std::max(t_mma, t_epi)) : std::max(t_load, t_mma + t_epi)) + 500.0;
         pl.cost = 5000.0 + waves * t_tile + std::min(t_load, 4000.0);
         pl.grid = std::min(tiles, slots);
         pl.ok = true;

@@ -127,6 +127,101 @@ class SampledConv2dFn(torch.autograd.Function):
         return dx, gWm, gWr, gbm, gbr, None, None, None, None, None, None
 
 
+def _pad_nhwc(xh, padding):
+    if not padding:
+        return xh
+    N, H, W, Cin = xh.shape
+    xp = torch.zeros(N, H + 2 * padding, W + 2 * padding, Cin, dtype=torch.float32, device=xh.device)
+    xp[:, padding:padding + H, padding:padding + W] = xh
+    return xp
+
+
+class LrtConv2dFn(torch.autograd.Function):
+    """LRTLayer.forward with layer_fn=conv2d (reference reparam_layers.py:39-72, conv.py:75-107):
+        act_mu = conv(x, W_mu, b_mu);  act_var = conv(x^2, softplus(W_rho)^2, softplus(b_rho)^2)
+        out = act_mu + sqrt(1e-16 + act_var) * eps            (training)      out = act_mu   (eval)
+    with eps of the OUTPUT's shape.  Both convolutions and every elementwise piece run on libmfvidip kernels."""
+
+    @staticmethod
+    def forward(ctx, x, W_mu, W_rho, b_mu, b_rho, eps, stride, padding, training, math):
+        L.require_cuda(x, "Conv2dLRT")
+        N, Cin, H, W = x.shape
+        Cout, _, KH, KW = W_mu.shape
+        has_bias = b_mu is not None
+        dev = x.device
+        xh = _pad_nhwc(to_nhwc(x.detach().float()), padding)
+        Hin, Win = xh.shape[1], xh.shape[2]
+        Ho, Wo = (Hin - KH) // stride + 1, (Win - KW) // stride + 1
+        d = L.ConvDesc(N, Cin, Cout, KH, KW, stride, Hin, Win, Ho, Wo, math)
+        wt = W_mu.detach().permute(2, 3, 0, 1).contiguous()           # tap-major [KH][KW][Cout][Cin]
+        bm = b_mu.detach().contiguous() if has_bias else None
+        act_mu = torch.empty(N, Ho, Wo, Cout, dtype=torch.float32, device=dev)
+        L.call("mfvi_conv2d_fwd", C.byref(d), L.view(xh), wt.data_ptr(), L.ptr(bm), 0, L.view(act_mu), None)
+        saved = [xh, wt, W_rho, b_rho]
+        if training:
+            rt = W_rho.detach().permute(2, 3, 0, 1).contiguous()
+            s2 = torch.empty_like(rt)
+            L.call("mfvi_softplus_sq_fwd", rt.data_ptr(), rt.numel(), s2.data_ptr())
+            b2 = None
+            if has_bias:
+                b2 = torch.empty_like(bm)
+                L.call("mfvi_softplus_sq_fwd", b_rho.detach().contiguous().data_ptr(), b2.numel(), b2.data_ptr())
+            x2 = torch.empty_like(xh)
+            L.call("mfvi_square_fwd", xh.data_ptr(), xh.numel(), x2.data_ptr())
+            var = torch.empty_like(act_mu)
+            L.call("mfvi_conv2d_fwd", C.byref(d), L.view(x2), s2.data_ptr(), L.ptr(b2), 0, L.view(var), None)
+            eh = to_nhwc(eps.to(dev, torch.float32))
+            out = torch.empty_like(act_mu)
+            L.call("mfvi_lrt_noise_fwd", act_mu.data_ptr(), var.data_ptr(), eh.data_ptr(), out.numel(), out.data_ptr())
+            saved += [rt, s2, x2, var, eh]
+        else:
+            out = act_mu
+        ctx.save_for_backward(*saved)
+        ctx.geom = (d, padding, training, has_bias, (N, Cin, H, W))
+        return to_nchw(out)
+
+    @staticmethod
+    def backward(ctx, dy):
+        d, padding, training, has_bias, (N, Cin, H, W) = ctx.geom
+        xh, wt, W_rho, b_rho = ctx.saved_tensors[:4]
+        dev = dy.device
+        dyh = to_nhwc(dy.float())
+        dwt = torch.zeros_like(wt)
+        db = torch.zeros(d.Cout, dtype=torch.float32, device=dev) if has_bias else None
+        L.call("mfvi_conv2d_wgrad", C.byref(d), L.view(xh), L.view(dyh), dwt.data_ptr(), L.ptr(db), 0)
+        need_dx = ctx.needs_input_grad[0]
+        dxh = None
+        if need_dx:
+            dxh = torch.empty_like(xh)
+            L.call("mfvi_conv2d_dgrad", C.byref(d), L.view(dyh), wt.data_ptr(), 0, L.view(dxh), 0)
+        gWr = gbr = None
+        if training:
+            rt, s2, x2, var, eh = ctx.saved_tensors[4:]
+            dvar = torch.empty_like(var)
+            L.call("mfvi_lrt_noise_bwd", dyh.data_ptr(), var.data_ptr(), eh.data_ptr(), dvar.numel(), dvar.data_ptr())
+            ds2 = torch.zeros_like(s2)
+            db2 = torch.zeros(d.Cout, dtype=torch.float32, device=dev) if has_bias else None
+            L.call("mfvi_conv2d_wgrad", C.byref(d), L.view(x2), L.view(dvar), ds2.data_ptr(), L.ptr(db2), 0)
+            grt = torch.empty_like(rt)
+            L.call("mfvi_softplus_sq_bwd", rt.data_ptr(), ds2.data_ptr(), rt.numel(), grt.data_ptr(), 0)
+            gWr = grt.permute(2, 3, 0, 1).contiguous()
+            if has_bias:
+                gbr = torch.empty_like(db2)
+                L.call("mfvi_softplus_sq_bwd", b_rho.detach().contiguous().data_ptr(), db2.data_ptr(), db2.numel(),
+                       gbr.data_ptr(), 0)
+            if need_dx:
+                dx2 = torch.empty_like(xh)
+                L.call("mfvi_conv2d_dgrad", C.byref(d), L.view(dvar), s2.data_ptr(), 0, L.view(dx2), 0)
+                L.call("mfvi_square_bwd", xh.data_ptr(), dx2.data_ptr(), xh.numel(), dxh.data_ptr(), 1)
+        dx = None
+        if need_dx:
+            if padding:
+                dxh = dxh[:, padding:padding + H, padding:padding + W].contiguous()
+            dx = to_nchw(dxh)
+        gWm = dwt.permute(2, 3, 0, 1).contiguous()
+        return dx, gWm, gWr, db, gbr, None, None, None, None, None
+
+
 class KlFn(torch.autograd.Function):
     """VIModule._kl (reference module.py:64-80) for one (mu, rho) pair: sum of closed-form Gaussian KLs,
     returned as a 0-dim fp32 tensor."""

@@ -20,60 +20,115 @@ from typing import Callable, Dict, Iterable, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-from .utils.common_utils import peak_signal_noise_ratio, structural_similarity
+
+
+class DeviceBookkeeping:
+    """Per-iteration bookkeeping of the runners (reference bayesian_optimization.py:1374-1416) as ONE kernel per
+    iteration, registered as a post-step hook of the trainer so that it is replayed inside the step's CUDA graph; the
+    iteration index comes from the trainer's device-side step counter.  Nothing is read back until `metrics()`."""
+
+    N_ACC = 8
+
+    def __init__(self, trainer, gt=None, noisy=None, exp_weight: float = 0.99, ring: int = 25):
+        from . import _lib as L
+        self.L, self.tr = L, trainer
+        e = trainer.eng
+        self.S, self.H, self.W, _ = e.out.shape
+        dev = e.device
+        f = lambda t: None if t is None else torch.as_tensor(t, dtype=torch.float32).reshape(self.H, self.W).to(dev).contiguous()
+        self.gt, self.noisy = f(gt), f(noisy)
+        self.exp_weight, self.ring = float(exp_weight), int(ring)
+        self.out_avg = torch.zeros(2, self.H, self.W, device=dev)
+        self.ring_epi = torch.zeros(max(ring, 1), self.H, self.W, device=dev)
+        self.ring_ale = torch.zeros(max(ring, 1), self.H, self.W, device=dev)
+        self.acc = torch.zeros(self.N_ACC, dtype=torch.float64, device=dev)     # [0..4] squared errors, [5..6] SSIM sums
+        trainer.post_step_hooks.append(self.record)
+
+    def record(self):
+        """Enqueue the bookkeeping of the step that was just computed (called by the trainer before the step counter
+        advances; asynchronous)."""
+        L, e = self.L, self.tr.eng
+        L.call("mfvi_fill_f32", self.acc.data_ptr(), 2 * self.N_ACC, 0.0)
+        L.call("mfvi_bookkeep_step", L.view(e.out), self.S, self.H, self.W, self.exp_weight, L.ptr(self.gt),
+               L.ptr(self.noisy), self.out_avg.data_ptr(), self.ring_epi.data_ptr(), self.ring_ale.data_ptr(), self.ring,
+               self.tr.step_dev.data_ptr(), 0, self.acc.data_ptr(),
+               meta={"bytes": 4.0 * self.H * self.W * (2 * self.S + 8)})
+
+    def metrics(self, ssim: bool = True) -> Dict[str, float]:
+        """PSNR / MSE / SSIM of the last recorded iteration (one synchronising read of 8 doubles)."""
+        L = self.L
+        n = self.H * self.W
+        if ssim and self.gt is not None:
+            L.call("mfvi_ssim", self.gt.data_ptr(), self.out_avg.data_ptr(), self.H, self.W, 1, self.acc[5:].data_ptr())
+        a = self.acc.cpu().tolist()
+        psnr = lambda sse: 10.0 * math.log10(n / sse) if sse > 0 else float("inf")
+        m = {"mse_corrupted": a[3] / n, "mse_gt": a[4] / n}
+        if self.noisy is not None:
+            m["psnr_noisy"] = psnr(a[0])
+        if self.gt is not None:
+            m.update(psnr_gt=psnr(a[1]), psnr_gt_sm=psnr(a[2]))
+            if ssim:
+                m["ssim_gt_sm"] = a[5] / n
+        return m
+
+    def uncertainty(self, n_valid: Optional[int] = None):
+        """(epistemic, aleatoric, err2) maps from the ring buffers (:1410-1411); err2 is None without a ground truth."""
+        L = self.L
+        n = min(self.tr.steps_done, self.ring) if n_valid is None else n_valid
+        epi, ale = torch.empty_like(self.out_avg[0]), torch.empty_like(self.out_avg[0])
+        err2 = torch.empty_like(epi) if self.gt is not None else None
+        L.call("mfvi_ring_uncertainty", self.ring_epi.data_ptr(), self.ring_ale.data_ptr(), max(n, 1), self.H, self.W,
+               L.ptr(self.gt), epi.data_ptr(), ale.data_ptr(), L.ptr(err2))
+        return epi, ale, err2
+
+    def uce(self, n_bins: int = 15) -> float:
+        """Uncertainty calibration error of (epistemic + aleatoric) against the squared error of the ring means
+        (reference utils/uce.py, recipe eval_denoising.ipynb:467-482)."""
+        from .utils.uce import uceloss
+        epi, ale, err2 = self.uncertainty()
+        return float(uceloss(err2.reshape(-1), (epi + ale).reshape(-1), n_bins=n_bins)[0])
 
 
 def run_den_mfvi(img_gt: np.ndarray, *, temp: float, sigma: float, lr: float = 1e-3, num_iter: int = 100,
                  mc_samples: int = 1, p_sigma: float = 0.1, seed: int = 1, device="cuda:0", input_depth: int = 16,
                  reg_noise_std: float = 0.1, exp_weight: float = 0.99, mc_ring: int = 25, show_every: int = 100,
                  math_mode: Optional[int] = None, rank: int = 0, world_size: int = 1, process_group=None,
-                 return_history: bool = False):
+                 return_history: bool = False, spec=None, img_noisy: Optional[np.ndarray] = None):
     """img_gt: (1,H,W) ground-truth image in [0,1] with H, W multiples of 32.  Returns psnr_gt_sm of the last
-    iteration (and, with return_history, a dict of the per-`show_every` metrics and the final uncertainty maps)."""
+    iteration (and, with return_history, a dict of the per-`show_every` metrics and the final uncertainty maps).
+    `spec` (a SkipSpec) overrides the runner's 5-scale net; `img_noisy` overrides the seeded noisy observation."""
     from . import MfviDipTrainer, SkipSpec, _lib as L
     from .utils.common_utils import get_noise
     dev = torch.device(device)
     np.random.seed(seed)
     torch.manual_seed(seed)
-    gt = torch.as_tensor(img_gt, dtype=torch.float32)[None].to(dev)                  # (1,1,H,W)
-    noisy = np.clip(img_gt + np.random.normal(scale=p_sigma, size=img_gt.shape), 0, 1).astype(np.float32)
-    noisy_t = torch.from_numpy(noisy)[None].to(dev)
+    if img_noisy is None:
+        img_noisy = np.clip(img_gt + np.random.normal(scale=p_sigma, size=img_gt.shape), 0, 1).astype(np.float32)
     H, W = img_gt.shape[-2:]
-    net_input = get_noise(input_depth, 'noise', (H, W))
-    tr = MfviDipTrainer(SkipSpec(input_depth, 2), "den", net_input, temp=temp, sigma=sigma, lr=lr, mc_samples=mc_samples,
-                        seed=seed, reg_noise_std=reg_noise_std, device=dev, target=noisy_t,
+    spec = spec or SkipSpec(input_depth, 2)
+    net_input = get_noise(spec.num_input_channels, 'noise', (H, W))
+    tr = MfviDipTrainer(spec, "den", net_input, temp=temp, sigma=sigma, lr=lr, mc_samples=mc_samples,
+                        seed=seed, reg_noise_std=reg_noise_std, device=dev, target=torch.from_numpy(img_noisy)[None],
                         math_mode=L.MATH_TF32 if math_mode is None else math_mode, rank=rank, world_size=world_size,
                         process_group=process_group)
+    bk = DeviceBookkeeping(tr, gt=img_gt, noisy=img_noisy, exp_weight=exp_weight, ring=mc_ring)
     n_steps = num_iter + 1                       # the reference runs num_iter + 1 iterations (:1287)
-    out_avg = None
-    ring_epi = torch.zeros(mc_ring, 1, H, W, device=dev)
-    ring_ale = torch.zeros(mc_ring, 1, H, W, device=dev)
-    hist: Dict[str, List[float]] = {"it": [], "psnr_noisy": [], "psnr_gt": [], "psnr_gt_sm": [], "ssim_gt_sm": [], "loss": []}
+    hist: Dict[str, list] = {"it": [], "psnr_noisy": [], "psnr_gt": [], "psnr_gt_sm": [], "ssim_gt_sm": [], "loss": []}
     for i in range(n_steps):
-        tr.step()
-        out = tr.eng.out_nchw()                                   # (S,2,H,W): ch0 = mean, ch1 = -log var
-        mean = out[:, :1].mean(0, keepdim=True)
-        var = torch.exp(-out[:, 1:]).mean(0, keepdim=True)        # out[:,1:] = exp(-s)   (:1375)
-        cur = torch.cat([mean, var], 1)
-        out_avg = cur.clone() if out_avg is None else out_avg * exp_weight + cur * (1 - exp_weight)   # (:1378-1381)
-        ring_epi[i % mc_ring] = mean[0].clamp(0, 1)
-        ring_ale[i % mc_ring] = var[0].clamp(0, 1)
+        tr.step()                                 # hot loop + bookkeeping kernel, no host synchronisation
         if i % show_every == 0 or i == n_steps - 1:
-            sm = out_avg[:, :1].clamp(0, 1)
-            nll, kl, loss = tr.loss_terms()
+            m = bk.metrics()
             hist["it"].append(i)
-            hist["loss"].append(loss)
-            hist["psnr_noisy"].append(peak_signal_noise_ratio(noisy_t, mean.clamp(0, 1)))
-            hist["psnr_gt"].append(peak_signal_noise_ratio(gt, mean.clamp(0, 1)))
-            hist["psnr_gt_sm"].append(peak_signal_noise_ratio(gt, sm))
-            hist["ssim_gt_sm"].append(structural_similarity(gt, sm))
+            hist["loss"].append(tr.loss_terms()[2])
+            for k in ("psnr_noisy", "psnr_gt", "psnr_gt_sm", "ssim_gt_sm"):
+                hist[k].append(m[k])
     psnr_gt_sm = hist["psnr_gt_sm"][-1]
     if not return_history:
         return psnr_gt_sm
-    n_valid = min(n_steps, mc_ring)
-    hist["epistemic"] = ring_epi[:n_valid].var(0, unbiased=True).cpu() if n_valid > 1 else torch.zeros(1, H, W)
-    hist["aleatoric"] = ring_ale[:n_valid].mean(0).cpu()
-    hist["recon"] = out_avg[0, :1].clamp(0, 1).cpu()
+    epi, ale, _ = bk.uncertainty()
+    hist["epistemic"], hist["aleatoric"] = epi.cpu(), ale.cpu()
+    hist["uce"] = bk.uce()
+    hist["recon"] = bk.out_avg[:1].clamp(0, 1).cpu()
     return psnr_gt_sm, hist
 
 

@@ -107,6 +107,7 @@ class MfviDipTrainer:
         self.v = torch.zeros_like(e.theta)
         self.losses = torch.zeros(2, dtype=torch.float64, device=device)
         self.init_parameters(self.seed)
+        self.post_step_hooks = []               # callables enqueued after AdamW, before the step counter advances
         self.use_graph = use_graph
         self._graph = None
         self._warm = 0
@@ -149,6 +150,8 @@ class MfviDipTrainer:
         L.call("mfvi_adamw_step", e.theta.data_ptr(), e.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                e.n_theta_pad, self.lr, self.betas[0], self.betas[1], self.adam_eps, self.weight_decay, 1,
                self.step_dev.data_ptr(), e._aptr(NLL) if self.nan_guard else None, meta={"bytes": 28.0 * e.n_theta_pad})
+        for hook in self.post_step_hooks:      # e.g. runners.DeviceBookkeeping.record (captured into the graph)
+            hook()
         L.call("mfvi_counter_add", self.step_dev.data_ptr(), 1)
 
     def step(self):
@@ -170,25 +173,50 @@ class MfviDipTrainer:
         self._graph.replay()
 
     # ------------------------------------------------------------------ host-buffer entry (the e2e path of bench.py)
+    def _target_tensor(self):
+        tgt = getattr(self.head, "target", None)
+        return self.head.sino_t if tgt is None else tgt
+
     def host_buffers(self):
         """Pinned host staging buffers: (net_input NHWC (H,W,C), target as the head stores it, result[2] doubles)."""
-        tgt = getattr(self.head, "target", None)
-        if tgt is None:
-            tgt = self.head.sino_t
+        tgt = self._target_tensor()
         return (torch.empty_like(self.saved, device="cpu").pin_memory(), torch.empty_like(tgt, device="cpu").pin_memory(),
                 torch.zeros(2, dtype=torch.float64).pin_memory())
 
     def step_from_host(self, net_input_host, target_host, result_host):
-        """One step with HOST inputs: H2D copy of the fixed net input and the target, the step, D2H of [kl, nll].
-        Asynchronous; synchronise before reading result_host."""
-        tgt = getattr(self.head, "target", None)
-        if tgt is None:
-            tgt = self.head.sino_t
-        self.saved.copy_(net_input_host, non_blocking=True)
-        tgt.copy_(target_host, non_blocking=True)
+        """One step with HOST inputs: H2D copy of the net input and the target, the step, D2H of [kl, nll].
+        Asynchronous and pipelined one step deep: the H2D copies go to one of two device staging slots on a copy stream
+        (so they overlap the previous step's kernels), the compute stream moves the slot into the step's fixed input
+        buffers (device-to-device) before replaying the graph, and the D2H of the losses follows the graph.  Returns
+        (h2d_bytes, d2h_bytes, done_event); `done_event.synchronize()` before reading result_host or reusing the slot's
+        host buffers."""
+        tgt = self._target_tensor()
+        if not hasattr(self, "_stage"):
+            self._copy_stream = torch.cuda.Stream(device=self.eng.device)
+            self._stage = [(torch.empty_like(self.saved), torch.empty_like(tgt)) for _ in range(2)]
+            self._ev_h2d = [torch.cuda.Event() for _ in range(2)]
+            self._ev_used = [None, None]
+            self._slot = 0
+        k = self._slot
+        self._slot ^= 1
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(self._copy_stream):
+            if self._ev_used[k] is not None:
+                self._copy_stream.wait_event(self._ev_used[k])     # the step that last read this slot has consumed it
+            self._stage[k][0].copy_(net_input_host, non_blocking=True)
+            self._stage[k][1].copy_(target_host, non_blocking=True)
+            self._ev_h2d[k].record(self._copy_stream)
+        main.wait_event(self._ev_h2d[k])
+        self.saved.copy_(self._stage[k][0], non_blocking=True)
+        tgt.copy_(self._stage[k][1], non_blocking=True)
+        used = torch.cuda.Event()
+        used.record(main)
+        self._ev_used[k] = used
         self.step()
         result_host.copy_(self.eng.arena[:2], non_blocking=True)
-        return self.saved.numel() * 4 + tgt.numel() * 4, 16
+        done = torch.cuda.Event()
+        done.record(main)
+        return self.saved.numel() * 4 + tgt.numel() * 4, 16, done
 
     # ------------------------------------------------------------------
     def loss_terms(self):

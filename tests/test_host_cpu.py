@@ -78,8 +78,11 @@ def test_replace_layers_substring_semantics():
         net = MeanFieldVI(_build("den"), prior={"mu": 0.0, "sigma": 0.1}, replace_layers=mode, reparam="")
         counts[mode] = sum(isinstance(m, Conv2dRT) for m in net.modules())
     assert counts == {"all": 26, "up": 11, "down": 0, "none": 0}
-    with pytest.raises(NotImplementedError):
-        MeanFieldVI(_build("den"), reparam="local")
+    # the reference's default reparam='local' builds local-reparameterisation layers (freq_to_bayes.py:22-25)
+    from mfvi_dip_mia_b200.BayTorch.modules import Conv2dLRT
+    local = MeanFieldVI(_build("den"))
+    assert sum(isinstance(m, Conv2dLRT) for m in local.modules()) == 26 and not local.fused
+    assert set(local.state_dict()) == set(MeanFieldVI(_build("den"), reparam="").state_dict())
 
 
 def test_no_cpu_fallback():
