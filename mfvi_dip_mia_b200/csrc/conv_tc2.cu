@@ -488,12 +488,26 @@ static Plan make_plan(int S, int Mh, int Mw, int hh, int hw, int taps, int plane
         const double t_load = (static_cast<double>(planes) * pl.box_rows * kw_total * 4 + static_cast<double>(taps) * BN * kw_total * 4) / 40.0 * cpsm;
         // measured (profiles/r01_umma_rate_probe.txt, conv timelines): a kind::tf32 M=128 MMA issues every ~39 cycles up to
         // N=48 and ~N/2 beyond, plus ~6 cycles of loop overhead; an epilogue unit (128 rows x 16 columns) costs ~300 cycles
-        const double mma_cyc = std::max(39.0 + 0.2 * (BN - 16), 0.5 * BN) + 6.0;
-        const double t_mma = static_cast<double>(pl.n_mt) * taps * (kw_total / 8) * mma_cyc * cpsm;
-        const int n_units = cdiv(std::min(Nvalid, BN), 16);
-        const double t_epi = static_cast<double>(pl.n_mt) * n_units * 300.0;
-        // with a single accumulator stage the epilogue of tile i cannot overlap the MMAs of tile i+1
-        const double t_tile = (pl.acc_stages == 2 ? std::max(t_load, std::max(t_mma, t_epi)) : std::max(t_load, t_mma + t_epi)) + 500.0;
+        // The forward keeps the older model: its constants under-state the MMA and epilogue costs, but it was tuned on
+        // measured layer times and its preference for large tiles hides the TMA latency that the two activation stages
+        // cannot prefetch across tiles (the "realistic" model picks 1-row tiles for 36->16 at 256^2: 124 us instead of 84).
+        // For the data gradient the realistic model wins (36->16: 76 -> 61 us): it knows that a single accumulator stage
+        // serialises the wide dgrad epilogue behind the MMAs.
+        static const int forced = env_int("MFVI_TC2_COST", -1);
+        const int model = forced >= 0 ? forced : (dgrad ? 1 : 0);
+        double t_tile;
+        if (model == 0) {
+          const double t_mma = static_cast<double>(pl.n_mt) * taps * (kw_total / 8) * std::max(BN / 2, 16) * cpsm;
+          const double t_epi = static_cast<double>(pl.n_mt) * (BN / 16) * 120.0;
+          t_tile = std::max(t_load, std::max(t_mma, t_epi)) + 500.0;
+        } else {
+          const double mma_cyc = std::max(39.0 + 0.2 * (BN - 16), 0.5 * BN) + 6.0;
+          const double t_mma = static_cast<double>(pl.n_mt) * taps * (kw_total / 8) * mma_cyc * cpsm;
+          const int n_units = cdiv(std::min(Nvalid, BN), 16);
+          const double t_epi = static_cast<double>(pl.n_mt) * n_units * 300.0;
+          // with a single accumulator stage the epilogue of tile i cannot overlap the MMAs of tile i+1
+          t_tile = (pl.acc_stages == 2 ? std::max(t_load, std::max(t_mma, t_epi)) : std::max(t_load, t_mma + t_epi)) + 500.0;
+        }
         pl.cost = 5000.0 + waves * t_tile + std::min(t_load, 4000.0);
         pl.grid = std::min(tiles, slots);
         pl.ok = true;

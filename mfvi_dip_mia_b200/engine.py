@@ -19,6 +19,7 @@ tensor work and is CUDA-graph capturable.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -237,8 +238,14 @@ class SkipEngine:
         self.need_input_grad = need_input_grad
         # weight-gradient kernels only feed dw (consumed after the whole backward), so they run on a side stream
         # concurrently with the dgrad / elementwise chain (fork-join by events; becomes a parallel branch of the graph)
+        # The 1x1 skip-branch convolutions (forward) and their backward chain (BN backward, dgrad into the scale's input
+        # gradient) hang off the long down/up chain, so they run on a third stream ("skip" lane) and join where the
+        # concatenation needs them.  Ops carry their lane in meta["lane"]; meta["after"] names the lane that produced
+        # their inputs; ("__join__", (), {"lane": X}) makes the main stream wait for lane X.
         self.overlap_wgrad = True
+        self.overlap_skip = os.environ.get("MFVI_SKIP_LANE", "1") != "0"
         self._side = torch.cuda.Stream(device=device)
+        self._side2 = torch.cuda.Stream(device=device)
         self._build_plan()
         # per-BN tables for the running-stat update
         self._bn_ch_off = torch.tensor([b.ch_off for b in lay.bns], dtype=torch.int32, device=device)
@@ -354,6 +361,7 @@ class SkipEngine:
             ys = d_s = None
             if sc.skip_conv is not None:
                 ys, d_s = self._conv_fwd(sc.skip_conv, self._interior(T, Tpad - ps), sc.skip_bn)
+                self.fwd_ops[-1][2].update(lane="skip", after="main")
             x_d1 = self._interior(T, Tpad - pd)
             y1, d_1 = self._conv_fwd(sc.d1, x_d1, sc.d1_bn)
             X2 = self._bn_act_pad(y1, sc.d1_bn, *self._bn_args(sc.d1_bn), 1, pd)
@@ -372,6 +380,8 @@ class SkipEngine:
             null_view = L.View(None, 0, 0, 0)
             sb = self._bn_args(sc.skip_bn) if Cs else (None, None, None)
             zb = self._bn_args(z_bn)
+            if Cs:
+                self.fwd_ops.append(("__join__", (), {"lane": "skip"}))
             self.fwd_ops.append(("mfvi_cat_up_fwd", (L.view(ys) if Cs else null_view, Cs, *sb, L.view(z), Cd, *zb,
                                                      S, Hs, Ws, mode, L.view(A), self._aptr(sc.cat_bn.sums_off)),
                                  self._ew_meta(ys, z, A)))
@@ -399,16 +409,29 @@ class SkipEngine:
                     L.view(dA), S, Hs, Ws, mode, L.view(ys) if Cs else null_view, Cs, *sb,
                     L.view(gs) if Cs else null_view, self._aptr(sc.skip_bn.red_off) if Cs else None,
                     L.view(z), Cd, *zb, L.view(gd), self._aptr(z_bn.red_off)), self._ew_meta(dA, ys, z, gs, gd)))
-                # BN backward of the two branches (their LeakyReLU was folded into cat_up_bwd)
+                # BN backward of the two branches (their LeakyReLU was folded into cat_up_bwd).  The skip branch goes to the
+                # "skip" lane: BN backward, then its dgrad into the (zero-filled) input gradient of this scale, which the
+                # first down conv's dgrad accumulates onto after the join.
+                need_dT = i > 0 or self.need_input_grad
+                dT = self._buf(T.shape[1], T.shape[2], T.shape[3]) if need_dT else None
+                if Cs:
+                    x_s = self._interior(T, Tpad - ps)
+                    ms = self._conv_meta(sc.skip_conv, d_s, x_s, gs)
+                    ops.append(("mfvi_bn_bwd_apply", (
+                        L.view(gs), L.view(ys), S, Hs, Ws, Cs, sb[0], self._aptr(sc.skip_bn.red_off), sb[1], L.view(gs),
+                        self.g_gamma.data_ptr() + 4 * sc.skip_bn.ch_off, self.g_beta.data_ptr() + 4 * sc.skip_bn.ch_off),
+                        dict(self._ew_meta(gs, ys, gs), lane="skip", after="main")))
+                    ops.append(("mfvi_conv2d_wgrad", (C.byref(d_s), L.view(x_s), L.view(gs), self.dw.data_ptr() + 4 * sc.skip_conv.w_off,
+                                                      self._dbias_ptr(sc.skip_conv, True), lay.P_pad), dict(ms, after="skip")))
+                    if need_dT:
+                        ops.append(("mfvi_fill_f32", (dT.data_ptr(), dT.numel(), 0.0), dict(self._ew_meta(dT), lane="skip", after="skip")))
+                        ops.append(("mfvi_conv2d_dgrad", (C.byref(d_s), L.view(gs), self.w.data_ptr() + 4 * sc.skip_conv.w_off,
+                                                          lay.P_pad, L.view(self._interior(dT, Tpad - ps)), 1),
+                                    dict(ms, lane="skip", after="skip")))
                 ops.append(("mfvi_bn_bwd_apply", (
                     L.view(gd), L.view(z), S, z.shape[1], z.shape[2], Cd, zb[0], self._aptr(z_bn.red_off), zb[1], L.view(gd),
                     self.g_gamma.data_ptr() + 4 * z_bn.ch_off, self.g_beta.data_ptr() + 4 * z_bn.ch_off),
                     self._ew_meta(gd, z, gd)))
-                if Cs:
-                    ops.append(("mfvi_bn_bwd_apply", (
-                        L.view(gs), L.view(ys), S, Hs, Ws, Cs, sb[0], self._aptr(sc.skip_bn.red_off), sb[1], L.view(gs),
-                        self.g_gamma.data_ptr() + 4 * sc.skip_bn.ch_off, self.g_beta.data_ptr() + 4 * sc.skip_bn.ch_off),
-                        self._ew_meta(gs, ys, gs)))
                 if inner_bwd is not None:
                     dTn = inner_bwd(ops, gd)
                     dy2 = self._bn_act_pad_bwd(ops, dTn, y2, sc.d2_bn, 1, Tn_pad)
@@ -416,27 +439,17 @@ class SkipEngine:
                     dy2 = gd
                 dX2 = self._conv_bwd(ops, sc.d2, d_2, X2, dy2)
                 dy1 = self._bn_act_pad_bwd(ops, dX2, y1, sc.d1_bn, 1, pd)
-                need_dT = i > 0 or self.need_input_grad
-                dT = None
-                if need_dT:
-                    dT = self._buf(T.shape[1], T.shape[2], T.shape[3])
-                    dT_d1 = self._interior(dT, Tpad - pd)
-                    if Tpad != pd:
-                        ops.append(("mfvi_fill_f32", (dT.data_ptr(), dT.numel(), 0.0), self._ew_meta(dT)))
                 m1 = self._conv_meta(sc.d1, d_1, x_d1, dy1)
                 ops.append(("mfvi_conv2d_wgrad", (C.byref(d_1), L.view(x_d1), L.view(dy1), self.dw.data_ptr() + 4 * sc.d1.w_off,
                                                   self._dbias_ptr(sc.d1, True), lay.P_pad), m1))
                 if need_dT:
+                    dT_d1 = self._interior(dT, Tpad - pd)
+                    if Cs:
+                        ops.append(("__join__", (), {"lane": "skip"}))      # dT holds the skip branch's contribution
+                    elif Tpad != pd:
+                        ops.append(("mfvi_fill_f32", (dT.data_ptr(), dT.numel(), 0.0), self._ew_meta(dT)))
                     ops.append(("mfvi_conv2d_dgrad", (C.byref(d_1), L.view(dy1), self.w.data_ptr() + 4 * sc.d1.w_off, lay.P_pad,
-                                                      L.view(dT_d1), 1 if Tpad != pd else 0), m1))
-                if Cs:
-                    x_s = self._interior(T, Tpad - ps)
-                    ms = self._conv_meta(sc.skip_conv, d_s, x_s, gs)
-                    ops.append(("mfvi_conv2d_wgrad", (C.byref(d_s), L.view(x_s), L.view(gs), self.dw.data_ptr() + 4 * sc.skip_conv.w_off,
-                                                      self._dbias_ptr(sc.skip_conv, True), lay.P_pad), ms))
-                    if need_dT:
-                        ops.append(("mfvi_conv2d_dgrad", (C.byref(d_s), L.view(gs), self.w.data_ptr() + 4 * sc.skip_conv.w_off,
-                                                          lay.P_pad, L.view(self._interior(dT, Tpad - ps)), 1), ms))
+                                                      L.view(dT_d1), 1 if (Cs or Tpad != pd) else 0), m1))
                 return dT
 
             Tn_pad = in_pad(i + 1) if i < n - 1 else 0
@@ -478,28 +491,53 @@ class SkipEngine:
         """Eval mode of RTLayer (reparam_layers.py:33-35): w = mu for every sample."""
         self.w[:, :self.lay.P].copy_(self.mu.unsqueeze(0).expand(self.S, -1))
 
+    def _run(self, op_list):
+        """Launch an op list: ops tagged lane="skip" go to the skip stream, weight-gradient kernels to the wgrad stream
+        (each waits for the lane that produced its inputs), everything else to the current stream; every lane used is
+        joined back before returning.  With the per-kernel timeline on, everything runs on one stream."""
+        serial = L.timeline is not None
+        main = torch.cuda.current_stream(self.device)
+        streams = {"main": main, "wgrad": self._side, "skip": self._side2}
+        dirty = set()
+
+        def join(lane):
+            ev = torch.cuda.Event()
+            ev.record(streams[lane])
+            main.wait_event(ev)
+            dirty.discard(lane)
+
+        for name, args, meta in op_list:
+            lane = meta.get("lane", "main")
+            if name == "mfvi_conv2d_wgrad" and self.overlap_wgrad:
+                lane = "wgrad"
+            if lane == "skip" and not self.overlap_skip:
+                lane = "main"
+            if name == "__join__":
+                if meta["lane"] in dirty:
+                    join(meta["lane"])
+                continue
+            if serial or lane == "main":
+                after = meta.get("after", "main")
+                if not serial and after in dirty:          # a main-stream op consuming a side lane's result
+                    join(after)
+                L.call(name, *args, meta=meta)
+                continue
+            after = meta.get("after", "main")
+            if after != lane and (after == "main" or after in dirty):
+                ev = torch.cuda.Event()
+                ev.record(streams[after])
+                streams[lane].wait_event(ev)
+            L.call(name, *args, stream=streams[lane].cuda_stream, meta=meta)
+            dirty.add(lane)
+        for lane in list(dirty):
+            join(lane)
+
     def forward(self):
-        for name, args, meta in self.fwd_ops:
-            L.call(name, *args, meta=meta)
+        self._run(self.fwd_ops)
 
     def backward(self):
         """Consumes self.dout; fills dw[s], BN gamma/beta grads (and dx0 when requested)."""
-        overlap = self.overlap_wgrad and L.timeline is None
-        main = torch.cuda.current_stream(self.device)
-        side, forked = self._side, False
-        for name, args, meta in self.bwd_ops:
-            if overlap and name == "mfvi_conv2d_wgrad":
-                ev = torch.cuda.Event()
-                ev.record(main)
-                side.wait_event(ev)
-                L.call(name, *args, stream=side.cuda_stream, meta=meta)
-                forked = True
-            else:
-                L.call(name, *args, meta=meta)
-        if forked:
-            ev = torch.cuda.Event()
-            ev.record(side)
-            main.wait_event(ev)
+        self._run(self.bwd_ops)
 
     def reparam_kl(self, key: L.PhiloxKey, *, prior_mu: float, prior_sigma_plus_eps: float, direction: int,
                    kscale: float, kscale_dev=None, data_term: bool = True, gscale: float = 1.0, accumulate: bool = False,
