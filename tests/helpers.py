@@ -67,3 +67,9 @@ def fake_trial(temp, sigma, device, offset=0.0):
     if temp == 4.0:
         raise RuntimeError("boom")
     return offset + math.log10(temp) - 2.0 * math.log10(sigma) + (0.0 if device == "cpu:0" else 0.5)
+
+
+def quadratic_trial(temp, sigma, device, peak=(1e-6, 1e-3)):
+    """Analytic stand-in for a trial runner in the BO test: a smooth PSNR-like bowl in log10 space, maximum at `peak`."""
+    import math
+    return 30.0 - 0.6 * (math.log10(temp) - math.log10(peak[0])) ** 2 - 0.9 * (math.log10(sigma) - math.log10(peak[1])) ** 2

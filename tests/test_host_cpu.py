@@ -183,3 +183,65 @@ def test_trial_fanout_round_robin_and_nan_filter():
     assert all(abs(a - b) < 1e-12 for a, b in zip(Y, exp))
     g = log_grid([[-10, 0], [-10, 0]], 8)
     assert len(g) == 64 and abs(g[0][0] - 1e-10) < 1e-20 and abs(g[-1][1] - 1.0) < 1e-12
+
+
+# ----------------------------------------------------------------------------------------------- BO outer loop (row f4)
+def test_gp_posterior_and_ei_match_closed_form():
+    """ExactGPModel (constant mean + scaled RBF + Gaussian noise) against plain numpy GP algebra at the fitted
+    hyper-parameters, and expected_improvement against scipy's normal pdf / cdf (reference :3604-3633)."""
+    from scipy.stats import norm
+    from mfvi_dip_mia_b200.bo import expected_improvement, train_gp
+    g = torch.Generator().manual_seed(0)
+    Xt = torch.rand(12, 2, generator=g, dtype=torch.float64)
+    Yt = 20 + 5 * torch.sin(3 * Xt[:, 0]) * torch.cos(2 * Xt[:, 1]) + 0.05 * torch.randn(12, generator=g, dtype=torch.float64)
+    gp = train_gp(Xt, Yt, iter_max=300)
+    Xs = torch.rand(40, 2, generator=g, dtype=torch.float64)
+    mean, var = gp.predict(Xs)
+    ls, os_, nz, c = (float(v) for v in (gp.lengthscale, gp.outputscale, gp.noise, gp.constant))
+    assert nz > 1e-4 and ls > 0 and os_ > 0
+    k = lambda a, b: os_ * np.exp(-0.5 * ((a[:, None, :] - b[None, :, :]) ** 2).sum(-1) / ls ** 2)
+    A, B = Xt.numpy(), Xs.numpy()
+    K = k(A, A) + nz * np.eye(12)
+    m_ref = c + k(B, A) @ np.linalg.solve(K, Yt.numpy() - c)
+    v_ref = os_ - np.einsum("ij,ji->i", k(B, A), np.linalg.solve(K, k(A, B)))
+    assert np.allclose(mean.detach().numpy(), m_ref, atol=1e-8) and np.allclose(var.detach().numpy(), v_ref, atol=1e-8)
+    # the fit explains the data and the MLL improved over the initial hyper-parameters
+    assert float((gp.predict(Xt)[0] - Yt).abs().max()) < 1.0
+    ei = expected_improvement(gp, Xs, Xt).detach().numpy().reshape(-1)
+    best = float(gp.predict(Xt)[0].max())
+    sd = np.sqrt(np.maximum(v_ref, 1e-9))
+    u = (m_ref - best) / sd
+    assert np.allclose(ei, np.maximum(sd * (norm.pdf(u) + u * norm.cdf(u)), 0), atol=1e-8)
+
+
+def test_normalize_roundtrip_and_peak_local_max():
+    from mfvi_dip_mia_b200.bo import normalize_X, peak_local_max, unnormalize_X
+    X = torch.tensor([[1e-10, 1.0], [1e-5, 1e-5], [3.3e-7, 2e-2]], dtype=torch.float64)
+    Xn = normalize_X(X, [-10, 0], [-10, 0])
+    assert torch.allclose(Xn[0], torch.tensor([0.0, 1.0], dtype=torch.float64)) and torch.allclose(Xn[1], torch.tensor([0.5, 0.5], dtype=torch.float64))
+    assert torch.allclose(unnormalize_X(Xn, [-10, 0], [-10, 0]), X, rtol=1e-12)
+    yy, xx = np.mgrid[0:100, 0:100]
+    img = (np.exp(-((yy - 30) ** 2 + (xx - 40) ** 2) / 50.0) + 0.6 * np.exp(-((yy - 70) ** 2 + (xx - 80) ** 2) / 30.0)
+           + 0.05 * np.exp(-((yy - 10) ** 2 + (xx - 90) ** 2) / 20.0) + 2.0 * np.exp(-((yy - 2) ** 2 + (xx - 2) ** 2) / 8.0))
+    pk = peak_local_max(img, min_distance=5, threshold_rel=0.1, num_peaks=4)
+    # strongest first; the 0.05 bump is below 10 % of the maximum; the corner peak lies inside the excluded border
+    assert pk.tolist() == [[30, 40], [70, 80]]
+
+
+def test_bo_loop_closes_on_analytic_objective(tmp_path):
+    """bo(): trial fan-out -> GP fit -> EI candidates -> next round, on an analytic objective with a known optimum; the
+    per-round npz carries the reference's keys (bayesian_optimization.py:3876-3887)."""
+    from mfvi_dip_mia_b200.bo import bo
+    from tests.helpers import quadratic_trial
+    bo_params = {"temp": {"logbounds": [-10, 0], "candidates": [1e-9, 1e-5, 1e-1]},
+                 "sigma": {"logbounds": [-10, 0], "candidates": [1e-8, 1e-4, 1e-1]}}
+    X, Y = bo(quadratic_trial, bo_params, {"bo_results_path": str(tmp_path), "devices": ["cpu:0", "cpu:1"]}, rounds=3,
+              gp_iters=300, start_method="fork", verbose=False)
+    assert len(X) == len(Y) and len(X) > 9                       # 9 initial candidates + proposals of 2 rounds
+    z = np.load(tmp_path / "2_fig_data.npz")
+    for k in ["XX_lr", "XX_wd", "pred", "observed_X", "observed_Y", "expected_improvement", "confidence", "acq", "candidates"]:
+        assert k in z.files, k
+    assert z["pred"].shape == (100, 100) and z["acq"].shape == (100, 100) and z["candidates"].shape[1] == 2
+    assert (z["candidates"] >= 1e-10).all() and (z["candidates"] <= 1.0).all()
+    # proposals move towards the optimum (1e-6, 1e-3): the best observation improves on the initial grid's best
+    assert max(Y) > max(Y[:9]) - 1e-9 and max(Y) > 29.0
