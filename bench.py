@@ -154,6 +154,11 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # the contract is ONE JSON line on stdout: native libraries (NCCL's version banner) write to fd 1 as well, so fd 1 is
+    # pointed at stderr for the duration of the run and the JSON line goes to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — this path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
@@ -190,7 +195,16 @@ def run_ours(args):
     torch.cuda.synchronize()
     with ClockSampler(local) as clk:
         ms_total = timed(tr.step, args.steps)
+        # K steps can be shorter than nvidia-smi's sampling period: keep the SAME load running (untimed) until the sampler
+        # has seen it at least 3 times, so that the clock record describes the loaded state
+        extra, t_end = 0, time.time() + 2.0
+        while len(clk.rows) < 3 and time.time() < t_end:
+            for _ in range(25):
+                tr.step()
+            torch.cuda.synchronize()
+            extra += 25
     clocks = clk.summary()
+    clocks["window"] = f"timed region + {extra} untimed steps of the same load"
     launches = tr.launches_per_step * args.steps
     value = args.steps / (ms_total * 1e-3)
 
@@ -286,7 +300,8 @@ def run_ours(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "kernels": kernels}
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
 
 
 def main():

@@ -135,11 +135,12 @@ int mfvi_pad_act_bwd(MfviView dxp, int S, int H, int W, int C, int pad, MfviView
  * dgamma[c] = sum_s red[s][c][1], dbeta[c] = sum_s red[s][c][0] (written, not accumulated). */
 int mfvi_bn_bwd_apply(MfviView g, MfviView y, int S, int H, int W, int C, const double* sums, const double* red,
                       const float* gamma, MfviView dy, float* dgamma, float* dbeta, mfvi_stream_t st);
-/* backward of mfvi_cat_up_fwd w.r.t. the two activated branches, folded through their LeakyReLU:
+/* backward of mfvi_cat_up_fwd w.r.t. the two activated branches, folded through their LeakyReLU (part 0: both, 1: only the
+ * skip branch, 2: only the upsampled branch — the two are independent kernels and may run on different streams):
  *   gs = dA[:, :Cs] * lrelu'(bn(ys)), red_s += …;  gd = up2x^T(dA[:, Cs:]) * lrelu'(bn(yd)), red_d += … */
 int mfvi_cat_up_bwd(MfviView dA, int S, int H, int W, int mode, MfviView ys, int Cs, const double* sums_s,
                     const float* gamma_s, const float* beta_s, MfviView gs, double* red_s, MfviView yd, int Cd,
-                    const double* sums_d, const float* gamma_d, const float* beta_d, MfviView gd, double* red_d,
+                    const double* sums_d, const float* gamma_d, const float* beta_d, MfviView gd, double* red_d, int part,
                     mfvi_stream_t st);
 /* running_mean/var update of every BatchNorm of the net in one launch (momentum 0.1, unbiased var), applied
  * once per MC sample in order, as S sequential reference forwards would. sums arena double[..], per-BN

@@ -60,7 +60,7 @@ _SIGS = {
     "mfvi_cat_up_fwd": [View, _I, _P, _P, _P, View, _I, _P, _P, _P, _I, _I, _I, _I, View, _P],
     "mfvi_pad_act_bwd": [View, _I, _I, _I, _I, _I, View, _P, _P, _P, _I, View, _P],
     "mfvi_bn_bwd_apply": [View, View, _I, _I, _I, _I, _P, _P, _P, View, _P, _P],
-    "mfvi_cat_up_bwd": [View, _I, _I, _I, _I, View, _I, _P, _P, _P, View, _P, View, _I, _P, _P, _P, View, _P],
+    "mfvi_cat_up_bwd": [View, _I, _I, _I, _I, View, _I, _P, _P, _P, View, _P, View, _I, _P, _P, _P, View, _P, _I],
     "mfvi_bn_running_update": [_P, _P, _P, _P, _P, _I, _I, _F, _P, _P],
     "mfvi_gauss_nll_fwd_bwd": [_I, View, _I, _I, _I, _I, _I, _P, _P, _P, View],
     "mfvi_mse_fwd_bwd": [_P, _LL, _P, _SZ, _I, _P, _P],

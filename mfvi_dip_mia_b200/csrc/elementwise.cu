@@ -695,18 +695,21 @@ int mfvi_bn_bwd_apply(MfviView g, MfviView y, int S, int H, int W, int C, const 
 
 int mfvi_cat_up_bwd(MfviView dA, int S, int H, int W, int mode, MfviView ys, int Cs, const double* sums_s,
                     const float* gamma_s, const float* beta_s, MfviView gs, double* red_s, MfviView yd, int Cd,
-                    const double* sums_d, const float* gamma_d, const float* beta_d, MfviView gd, double* red_d,
+                    const double* sums_d, const float* gamma_d, const float* beta_d, MfviView gd, double* red_d, int part,
                     mfvi_stream_t st) {
-  MFVI_REQUIRE(dA.ptr && yd.ptr && gd.ptr && red_d, "cat_up_bwd: null pointer");
+  MFVI_REQUIRE(part >= 0 && part <= 2, "cat_up_bwd: part must be 0 (both branches), 1 (skip branch) or 2 (upsampled branch)");
+  MFVI_REQUIRE(dA.ptr, "cat_up_bwd: null pointer");
   MFVI_REQUIRE(H % 2 == 0 && W % 2 == 0, "cat_up_bwd: H,W must be even");
   MFVI_REQUIRE(Cs + Cd <= kMaxC && Cd >= 1, "cat_up_bwd: channel count out of range");
-  if (Cs > 0) {
+  if (Cs > 0 && part != 2) {
     MFVI_REQUIRE(ys.ptr && gs.ptr && red_s, "cat_up_bwd: null skip branch");
     const EwGeom ge = ew_geom(Cs, view_vec_ok(dA) && view_vec_ok(ys) && view_vec_ok(gs));
     dim3 grid(ew_grid(H * W, ge.PPB, S), S);
     MFVI_EW_DISPATCH(ge, k_cat_bwd_skip, grid, dA, H, W, ys, Cs, sums_s, gamma_s, beta_s, gs, red_s);
     if (int rc = check_launch("cat_up_bwd(skip)")) return rc;
   }
+  if (part == 1) return 0;
+  MFVI_REQUIRE(yd.ptr && gd.ptr && red_d, "cat_up_bwd: null upsampled branch");
   const EwGeom ge = ew_geom(Cd, view_vec_ok(dA) && view_vec_ok(yd) && view_vec_ok(gd) && Cs % 4 == 0);
   MFVI_REQUIRE(ge.G <= kEwThreads, "cat_up_bwd: too many channel groups");
   dim3 grid(ew_grid((H / 2) * (W / 2), ge.PPB, S), S);

@@ -405,10 +405,13 @@ class SkipEngine:
                 dA = self._bn_act_pad_bwd(ops, dXA, A, sc.cat_bn, 0, pu)
                 gd = self._buf(z.shape[1], z.shape[2], Cd)
                 gs = self._buf(Hs, Ws, Cs) if Cs else None
-                ops.append(("mfvi_cat_up_bwd", (
-                    L.view(dA), S, Hs, Ws, mode, L.view(ys) if Cs else null_view, Cs, *sb,
-                    L.view(gs) if Cs else null_view, self._aptr(sc.skip_bn.red_off) if Cs else None,
-                    L.view(z), Cd, *zb, L.view(gd), self._aptr(z_bn.red_off)), self._ew_meta(dA, ys, z, gs, gd)))
+                cat_args = (L.view(dA), S, Hs, Ws, mode, L.view(ys) if Cs else null_view, Cs, *sb,
+                            L.view(gs) if Cs else null_view, self._aptr(sc.skip_bn.red_off) if Cs else None,
+                            L.view(z), Cd, *zb, L.view(gd), self._aptr(z_bn.red_off))
+                # the upsampled branch continues the main chain; the skip branch's half goes to the skip lane
+                ops.append(("mfvi_cat_up_bwd", cat_args + (2,), self._ew_meta(dA[..., Cs:], z, gd)))
+                if Cs:
+                    ops.append(("mfvi_cat_up_bwd", cat_args + (1,), dict(self._ew_meta(dA[..., :Cs], ys, gs), lane="skip", after="main")))
                 # BN backward of the two branches (their LeakyReLU was folded into cat_up_bwd).  The skip branch goes to the
                 # "skip" lane: BN backward, then its dgrad into the (zero-filled) input gradient of this scale, which the
                 # first down conv's dgrad accumulates onto after the join.
@@ -420,7 +423,7 @@ class SkipEngine:
                     ops.append(("mfvi_bn_bwd_apply", (
                         L.view(gs), L.view(ys), S, Hs, Ws, Cs, sb[0], self._aptr(sc.skip_bn.red_off), sb[1], L.view(gs),
                         self.g_gamma.data_ptr() + 4 * sc.skip_bn.ch_off, self.g_beta.data_ptr() + 4 * sc.skip_bn.ch_off),
-                        dict(self._ew_meta(gs, ys, gs), lane="skip", after="main")))
+                        dict(self._ew_meta(gs, ys, gs), lane="skip", after="skip")))
                     ops.append(("mfvi_conv2d_wgrad", (C.byref(d_s), L.view(x_s), L.view(gs), self.dw.data_ptr() + 4 * sc.skip_conv.w_off,
                                                       self._dbias_ptr(sc.skip_conv, True), lay.P_pad), dict(ms, after="skip")))
                     if need_dT:
