@@ -259,8 +259,23 @@ __device__ __forceinline__ void up_taps(int i, int n, int mode, int& i0, int& i1
 }
 
 // F2: A = cat(lrelu(bn(ys)), up2x(lrelu(bn(yd)))), sumsA += (sum, sumsq)      grid = (chunks, S)
+// The x2 upsample is evaluated per 2x2 output QUAD: quad (a, b), a in [0, H/2], b in [0, W/2], covers output rows
+// {2a-1, 2a} and columns {2b-1, 2b} (those inside the image), which all read the same four low-resolution pixels
+// rows {max(a-1,0), min(a,h2-1)} x columns {max(b-1,0), min(b,w2-1)} — 4 loads and 4 BatchNorm+LeakyReLU evaluations
+// for 4 outputs instead of 16.  Weights per output row (align_corners=False, as up_taps): odd row 2a-1 -> (0.75, 0.25),
+// even row 2a -> (0.25, 0.75), row 0 -> (1, 0); nearest: (1, 0) / (0, 1).  Same arithmetic per output as the per-pixel form.
+__device__ __forceinline__ void quad_weights(int a, int mode, float (&wodd)[2], float (&wevn)[2]) {
+  if (mode == 1) {
+    wodd[0] = 1.f; wodd[1] = 0.f; wevn[0] = 0.f; wevn[1] = 1.f;
+  } else {
+    wodd[0] = 0.75f; wodd[1] = 0.25f;
+    wevn[0] = a == 0 ? 1.f : 0.25f;
+    wevn[1] = a == 0 ? 0.f : 0.75f;
+  }
+}
+
 template <int V>
-__global__ void __launch_bounds__(kEwThreads, 4)
+__global__ void __launch_bounds__(kEwThreads, 3)
 k_cat_up_fwd(MfviView ys, int Cs, const double* __restrict__ sums_s, const float* __restrict__ gamma_s,
              const float* __restrict__ beta_s, MfviView yd, int Cd, const double* __restrict__ sums_d,
              const float* __restrict__ gamma_d, const float* __restrict__ beta_d, int H, int W, int mode, MfviView A,
@@ -286,43 +301,59 @@ k_cat_up_fwd(MfviView ys, int Cs, const double* __restrict__ sums_s, const float
     const float* sbase = skip ? ys.ptr + (size_t)s * ys.sstride + c0 : nullptr;
     const float* dbase = yd.ptr + (size_t)s * yd.sstride + (c0 - Cs);
     float* abase = A.ptr + (size_t)s * A.sstride + c0;
-    for (PixIter it(H * W, W, PPB, slot); it.valid(); it.next()) {
-      const int h = it.h, w = it.w;
-      Vec<V> o;
-      if (skip) {
-        o.load(sbase + (size_t)h * ys.hstride + (size_t)w * ys.wstride);
+    for (PixIter it((h2 + 1) * (w2 + 1), w2 + 1, PPB, slot); it.valid(); it.next()) {
+      const int a = it.h, b = it.w;
+      const int rows[2] = {2 * a - 1, 2 * a}, cols[2] = {2 * b - 1, 2 * b};
+      const bool rok[2] = {a >= 1, a < h2}, cok[2] = {b >= 1, b < w2};
+      Vec<V> z[2][2];
+      float wr[2][2], wc[2][2];     // [output row/col parity: 0 = odd (2a-1), 1 = even (2a)][tap]
+      if (!skip) {
+        const int r0 = a >= 1 ? a - 1 : 0, r1 = a < h2 ? a : h2 - 1;
+        const int q0 = b >= 1 ? b - 1 : 0, q1 = b < w2 ? b : w2 - 1;
+        z[0][0].load(dbase + (size_t)r0 * yd.hstride + (size_t)q0 * yd.wstride);
+        z[0][1].load(dbase + (size_t)r0 * yd.hstride + (size_t)q1 * yd.wstride);
+        z[1][0].load(dbase + (size_t)r1 * yd.hstride + (size_t)q0 * yd.wstride);
+        z[1][1].load(dbase + (size_t)r1 * yd.hstride + (size_t)q1 * yd.wstride);
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-          const float z = fmaf(o.v[j], bn.sc[j], bn.sh[j]);
-          o.v[j] = z > 0.f ? z : kLreluSlope * z;
-        }
-      } else {
-        int ha, hb, wa, wb;
-        float wha, whb, wwa, wwb;
-        up_taps(h, h2, mode, ha, hb, wha, whb);
-        up_taps(w, w2, mode, wa, wb, wwa, wwb);
-        Vec<V> t00, t01, t10, t11;
-        t00.load(dbase + (size_t)ha * yd.hstride + (size_t)wa * yd.wstride);
-        t01.load(dbase + (size_t)ha * yd.hstride + (size_t)wb * yd.wstride);
-        t10.load(dbase + (size_t)hb * yd.hstride + (size_t)wa * yd.wstride);
-        t11.load(dbase + (size_t)hb * yd.hstride + (size_t)wb * yd.wstride);
+        for (int u = 0; u < 2; ++u)
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-          const float sc = bn.sc[j], sh = bn.sh[j];
-          float z00 = fmaf(t00.v[j], sc, sh), z01 = fmaf(t01.v[j], sc, sh);
-          float z10 = fmaf(t10.v[j], sc, sh), z11 = fmaf(t11.v[j], sc, sh);
-          z00 = z00 > 0.f ? z00 : kLreluSlope * z00;
-          z01 = z01 > 0.f ? z01 : kLreluSlope * z01;
-          z10 = z10 > 0.f ? z10 : kLreluSlope * z10;
-          z11 = z11 > 0.f ? z11 : kLreluSlope * z11;
-          o.v[j] = wha * (wwa * z00 + wwb * z01) + whb * (wwa * z10 + wwb * z11);
-        }
+          for (int v = 0; v < 2; ++v)
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+              const float t = fmaf(z[u][v].v[j], bn.sc[j], bn.sh[j]);
+              z[u][v].v[j] = t > 0.f ? t : kLreluSlope * t;
+            }
+        quad_weights(a, mode, wr[0], wr[1]);
+        quad_weights(b, mode, wc[0], wc[1]);
       }
-      o.store(abase + (size_t)h * A.hstride + (size_t)w * A.wstride);
 #pragma unroll
-      for (int j = 0; j < V; ++j) {
-        acc.fa[j] += o.v[j];
-        acc.fb[j] = fmaf(o.v[j], o.v[j], acc.fb[j]);
+      for (int u = 0; u < 2; ++u) {
+        if (!rok[u]) continue;
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          if (!cok[v]) continue;
+          const int h = rows[u], w = cols[v];
+          Vec<V> o;
+          if (skip) {
+            o.load(sbase + (size_t)h * ys.hstride + (size_t)w * ys.wstride);
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+              const float t = fmaf(o.v[j], bn.sc[j], bn.sh[j]);
+              o.v[j] = t > 0.f ? t : kLreluSlope * t;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < V; ++j)
+              o.v[j] = wr[u][0] * (wc[v][0] * z[0][0].v[j] + wc[v][1] * z[0][1].v[j]) +
+                       wr[u][1] * (wc[v][0] * z[1][0].v[j] + wc[v][1] * z[1][1].v[j]);
+          }
+          o.store(abase + (size_t)h * A.hstride + (size_t)w * A.wstride);
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            acc.fa[j] += o.v[j];
+            acc.fb[j] = fmaf(o.v[j], o.v[j], acc.fb[j]);
+          }
+        }
       }
       acc.tick();
     }
@@ -663,7 +694,7 @@ int mfvi_cat_up_fwd(MfviView ys, int Cs, const double* sums_s, const float* gamm
   const bool al = view_vec_ok(yd) && view_vec_ok(A) && (Cs == 0 || view_vec_ok(ys)) && Cs % 4 == 0 && Cd % 4 == 0;
   const EwGeom ge = ew_geom(Cs + Cd, al);
   MFVI_REQUIRE(ge.G <= kEwThreads, "cat_up_fwd: too many channel groups");
-  dim3 grid(ew_grid(H * W, ge.PPB, S), S);
+  dim3 grid(ew_grid((H / 2 + 1) * (W / 2 + 1), ge.PPB, S), S);
   MFVI_EW_DISPATCH(ge, k_cat_up_fwd, grid, ys, Cs, sums_s, gamma_s, beta_s, yd, Cd, sums_d, gamma_d, beta_d, H, W, mode,
                    A, sumsA);
   return check_launch("cat_up_fwd");
