@@ -279,7 +279,11 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUt
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const uint32_t blk_bytes = static_cast<uint32_t>(p.TP) * 128u;          // one 32-channel block of TP pixel rows
-  const uint32_t a_bytes = 4u * blk_bytes;                                // M = 128 -> 4 blocks reserved
+  // M = 128 reads four 32-channel blocks of dy.  With Cout <= 32 only one exists: the descriptor's block stride (LBO) is then 0, so
+  // the other three alias it (their output rows are duplicates that the epilogue drops) and the stage holds ONE dy block —
+  // which lets the pixel tile (the K chunk per TMA round trip) be 4x longer for the latency-bound small-channel layers
+  const uint32_t a_blocks = p.MB == 1 ? 1u : 4u;
+  const uint32_t a_bytes = a_blocks * blk_bytes;
   const uint32_t stage_bytes = a_bytes + static_cast<uint32_t>(p.NB) * blk_bytes;
   uint8_t* ctrl = smem + static_cast<size_t>(p.stages) * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
@@ -351,7 +355,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUt
         const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(st) * stage_bytes);
         const uint32_t b_addr = a_addr + a_bytes;
         const uint32_t hi = desc_hi(512, kLayoutSw128Base32);
-        uint32_t a_lo = desc_lo(a_addr, blk_bytes), b_lo = desc_lo(b_addr, blk_bytes);
+        uint32_t a_lo = desc_lo(a_addr, p.MB == 1 ? 0u : blk_bytes), b_lo = desc_lo(b_addr, blk_bytes);
         for (int k = 0; k < ksteps; ++k, a_lo += 64u, b_lo += 64u)
           tc_mma_tf32_elect(tmem_base, desc_pack(a_lo, hi), desc_pack(b_lo, hi), idesc, (it > 0 || k > 0) ? 1u : 0u);
         tc_commit_elect(smem_u32(&empty_bar[st]));
@@ -631,8 +635,10 @@ int mfvi_conv2d_wgrad_tc(const MfviConvDesc* d, MfviView x, MfviView dy, float* 
   TcWgradArgs a{};
   a.Cout = d->Cout; a.Cin = d->Cin; a.KW = d->KW; a.Ho = d->Hout; a.Wo = d->Wout;
   a.MB = (d->Cout + 31) / 32; a.NB = (d->Cin + 31) / 32; a.cstride = d->stride; a.x_rows2 = d->Hin / 2;
-  int TP = 128;
-  while (TP > 8 && static_cast<size_t>(4 + a.NB) * TP * 128 > 48 * 1024) TP >>= 1;
+  const int a_blocks = a.MB == 1 ? 1 : 4;        // see k_wgrad_tc: one dy block is aliased four times when Cout <= 32
+  int TP = a.MB == 1 ? 256 : 128;
+  const size_t stage_cap = a.MB == 1 ? 64 * 1024 : 48 * 1024;
+  while (TP > 8 && static_cast<size_t>(a_blocks + a.NB) * TP * 128 > stage_cap) TP >>= 1;
   // the pixel tile must cover exactly TP rows (every K row enters the sum): TW | TP
   int TW = d->Wout >= TP ? TP : d->Wout;
   while (TW > 1 && TP % TW) --TW;
@@ -650,7 +656,7 @@ int mfvi_conv2d_wgrad_tc(const MfviConvDesc* d, MfviView x, MfviView dy, float* 
   chunks = std::max(1, std::min(chunks, a.n_tiles));
   a.tiles_per_cta = (a.n_tiles + chunks - 1) / chunks;
   chunks = (a.n_tiles + a.tiles_per_cta - 1) / a.tiles_per_cta;
-  a.stages = 4;
+  a.stages = static_cast<size_t>(a_blocks + a.NB) * TP * 128 > 48 * 1024 ? 3 : 4;
   a.tmem_cols = pow2_cols(a.NB * 32);
   a.dw = dw; a.w_sstride = w_sstride;
   CUtensorMap tmDy, tmX;
@@ -659,7 +665,7 @@ int mfvi_conv2d_wgrad_tc(const MfviConvDesc* d, MfviView x, MfviView dy, float* 
   if (db && d->S > 1) return -1;
   if (!map_activation(&tmX, x, d->Cin, d->Hin, d->Win, d->S, TH, TW, xb, true, d->stride)) return -1;
   a.x_bcast = xb ? 1 : 0;
-  const size_t smem = 1024 + static_cast<size_t>(a.stages) * (4 + a.NB) * TP * 128 + 18 * 8 + 64;
+  const size_t smem = 1024 + static_cast<size_t>(a.stages) * (a_blocks + a.NB) * TP * 128 + 18 * 8 + 64;
   static size_t attr = 0;
   if (smem > attr) {
     cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
