@@ -60,12 +60,18 @@ def test_tc_conv_matches_fp32_kernels(shape):
         assert rel_err(a, b) < TF32_TOL, (shape, n, rel_err(a, b))
 
 
-def test_tc_conv_broadcast_input_and_accumulate():
+@pytest.mark.parametrize("shape,S", [((16, 16, 3, 64, 64), 2), ((16, 16, 3, 128, 128, 2), 8), ((32, 16, 3, 40, 24, 2), 2),
+                                     ((16, 4, 1, 64, 64), 8), ((16, 8, 3, 32, 32), 4), ((16, 16, 5, 32, 32, 2), 6)])
+def test_tc_conv_broadcast_input(shape, S):
+    """One input image shared by all samples (sample stride 0: the first layers of the net).  Covers the sample-folded
+    weight-gradient mode (samples stacked along M when S*Cout <= 128) and shapes that do not qualify for it."""
     from mfvi_dip_mia_b200 import _lib as L
-    shape = (16, 16, 3, 64, 64)
-    ref = _run(shape, L.MATH_FP32, broadcast_x=True)
-    got = _run(shape, L.MATH_TF32, broadcast_x=True)
-    assert rel_err(got[0], ref[0]) < TF32_TOL
+    ref = _run(shape, L.MATH_FP32, S=S, broadcast_x=True)
+    got = _run(shape, L.MATH_TF32, S=S, broadcast_x=True)
+    for n, (a, b) in zip(["y", "dx", "dw", "stats"], zip(got, ref)):
+        if n == "dx":
+            continue                      # the gradient of a broadcast input is not defined per sample (never requested)
+        assert rel_err(a, b) < TF32_TOL, (shape, S, n, rel_err(a, b))
 
 
 @pytest.mark.parametrize("task", ["den", "inp"])
