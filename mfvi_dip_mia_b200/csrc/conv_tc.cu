@@ -267,6 +267,9 @@ struct TcWgradArgs {
   int cstride;          // conv stride; 2 = x is read through the parity-split 5-D map
   int x_rows2;          // Hin/2
   int x_bcast;
+  int sgrp;             // > 0: "sample-blocked" mode — x is ONE image shared by all samples and Cout <= 32, so each of the four
+                        // 32-row blocks of the M = 128 operand holds the dy of a different sample (rows >= Cout zero-filled by
+                        // TMA) and a CTA serves `sgrp` = 4 samples at once: 4x fewer MMAs and x loads (first-layer wgrads)
   int stages;
   uint32_t tmem_cols;
   float* dw;            // [S][taps][Cout][Cin]
@@ -292,7 +295,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUt
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full_bar + 17);
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for ptxas
-  const int smp = blockIdx.z, tap = blockIdx.y;
+  const int smp = p.sgrp > 0 ? blockIdx.z * p.sgrp : blockIdx.z, tap = blockIdx.y;     // (first) sample of this CTA
   const int r = tap / p.KW, s = tap % p.KW;
   const int t_begin = blockIdx.x * p.tiles_per_cta;
   const int t_end = min(t_begin + p.tiles_per_cta, p.n_tiles);
@@ -333,7 +336,11 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUt
         const int h0 = (t / p.tiles_w) * p.TH, w0 = (t % p.tiles_w) * p.TW;
         const uint32_t a_dst = smem_u32(smem + static_cast<size_t>(st) * stage_bytes);
         const uint32_t b_dst = a_dst + a_bytes;
-        for (int j = 0; j < p.MB; ++j) tma_load_4d(a_dst + j * blk_bytes, &tmDy, fb, 32 * j, w0, h0, smp);
+        if (p.sgrp > 0) {
+          for (int j = 0; j < p.sgrp; ++j) tma_load_4d(a_dst + j * blk_bytes, &tmDy, fb, 0, w0, h0, smp + j);   // block j = sample smp+j
+        } else {
+          for (int j = 0; j < p.MB; ++j) tma_load_4d(a_dst + j * blk_bytes, &tmDy, fb, 32 * j, w0, h0, smp);
+        }
         if (p.cstride == 2) {
           const int rows = p.x_bcast ? 0 : smp * p.x_rows2;
           for (int j = 0; j < p.NB; ++j)
@@ -364,10 +371,12 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUt
     }
   } else {
     const int q = warp & 3;
-    const int co = q * 32 + lane;
+    // accumulator row -> (sample, output channel): one sample per 32-row block in sample-blocked mode
+    const int osmp = p.sgrp > 0 ? smp + q : smp;
+    const int co = p.sgrp > 0 ? lane : q * 32 + lane;
     mbar_wait(smem_u32(tmem_full_bar), 0);
     tc_fence_after();
-    float* dst = p.dw + static_cast<size_t>(smp) * p.w_sstride + (static_cast<size_t>(tap) * p.Cout + co) * p.Cin;
+    float* dst = p.dw + static_cast<size_t>(osmp) * p.w_sstride + (static_cast<size_t>(tap) * p.Cout + co) * p.Cin;
     for (int c = 0; c < BN; c += 16) {
       float v[16];
       tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c), v);
@@ -635,6 +644,10 @@ int mfvi_conv2d_wgrad_tc(const MfviConvDesc* d, MfviView x, MfviView dy, float* 
   TcWgradArgs a{};
   a.Cout = d->Cout; a.Cin = d->Cin; a.KW = d->KW; a.Ho = d->Hout; a.Wo = d->Wout;
   a.MB = (d->Cout + 31) / 32; a.NB = (d->Cin + 31) / 32; a.cstride = d->stride; a.x_rows2 = d->Hin / 2;
+  if (x.sstride == 0 && dy.sstride != 0 && d->Cout <= 32 && d->S >= 4 && d->S % 4 == 0) {      // see TcWgradArgs::sgrp
+    a.sgrp = 4;
+    a.MB = 4;
+  }
   const int a_blocks = a.MB == 1 ? 1 : 4;        // see k_wgrad_tc: one dy block is aliased four times when Cout <= 32
   int TP = a.MB == 1 ? 256 : 128;
   const size_t stage_cap = a.MB == 1 ? 64 * 1024 : 48 * 1024;
@@ -652,7 +665,8 @@ int mfvi_conv2d_wgrad_tc(const MfviConvDesc* d, MfviView x, MfviView dy, float* 
   a.tiles_w = (d->Wout + TW - 1) / TW;
   a.n_tiles = a.tiles_w * ((d->Hout + TH - 1) / TH);
   const int taps = d->KH * d->KW;
-  int chunks = (2 * kNumSMs + taps * d->S - 1) / (taps * d->S);
+  const int Sz = a.sgrp > 0 ? d->S / a.sgrp : d->S;          // CTA columns along the sample axis
+  int chunks = (2 * kNumSMs + taps * Sz - 1) / (taps * Sz);
   chunks = std::max(1, std::min(chunks, a.n_tiles));
   a.tiles_per_cta = (a.n_tiles + chunks - 1) / chunks;
   chunks = (a.n_tiles + a.tiles_per_cta - 1) / a.tiles_per_cta;
@@ -673,7 +687,7 @@ int mfvi_conv2d_wgrad_tc(const MfviConvDesc* d, MfviView x, MfviView dy, float* 
     attr = 220 * 1024;
   }
   MFVI_REQUIRE(smem <= 220 * 1024, "conv2d_wgrad_tc: stage does not fit in shared memory");
-  dim3 grid(chunks, taps, d->S);
+  dim3 grid(chunks, taps, Sz);
   launch_k(k_wgrad_tc, grid, kThreads, smem, as_stream(st), tmDy, tmX, a);
   if (int rc = check_launch("conv2d_wgrad_tc")) return rc;
   if (dbias != nullptr) return mfvi_conv2d_bias_grad_tc(d, dy, dbias, w_sstride, st);
