@@ -21,9 +21,10 @@ for row in r:
     scale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1.0)
     d[row[iM]] = v * scale
 items = list(launch.values())
-starts = [i for i, d in enumerate(items) if d["kernel"].endswith("k_fill")]
+# a step starts with the accumulator fill that precedes the input-jitter kernel (other k_fill launches zero dT buffers mid-step)
+starts = [i - 1 for i, d in enumerate(items) if "k_input_jitter_pad" in d["kernel"] and i > 0]
 step = items[starts[0]:starts[1]] if len(starts) >= 2 else items
-fam_of = [("k_conv_halo", None), ("k_wgrad_alias", "mfvi_conv2d_wgrad"), ("k_wgrad_tc", "mfvi_conv2d_wgrad"),
+fam_of = [("k_conv_halo", None), ("k_conv_pointwise", None), ("k_wgrad_alias", "mfvi_conv2d_wgrad"), ("k_wgrad_tc", "mfvi_conv2d_wgrad"),
           ("k_conv_wgrad", "mfvi_conv2d_wgrad"), ("k_bias_grad", "mfvi_conv2d_wgrad"), ("k_pad_act_bwd", "mfvi_pad_act_bwd"),
           ("k_bn_bwd_apply", "mfvi_bn_bwd_apply"), ("k_bn_act_pad_fwd", "mfvi_bn_act_pad_fwd"), ("k_cat_up_fwd", "mfvi_cat_up_fwd"),
           ("k_cat_bwd", "mfvi_cat_up_bwd"), ("k_kl_reparam", "mfvi_kl_reparam_fwd_bwd"), ("k_sample_weights", "mfvi_sample_weights"),
@@ -45,7 +46,7 @@ for d in step:
         if pat in k:
             f = name
             break
-    if f is None and ("k_conv_halo" in k or "k_conv_tc" in k or "k_conv_igemm" in k):
+    if f is None and ("k_conv_halo" in k or "k_conv_tc" in k or "k_conv_igemm" in k or "k_conv_pointwise" in k):
         # forward launches come before the loss kernel; in the backward, wgrad is recognised above, the rest is dgrad
         f = "mfvi_conv2d_dgrad" if seen_nll else "mfvi_conv2d_fwd"
     if f:
