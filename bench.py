@@ -47,7 +47,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -159,6 +159,19 @@ def run_ours(args):
     sys.stdout.flush()
     json_fd = os.dup(1)
     os.dup2(2, 1)
+
+    # A collective that never completes (a rank died, mismatched call counts) would otherwise hang until the caller's
+    # timeout: after 10 minutes every rank gives up on its own, rank 0 reporting why on the JSON channel.
+    state = {"printed": False}
+
+    def _give_up():
+        if rank == 0 and not state["printed"]:
+            os.write(json_fd, (json.dumps({"metric": METRIC, "error": "bench.py watchdog: no result after 600 s "
+                                           "(hung collective or device?)", "n_gpus": world}) + "\n").encode())
+        os._exit(0 if state["printed"] else 3)
+    watchdog = threading.Timer(600.0, _give_up)
+    watchdog.daemon = True
+    watchdog.start()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — this path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
@@ -195,14 +208,14 @@ def run_ours(args):
     torch.cuda.synchronize()
     with ClockSampler(local) as clk:
         ms_total = timed(tr.step, args.steps)
-        # K steps can be shorter than nvidia-smi's sampling period: keep the SAME load running (untimed) until the sampler
-        # has seen it at least 3 times, so that the clock record describes the loaded state
-        extra, t_end = 0, time.time() + 2.0
-        while len(clk.rows) < 3 and time.time() < t_end:
-            for _ in range(25):
-                tr.step()
-            torch.cuda.synchronize()
-            extra += 25
+        # K steps can be shorter than nvidia-smi's sampling period: keep the SAME load running (untimed) for ~1 s so that the
+        # clock record describes the loaded state.  The number of extra steps is derived from ms_total, which is already the
+        # max over ranks and therefore IDENTICAL on every rank — every rank must issue the same number of all-reduces (a
+        # per-rank "until my sampler has 3 rows" loop deadlocks NCCL as soon as two ranks disagree; seen at 8 GPUs).
+        extra = int(min(4000, max(25, 1000.0 / max(ms_total / args.steps, 1e-3))))
+        for _ in range(extra):
+            tr.step()
+        torch.cuda.synchronize()
     clocks = clk.summary()
     clocks["window"] = f"timed region + {extra} untimed steps of the same load"
     launches = tr.launches_per_step * args.steps
@@ -302,6 +315,7 @@ def run_ours(args):
         line["cpu_baseline"] = cpu
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())
+    state["printed"] = True            # the watchdog stays armed for the final rendezvous, but no longer reports an error
 
 
 def main():
