@@ -55,6 +55,27 @@ def linear_rt(x, W_mu, W_rho, bias_mu, bias_rho, eps_w, eps_b, training=True):
     return F.linear(x, w, b)
 
 
+def conv2d_lrt(x, W_mu, W_rho, bias_mu, bias_rho, eps, stride=1, padding=0, training=True):
+    """LRTLayer.forward with layer_fn = conv2d (BayTorch/modules/reparam_layers.py:59-72, conv.py:75-107): the OUTPUT is
+    sampled, act_mu + sqrt(1e-16 + conv(x^2, softplus(W_rho)^2, softplus(bias_rho)^2)) * eps, eps of the output's shape."""
+    act_mu = F.conv2d(x, W_mu, bias_mu, stride=stride, padding=padding)
+    if not training:
+        return act_mu
+    bias_var = softplus(bias_rho) ** 2 if bias_mu is not None else None
+    act_std = torch.sqrt(1e-16 + F.conv2d(x ** 2, softplus(W_rho) ** 2, bias_var, stride=stride, padding=padding))
+    return rsample(act_mu, act_std, eps)
+
+
+def linear_lrt(x, W_mu, W_rho, bias_mu, bias_rho, eps, training=True):
+    """LRTLayer.forward with layer_fn = linear (BayTorch/modules/linear.py:29-50)."""
+    act_mu = F.linear(x, W_mu, bias_mu)
+    if not training:
+        return act_mu
+    bias_var = softplus(bias_rho) ** 2 if bias_mu is not None else None
+    act_std = torch.sqrt(1e-16 + F.linear(x ** 2, softplus(W_rho) ** 2, bias_var))
+    return rsample(act_mu, act_std, eps)
+
+
 # --------------------------------------------------------------------------------------
 # a7  KL
 # --------------------------------------------------------------------------------------

@@ -131,3 +131,42 @@ def test_nll_radon_metrics_match_reference():
     assert abs(O.psnr(g["a"], g["b"]) - float(g["psnr"])) < 1e-4
     assert abs(O.ssim(g["a"], g["b"]) - float(g["ssim"])) < 1e-5
     assert abs(O.uce(g["err"], g["unc"]) - float(g["uce"])) < 1e-7
+
+
+@pytest.mark.parametrize("i", [0, 1, 2])
+def test_metrics_match_reference(i):
+    """PSNR / SSIM / UCE (the trajectory-parity metrics and the device-side bookkeeping's checkers) against the imported
+    reference's utils/common_utils.py:297-353 and utils/uce.py (tests/golden/metrics.npz); the package's host-side
+    restatements (mfvi_dip_mia_b200/utils) are held to the same vectors."""
+    from mfvi_dip_mia_b200.utils.common_utils import peak_signal_noise_ratio, structural_similarity
+    from mfvi_dip_mia_b200.utils.uce import uceloss
+    g = group(load_npz("metrics.npz"), f"m{i}/")
+    a, b = g["a"], g["b"]
+    assert abs(O.psnr(a, b) - float(g["psnr"])) < 1e-4
+    assert abs(O.ssim(a, b) - float(g["ssim"])) < 1e-6
+    assert abs(O.uce(g["err"], g["unc"], 15) - float(g["uce"])) < 1e-7
+    assert abs(peak_signal_noise_ratio(a, b) - float(g["psnr"])) < 1e-4
+    assert abs(structural_similarity(a, b) - float(g["ssim"])) < 1e-6
+    assert abs(float(uceloss(g["err"], g["unc"], n_bins=15)[0]) - float(g["uce"])) < 1e-7
+
+
+@pytest.mark.parametrize("name", ["l1x1", "l3s1p1", "l3s2", "l5s1nb", "lin"])
+def test_lrt_layers_match_reference(name):
+    """Local-reparameterisation layers (row f3): oracle.conv2d_lrt / linear_lrt against the imported reference
+    (tests/golden/lrt_layers.npz: Conv2dLRT / LinearLRT with the output-space eps injected), forward, backward, eval."""
+    g = group(load_npz("lrt_layers.npz"), name + "/")
+    has_bias = "bias_mu" in g
+    leaves = {k: g[k].clone().requires_grad_(True) for k in ["x", "W_mu", "W_rho"] + (["bias_mu", "bias_rho"] if has_bias else [])}
+    bm, br = (leaves["bias_mu"], leaves["bias_rho"]) if has_bias else (None, None)
+    if name == "lin":
+        y = O.linear_lrt(leaves["x"], leaves["W_mu"], leaves["W_rho"], bm, br, g["eps"])
+        y_eval = O.linear_lrt(g["x"], g["W_mu"], g["W_rho"], g.get("bias_mu"), g.get("bias_rho"), None, training=False)
+    else:
+        cin, cout, k, st, pad = [int(v) for v in g["meta"][:5]]
+        y = O.conv2d_lrt(leaves["x"], leaves["W_mu"], leaves["W_rho"], bm, br, g["eps"], stride=st, padding=pad)
+        y_eval = O.conv2d_lrt(g["x"], g["W_mu"], g["W_rho"], g.get("bias_mu"), g.get("bias_rho"), None, stride=st, padding=pad,
+                              training=False)
+    assert rel_err(y, g["y"]) < 1e-6 and rel_err(y_eval, g["y_eval"]) < 1e-6
+    y.backward(g["dy"])
+    for k in leaves:
+        assert rel_err(leaves[k].grad, g["d" + k]) < 1e-5, k
