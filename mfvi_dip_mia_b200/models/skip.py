@@ -24,18 +24,36 @@ def _tag_children(seq: nn.Sequential, string: str, number: int) -> int:
     return number + 1
 
 
+_DROPOUT_DEFAULTS = {"dropout_mode_down": '2d', "dropout_p_down": 0.5, "dropout_mode_up": '2d', "dropout_p_up": 0.5,
+                     "dropout_mode_skip": 'None', "dropout_p_skip": 0.5, "dropout_mode_output": 'None', "dropout_p_output": 0.5}
+
+
 def skip(num_input_channels=2, num_output_channels=3,
          num_channels_down=[16, 32, 64, 128, 128], num_channels_up=[16, 32, 64, 128, 128],
          num_channels_skip=[4, 4, 4, 4, 4],
          filter_size_down=3, filter_size_up=3, filter_skip_size=1, need_sigmoid=True, need_bias=True,
-         pad='zero', upsample_mode='nearest', downsample_mode='stride', act_fun='LeakyReLU', need1x1_up=True,
-         dropout_mode_down='2d', dropout_p_down=0.5, dropout_mode_up='2d', dropout_p_up=0.5,
-         dropout_mode_skip='None', dropout_p_skip=0.5, dropout_mode_output='None', dropout_p_output=0.5):
+         pad='zero', upsample_mode='nearest', downsample_mode='stride', act_fun='LeakyReLU', need1x1_up=True, **dropout):
+    """Keyword-compatible with the reference's skip(): the eight dropout_mode_* / dropout_p_* keywords (same defaults) arrive
+    in **dropout and are passed to the conv blocks, which reject the MC-dropout modes."""
+    unknown = set(dropout) - set(_DROPOUT_DEFAULTS)
+    if unknown:
+        raise TypeError(f"skip() got unexpected keyword arguments {sorted(unknown)}")
+    drop = {**_DROPOUT_DEFAULTS, **dropout}
     n = len(num_channels_down)
     assert n == len(num_channels_up) == len(num_channels_skip)
     per_scale = lambda v: list(v) if isinstance(v, (list, tuple)) else [v] * n
     upsample_mode, downsample_mode = per_scale(upsample_mode), per_scale(downsample_mode)
     filter_size_down, filter_size_up = per_scale(filter_size_down), per_scale(filter_size_up)
+
+    def block(seq, cin, cout, k, stride, where, tag, it, down_mode='stride', with_act=True):
+        """conv -> bn -> act appended to `seq`, then the positional children get their reference names."""
+        push(seq, conv(cin, cout, k, stride, bias=need_bias, pad=pad, downsample_mode=down_mode,
+                       dropout_mode=drop[f"dropout_mode_{where}"], dropout_p=drop[f"dropout_p_{where}"], iterator=it,
+                       string=tag))
+        push(seq, bn(cout))
+        if with_act:
+            push(seq, act(act_fun))
+        return _tag_children(seq, tag, it)
 
     model = nn.Sequential()
     level = model
@@ -44,49 +62,29 @@ def skip(num_input_channels=2, num_output_channels=3,
     it_up = 2 * n if need1x1_up else n
     for i in range(n):
         deeper, side = nn.Sequential(), nn.Sequential()
-        has_skip = num_channels_skip[i] != 0
-        push(level, Concat(1, side, deeper) if has_skip else deeper)
-        c_deep = num_channels_up[i + 1] if i < n - 1 else num_channels_down[i]
-        push(level, bn(num_channels_skip[i] + c_deep))
-        if has_skip:
-            push(side, conv(cin, num_channels_skip[i], filter_skip_size, bias=need_bias, pad=pad,
-                            dropout_mode=dropout_mode_skip, dropout_p=dropout_p_skip, iterator=it_skip, string='skip'))
-            push(side, bn(num_channels_skip[i]))
-            push(side, act(act_fun))
-            it_skip = _tag_children(side, 'skip', it_skip)
-        push(deeper, conv(cin, num_channels_down[i], filter_size_down[i], 2, bias=need_bias, pad=pad,
-                          downsample_mode=downsample_mode[i], dropout_mode=dropout_mode_down, dropout_p=dropout_p_down,
-                          iterator=it_deep, string='deeper'))
-        push(deeper, bn(num_channels_down[i]))
-        push(deeper, act(act_fun))
-        it_deep = _tag_children(deeper, 'deeper', it_deep)
-        push(deeper, conv(num_channels_down[i], num_channels_down[i], filter_size_down[i], bias=need_bias, pad=pad,
-                          dropout_mode=dropout_mode_down, dropout_p=dropout_p_down, iterator=it_deep, string='deeper'))
-        push(deeper, bn(num_channels_down[i]))
-        push(deeper, act(act_fun))
-        it_deep = _tag_children(deeper, 'deeper', it_deep)
+        c_skip, c_down, c_up = num_channels_skip[i], num_channels_down[i], num_channels_up[i]
+        push(level, Concat(1, side, deeper) if c_skip != 0 else deeper)
+        c_deep = num_channels_up[i + 1] if i < n - 1 else c_down
+        push(level, bn(c_skip + c_deep))
+        if c_skip != 0:
+            it_skip = block(side, cin, c_skip, filter_skip_size, 1, 'skip', 'skip', it_skip)
+        it_deep = block(deeper, cin, c_down, filter_size_down[i], 2, 'down', 'deeper', it_deep, downsample_mode[i])
+        it_deep = block(deeper, c_down, c_down, filter_size_down[i], 1, 'down', 'deeper', it_deep)
         inner = nn.Sequential()
         if i < n - 1:
             push(deeper, inner)
         push(deeper, nn.Upsample(scale_factor=2, mode=upsample_mode[i]))
-        push(level, conv(num_channels_skip[i] + c_deep, num_channels_up[i], filter_size_up[i], 1, bias=need_bias,
-                         pad=pad, dropout_mode=dropout_mode_up, dropout_p=dropout_p_up, iterator=it_up - 1, string='up'))
-        push(level, bn(num_channels_up[i]))
-        push(level, act(act_fun))
-        _tag_children(level, 'up', it_up - 1)
+        block(level, c_skip + c_deep, c_up, filter_size_up[i], 1, 'up', 'up', it_up - 1)
         if need1x1_up:
-            push(level, conv(num_channels_up[i], num_channels_up[i], 1, bias=need_bias, pad=pad,
-                             dropout_mode=dropout_mode_up, dropout_p=dropout_p_up, iterator=it_up, string='up'))
-            push(level, bn(num_channels_up[i]))
-            push(level, act(act_fun))
-            _tag_children(level, 'up', it_up)
+            block(level, c_up, c_up, 1, 1, 'up', 'up', it_up)
             it_up -= 1
         it_up -= 1
-        cin = num_channels_down[i]
+        cin = c_down
         level = inner
     final_iter = 2 * n + 1 if need1x1_up else n + 1
     push(model, conv(num_channels_up[0], num_output_channels, 1, bias=need_bias, pad=pad,
-                     dropout_mode=dropout_mode_output, dropout_p=dropout_p_output, iterator=final_iter, string='up'))
+                     dropout_mode=drop["dropout_mode_output"], dropout_p=drop["dropout_p_output"], iterator=final_iter,
+                     string='up'))
     if need_sigmoid:
         push(model, nn.Sigmoid())
 

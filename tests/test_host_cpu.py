@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.helpers import GOLDEN
+from tests.helpers import GOLDEN, load_npz
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -245,3 +245,21 @@ def test_bo_loop_closes_on_analytic_objective(tmp_path):
     assert (z["candidates"] >= 1e-10).all() and (z["candidates"] <= 1.0).all()
     # proposals move towards the optimum (1e-6, 1e-3): the best observation improves on the initial grid's best
     assert max(Y) > max(Y[:9]) - 1e-9 and max(Y) > 29.0
+
+
+def test_initialisation_draw_order_matches_reference():
+    """VIModule.reset_parameters / MeanFieldVI conversion draw the initial values from torch's global RNG in the reference's
+    order (W_mu, W_rho, bias_mu, bias_rho per converted layer, module.py:56-62): under the fixture's seed every parameter
+    norm equals the imported reference's (tests/golden/den256_summary.npz)."""
+    from mfvi_dip_mia_b200.BayTorch import MeanFieldVI
+    from mfvi_dip_mia_b200.models import get_net
+    d = load_npz("den256_summary.npz")
+    temp, sigma = float(d["temp"]), float(d["sigma"])
+    torch.manual_seed(int(d["init_seed"]))
+    net = get_net(16, "skip", "reflection", skip_n33d=[16, 32, 64, 128, 128], skip_n33u=[16, 32, 64, 128, 128],
+                  skip_n11=4, num_scales=5, n_channels=2, upsample_mode="bilinear")
+    net = MeanFieldVI(net, prior={"mu": 0.0, "sigma": np.sqrt(temp) * sigma}, replace_layers="all", reparam="")
+    names = json.loads(str(d["grad_names"]))
+    pn = dict(net.named_parameters())
+    got = np.array([float(pn[k].detach().double().norm()) for k in names])
+    assert np.allclose(got, d["param_norms"], rtol=1e-6)
