@@ -102,6 +102,22 @@ int mfvi_conv2d_dgrad(const MfviConvDesc* d, MfviView dy, const float* w, long l
 int mfvi_conv2d_wgrad(const MfviConvDesc* d, MfviView x, MfviView dy, float* dw, float* dbias, long long w_sstride,
                       mfvi_stream_t st);
 
+/* Planning-only query (no reference counterpart; host-only, touches no device, works without a GPU): which kernel family
+ * mfvi_conv2d_{fwd,dgrad,wgrad} would run for this geometry and these views — "pointwise", "halo", "alias", "tc" (tcgen05
+ * paths) or "simt" (fp32 CUDA cores) — with its launch geometry and a one-line tile plan.  pass: 0 = forward (a = x, b = y),
+ * 1 = data gradient (a = dy, b = dx), 2 = weight gradient (a = x, b = dy).  Only the alignment and strides of the views
+ * are looked at.  tests/test_host_cpu.py pins the dispatch table of the four task networks with it. */
+typedef struct {
+  char family[24];
+  unsigned grid[3];
+  unsigned block;
+  unsigned long long smem_bytes;
+  int launches;      /* kernels one call enqueues (the convolution itself plus e.g. the bias-gradient reduction) */
+  char detail[200];  /* tile plan of the convolution kernel, "key=value ..." */
+} MfviPlanInfo;
+int mfvi_conv2d_plan(const MfviConvDesc* d, int pass, MfviView a, MfviView b, long long w_sstride, int accumulate,
+                     int with_bias, MfviPlanInfo* out);
+
 /* ---- a7 + a8: tempered KL and the reparameterisation chain, one flat pass ----------------------------
  * VIModule._kl / kl_divergence (BayTorch/modules/module.py:64-80), MeanFieldVI.kl (freq_to_bayes.py:43-48)
  * and the autograd of  w = mu + softplus(rho)*eps  (module.py:82-85):

@@ -38,6 +38,12 @@ class ConvDesc(C.Structure):
                 ("math", C.c_int)]
 
 
+class PlanInfo(C.Structure):
+    """MfviPlanInfo: answer of mfvi_conv2d_plan (host-only query, works without a GPU)."""
+    _fields_ = [("family", C.c_char * 24), ("grid", C.c_uint * 3), ("block", C.c_uint), ("smem_bytes", C.c_ulonglong),
+                ("launches", C.c_int), ("detail", C.c_char * 200)]
+
+
 _P = C.c_void_p
 _LL = C.c_longlong
 _I = C.c_int
@@ -83,7 +89,7 @@ _SIGS = {
     "mfvi_nhwc_to_nchw": [_P, _P, _I, _I, _I, _I],
 }
 
-EXPORTS = ["mfvi_abi_version", "mfvi_last_error"] + list(_SIGS)
+EXPORTS = ["mfvi_abi_version", "mfvi_last_error", "mfvi_conv2d_plan"] + list(_SIGS)
 
 
 def _load():
@@ -101,6 +107,8 @@ def _load():
         fn = getattr(lib, name)
         fn.argtypes = list(args) + [_P]
         fn.restype = C.c_int
+    lib.mfvi_conv2d_plan.argtypes = [_CD, _I, View, View, _LL, _I, _I, C.POINTER(PlanInfo)]   # no stream: nothing is launched
+    lib.mfvi_conv2d_plan.restype = C.c_int
     return lib
 
 
@@ -127,6 +135,24 @@ def call(name: str, *args, stream=None, meta=None):
     launch_count += 1
     if rc != 0:
         raise MfviError(f"{name} failed (rc={rc}): {lib.mfvi_last_error().decode()}")
+
+
+PASS_FWD, PASS_DGRAD, PASS_WGRAD = 0, 1, 2
+
+
+def conv_plan(desc: ConvDesc, pass_: int, a: View, b: View, w_sstride: int, accumulate: int = 0, with_bias: bool = True) -> dict:
+    """Which kernel family mfvi_conv2d_{fwd,dgrad,wgrad} would run for this geometry and these views, with its launch
+    geometry and tile plan — a host-only query (no device is touched; usable on a machine without a GPU)."""
+    info = PlanInfo()
+    rc = lib.mfvi_conv2d_plan(C.byref(desc), pass_, a, b, w_sstride, accumulate, 1 if with_bias else 0, C.byref(info))
+    if rc != 0:
+        raise MfviError(f"mfvi_conv2d_plan failed (rc={rc}): {lib.mfvi_last_error().decode()}")
+    plan = {}
+    for kv in info.detail.decode().split():
+        k, _, v = kv.partition("=")
+        plan[k] = int(v) if v.lstrip("-").isdigit() else v
+    return {"family": info.family.decode(), "grid": tuple(info.grid), "block": info.block, "smem_bytes": info.smem_bytes,
+            "launches": info.launches, "plan": plan}
 
 
 def require_cuda(t: torch.Tensor, what: str):

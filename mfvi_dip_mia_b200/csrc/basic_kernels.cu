@@ -22,7 +22,31 @@ bool pdl_enabled() {
   return on;
 }
 
+static thread_local DryRunInfo* g_dry = nullptr;
+
+DryRunInfo* dry_run() { return g_dry; }
+void set_dry_run(DryRunInfo* info) { g_dry = info; }
+
+void dry_note(dim3 grid, dim3 block, size_t smem) {
+  if (g_dry == nullptr) return;
+  if (g_dry->launches == 0) {          // the first launch of a call is the convolution; later ones are helpers (bias grad)
+    g_dry->grid[0] = grid.x; g_dry->grid[1] = grid.y; g_dry->grid[2] = grid.z;
+    g_dry->block = block.x * block.y * block.z;
+    g_dry->smem = smem;
+  }
+  ++g_dry->launches;
+}
+
+void dry_detail(const char* fmt, ...) {
+  if (g_dry == nullptr || g_dry->launches != 0) return;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_dry->detail, sizeof(g_dry->detail), fmt, ap);
+  va_end(ap);
+}
+
 int check_launch(const char* what) {
+  if (g_dry != nullptr) return 0;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: %s", what, cudaGetErrorString(e));

@@ -33,8 +33,27 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 #endif
 bool pdl_enabled();
 
+// Planning-only mode (mfvi_conv2d_plan): the host side of a conv launch runs unchanged — shape checks, dispatch, tile
+// planning, argument setup — but tensor maps are not encoded, function attributes are not set and nothing is launched;
+// the launch geometry is recorded instead.  It lets the dispatch table and the tile plans of every layer be inspected and
+// tested on a machine without a GPU.  dry_run() is thread-local and null outside mfvi_conv2d_plan.
+struct DryRunInfo {
+  int launches;
+  unsigned grid[3], block;
+  size_t smem;
+  char detail[200];
+};
+DryRunInfo* dry_run();
+void set_dry_run(DryRunInfo* info);
+void dry_note(dim3 grid, dim3 block, size_t smem);
+void dry_detail(const char* fmt, ...);
+
 template <typename... P, typename... A>
 static inline cudaError_t launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  if (dry_run() != nullptr) {
+    dry_note(grid, block, smem);
+    return cudaSuccess;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;

@@ -150,6 +150,7 @@ static int launch(const MfviConvDesc* d, bool dgrad, MfviView in, MfviView out, 
   const int cap = (kNumSMs * 8 + d->S - 1) / d->S;
   if (chunks > cap) chunks = cap;
   dim3 grid(chunks, d->S);
+  dry_detail("KP=%d NP=%d", KP, NP);
 #define PW_CASE(KQ, NQ)                                                                          \
   if (KP == KQ && NP == NQ) {                                                                    \
     if (stats != nullptr) launch_k(k_conv_pointwise<KQ, NQ, true>, grid, kThreads, 0, as_stream(st), p);  \

@@ -349,14 +349,15 @@ static int launch_igemm(const ConvArgs& a, cudaStream_t st) {
   const int M = DGRAD ? d.Hin * d.Win : d.Hout * d.Wout;
   const int N = DGRAD ? d.Cin : d.Cout;
   const int gm = (M + BM - 1) / BM;
-  if (N > 32) {
-    dim3 grid(gm, (N + 63) / 64, d.S);
+  const dim3 grid(gm, N > 32 ? (N + 63) / 64 : 1, d.S);
+  if (dry_run() != nullptr) {
+    dry_detail("igemm BM=%d BN=%d", BM, N > 32 ? 64 : (N > 16 ? 32 : 16));
+    dry_note(grid, 256, 0);
+  } else if (N > 32) {
     k_conv_igemm<64, DGRAD><<<grid, 256, 0, st>>>(a);
   } else if (N > 16) {
-    dim3 grid(gm, 1, d.S);
     k_conv_igemm<32, DGRAD><<<grid, 256, 0, st>>>(a);
   } else {
-    dim3 grid(gm, 1, d.S);
     k_conv_igemm<16, DGRAD><<<grid, 256, 0, st>>>(a);
   }
   return check_launch(DGRAD ? "conv2d_dgrad" : "conv2d_fwd");
@@ -427,13 +428,18 @@ int mfvi_conv2d_wgrad_simt(const MfviConvDesc* d, MfviView x, MfviView dy, float
   int threads = T * (a.BCO / 4) * (a.BCI / 4);
   threads = std::max(64, (threads + 31) / 32 * 32);
   static thread_local size_t attr_set = 0;
-  if (smem > 48 * 1024 && smem > attr_set) {
+  if (smem > 48 * 1024 && smem > attr_set && dry_run() == nullptr) {
     cudaError_t e = cudaFuncSetAttribute(k_conv_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     MFVI_REQUIRE(e == cudaSuccess, "conv2d_wgrad: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
     attr_set = 200 * 1024;
   }
   dim3 grid(chunks, tiles, d->S);
-  k_conv_wgrad<<<grid, threads, smem, as_stream(st)>>>(a);
+  if (dry_run() != nullptr) {
+    dry_detail("BCO=%d BCI=%d BW=%d rows_per_cta=%d", a.BCO, a.BCI, a.BW, a.rows_per_cta);
+    dry_note(grid, threads, smem);
+  } else {
+    k_conv_wgrad<<<grid, threads, smem, as_stream(st)>>>(a);
+  }
   return check_launch("conv2d_wgrad");
 }
 

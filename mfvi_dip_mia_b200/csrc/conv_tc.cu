@@ -451,6 +451,7 @@ static PFN_cuTensorMapEncodeTiled get_encode() {
 // 4-D fp32 tensor map, 128B swizzle, zero fill. dims/box innermost first; strides in bytes for dims 1..3.
 static bool encode_map(CUtensorMap* m, const void* base, const uint64_t* dims, const uint64_t* strides, const uint32_t* box,
                        const uint32_t* estr, bool mn_major = false, int rank = 4) {
+  if (dry_run() != nullptr) return true;
   PFN_cuTensorMapEncodeTiled enc = get_encode();
   if (enc == nullptr) return false;
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), dims, strides, box, estr,
@@ -560,13 +561,14 @@ int mfvi_conv2d_fwd_tc(const MfviConvDesc* d, MfviView x, const float* w, const 
   }
   const size_t smem = conv_smem_bytes(a.stages, a.b_bytes, a.BN);
   static size_t attr = 0;
-  if (smem > attr) {
+  if (smem > attr && dry_run() == nullptr) {
     cudaError_t e = cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     MFVI_REQUIRE(e == cudaSuccess, "conv2d_fwd_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
     attr = 200 * 1024;
   }
   const int tiles_h = (a.Mh + a.TH - 1) / a.TH;
   dim3 grid(a.tiles_w * tiles_h, 1, d->S);
+  dry_detail("TH=%d TW=%d BN=%d stages=%d tmem_cols=%u", a.TH, a.TW, a.BN, a.stages, a.tmem_cols);
   launch_k(k_conv_tc, grid, kThreads, smem, as_stream(st), tmA, tmB, a);
   return check_launch("conv2d_fwd_tc");
 }
@@ -608,13 +610,14 @@ int mfvi_conv2d_dgrad_tc(const MfviConvDesc* d, MfviView dy, const float* w, lon
   }
   const size_t smem = conv_smem_bytes(a.stages, a.b_bytes, a.BN);
   static size_t attr = 0;
-  if (smem > attr) {
+  if (smem > attr && dry_run() == nullptr) {
     cudaError_t e = cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     MFVI_REQUIRE(e == cudaSuccess, "conv2d_dgrad_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
     attr = 200 * 1024;
   }
   const int tiles_h = (a.Mh + a.TH - 1) / a.TH;
   dim3 grid(a.tiles_w * tiles_h, d->stride == 2 ? 4 : 1, d->S);
+  dry_detail("TH=%d TW=%d BN=%d stages=%d tmem_cols=%u", a.TH, a.TW, a.BN, a.stages, a.tmem_cols);
   launch_k(k_conv_tc, grid, kThreads, smem, as_stream(st), tmA, tmB, a);
   return check_launch("conv2d_dgrad_tc");
 }
@@ -681,13 +684,15 @@ int mfvi_conv2d_wgrad_tc(const MfviConvDesc* d, MfviView x, MfviView dy, float* 
   a.x_bcast = xb ? 1 : 0;
   const size_t smem = 1024 + static_cast<size_t>(a.stages) * (a_blocks + a.NB) * TP * 128 + 18 * 8 + 64;
   static size_t attr = 0;
-  if (smem > attr) {
+  if (smem > attr && dry_run() == nullptr) {
     cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     MFVI_REQUIRE(e == cudaSuccess, "conv2d_wgrad_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
     attr = 220 * 1024;
   }
   MFVI_REQUIRE(smem <= 220 * 1024, "conv2d_wgrad_tc: stage does not fit in shared memory");
   dim3 grid(chunks, taps, Sz);
+  dry_detail("TH=%d TW=%d TP=%d MB=%d NB=%d sgrp=%d stages=%d tmem_cols=%u tiles_per_cta=%d", a.TH, a.TW, a.TP, a.MB, a.NB, a.sgrp,
+             a.stages, a.tmem_cols, a.tiles_per_cta);
   launch_k(k_wgrad_tc, grid, kThreads, smem, as_stream(st), tmDy, tmX, a);
   if (int rc = check_launch("conv2d_wgrad_tc")) return rc;
   if (dbias != nullptr) return mfvi_conv2d_bias_grad_tc(d, dy, dbias, w_sstride, st);

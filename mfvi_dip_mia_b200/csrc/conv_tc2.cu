@@ -641,7 +641,7 @@ static int launch(const MfviConvDesc* d, bool dgrad, MfviView a, int Ca, int Ha,
     tmB = tmBt;
   }
   static size_t attr = 0;
-  if (pl.smem > attr) {
+  if (pl.smem > attr && dry_run() == nullptr) {
     cudaError_t e = cudaFuncSetAttribute(k_conv_halo<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     MFVI_REQUIRE(e == cudaSuccess, "%s: cannot raise dynamic shared memory: %s", what, cudaGetErrorString(e));
@@ -651,6 +651,8 @@ static int launch(const MfviConvDesc* d, bool dgrad, MfviView a, int Ca, int Ha,
     fprintf(stderr, "[tc2] %s Kc=%d N=%d k%d M=%dx%d S=%d: TH=%d TW=%d Pw=%d n_mt=%d BN=%d nb=%d g=%d acc_stages=%d smem=%zu grid=%d tiles=%d\n",
             what, Ca, Nvalid, d->KH, Mh, Mw, d->S, pl.TH, pl.TW, pl.Pw, pl.n_mt, pl.BN, pl.n_nb, pl.g, pl.acc_stages, pl.smem, pl.grid,
             p.total_tiles);
+  dry_detail("TH=%d TW=%d Pw=%d n_mt=%d BN=%d nb=%d chunks=%d g=%d acc_stages=%d tmem_cols=%u tiles=%d cls=%d planes=%d", pl.TH, pl.TW,
+             pl.Pw, pl.n_mt, pl.BN, pl.n_nb, p.n_chunks, pl.g, pl.acc_stages, pl.tmem_cols, p.total_tiles, n_cls, planes);
   if (dgrad)
     launch_k(k_conv_halo<true>, pl.grid, kThreads, pl.smem, as_stream(st), tmA, tmAt, tmB, tmBt, p);
   else

@@ -275,7 +275,7 @@ int mfvi_conv2d_wgrad_tc2(const MfviConvDesc* d, MfviView x, MfviView dy, float*
   if (!encode_act(&tmX, x, d->Cin, d->Hin, d->Win, d->S, a.x_bcast != 0, a.Pw, a.TH + halo)) return -1;
   const size_t smem = 1024 + static_cast<size_t>(a.n_stages) * a.stage_bytes + 256;
   static size_t attr = 0;
-  if (smem > attr) {
+  if (smem > attr && dry_run() == nullptr) {
     cudaError_t e = cudaFuncSetAttribute(k_wgrad_alias, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     MFVI_REQUIRE(e == cudaSuccess, "conv2d_wgrad_tc2: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
     attr = 200 * 1024;
@@ -284,6 +284,8 @@ int mfvi_conv2d_wgrad_tc2(const MfviConvDesc* d, MfviView x, MfviView dy, float*
   if (env_int("MFVI_TC2_VERBOSE", 0))
     fprintf(stderr, "[wgrad2] %d->%d k%d %dx%d S=%d: TH=%d TW=%d Pw=%d n_k=%d cblk=%d stage=%u grid=%d tiles/cta=%d\n", d->Cin, d->Cout, d->KH,
             d->Hout, d->Wout, d->S, a.TH, a.TW, a.Pw, a.n_k, a.n_cblk, a.stage_bytes, d->S * a.ctas_per_sample, a.tiles_per_cta);
+  dry_detail("TH=%d TW=%d Pw=%d n_k=%d cblk=%d stage_bytes=%u tmem_cols=%u tiles_per_cta=%d", a.TH, a.TW, a.Pw, a.n_k, a.n_cblk,
+             a.stage_bytes, a.tmem_cols, a.tiles_per_cta);
   launch_k(k_wgrad_alias, d->S * a.ctas_per_sample, kThreads, smem, as_stream(st), tmDy, tmX, a);
   return check_launch("conv2d_wgrad_tc2");
 }

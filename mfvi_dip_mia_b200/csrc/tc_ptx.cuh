@@ -6,6 +6,8 @@
 #include <stdint.h>
 
 namespace mfvi {
+struct DryRunInfo;
+DryRunInfo* dry_run();      // common.cuh: planning-only mode, no tensor map is encoded
 namespace tc {
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -180,6 +182,7 @@ inline PFN_cuTensorMapEncodeTiled tma_encode_fn() {
 // fp32 tiled tensor map, zero fill.  dims/box innermost first; strides in bytes for dims 1..rank-1.
 inline bool tma_encode(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box,
                        CUtensorMapSwizzle swz) {
+  if (dry_run() != nullptr) return true;
   PFN_cuTensorMapEncodeTiled enc = tma_encode_fn();
   if (enc == nullptr) return false;
   const uint32_t estr[5] = {1, 1, 1, 1, 1};

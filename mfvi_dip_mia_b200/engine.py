@@ -190,7 +190,10 @@ class SkipEngine:
     def __init__(self, spec: SkipSpec, H: int, W: int, S: int, device, *, math: int = L.MATH_FP32,
                  layout: Optional[SkipLayout] = None, need_input_grad: bool = False):
         device = torch.device(device)
-        if device.type != "cuda":
+        # device "meta" builds the kernel plan only (buffer shapes, strides and alignments, no memory): conv_dispatch_table()
+        # can then be inspected on a machine without a GPU; nothing can be executed
+        self.plan_only = device.type == "meta"
+        if device.type != "cuda" and not self.plan_only:
             raise L.MfviError(f"SkipEngine needs a CUDA device, got {device}: there is no CPU fallback")
         n = len(spec.down)
         if H % (1 << n) or W % (1 << n):
@@ -244,8 +247,8 @@ class SkipEngine:
         # their inputs; ("__join__", (), {"lane": X}) makes the main stream wait for lane X.
         self.overlap_wgrad = True
         self.overlap_skip = os.environ.get("MFVI_SKIP_LANE", "1") != "0"
-        self._side = torch.cuda.Stream(device=device)
-        self._side2 = torch.cuda.Stream(device=device)
+        self._side = None if self.plan_only else torch.cuda.Stream(device=device)
+        self._side2 = None if self.plan_only else torch.cuda.Stream(device=device)
         self._build_plan()
         # per-BN tables for the running-stat update
         self._bn_ch_off = torch.tensor([b.ch_off for b in lay.bns], dtype=torch.int32, device=device)
@@ -498,6 +501,8 @@ class SkipEngine:
         """Launch an op list: ops tagged lane="skip" go to the skip stream, weight-gradient kernels to the wgrad stream
         (each waits for the lane that produced its inputs), everything else to the current stream; every lane used is
         joined back before returning.  With the per-kernel timeline on, everything runs on one stream."""
+        if self.plan_only:
+            raise L.MfviError("this SkipEngine was built on device 'meta' (plan only): it cannot execute")
         serial = L.timeline is not None
         main = torch.cuda.current_stream(self.device)
         streams = {"main": main, "wgrad": self._side, "skip": self._side2}
@@ -559,6 +564,28 @@ class SkipEngine:
         L.call("mfvi_bn_running_update", self.arena.data_ptr(), self._bn_ch_off.data_ptr(), self._bn_sums_off.data_ptr(),
                self._bn_C.data_ptr(), self._bn_count.data_ptr(), len(self.lay.bns), self.S, float(momentum),
                self.running_mean.data_ptr(), self.running_var.data_ptr())
+
+    def conv_dispatch_table(self) -> List[dict]:
+        """One row per convolution launch of the plan (forward, data gradient, weight gradient): the kernel family
+        libmfvidip would run for it and its tile plan, asked from the library's own dispatch code in planning-only mode
+        (mfvi_conv2d_plan).  Works on a plan-only (device 'meta') engine, i.e. without a GPU."""
+        rows = []
+        for name, args, meta in self.fwd_ops + self.bwd_ops:
+            if name == "mfvi_conv2d_fwd":
+                d, x, _, b, wss, y, _ = args
+                info = L.conv_plan(d._obj, L.PASS_FWD, x, y, wss, 0, b is not None)
+            elif name == "mfvi_conv2d_dgrad":
+                d, dy, _, wss, dx, acc = args
+                info = L.conv_plan(d._obj, L.PASS_DGRAD, dy, dx, wss, acc)
+            elif name == "mfvi_conv2d_wgrad":
+                d, x, dy, _, db, wss = args
+                info = L.conv_plan(d._obj, L.PASS_WGRAD, x, dy, wss, 0, db is not None)
+            else:
+                continue
+            g = d._obj
+            rows.append(dict(info, op=name[len("mfvi_conv2d_"):], layer=meta["layer"], shape=meta["shape"], S=g.S, Cin=g.Cin,
+                             Cout=g.Cout, K=g.KH, stride=g.stride, Hin=g.Hin, Win=g.Win, Hout=g.Hout, Wout=g.Wout))
+        return rows
 
     # ---------------------------------------------------------------- parameter views (reference shapes)
     def param_views(self, src: str = "theta") -> Dict[str, torch.Tensor]:

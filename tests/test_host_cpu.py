@@ -263,3 +263,62 @@ def test_initialisation_draw_order_matches_reference():
     pn = dict(net.named_parameters())
     got = np.array([float(pn[k].detach().double().norm()) for k in names])
     assert np.allclose(got, d["param_norms"], rtol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Convolution dispatch and tile plans, asked from the library's own host code in planning-only mode (no GPU needed)
+_TASK_NETS = {
+    "den": (dict(), 256),                                                              # test_configs/mfvi_den.json (metric shape)
+    "sr": (dict(num_input_channels=32), 512),                                          # test_configs/mfvi_sr.json
+    "ct": (dict(num_output_channels=1), 512),                                          # test_configs/mfvi_ct.json
+    "inp": (dict(num_output_channels=4, down=(16, 32, 64, 128, 128, 128), up=(16, 32, 64, 128, 128, 128), skip=(0,) * 6,
+                 filter_down=5, need1x1_up=False, upsample_mode="nearest"), 512),      # test_configs/mfvi_inp.json
+}
+
+
+def _cdiv(a, b):
+    return -(-a // b)
+
+
+@pytest.mark.parametrize("S", [1, 2, 8])
+@pytest.mark.parametrize("task", sorted(_TASK_NETS))
+def test_conv_dispatch_table_of_the_task_networks(task, S):
+    """Every convolution launch (forward, data gradient, weight gradient) of the four task networks at their full sizes,
+    for the per-GPU sample counts of 8-, 4- and 1-GPU runs: under MFVI_MATH_TF32 none falls back to the fp32 CUDA-core
+    kernels, and every tile plan respects the hardware limits (227 KB shared memory, 512 TMEM columns) and covers its
+    output exactly.  The plans come from mfvi_conv2d_plan, i.e. from the same host code that launches the kernels."""
+    from mfvi_dip_mia_b200 import SkipEngine, SkipSpec, _lib as L
+    kw, H = _TASK_NETS[task]
+    eng = SkipEngine(SkipSpec(**kw), H, H, S, "meta", math=L.MATH_TF32)
+    rows = eng.conv_dispatch_table()
+    n_conv = len(eng.lay.convs)
+    assert sum(r["op"] == "fwd" for r in rows) == n_conv and sum(r["op"] == "wgrad" for r in rows) == n_conv
+    # the convolutions that read the network input have no data gradient (skip_1 / deeper_1, SURVEY.md section 8d)
+    assert sum(r["op"] == "dgrad" for r in rows) == n_conv - (2 if eng.lay.scales[0].skip_conv is not None else 1)
+    for r in rows:
+        where = f"{task} S={S} {r['op']} {r['layer']} {r['shape']}"
+        assert r["family"] in ("pointwise", "halo", "alias", "tc"), f"{where}: fell back to {r['family']}"
+        assert r["smem_bytes"] <= 227 * 1024 and 32 <= r["block"] <= 1024 and min(r["grid"]) >= 1, where
+        assert r["launches"] == (2 if (r["op"] == "wgrad" and r["layer"] == eng.lay.final.key.rsplit(".", 1)[-1]) else 1), where
+        p = r["plan"]
+        assert p.get("tmem_cols", 32) in (32, 64, 128, 256, 512), where
+        if r["family"] == "halo":
+            dgrad = r["op"] == "dgrad"
+            Mh, Mw = (r["Hin"], r["Win"]) if dgrad else (r["Hout"], r["Wout"])
+            if p["cls"] == 4:                                       # stride-2 dgrad: four output-parity classes of dx
+                Mh, Mw = (Mh + 1) // 2, (Mw + 1) // 2
+            assert p["n_mt"] * 128 >= (p["TH"] - 1) * p["Pw"] + p["TW"], where        # the M tiles cover the flat tile
+            assert p["acc_stages"] * p["n_mt"] * p["BN"] <= p["tmem_cols"], where
+            assert p["BN"] * p["nb"] >= (r["Cin"] if dgrad else r["Cout"]), where
+            assert p["tiles"] == r["S"] * p["nb"] * p["cls"] * _cdiv(Mh, p["TH"]) * _cdiv(Mw, p["TW"]), where
+            assert r["grid"][0] <= min(p["tiles"], 2 * 148), where                    # persistent CTAs, at most 2 per SM
+    # exact-fp32 parity mode: every convolution runs on the CUDA-core kernels
+    rows32 = SkipEngine(SkipSpec(**kw), H, H, S, "meta", math=L.MATH_FP32).conv_dispatch_table()
+    assert len(rows32) == len(rows) and {r["family"] for r in rows32} == {"simt"}
+
+
+def test_plan_only_engine_cannot_execute():
+    from mfvi_dip_mia_b200 import SkipEngine, SkipSpec, _lib as L
+    eng = SkipEngine(SkipSpec(), 64, 64, 2, "meta")
+    with pytest.raises(L.MfviError, match="plan only"):
+        eng.forward()
