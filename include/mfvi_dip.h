@@ -102,6 +102,16 @@ int mfvi_conv2d_dgrad(const MfviConvDesc* d, MfviView dy, const float* w, long l
 int mfvi_conv2d_wgrad(const MfviConvDesc* d, MfviView x, MfviView dy, float* dw, float* dbias, long long w_sstride,
                       mfvi_stream_t st);
 
+/* EXPERIMENTAL — bf16-operand mode, stage A (north_star: "bf16 operands with fp32 accumulate stated
+ * separately"); not called by the engine yet.  Same convolutions on tcgen05 kind::f16: x / dy / w hold bf16 (MfviView.ptr is
+ * then a bf16 pointer; view strides, w_sstride and w_cpitch count bf16 elements and must be multiples of 8; a layer's weight
+ * block is [KH][KW][Cout][w_cpitch]); y / dx, the bias (sample stride bias_sstride, in floats) and the BatchNorm statistics are
+ * fp32.  No fallback: a shape the tensor-core kernel does not take is an error. */
+int mfvi_conv2d_fwd_bf16(const MfviConvDesc* d, MfviView x, const void* w, int w_cpitch, long long w_sstride, const float* bias,
+                         long long bias_sstride, MfviView y, double* stats, mfvi_stream_t st);
+int mfvi_conv2d_dgrad_bf16(const MfviConvDesc* d, MfviView dy, const void* w, int w_cpitch, long long w_sstride, MfviView dx,
+                           int accumulate, mfvi_stream_t st);
+
 /* Planning-only query (no reference counterpart; host-only, touches no device, works without a GPU): which kernel family
  * mfvi_conv2d_{fwd,dgrad,wgrad} would run for this geometry and these views — "pointwise", "halo", "alias", "tc" (tcgen05
  * paths) or "simt" (fp32 CUDA cores) — with its launch geometry and a one-line tile plan.  pass: 0 = forward (a = x, b = y),

@@ -61,6 +61,9 @@ _SIGS = {
     "mfvi_conv2d_fwd": [_CD, View, _P, _P, _LL, View, _P],
     "mfvi_conv2d_dgrad": [_CD, View, _P, _LL, View, _I],
     "mfvi_conv2d_wgrad": [_CD, View, View, _P, _P, _LL],
+    # bf16-operand convolutions (EXPERIMENTAL, stage A of DESIGN.md section 8; not used by the engine yet)
+    "mfvi_conv2d_fwd_bf16": [_CD, View, _P, _I, _LL, _P, _LL, View, _P],
+    "mfvi_conv2d_dgrad_bf16": [_CD, View, _P, _I, _LL, View, _I],
     "mfvi_kl_reparam_fwd_bwd": [_P, _P, _SZ, _F, _D, _I, _F, _P, _P, _LL, _I, _P, _LL, PhiloxKey, _F, _P, _P, _P, _I],
     "mfvi_bn_act_pad_fwd": [View, _I, _I, _I, _I, _P, _P, _P, _I, _I, View],
     "mfvi_cat_up_fwd": [View, _I, _P, _P, _P, View, _I, _P, _P, _P, _I, _I, _I, _I, View, _P],
@@ -167,8 +170,9 @@ def ptr(t):
 
 
 def view(t: torch.Tensor, broadcast: bool = False) -> View:
-    """MfviView of an NHWC tensor (S,H,W,C) (channel stride must be 1; other strides arbitrary, in elements)."""
-    assert t.dim() == 4 and t.dtype == torch.float32 and (t.stride(3) == 1 or t.shape[3] == 1), (t.shape, t.stride())
+    """MfviView of an NHWC tensor (S,H,W,C) (channel stride must be 1; other strides arbitrary, in elements).
+    bf16 tensors are accepted for the bf16-operand entry points (strides then count bf16 elements)."""
+    assert t.dim() == 4 and t.dtype in (torch.float32, torch.bfloat16) and (t.stride(3) == 1 or t.shape[3] == 1), (t.shape, t.stride())
     ss = 0 if (broadcast or t.shape[0] == 1) else t.stride(0)
     return View(t.data_ptr(), ss, t.stride(1), t.stride(2))
 

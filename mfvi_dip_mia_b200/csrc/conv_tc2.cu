@@ -80,7 +80,17 @@ __device__ __forceinline__ TileCoord decode_tile(const Args& p, int t) {
   return c;
 }
 
-template <bool DGRAD>
+// BF16 = operands are bf16 (tcgen05 kind::f16, K = 16 channels per 32-byte k-step).  The kernel is written in BYTES — chunk widths
+// `cw` count 4-byte words of an operand row (8 / 16 / 32 words = 32 / 64 / 128-byte rows), `ck0` counts elements (TMA coordinates)
+// — so the K-major operands keep every descriptor constant; only the MMA kind, the instruction descriptor and the MN-major weight
+// operand of the data gradient differ (64-element atoms of plain SWIZZLE_128B instead of the 32-element atoms tf32 needs).
+template <bool BF16>
+__device__ __forceinline__ void mma_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (BF16) tc_mma_f16_elect(d_tmem, adesc, bdesc, idesc, accumulate);
+  else tc_mma_tf32_elect(d_tmem, adesc, bdesc, idesc, accumulate);
+}
+
+template <bool DGRAD, bool BF16 = false>
 __global__ void __launch_bounds__(kThreads, 2)
 k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAt,
             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBt, const Args p) {
@@ -179,10 +189,18 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               mbar_expect_tx(fb, static_cast<uint32_t>(p.g * p.BN * p.cw[c]) * 4u);
               tma_load_4d(dst, map, fb, p.ck0[c], n0, grp * p.g, bs);                      // box (w k, BN n, g taps)
             } else {
-              const uint32_t blk = static_cast<uint32_t>(p.g * p.cw[c]) * 128u;            // one 32-wide n block
-              mbar_expect_tx(fb, blk * static_cast<uint32_t>(p.BN / 32));
-              for (int j = 0; j < p.BN / 32; ++j)
-                tma_load_4d(dst + j * blk, map, fb, n0 + 32 * j, p.ck0[c], grp * p.g, bs);  // box (32 n, w k, g taps)
+              // one 128-byte row of n per k row: 32 (tf32) / 64 (bf16) input channels; a chunk has w (tf32) / 2w (bf16) k rows
+              if (!BF16) {
+                const uint32_t blk = static_cast<uint32_t>(p.g * p.cw[c]) * 128u;            // one 32-wide n block
+                mbar_expect_tx(fb, blk * static_cast<uint32_t>(p.BN / 32));
+                for (int j = 0; j < p.BN / 32; ++j)
+                  tma_load_4d(dst + j * blk, map, fb, n0 + 32 * j, p.ck0[c], grp * p.g, bs);  // box (32 n, w k, g taps)
+              } else {
+                const uint32_t blk = static_cast<uint32_t>(p.g * p.cw[c]) * 256u;            // one 64-wide n block
+                mbar_expect_tx(fb, blk * static_cast<uint32_t>(p.BN / 64));
+                for (int j = 0; j < p.BN / 64; ++j)
+                  tma_load_4d(dst + j * blk, map, fb, n0 + 64 * j, p.ck0[c], grp * p.g, bs);  // box (64 n, 2w k, g taps)
+              }
             }
           }
         }
@@ -190,7 +208,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ===== MMA issuer
-    const uint32_t idesc = make_idesc(128, p.BN, 0, DGRAD ? 1 : 0);
+    const uint32_t idesc = make_idesc(128, p.BN, 0, DGRAD ? 1 : 0, BF16 ? kFmtBF16 : kFmtTF32);
     uint32_t ia = 0, ib = 0, it = 0;
     int tile_i = 0;
     long long cyc_wait_a = 0, cyc_wait_b = 0, cyc_issue = 0, n_mma = 0;
@@ -224,10 +242,13 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint32_t b_base = smem_u32(b_stages + static_cast<size_t>(sb) * p.b_stage_bytes);
             // descriptors: hi words fixed per chunk, lo words advance by (bytes >> 4)
             const uint32_t a_hi = desc_hi(sbo, layout);
-            const uint32_t b_hi = DGRAD ? desc_hi(512, kLayoutSw128Base32) : a_hi;
-            const uint32_t b_lo0 = DGRAD ? desc_lo(b_base, static_cast<uint32_t>(p.g * w) * 128u) : desc_lo(b_base, 16);
-            const uint32_t b_tap = DGRAD ? static_cast<uint32_t>(w) * 8u : (static_cast<uint32_t>(p.BN) * rb) >> 4;   // per tap
-            constexpr uint32_t b_k = DGRAD ? 64u : 2u;                                                                // per k-step
+            // MN-major weight operand of the data gradient: rows = k (output channels), 128 bytes of n per row, n blocks LBO
+            // apart; tf32: 32-element atoms, 4-row k groups (SBO 512), 8 rows per k-step; bf16: 64-element atoms of plain
+            // SWIZZLE_128B, 8-row k groups (SBO 1024), 16 rows per k-step
+            const uint32_t b_hi = DGRAD ? (BF16 ? desc_hi(1024, kLayoutSw128) : desc_hi(512, kLayoutSw128Base32)) : a_hi;
+            const uint32_t b_lo0 = DGRAD ? desc_lo(b_base, static_cast<uint32_t>(p.g * w) * (BF16 ? 256u : 128u)) : desc_lo(b_base, 16);
+            const uint32_t b_tap = DGRAD ? static_cast<uint32_t>(w) * (BF16 ? 16u : 8u) : (static_cast<uint32_t>(p.BN) * rb) >> 4;   // per tap
+            constexpr uint32_t b_k = DGRAD ? (BF16 ? 128u : 64u) : 2u;                                                // per k-step
             const uint32_t a_lo0 = desc_lo(a_base, 16);
             const uint32_t a_mt = (128u * rb) >> 4, rb16 = rb >> 4;
             const int tap0 = grp * p.g;
@@ -246,10 +267,10 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 uint32_t al0 = a_t, al1 = a_t + 2u, al2 = a_t + 4u, al3 = a_t + 6u;
                 const uint32_t bl0 = b_t, bl1 = b_t + b_k, bl2 = b_t + 2u * b_k, bl3 = b_t + 3u * b_k;
                 for (int j = 0; j < p.n_mt; ++j) {
-                  tc_mma_tf32_elect(d_col, desc_pack(al0, a_hi), desc_pack(bl0, b_hi), idesc, acc0);
-                  tc_mma_tf32_elect(d_col, desc_pack(al1, a_hi), desc_pack(bl1, b_hi), idesc, 1u);
-                  tc_mma_tf32_elect(d_col, desc_pack(al2, a_hi), desc_pack(bl2, b_hi), idesc, 1u);
-                  tc_mma_tf32_elect(d_col, desc_pack(al3, a_hi), desc_pack(bl3, b_hi), idesc, 1u);
+                  mma_elect<BF16>(d_col, desc_pack(al0, a_hi), desc_pack(bl0, b_hi), idesc, acc0);
+                  mma_elect<BF16>(d_col, desc_pack(al1, a_hi), desc_pack(bl1, b_hi), idesc, 1u);
+                  mma_elect<BF16>(d_col, desc_pack(al2, a_hi), desc_pack(bl2, b_hi), idesc, 1u);
+                  mma_elect<BF16>(d_col, desc_pack(al3, a_hi), desc_pack(bl3, b_hi), idesc, 1u);
                   al0 += a_mt; al1 += a_mt; al2 += a_mt; al3 += a_mt;
                   d_col += p.BN;
                 }
@@ -257,15 +278,15 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 uint32_t al0 = a_t, al1 = a_t + 2u;
                 const uint32_t bl1 = b_t + b_k;
                 for (int j = 0; j < p.n_mt; ++j) {
-                  tc_mma_tf32_elect(d_col, desc_pack(al0, a_hi), desc_pack(b_t, b_hi), idesc, acc0);
-                  tc_mma_tf32_elect(d_col, desc_pack(al1, a_hi), desc_pack(bl1, b_hi), idesc, 1u);
+                  mma_elect<BF16>(d_col, desc_pack(al0, a_hi), desc_pack(b_t, b_hi), idesc, acc0);
+                  mma_elect<BF16>(d_col, desc_pack(al1, a_hi), desc_pack(bl1, b_hi), idesc, 1u);
                   al0 += a_mt; al1 += a_mt;
                   d_col += p.BN;
                 }
               } else {
                 uint32_t al0 = a_t;
                 for (int j = 0; j < p.n_mt; ++j) {
-                  tc_mma_tf32_elect(d_col, desc_pack(al0, a_hi), desc_pack(b_t, b_hi), idesc, acc0);
+                  mma_elect<BF16>(d_col, desc_pack(al0, a_hi), desc_pack(b_t, b_hi), idesc, acc0);
                   al0 += a_mt;
                   d_col += p.BN;
                 }
@@ -407,10 +428,11 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int rup(int a, int b) { return cdiv(a, b) * b; }
 
-static bool view_ok(const MfviView& v, int C) {
+// q = elements per 16 bytes (4 for fp32 views, 8 for bf16 views)
+static bool view_ok(const MfviView& v, int C, int q = 4) {
   // TMA needs a 16-byte aligned base and 16-byte multiples for every stride; the channel count itself is free
-  return (reinterpret_cast<uintptr_t>(v.ptr) % 16 == 0) && C >= 1 && (v.wstride % 4 == 0) && (v.hstride % 4 == 0) &&
-         (v.sstride % 4 == 0) && v.wstride >= C && v.hstride >= v.wstride;
+  return (reinterpret_cast<uintptr_t>(v.ptr) % 16 == 0) && C >= 1 && (v.wstride % q == 0) && (v.hstride % q == 0) &&
+         (v.sstride % q == 0) && v.wstride >= C && v.hstride >= v.wstride;
 }
 
 static CUtensorMapSwizzle swz_of(int width) {
@@ -433,7 +455,7 @@ static int env_int(const char* name, int dflt) {
 // (Mh, Mw): the pixel space the M tiles cover (output pixels; for stride-2 dgrad one output-parity class);  (hh, hw): halo
 // of the box;  planes: 4 parity planes per stage for the stride-2 forward;  n_cls: 4 parity classes for the stride-2 dgrad
 static Plan make_plan(int S, int Mh, int Mw, int hh, int hw, int taps, int planes, int n_cls, int n_chunks, const int* cw,
-                      int Nvalid, bool dgrad) {
+                      int Nvalid, bool dgrad, bool bf16 = false) {
   Plan best;
   best.cost = 1e30;
   int kw_total = 0, rb_max = 0;
@@ -441,7 +463,7 @@ static Plan make_plan(int S, int Mh, int Mw, int hh, int hw, int taps, int plane
     kw_total += cw[i];
     rb_max = std::max(rb_max, cw[i] * 4);
   }
-  const int nq = dgrad ? 32 : 16;
+  const int nq = dgrad ? (bf16 ? 64 : 32) : 16;      // N granule: one MN-major atom (dgrad), the UMMA N step (forward)
   const int BN_full = rup(Nvalid, nq);
   const int force_th = env_int("MFVI_TC2_TH", 0), force_strips = env_int("MFVI_TC2_STRIPS", 0), force_bn = env_int("MFVI_TC2_BN", 0);
   for (int split = 1; split <= 8; split *= 2) {
@@ -535,12 +557,18 @@ static int split_chunks(int Kc, int* ck0, int* cw) {
 }
 
 // a: the activation read through TMA (x for forward, dy for dgrad); Ca channels, (Ha, Wa) pixels.
-static int launch(const MfviConvDesc* d, bool dgrad, MfviView a, int Ca, int Ha, int Wa, const float* w, long long w_sstride,
+// bf16: `a` and `w` hold bf16 elements (view strides, w_sstride and the weight row pitch `w_cpitch` count bf16 elements; the
+// weight block is [tap][Cout][w_cpitch] with w_cpitch a multiple of 8 so that every TMA stride is a multiple of 16 bytes); the
+// output, bias and statistics stay fp32.
+static int launch(const MfviConvDesc* d, bool dgrad, MfviView a, int Ca, int Ha, int Wa, const void* w, long long w_sstride,
                   MfviView o, int Mh, int Mw, int Nvalid, const float* bias, double* stats, int accumulate, mfvi_stream_t st,
-                  const char* what) {
+                  const char* what, bool bf16 = false, int w_cpitch = 0, long long bias_sstride = -1) {
   Args p{};
-  p.n_chunks = split_chunks(Ca, p.ck0, p.cw);
+  const int esz = bf16 ? 2 : 4, epw = bf16 ? 2 : 1;          // bytes per element, elements per 4-byte word
+  if (w_cpitch == 0) w_cpitch = d->Cin;
+  p.n_chunks = split_chunks(cdiv(Ca, epw), p.ck0, p.cw);   // chunk widths in words ...
   if (p.n_chunks <= 0) return -1;
+  for (int i = 0; i < p.n_chunks; ++i) p.ck0[i] *= epw;      // ... first channel of a chunk in elements
   const int taps = d->KH * d->KW;
   if (taps > 25) return -1;
   const bool s2 = d->stride == 2;
@@ -560,7 +588,7 @@ static int launch(const MfviConvDesc* d, bool dgrad, MfviView a, int Ca, int Ha,
       Th_space = (Mh + 1) / 2; Tw_space = (Mw + 1) / 2;    // largest parity class of dx
     }
   }
-  const Plan pl = make_plan(d->S, Th_space, Tw_space, hh, hw, taps, planes, n_cls, p.n_chunks, p.cw, Nvalid, dgrad);
+  const Plan pl = make_plan(d->S, Th_space, Tw_space, hh, hw, taps, planes, n_cls, p.n_chunks, p.cw, Nvalid, dgrad, bf16);
   if (!pl.ok) return -1;
   p.cstride = d->stride; p.hh = hh; p.hw = hw; p.planes = planes; p.plane_rows = pl.plane_rows; p.n_cls = n_cls;
   p.org_h = dgrad ? hh : 0; p.org_w = dgrad ? hw : 0;
@@ -593,7 +621,7 @@ static int launch(const MfviConvDesc* d, bool dgrad, MfviView a, int Ca, int Ha,
   p.b_bcast = (w_sstride == 0 || d->S == 1) ? 1 : 0;
   p.n_a = pl.n_a; p.n_b = pl.n_b; p.acc_stages = pl.acc_stages;
   p.a_stage_bytes = pl.a_stage; p.b_stage_bytes = pl.b_stage; p.tmem_cols = pl.tmem_cols;
-  p.o = o; p.bias = bias; p.bias_sstride = w_sstride; p.stats = stats; p.accumulate = accumulate;
+  p.o = o; p.bias = bias; p.bias_sstride = bias_sstride >= 0 ? bias_sstride : w_sstride; p.stats = stats; p.accumulate = accumulate;
   p.vecO = ((reinterpret_cast<uintptr_t>(o.ptr) % 16 == 0) && o.sstride % 4 == 0 && o.hstride % 4 == 0 && o.wstride % 4 == 0) ? 1 : 0;
   if (const char* e = getenv("MFVI_TC2_DBG")) p.dbg = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));   // device pointer (debug)
   p.dbg_mode = env_int("MFVI_TC2_DBGMODE", 0);
@@ -604,35 +632,39 @@ static int launch(const MfviConvDesc* d, bool dgrad, MfviView a, int Ca, int Ha,
   for (int i = 0; i < p.n_chunks; ++i) {
     if (p.cw[i] == 32) has32 = true; else tail_w = p.cw[i];
   }
+  // `width` = chunk width in words (it selects the swizzle); boxes, dims and coordinates count elements, strides count bytes
   CUtensorMap tmA, tmAt, tmB, tmBt;
+  const CUtensorMapDataType dt = bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const uint64_t ez = static_cast<uint64_t>(esz);
   auto enc_a = [&](CUtensorMap* m, int width) {
     if (planes == 4) {
       const uint64_t dims[5] = {static_cast<uint64_t>(Ca), 2, static_cast<uint64_t>(Wa / 2), 2,
                                 static_cast<uint64_t>(Ha / 2) * (a_bcast ? 1 : d->S)};
-      const uint64_t strides[4] = {static_cast<uint64_t>(a.wstride) * 4, static_cast<uint64_t>(a.wstride) * 8,
-                                   static_cast<uint64_t>(a.hstride) * 4, static_cast<uint64_t>(a.hstride) * 8};
-      const uint32_t box[5] = {static_cast<uint32_t>(width), 1, static_cast<uint32_t>(pl.Pw), 1, static_cast<uint32_t>(pl.TH + hh)};
-      return tma_encode(m, a.ptr, 5, dims, strides, box, swz_of(width));
+      const uint64_t strides[4] = {static_cast<uint64_t>(a.wstride) * ez, static_cast<uint64_t>(a.wstride) * 2 * ez,
+                                   static_cast<uint64_t>(a.hstride) * ez, static_cast<uint64_t>(a.hstride) * 2 * ez};
+      const uint32_t box[5] = {static_cast<uint32_t>(width * epw), 1, static_cast<uint32_t>(pl.Pw), 1, static_cast<uint32_t>(pl.TH + hh)};
+      return tma_encode(m, a.ptr, 5, dims, strides, box, swz_of(width), dt);
     }
     const uint64_t dims[4] = {static_cast<uint64_t>(Ca), static_cast<uint64_t>(Wa), static_cast<uint64_t>(Ha),
                               static_cast<uint64_t>(p.a_bcast ? 1 : d->S)};
-    const uint64_t sbytes = p.a_bcast ? static_cast<uint64_t>(a.hstride) * Ha * 4 : static_cast<uint64_t>(a.sstride) * 4;
-    const uint64_t strides[3] = {static_cast<uint64_t>(a.wstride) * 4, static_cast<uint64_t>(a.hstride) * 4, sbytes};
-    const uint32_t box[4] = {static_cast<uint32_t>(width), static_cast<uint32_t>(pl.Pw), static_cast<uint32_t>(pl.TH + hh), 1};
-    return tma_encode(m, a.ptr, 4, dims, strides, box, swz_of(width));
+    const uint64_t sbytes = p.a_bcast ? static_cast<uint64_t>(a.hstride) * Ha * ez : static_cast<uint64_t>(a.sstride) * ez;
+    const uint64_t strides[3] = {static_cast<uint64_t>(a.wstride) * ez, static_cast<uint64_t>(a.hstride) * ez, sbytes};
+    const uint32_t box[4] = {static_cast<uint32_t>(width * epw), static_cast<uint32_t>(pl.Pw), static_cast<uint32_t>(pl.TH + hh), 1};
+    return tma_encode(m, a.ptr, 4, dims, strides, box, swz_of(width), dt);
   };
   auto enc_b = [&](CUtensorMap* m, int width) {
     const uint64_t dims[4] = {static_cast<uint64_t>(d->Cin), static_cast<uint64_t>(d->Cout), static_cast<uint64_t>(p.taps),
                               static_cast<uint64_t>(p.b_bcast ? 1 : d->S)};
-    const uint64_t tap_bytes = static_cast<uint64_t>(d->Cout) * d->Cin * 4;
-    const uint64_t strides[3] = {static_cast<uint64_t>(d->Cin) * 4, tap_bytes,
-                                 p.b_bcast ? tap_bytes * p.taps : static_cast<uint64_t>(w_sstride) * 4};
+    const uint64_t tap_bytes = static_cast<uint64_t>(d->Cout) * w_cpitch * ez;
+    const uint64_t strides[3] = {static_cast<uint64_t>(w_cpitch) * ez, tap_bytes,
+                                 p.b_bcast ? tap_bytes * p.taps : static_cast<uint64_t>(w_sstride) * ez};
     if (!dgrad) {
-      const uint32_t box[4] = {static_cast<uint32_t>(width), static_cast<uint32_t>(pl.BN), static_cast<uint32_t>(pl.g), 1};
-      return tma_encode(m, w, 4, dims, strides, box, swz_of(width));
+      const uint32_t box[4] = {static_cast<uint32_t>(width * epw), static_cast<uint32_t>(pl.BN), static_cast<uint32_t>(pl.g), 1};
+      return tma_encode(m, w, 4, dims, strides, box, swz_of(width), dt);
     }
-    const uint32_t box[4] = {32, static_cast<uint32_t>(width), static_cast<uint32_t>(pl.g), 1};
-    return tma_encode(m, w, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    // MN-major: one 128-byte row of n (input channels) per k (output channel)
+    const uint32_t box[4] = {bf16 ? 64u : 32u, static_cast<uint32_t>(width * epw), static_cast<uint32_t>(pl.g), 1};
+    return tma_encode(m, w, 4, dims, strides, box, bf16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, dt);
   };
   const int wide = has32 ? 32 : tail_w, narrow = tail_w ? tail_w : 32;
   if (!enc_a(&tmA, wide) || !enc_a(&tmAt, narrow) || !enc_b(&tmB, wide) || !enc_b(&tmBt, narrow)) return -1;
@@ -647,13 +679,24 @@ static int launch(const MfviConvDesc* d, bool dgrad, MfviView a, int Ca, int Ha,
     MFVI_REQUIRE(e == cudaSuccess, "%s: cannot raise dynamic shared memory: %s", what, cudaGetErrorString(e));
     attr = 200 * 1024;
   }
+  static size_t attr16 = 0;
+  if (bf16 && pl.smem > attr16 && dry_run() == nullptr) {
+    cudaError_t e = cudaFuncSetAttribute(k_conv_halo<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    MFVI_REQUIRE(e == cudaSuccess, "%s: cannot raise dynamic shared memory: %s", what, cudaGetErrorString(e));
+    attr16 = 200 * 1024;
+  }
   if (env_int("MFVI_TC2_VERBOSE", 0))
     fprintf(stderr, "[tc2] %s Kc=%d N=%d k%d M=%dx%d S=%d: TH=%d TW=%d Pw=%d n_mt=%d BN=%d nb=%d g=%d acc_stages=%d smem=%zu grid=%d tiles=%d\n",
             what, Ca, Nvalid, d->KH, Mh, Mw, d->S, pl.TH, pl.TW, pl.Pw, pl.n_mt, pl.BN, pl.n_nb, pl.g, pl.acc_stages, pl.smem, pl.grid,
             p.total_tiles);
   dry_detail("TH=%d TW=%d Pw=%d n_mt=%d BN=%d nb=%d chunks=%d g=%d acc_stages=%d tmem_cols=%u tiles=%d cls=%d planes=%d", pl.TH, pl.TW,
              pl.Pw, pl.n_mt, pl.BN, pl.n_nb, p.n_chunks, pl.g, pl.acc_stages, pl.tmem_cols, p.total_tiles, n_cls, planes);
-  if (dgrad)
+  if (bf16 && dgrad)
+    launch_k(k_conv_halo<true, true>, pl.grid, kThreads, pl.smem, as_stream(st), tmA, tmAt, tmB, tmBt, p);
+  else if (bf16)
+    launch_k(k_conv_halo<false, true>, pl.grid, kThreads, pl.smem, as_stream(st), tmA, tmAt, tmB, tmBt, p);
+  else if (dgrad)
     launch_k(k_conv_halo<true>, pl.grid, kThreads, pl.smem, as_stream(st), tmA, tmAt, tmB, tmBt, p);
   else
     launch_k(k_conv_halo<false>, pl.grid, kThreads, pl.smem, as_stream(st), tmA, tmAt, tmB, tmBt, p);
@@ -688,6 +731,36 @@ int mfvi_conv2d_dgrad_tc2(const MfviConvDesc* d, MfviView dy, const float* w, lo
     return -1;
   return tc2::launch(d, true, dy, d->Cout, d->Hout, d->Wout, w, w_sstride, dx, d->Hin, d->Win, d->Cin, nullptr, nullptr, accumulate, st,
                      "conv2d_dgrad_tc2");
+}
+
+// ---- bf16-operand mode, stage A of DESIGN.md section 8 (EXPERIMENTAL: not yet called by the engine).  x / dy / w hold bf16;
+// view strides, w_sstride and w_cpitch (row pitch of the [tap][Cout][w_cpitch] weight block, a multiple of 8) count bf16
+// elements; y / dx, the bias (sample stride bias_sstride, in floats) and the statistics are fp32.  Unlike the fp32 entry points
+// there is no fallback: a shape the halo kernel does not take is an error.
+int mfvi_conv2d_fwd_bf16(const MfviConvDesc* d, MfviView x, const void* w, int w_cpitch, long long w_sstride, const float* bias,
+                         long long bias_sstride, MfviView y, double* stats, mfvi_stream_t st) {
+  MFVI_REQUIRE(d != nullptr && x.ptr != nullptr && w != nullptr && y.ptr != nullptr, "conv2d_fwd_bf16: null argument");
+  MFVI_REQUIRE(tc2::view_ok(x, d->Cin, 8) && reinterpret_cast<uintptr_t>(w) % 16 == 0 && w_sstride % 8 == 0 && w_cpitch % 8 == 0 &&
+                   w_cpitch >= d->Cin && d->Cout <= 256 && (d->stride == 1 || d->stride == 2),
+               "conv2d_fwd_bf16: bf16 operands need 16-byte aligned pixels and weight rows (strides multiples of 8 elements)");
+  const int rc = tc2::launch(d, false, x, d->Cin, d->Hin, d->Win, w, w_sstride, y, d->Hout, d->Wout, d->Cout, bias, stats, 0, st,
+                             "conv2d_fwd_bf16", true, w_cpitch, bias != nullptr ? bias_sstride : 0);
+  MFVI_REQUIRE(rc >= 0, "conv2d_fwd_bf16: %d->%d k%dx%d s%d %dx%d is not taken by the halo kernel", d->Cin, d->Cout, d->KH, d->KW,
+               d->stride, d->Hout, d->Wout);
+  return rc;
+}
+
+int mfvi_conv2d_dgrad_bf16(const MfviConvDesc* d, MfviView dy, const void* w, int w_cpitch, long long w_sstride, MfviView dx,
+                           int accumulate, mfvi_stream_t st) {
+  MFVI_REQUIRE(d != nullptr && dy.ptr != nullptr && w != nullptr && dx.ptr != nullptr, "conv2d_dgrad_bf16: null argument");
+  MFVI_REQUIRE(tc2::view_ok(dy, d->Cout, 8) && reinterpret_cast<uintptr_t>(w) % 16 == 0 && w_sstride % 8 == 0 && w_cpitch % 8 == 0 &&
+                   w_cpitch >= d->Cin && d->Cin <= 256 && (d->stride == 1 || d->stride == 2),
+               "conv2d_dgrad_bf16: bf16 operands need 16-byte aligned pixels and weight rows (strides multiples of 8 elements)");
+  const int rc = tc2::launch(d, true, dy, d->Cout, d->Hout, d->Wout, w, w_sstride, dx, d->Hin, d->Win, d->Cin, nullptr, nullptr,
+                             accumulate, st, "conv2d_dgrad_bf16", true, w_cpitch);
+  MFVI_REQUIRE(rc >= 0, "conv2d_dgrad_bf16: %d->%d k%dx%d s%d %dx%d is not taken by the halo kernel", d->Cin, d->Cout, d->KH, d->KW,
+               d->stride, d->Hout, d->Wout);
+  return rc;
 }
 
 }  // extern "C"

@@ -85,6 +85,16 @@ __device__ __forceinline__ void tc_mma_tf32_elect(uint32_t d_tmem, uint64_t ades
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f16 (bf16 / fp16 operands, K = 16 per instruction, fp32 accumulate); operand formats come from the instruction descriptor
+__device__ __forceinline__ void tc_mma_f16_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
   asm volatile(
       "{\n\t.reg .pred e;\n\t"
@@ -149,12 +159,14 @@ __device__ __forceinline__ uint64_t desc_pack(uint32_t lo, uint32_t hi) {
   return d;
 }
 
-// Instruction descriptor: D=f32, A=B=tf32, majors, N>>3 at [17,23), M>>4 at [24,29).
-__host__ __device__ inline uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+// Instruction descriptor: D=f32, A=B=`fmt` (kind::tf32: 2 = TF32; kind::f16: 0 = F16, 1 = BF16), majors, N>>3 at [17,23),
+// M>>4 at [24,29).
+constexpr uint32_t kFmtF16 = 0, kFmtBF16 = 1, kFmtTF32 = 2;
+__host__ __device__ inline uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major, uint32_t fmt = kFmtTF32) {
   uint32_t d = 0;
   d |= 1u << 4;                       // c_format = F32
-  d |= 2u << 7;                       // a_format = TF32
-  d |= 2u << 10;                      // b_format = TF32
+  d |= fmt << 7;                      // a_format
+  d |= fmt << 10;                     // b_format
   d |= static_cast<uint32_t>(a_mn_major & 1) << 15;
   d |= static_cast<uint32_t>(b_mn_major & 1) << 16;
   d |= static_cast<uint32_t>(N >> 3) << 17;
@@ -179,14 +191,15 @@ inline PFN_cuTensorMapEncodeTiled tma_encode_fn() {
   return fn;
 }
 
-// fp32 tiled tensor map, zero fill.  dims/box innermost first; strides in bytes for dims 1..rank-1.
+// Tiled tensor map (fp32 unless `dtype` says otherwise), zero fill.  dims/box innermost first, in elements; strides in bytes
+// for dims 1..rank-1.
 inline bool tma_encode(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box,
-                       CUtensorMapSwizzle swz) {
+                       CUtensorMapSwizzle swz, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT32) {
   if (dry_run() != nullptr) return true;
   PFN_cuTensorMapEncodeTiled enc = tma_encode_fn();
   if (enc == nullptr) return false;
   const uint32_t estr[5] = {1, 1, 1, 1, 1};
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  return enc(m, dtype, rank, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
              swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 

@@ -10,13 +10,17 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "gpu_next: bring-up tests of code that is not on the product path yet; they need a CUDA "
+                                       "device AND MFVI_TEST_NEXT=1 (python -m pytest tests -m gpu_next)")
 
 
 def pytest_collection_modifyitems(config, items):
     import torch
-    if torch.cuda.is_available():
-        return
+    have_gpu = torch.cuda.is_available()
     skip = pytest.mark.skip(reason="no CUDA device")
+    skip_next = pytest.mark.skip(reason="bring-up test: needs a CUDA device and MFVI_TEST_NEXT=1")
     for item in items:
-        if "gpu" in item.keywords:
+        if "gpu" in item.keywords and not have_gpu:
             item.add_marker(skip)
+        if "gpu_next" in item.keywords and not (have_gpu and os.environ.get("MFVI_TEST_NEXT") == "1"):
+            item.add_marker(skip_next)
