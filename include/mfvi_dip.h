@@ -111,6 +111,18 @@ int mfvi_conv2d_fwd_bf16(const MfviConvDesc* d, MfviView x, const void* w, int w
                          long long bias_sstride, MfviView y, double* stats, mfvi_stream_t st);
 int mfvi_conv2d_dgrad_bf16(const MfviConvDesc* d, MfviView dy, const void* w, int w_cpitch, long long w_sstride, MfviView dx,
                            int accumulate, mfvi_stream_t st);
+/* stage C: producers of the bf16 operands.  mfvi_bn_act_pad_fwd / mfvi_bn_bwd_apply with a bf16 OUTPUT view (same arithmetic in
+ * fp32, rounded to nearest-even at the store); an fp32 -> bf16 copy of an NHWC view (network input, loss gradient); and the
+ * sampled weights of all layers repacked to bf16 rows of w_cpitch = Cin rounded up to 8 (HOST arrays of n_layers entries:
+ * element offsets of each layer's block in the fp32 / bf16 storage of one sample, rows = KH*KW*Cout, Cin). */
+int mfvi_bn_act_pad_fwd_bf16(MfviView y, int S, int H, int W, int C, const double* sums, const float* gamma,
+                             const float* beta, int act, int pad, MfviView xp, mfvi_stream_t st);
+int mfvi_bn_bwd_apply_bf16(MfviView g, MfviView y, int S, int H, int W, int C, const double* sums, const double* red,
+                           const float* gamma, MfviView dy, float* dgamma, float* dbeta, mfvi_stream_t st);
+int mfvi_view_f32_to_bf16(MfviView src, int S, int H, int W, int C, MfviView dst, mfvi_stream_t st);
+int mfvi_pack_weights_bf16(const float* w, long long w_sstride, int S, int n_layers, const long long* w_off,
+                           const long long* w16_off, const int* rows, const int* cin, void* w16, long long w16_sstride,
+                           mfvi_stream_t st);
 
 /* Planning-only query (no reference counterpart; host-only, touches no device, works without a GPU): which kernel family
  * mfvi_conv2d_{fwd,dgrad,wgrad} would run for this geometry and these views — "pointwise", "halo", "alias", "tc" (tcgen05

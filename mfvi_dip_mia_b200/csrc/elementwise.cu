@@ -3,6 +3,8 @@
 // forward and backward.  NHWC fp32, HBM-bound: each thread owns one channel quad of one pixel (float4 when
 // C % 4 == 0), threads of a CTA are laid out [pixel-slot][channel-group] so that a warp touches contiguous
 // memory; per-(sample,channel) reductions go registers -> shared -> one double atomic per channel per CTA.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace mfvi {
@@ -47,6 +49,22 @@ struct Vec<1> {
   __device__ __forceinline__ void load(const float* p) { v[0] = *p; }
   __device__ __forceinline__ void store(float* p) const { *p = v[0]; }
 };
+
+// bf16 outputs (bf16-operand mode, DESIGN.md section 8, stage C): the value is computed in fp32 exactly as for an fp32 output
+// and rounded to nearest-even at the store; V = 4 is one 8-byte store.
+template <int V>
+__device__ __forceinline__ void store_bf16(__nv_bfloat16* p, const float (&v)[V]) {
+  if (V == 4) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[V > 1 ? 2 : 0], v[V > 1 ? 3 : 0]);
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&lo);
+    u.y = *reinterpret_cast<const uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(p) = u;
+  } else {
+#pragma unroll
+    for (int j = 0; j < V; ++j) p[j] = __float2bfloat16_rn(v[j]);
+  }
+}
 
 // Per-CTA tables: scale[c] = gamma*invstd, shift[c] = beta - mean*scale  (z = y*scale + shift),
 // mean[c], invstd[c] for sample s.
@@ -211,7 +229,7 @@ __device__ __forceinline__ void cta_reduce_cells(const double* cells, int G, int
 }
 
 // F1: xp = reflect_pad(act(bn(y)))            grid = (chunks, S)
-template <int V>
+template <int V, bool OBF = false>       // OBF: xp is a bf16 view (strides in bf16 elements)
 __global__ void __launch_bounds__(kEwThreads)
 k_bn_act_pad_fwd(MfviView y, int H, int W, int C, const double* __restrict__ sums, const float* __restrict__ gamma,
                  const float* __restrict__ beta, int act, int pad, MfviView xp, int G, int PPB) {
@@ -229,6 +247,7 @@ k_bn_act_pad_fwd(MfviView y, int H, int W, int C, const double* __restrict__ sum
   const int Hp = H + 2 * pad, Wp = W + 2 * pad;
   const float* ybase = y.ptr + (size_t)s * y.sstride + c0;
   float* xbase = xp.ptr + (size_t)s * xp.sstride + c0;
+  __nv_bfloat16* xbase16 = reinterpret_cast<__nv_bfloat16*>(xp.ptr) + (size_t)s * xp.sstride + c0;
   for (PixIter it(Hp * Wp, Wp, PPB, slot); it.valid(); it.next()) {
     const int h = reflect_idx(it.h - pad, H), w = reflect_idx(it.w - pad, W);
     Vec<V> t;
@@ -239,7 +258,8 @@ k_bn_act_pad_fwd(MfviView y, int H, int W, int C, const double* __restrict__ sum
       if (act) z = z > 0.f ? z : kLreluSlope * z;
       t.v[j] = z;
     }
-    t.store(xbase + (size_t)it.h * xp.hstride + (size_t)it.w * xp.wstride);
+    if (!OBF) t.store(xbase + (size_t)it.h * xp.hstride + (size_t)it.w * xp.wstride);
+    else store_bf16<V>(xbase16 + (size_t)it.h * xp.hstride + (size_t)it.w * xp.wstride, t.v);
   }
 }
 
@@ -432,7 +452,7 @@ k_pad_act_bwd(MfviView dxp, int H, int W, int C, int pad, MfviView y, const doub
 }
 
 // B2: dy = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)); block (0,0) also writes dgamma/dbeta.
-template <int V>
+template <int V, bool OBF = false>       // OBF: dy is a bf16 view (strides in bf16 elements)
 __global__ void __launch_bounds__(kEwThreads)
 k_bn_bwd_apply(MfviView g, MfviView y, int S, int H, int W, int C, const double* __restrict__ sums,
                const double* __restrict__ red, const float* __restrict__ gamma, MfviView dy,
@@ -479,6 +499,7 @@ k_bn_bwd_apply(MfviView g, MfviView y, int S, int H, int W, int C, const double*
   const float* gbase = g.ptr + (size_t)s * g.sstride + c0;
   const float* ybase = y.ptr + (size_t)s * y.sstride + c0;
   float* obase = dy.ptr + (size_t)s * dy.sstride + c0;
+  __nv_bfloat16* obase16 = reinterpret_cast<__nv_bfloat16*>(dy.ptr) + (size_t)s * dy.sstride + c0;
   for (PixIter it(H * W, W, PPB, slot); it.valid(); it.next()) {
     const int h = it.h, w = it.w;
     Vec<V> gg, yy;
@@ -489,7 +510,8 @@ k_bn_bwd_apply(MfviView g, MfviView y, int S, int H, int W, int C, const double*
       const float xhat = (yy.v[j] - mean[j]) * invstd[j];
       gg.v[j] = k[j] * (gg.v[j] - m1[j] - xhat * m2[j]);
     }
-    gg.store(obase + (size_t)h * dy.hstride + (size_t)w * dy.wstride);
+    if (!OBF) gg.store(obase + (size_t)h * dy.hstride + (size_t)w * dy.wstride);
+    else store_bf16<V>(obase16 + (size_t)h * dy.hstride + (size_t)w * dy.wstride, gg.v);
   }
 }
 
@@ -669,6 +691,14 @@ using namespace mfvi;
       launch_k(KERNEL<1>, GRID, kEwThreads, 0, as_stream(st), __VA_ARGS__, (GEOM).G, (GEOM).PPB);  \
   } while (0)
 
+#define MFVI_EW_DISPATCH_BF16(GEOM, KERNEL, GRID, ...)                                               \
+  do {                                                                                              \
+    if ((GEOM).V == 4)                                                                              \
+      launch_k(KERNEL<4, true>, GRID, kEwThreads, 0, as_stream(st), __VA_ARGS__, (GEOM).G, (GEOM).PPB); \
+    else                                                                                            \
+      launch_k(KERNEL<1, true>, GRID, kEwThreads, 0, as_stream(st), __VA_ARGS__, (GEOM).G, (GEOM).PPB); \
+  } while (0)
+
 extern "C" {
 
 int mfvi_bn_act_pad_fwd(MfviView y, int S, int H, int W, int C, const double* sums, const float* gamma,
@@ -681,6 +711,32 @@ int mfvi_bn_act_pad_fwd(MfviView y, int S, int H, int W, int C, const double* su
   dim3 grid(ew_grid((H + 2 * pad) * (W + 2 * pad), ge.PPB, S), S);
   MFVI_EW_DISPATCH(ge, k_bn_act_pad_fwd, grid, y, H, W, C, sums, gamma, beta, act, pad, xp);
   return check_launch("bn_act_pad_fwd");
+}
+
+// bf16-operand mode (EXPERIMENTAL, DESIGN.md section 8 stage C): the same kernels with a bf16 OUTPUT view (strides in bf16
+// elements); inputs, statistics and arithmetic stay fp32, the result is rounded to nearest-even at the store.
+int mfvi_bn_act_pad_fwd_bf16(MfviView y, int S, int H, int W, int C, const double* sums, const float* gamma,
+                             const float* beta, int act, int pad, MfviView xp, mfvi_stream_t st) {
+  MFVI_REQUIRE(y.ptr && xp.ptr, "bn_act_pad_fwd_bf16: null pointer");
+  MFVI_REQUIRE(C >= 1 && C <= kMaxC, "bn_act_pad_fwd_bf16: C=%d out of range (1..%d)", C, kMaxC);
+  MFVI_REQUIRE(pad >= 0 && pad < H && pad < W, "bn_act_pad_fwd_bf16: pad must be smaller than the image");
+  const EwGeom ge = ew_geom(C, view_vec_ok(y) && view_vec_ok(xp));      // 4 bf16 = one 8-byte store: the fp32 test suffices
+  MFVI_REQUIRE(ge.G <= kEwThreads, "bn_act_pad_fwd_bf16: too many channel groups");
+  dim3 grid(ew_grid((H + 2 * pad) * (W + 2 * pad), ge.PPB, S), S);
+  MFVI_EW_DISPATCH_BF16(ge, k_bn_act_pad_fwd, grid, y, H, W, C, sums, gamma, beta, act, pad, xp);
+  return check_launch("bn_act_pad_fwd_bf16");
+}
+
+int mfvi_bn_bwd_apply_bf16(MfviView g, MfviView y, int S, int H, int W, int C, const double* sums, const double* red,
+                           const float* gamma, MfviView dy, float* dgamma, float* dbeta, mfvi_stream_t st) {
+  MFVI_REQUIRE(g.ptr && y.ptr && dy.ptr && sums && red, "bn_bwd_apply_bf16: null pointer");
+  MFVI_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "bn_bwd_apply_bf16: dgamma/dbeta must both be set or NULL");
+  MFVI_REQUIRE(C >= 1 && C <= kMaxC, "bn_bwd_apply_bf16: C out of range");
+  const EwGeom ge = ew_geom(C, view_vec_ok(g) && view_vec_ok(y) && view_vec_ok(dy));
+  MFVI_REQUIRE(ge.G <= kEwThreads, "bn_bwd_apply_bf16: too many channel groups");
+  dim3 grid(ew_grid(H * W, ge.PPB, S), S);
+  MFVI_EW_DISPATCH_BF16(ge, k_bn_bwd_apply, grid, g, y, S, H, W, C, sums, red, gamma, dy, dgamma, dbeta);
+  return check_launch("bn_bwd_apply_bf16");
 }
 
 int mfvi_cat_up_fwd(MfviView ys, int Cs, const double* sums_s, const float* gamma_s, const float* beta_s,

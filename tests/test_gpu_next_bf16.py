@@ -106,3 +106,79 @@ def test_bf16_conv_rejects_unaligned_views():
     y = torch.zeros(c["S"], c["H"], c["W"], 16, device=bad.device)
     with pytest.raises(L.MfviError, match="16-byte aligned"):
         L.call("mfvi_conv2d_fwd_bf16", C.byref(d), L.view(bad), c["wb"].data_ptr(), 16, c["wb"].stride(0), None, 0, L.view(y), None)
+
+
+# ---------------------------------------------------------------------------------------------------------------- stage C
+def _padded_bf16(S, H, W, Cn, dev):
+    """bf16 NHWC buffer with the channel pitch rounded up to 8 (poisoned), and its first Cn channels as the view."""
+    full = torch.full((S, H, W, _pitch8(Cn)), float("nan"), dtype=torch.bfloat16, device=dev)
+    return full, full[..., :Cn]
+
+
+@pytest.mark.parametrize("Cn,H,W,pad,act", [(16, 32, 32, 1, 1), (36, 17, 23, 1, 0), (128, 8, 8, 0, 1), (20, 16, 16, 2, 1), (2, 9, 9, 1, 1)])
+def test_bn_act_pad_fwd_bf16_is_the_rounded_fp32_kernel(Cn, H, W, pad, act):
+    from mfvi_dip_mia_b200 import _lib as L
+    dev, S = torch.device("cuda:0"), 3
+    g = torch.Generator(device=dev).manual_seed(1)
+    y = torch.randn(S, H, W, Cn, device=dev, generator=g)
+    sums = torch.stack([y.double().sum((1, 2)), (y.double() ** 2).sum((1, 2))], -1).contiguous()      # [S][C][2]
+    gamma, beta = torch.rand(Cn, device=dev, generator=g) + 0.5, torch.randn(Cn, device=dev, generator=g)
+    x32 = torch.zeros(S, H + 2 * pad, W + 2 * pad, Cn, device=dev)
+    full, x16 = _padded_bf16(S, H + 2 * pad, W + 2 * pad, Cn, dev)
+    args = (L.view(y), S, H, W, Cn, sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), act, pad)
+    L.call("mfvi_bn_act_pad_fwd", *args, L.view(x32))
+    L.call("mfvi_bn_act_pad_fwd_bf16", *args, L.view(x16))
+    torch.cuda.synchronize()
+    assert torch.equal(x16, x32.to(torch.bfloat16))
+    assert torch.isnan(full[..., Cn:]).all()                   # the pitch padding is never written
+
+
+@pytest.mark.parametrize("Cn,H,W", [(16, 32, 32), (36, 17, 23), (4, 64, 64), (128, 8, 8)])
+def test_bn_bwd_apply_bf16_is_the_rounded_fp32_kernel(Cn, H, W):
+    from mfvi_dip_mia_b200 import _lib as L
+    dev, S = torch.device("cuda:0"), 2
+    gen = torch.Generator(device=dev).manual_seed(2)
+    y, g = torch.randn(S, H, W, Cn, device=dev, generator=gen), torch.randn(S, H, W, Cn, device=dev, generator=gen)
+    sums = torch.stack([y.double().sum((1, 2)), (y.double() ** 2).sum((1, 2))], -1).contiguous()
+    mean = sums[..., 0] / (H * W)
+    invstd = 1.0 / torch.sqrt(sums[..., 1] / (H * W) - mean ** 2 + 1e-5)
+    xhat = (y.double() - mean[:, None, None]) * invstd[:, None, None]
+    red = torch.stack([g.double().sum((1, 2)), (g.double() * xhat).sum((1, 2))], -1).contiguous()
+    gamma = torch.rand(Cn, device=dev, generator=gen) + 0.5
+    dgam, dbet = torch.zeros(Cn, device=dev), torch.zeros(Cn, device=dev)
+    dy32 = torch.zeros_like(g)
+    _, dy16 = _padded_bf16(S, H, W, Cn, dev)
+    args = (L.view(g), L.view(y), S, H, W, Cn, sums.data_ptr(), red.data_ptr(), gamma.data_ptr())
+    L.call("mfvi_bn_bwd_apply", *args, L.view(dy32), dgam.data_ptr(), dbet.data_ptr())
+    L.call("mfvi_bn_bwd_apply_bf16", *args, L.view(dy16), dgam.data_ptr(), dbet.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(dy16, dy32.to(torch.bfloat16))
+
+
+def test_view_and_weight_conversions_round_like_torch():
+    from mfvi_dip_mia_b200 import _lib as L
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev).manual_seed(3)
+    src = torch.randn(2, 10, 12, 20, device=dev, generator=gen)[:, 1:9, 2:11, :18]        # a strided interior view
+    full, dst = _padded_bf16(2, 8, 9, 18, dev)
+    L.call("mfvi_view_f32_to_bf16", L.view(src), 2, 8, 9, 18, L.view(dst))
+    # two layers: 3x3 36->16 and 1x1 16->4, fp32 blocks back to back, bf16 blocks with rows of 40 / 16 channels
+    S, layers = 3, [(9 * 16, 36), (4, 16)]
+    P = sum(r * c for r, c in layers)
+    P16 = sum(r * _pitch8(c) for r, c in layers)
+    w = torch.randn(S, P + 5, device=dev, generator=gen)
+    w16 = torch.full((S, P16 + 8), float("nan"), dtype=torch.bfloat16, device=dev)
+    w_off, w16_off, o, o16 = [], [], 0, 0
+    for r, c in layers:
+        w_off.append(o); w16_off.append(o16)
+        o += r * c; o16 += r * _pitch8(c)
+    arr = lambda v, t: (t * len(v))(*v)
+    L.call("mfvi_pack_weights_bf16", w.data_ptr(), w.stride(0), S, len(layers), arr(w_off, C.c_longlong), arr(w16_off, C.c_longlong),
+           arr([r for r, _ in layers], C.c_int), arr([c for _, c in layers], C.c_int), w16.data_ptr(), w16.stride(0))
+    torch.cuda.synchronize()
+    assert torch.equal(dst, src.to(torch.bfloat16)) and torch.isnan(full[..., 18:]).all()
+    for (r, c), a, b in zip(layers, w_off, w16_off):
+        got = w16[:, b:b + r * _pitch8(c)].view(S, r, _pitch8(c))
+        assert torch.equal(got[..., :c], w[:, a:a + r * c].view(S, r, c).to(torch.bfloat16))
+        assert (got[..., c:] == 0).all()
+    assert torch.isnan(w16[:, P16:]).all()
