@@ -111,6 +111,10 @@ int mfvi_conv2d_fwd_bf16(const MfviConvDesc* d, MfviView x, const void* w, int w
                          long long bias_sstride, MfviView y, double* stats, mfvi_stream_t st);
 int mfvi_conv2d_dgrad_bf16(const MfviConvDesc* d, MfviView dy, const void* w, int w_cpitch, long long w_sstride, MfviView dx,
                            int accumulate, mfvi_stream_t st);
+/* stage B: weight gradient from bf16 x / dy into the fp32 dw block ([KH][KW][Cout][Cin], accumulated with atomics like
+ * mfvi_conv2d_wgrad).  dbias != NULL additionally reduces the bias gradient from `dy_f32`, an fp32 view of the same gradient. */
+int mfvi_conv2d_wgrad_bf16(const MfviConvDesc* d, MfviView x, MfviView dy, float* dw, long long w_sstride, MfviView dy_f32,
+                           float* dbias, mfvi_stream_t st);
 /* stage C: producers of the bf16 operands.  mfvi_bn_act_pad_fwd / mfvi_bn_bwd_apply with a bf16 OUTPUT view (same arithmetic in
  * fp32, rounded to nearest-even at the store); an fp32 -> bf16 copy of an NHWC view (network input, loss gradient); and the
  * sampled weights of all layers repacked to bf16 rows of w_cpitch = Cin rounded up to 8 (HOST arrays of n_layers entries:

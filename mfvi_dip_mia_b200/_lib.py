@@ -64,6 +64,7 @@ _SIGS = {
     # bf16-operand convolutions (EXPERIMENTAL, stage A of DESIGN.md section 8; not used by the engine yet)
     "mfvi_conv2d_fwd_bf16": [_CD, View, _P, _I, _LL, _P, _LL, View, _P],
     "mfvi_conv2d_dgrad_bf16": [_CD, View, _P, _I, _LL, View, _I],
+    "mfvi_conv2d_wgrad_bf16": [_CD, View, View, _P, _LL, View, _P],
     "mfvi_bn_act_pad_fwd_bf16": [View, _I, _I, _I, _I, _P, _P, _P, _I, _I, View],
     "mfvi_bn_bwd_apply_bf16": [View, View, _I, _I, _I, _I, _P, _P, _P, View, _P, _P],
     "mfvi_view_f32_to_bf16": [View, _I, _I, _I, _I, View],

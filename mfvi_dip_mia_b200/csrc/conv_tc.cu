@@ -20,14 +20,12 @@
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include "conv_tc_wgrad.cuh"
 
 namespace mfvi {
 namespace tc {
 
-constexpr int kBM = 128;        // UMMA_M (cta_group::1)
-constexpr int kBK = 32;         // fp32 per k-chunk = one 128-byte swizzle row
-constexpr int kUmmaK = 8;       // kind::tf32
-constexpr int kThreads = 192;
+constexpr int kBK = 32;         // fp32 per k-chunk = one 128-byte swizzle row   (kBM, kUmmaK, kThreads: conv_tc_wgrad.cuh)
 constexpr int kABytes = kBM * kBK * 4;   // 16 KB
 
 // ---------------------------------------------------------------------------------------------- fwd / dgrad
@@ -257,149 +255,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   }
 }
 
-// ---------------------------------------------------------------------------------------------- wgrad
-struct TcWgradArgs {
-  int Cout, Cin, KW;
-  int Ho, Wo;           // dy spatial size
-  int TH, TW, TP;       // pixel tile (K chunk) TP = TH*TW, multiple of 8
-  int tiles_w, n_tiles, tiles_per_cta;
-  int MB, NB;           // 32-channel blocks of dy (M) and x (N)
-  int cstride;          // conv stride; 2 = x is read through the parity-split 5-D map
-  int x_rows2;          // Hin/2
-  int x_bcast;
-  int sgrp;             // > 0: "sample-blocked" mode — x is ONE image shared by all samples and Cout <= 32, so each of the four
-                        // 32-row blocks of the M = 128 operand holds the dy of a different sample (rows >= Cout zero-filled by
-                        // TMA) and a CTA serves `sgrp` = 4 samples at once: 4x fewer MMAs and x loads (first-layer wgrads)
-  int stages;
-  uint32_t tmem_cols;
-  float* dw;            // [S][taps][Cout][Cin]
-  long long w_sstride;
-};
-
-__global__ void __launch_bounds__(kThreads)
-k_wgrad_tc(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, const TcWgradArgs p) {
-  pdl_trigger();
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  const uint32_t blk_bytes = static_cast<uint32_t>(p.TP) * 128u;          // one 32-channel block of TP pixel rows
-  // M = 128 reads four 32-channel blocks of dy.  With Cout <= 32 only one exists: the descriptor's block stride (LBO) is then 0, so
-  // the other three alias it (their output rows are duplicates that the epilogue drops) and the stage holds ONE dy block —
-  // which lets the pixel tile (the K chunk per TMA round trip) be 4x longer for the latency-bound small-channel layers
-  const uint32_t a_blocks = p.MB == 1 ? 1u : 4u;
-  const uint32_t a_bytes = a_blocks * blk_bytes;
-  const uint32_t stage_bytes = a_bytes + static_cast<uint32_t>(p.NB) * blk_bytes;
-  uint8_t* ctrl = smem + static_cast<size_t>(p.stages) * stage_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
-  uint64_t* empty_bar = full_bar + 8;
-  uint64_t* tmem_full_bar = full_bar + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full_bar + 17);
-
-  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for ptxas
-  const int smp = p.sgrp > 0 ? blockIdx.z * p.sgrp : blockIdx.z, tap = blockIdx.y;     // (first) sample of this CTA
-  const int r = tap / p.KW, s = tap % p.KW;
-  const int t_begin = blockIdx.x * p.tiles_per_cta;
-  const int t_end = min(t_begin + p.tiles_per_cta, p.n_tiles);
-  const int n_iters = t_end - t_begin;
-  const int BN = p.NB * 32;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmDy);
-    tma_prefetch_desc(&tmX);
-    for (int i = 0; i < p.stages; ++i) {
-      mbar_init(smem_u32(&full_bar[i]), 1);
-      mbar_init(smem_u32(&empty_bar[i]), 1);
-    }
-    mbar_init(smem_u32(tmem_full_bar), 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();
-  if (n_iters <= 0) {           // nothing to do (uniform per CTA)
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
-    return;
-  }
-
-  if (warp == 0) {
-    if (lane == 0) {
-      for (int it = 0; it < n_iters; ++it) {
-        const int st = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        mbar_wait(smem_u32(&empty_bar[st]), ph ^ 1);
-        const uint32_t fb = smem_u32(&full_bar[st]);
-        mbar_expect_tx(fb, static_cast<uint32_t>(p.MB + p.NB) * blk_bytes);
-        const int t = t_begin + it;
-        const int h0 = (t / p.tiles_w) * p.TH, w0 = (t % p.tiles_w) * p.TW;
-        const uint32_t a_dst = smem_u32(smem + static_cast<size_t>(st) * stage_bytes);
-        const uint32_t b_dst = a_dst + a_bytes;
-        if (p.sgrp > 0) {
-          for (int j = 0; j < p.sgrp; ++j) tma_load_4d(a_dst + j * blk_bytes, &tmDy, fb, 0, w0, h0, smp + j);   // block j = sample smp+j
-        } else {
-          for (int j = 0; j < p.MB; ++j) tma_load_4d(a_dst + j * blk_bytes, &tmDy, fb, 32 * j, w0, h0, smp);
-        }
-        if (p.cstride == 2) {
-          const int rows = p.x_bcast ? 0 : smp * p.x_rows2;
-          for (int j = 0; j < p.NB; ++j)
-            tma_load_5d(b_dst + j * blk_bytes, &tmX, fb, 32 * j, s & 1, w0 + (s >> 1), r & 1, rows + h0 + (r >> 1));
-        } else {
-          for (int j = 0; j < p.NB; ++j) tma_load_4d(b_dst + j * blk_bytes, &tmX, fb, 32 * j, w0 + s, h0 + r, p.x_bcast ? 0 : smp);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    const uint32_t idesc = make_idesc(kBM, BN, 1, 1);
-    const int ksteps = p.TP / kUmmaK;
-    for (int it = 0; it < n_iters; ++it) {
-      const int st = it % p.stages;
-      const uint32_t ph = (it / p.stages) & 1;
-      mbar_wait(smem_u32(&full_bar[st]), ph);
-      tc_fence_after();
-      {
-        const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(st) * stage_bytes);
-        const uint32_t b_addr = a_addr + a_bytes;
-        const uint32_t hi = desc_hi(512, kLayoutSw128Base32);
-        uint32_t a_lo = desc_lo(a_addr, p.MB == 1 ? 0u : blk_bytes), b_lo = desc_lo(b_addr, blk_bytes);
-        for (int k = 0; k < ksteps; ++k, a_lo += 64u, b_lo += 64u)
-          tc_mma_tf32_elect(tmem_base, desc_pack(a_lo, hi), desc_pack(b_lo, hi), idesc, (it > 0 || k > 0) ? 1u : 0u);
-        tc_commit_elect(smem_u32(&empty_bar[st]));
-        if (it == n_iters - 1) tc_commit_elect(smem_u32(tmem_full_bar));
-      }
-    }
-  } else {
-    const int q = warp & 3;
-    // accumulator row -> (sample, output channel): one sample per 32-row block in sample-blocked mode
-    const int osmp = p.sgrp > 0 ? smp + q : smp;
-    const int co = p.sgrp > 0 ? lane : q * 32 + lane;
-    mbar_wait(smem_u32(tmem_full_bar), 0);
-    tc_fence_after();
-    float* dst = p.dw + static_cast<size_t>(osmp) * p.w_sstride + (static_cast<size_t>(tap) * p.Cout + co) * p.Cin;
-    for (int c = 0; c < BN; c += 16) {
-      float v[16];
-      tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c), v);
-      if (co < p.Cout) {
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          if (c + j + 3 < p.Cin) {
-            atomicAdd(reinterpret_cast<float4*>(dst + c + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-          } else {
-            for (int jj = j; jj < j + 4; ++jj)
-              if (c + jj < p.Cin) atomicAdd(dst + c + jj, v[jj]);
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
-  }
-}
+// ---------------------------------------------------------------------------------------------- wgrad: conv_tc_wgrad.cuh
 
 // dbias[s][co] += sum over pixels of dy[s][.][.][co]   (HBM-bound column sum; V = 4 when C % 4 == 0, else scalar)
 template <int V>
@@ -449,13 +305,15 @@ static PFN_cuTensorMapEncodeTiled get_encode() {
 }
 
 // 4-D fp32 tensor map, 128B swizzle, zero fill. dims/box innermost first; strides in bytes for dims 1..3.
+// bf16: 2-byte elements; MN-major bf16 operands use the plain 128-byte swizzle (64-element atoms).
 static bool encode_map(CUtensorMap* m, const void* base, const uint64_t* dims, const uint64_t* strides, const uint32_t* box,
-                       const uint32_t* estr, bool mn_major = false, int rank = 4) {
+                       const uint32_t* estr, bool mn_major = false, int rank = 4, bool bf16 = false) {
   if (dry_run() != nullptr) return true;
   PFN_cuTensorMapEncodeTiled enc = get_encode();
   if (enc == nullptr) return false;
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+  CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   (mn_major && !bf16) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
@@ -471,6 +329,11 @@ static bool tc_stride_ok(int stride) {
 static bool view_tma_ok(const MfviView& v, int C) {
   return (reinterpret_cast<uintptr_t>(v.ptr) % 16 == 0) && (C % 4 == 0) && (v.wstride % 4 == 0) && (v.hstride % 4 == 0) &&
          (v.sstride % 4 == 0) && v.wstride >= C && v.hstride >= v.wstride;
+}
+// bf16 views: 16-byte aligned pixels = strides in multiples of 8 elements; the channel count itself is free (TMA zero-fills)
+static bool view_tma_ok_bf16(const MfviView& v, int C) {
+  return (reinterpret_cast<uintptr_t>(v.ptr) % 16 == 0) && C >= 1 && (v.wstride % 8 == 0) && (v.hstride % 8 == 0) &&
+         (v.sstride % 8 == 0) && v.wstride >= C && v.hstride >= v.wstride;
 }
 
 static uint32_t pow2_cols(int n) {
@@ -488,8 +351,29 @@ static void pick_tile(int Mh, int Mw, int& TH, int& TW) {
 
 // a: activation view read through TMA (x for fwd, dy for dgrad), its channel count Ca and spatial size (Ha, Wa).
 static bool map_activation(CUtensorMap* m, const MfviView& a, int Ca, int Ha, int Wa, int S, int TH, int TW, bool& bcast,
-                           bool mn_major = false, int cstride = 1) {
+                           bool mn_major = false, int cstride = 1, bool bf16 = false) {
   bcast = (a.sstride == 0) || S == 1;
+  if (bf16) {
+    // bf16 view (weight-gradient operands only): one 128-byte row = 64 channels, strides in 2-byte elements
+    if (TW > 256 || TH > 256) return false;
+    if (cstride == 2) {
+      if ((Ha & 1) || (Wa & 1) || (!bcast && a.sstride != static_cast<long long>(Ha) * a.hstride)) return false;
+      const uint64_t dims[5] = {static_cast<uint64_t>(Ca), 2, static_cast<uint64_t>(Wa / 2), 2,
+                                static_cast<uint64_t>(Ha / 2) * (bcast ? 1 : S)};
+      const uint64_t strides[4] = {static_cast<uint64_t>(a.wstride) * 2, static_cast<uint64_t>(a.wstride) * 4,
+                                   static_cast<uint64_t>(a.hstride) * 2, static_cast<uint64_t>(a.hstride) * 4};
+      const uint32_t box[5] = {64, 1, static_cast<uint32_t>(TW), 1, static_cast<uint32_t>(TH)};
+      const uint32_t estr[5] = {1, 1, 1, 1, 1};
+      return encode_map(m, a.ptr, dims, strides, box, estr, mn_major, 5, true);
+    }
+    const uint64_t dims[4] = {static_cast<uint64_t>(Ca), static_cast<uint64_t>(Wa), static_cast<uint64_t>(Ha),
+                              static_cast<uint64_t>(bcast ? 1 : S)};
+    const uint64_t sbytes = bcast ? static_cast<uint64_t>(a.hstride) * Ha * 2 : static_cast<uint64_t>(a.sstride) * 2;
+    const uint64_t strides[3] = {static_cast<uint64_t>(a.wstride) * 2, static_cast<uint64_t>(a.hstride) * 2, sbytes};
+    const uint32_t box[4] = {64, static_cast<uint32_t>(TW), static_cast<uint32_t>(TH), 1};
+    const uint32_t estr[4] = {1, 1, 1, 1};
+    return encode_map(m, a.ptr, dims, strides, box, estr, mn_major, 4, true);
+  }
   if (cstride == 2) {
     // parity-split view: dims (C, 2, W/2, 2, H/2 * S); the sample axis is folded into the row axis, which needs
     // densely stacked samples.  (TMA elementStrides are avoided on purpose.)
@@ -638,20 +522,27 @@ int mfvi_conv2d_bias_grad_tc(const MfviConvDesc* d, MfviView dy, float* dbias, l
   return check_launch("conv2d_bias_grad_tc");
 }
 
-int mfvi_conv2d_wgrad_tc(const MfviConvDesc* d, MfviView x, MfviView dy, float* dw, float* dbias, long long w_sstride,
-                         mfvi_stream_t st) {
+}  // extern "C"
+
+// bf16: x and dy are bf16 views (strides in bf16 elements); dw stays fp32 in the [tap][Cout][Cin] storage layout.  The bias
+// gradient is reduced from `dy_bias`, which must be an fp32 view of the same gradient (the engine keeps the loss gradient of the
+// final convolution, the only one with a bias gradient, in fp32 as well).
+static int wgrad_tc_launch(const MfviConvDesc* d, MfviView x, MfviView dy, float* dw, float* dbias, long long w_sstride,
+                           mfvi_stream_t st, bool bf16, MfviView dy_bias) {
   using namespace mfvi::tc;
-  if (!tc_stride_ok(d->stride) || !view_tma_ok(x, d->Cin) || !view_tma_ok(dy, d->Cout) || d->Cout > 128 || d->Cin > 256 ||
+  const bool views_ok = bf16 ? (view_tma_ok_bf16(x, d->Cin) && view_tma_ok_bf16(dy, d->Cout)) : (view_tma_ok(x, d->Cin) && view_tma_ok(dy, d->Cout));
+  if (!tc_stride_ok(d->stride) || !views_ok || d->Cout > 128 || d->Cin > 256 ||
       (reinterpret_cast<uintptr_t>(dw) % 16) || (w_sstride % 4))
     return -1;
+  const int cb = bf16 ? 64 : 32;                 // channels of one 128-byte operand row
   TcWgradArgs a{};
   a.Cout = d->Cout; a.Cin = d->Cin; a.KW = d->KW; a.Ho = d->Hout; a.Wo = d->Wout;
-  a.MB = (d->Cout + 31) / 32; a.NB = (d->Cin + 31) / 32; a.cstride = d->stride; a.x_rows2 = d->Hin / 2;
-  if (x.sstride == 0 && dy.sstride != 0 && d->Cout <= 32 && d->S >= 4 && d->S % 4 == 0) {      // see TcWgradArgs::sgrp
+  a.MB = (d->Cout + cb - 1) / cb; a.NB = (d->Cin + cb - 1) / cb; a.cstride = d->stride; a.x_rows2 = d->Hin / 2;
+  if (!bf16 && x.sstride == 0 && dy.sstride != 0 && d->Cout <= 32 && d->S >= 4 && d->S % 4 == 0) {      // see TcWgradArgs::sgrp
     a.sgrp = 4;
     a.MB = 4;
   }
-  const int a_blocks = a.MB == 1 ? 1 : 4;        // see k_wgrad_tc: one dy block is aliased four times when Cout <= 32
+  const int a_blocks = a.MB == 1 ? 1 : (bf16 ? 2 : 4);   // see k_wgrad_tc: one dy block is aliased across M when it is the only one
   int TP = a.MB == 1 ? 256 : 128;
   const size_t stage_cap = a.MB == 1 ? 64 * 1024 : 48 * 1024;
   while (TP > 8 && static_cast<size_t>(a_blocks + a.NB) * TP * 128 > stage_cap) TP >>= 1;
@@ -663,7 +554,7 @@ int mfvi_conv2d_wgrad_tc(const MfviConvDesc* d, MfviView x, MfviView dy, float* 
     TH = d->Hout;
     TP = TH * TW;
   }
-  if (TP % 8 || TW > 256 || TH > 256) return -1;
+  if (TP % (bf16 ? 16 : 8) || TW > 256 || TH > 256) return -1;
   a.TH = TH; a.TW = TW; a.TP = TP;
   a.tiles_w = (d->Wout + TW - 1) / TW;
   a.n_tiles = a.tiles_w * ((d->Hout + TH - 1) / TH);
@@ -674,18 +565,19 @@ int mfvi_conv2d_wgrad_tc(const MfviConvDesc* d, MfviView x, MfviView dy, float* 
   a.tiles_per_cta = (a.n_tiles + chunks - 1) / chunks;
   chunks = (a.n_tiles + a.tiles_per_cta - 1) / a.tiles_per_cta;
   a.stages = static_cast<size_t>(a_blocks + a.NB) * TP * 128 > 48 * 1024 ? 3 : 4;
-  a.tmem_cols = pow2_cols(a.NB * 32);
+  a.tmem_cols = pow2_cols(a.NB * cb);
   a.dw = dw; a.w_sstride = w_sstride;
   CUtensorMap tmDy, tmX;
   bool db = false, xb = false;
-  if (!map_activation(&tmDy, dy, d->Cout, d->Hout, d->Wout, d->S, TH, TW, db, true)) return -1;
+  if (!map_activation(&tmDy, dy, d->Cout, d->Hout, d->Wout, d->S, TH, TW, db, true, 1, bf16)) return -1;
   if (db && d->S > 1) return -1;
-  if (!map_activation(&tmX, x, d->Cin, d->Hin, d->Win, d->S, TH, TW, xb, true, d->stride)) return -1;
+  if (!map_activation(&tmX, x, d->Cin, d->Hin, d->Win, d->S, TH, TW, xb, true, d->stride, bf16)) return -1;
   a.x_bcast = xb ? 1 : 0;
   const size_t smem = 1024 + static_cast<size_t>(a.stages) * (a_blocks + a.NB) * TP * 128 + 18 * 8 + 64;
   static size_t attr = 0;
   if (smem > attr && dry_run() == nullptr) {
-    cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e == cudaSuccess) e = wgrad_tc_bf16_set_smem(220 * 1024);
     MFVI_REQUIRE(e == cudaSuccess, "conv2d_wgrad_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
     attr = 220 * 1024;
   }
@@ -693,10 +585,31 @@ int mfvi_conv2d_wgrad_tc(const MfviConvDesc* d, MfviView x, MfviView dy, float* 
   dim3 grid(chunks, taps, Sz);
   dry_detail("TH=%d TW=%d TP=%d MB=%d NB=%d sgrp=%d stages=%d tmem_cols=%u tiles_per_cta=%d", a.TH, a.TW, a.TP, a.MB, a.NB, a.sgrp,
              a.stages, a.tmem_cols, a.tiles_per_cta);
-  launch_k(k_wgrad_tc, grid, kThreads, smem, as_stream(st), tmDy, tmX, a);
+  if (bf16) wgrad_tc_bf16_launch(grid, smem, as_stream(st), tmDy, tmX, a);
+  else launch_k(k_wgrad_tc<false>, grid, kThreads, smem, as_stream(st), tmDy, tmX, a);
   if (int rc = check_launch("conv2d_wgrad_tc")) return rc;
-  if (dbias != nullptr) return mfvi_conv2d_bias_grad_tc(d, dy, dbias, w_sstride, st);
+  if (dbias != nullptr) return mfvi_conv2d_bias_grad_tc(d, bf16 ? dy_bias : dy, dbias, w_sstride, st);
   return 0;
+}
+
+
+extern "C" {
+
+int mfvi_conv2d_wgrad_tc(const MfviConvDesc* d, MfviView x, MfviView dy, float* dw, float* dbias, long long w_sstride,
+                         mfvi_stream_t st) {
+  return wgrad_tc_launch(d, x, dy, dw, dbias, w_sstride, st, false, dy);
+}
+
+// bf16-operand mode, stage B of DESIGN.md section 8 (EXPERIMENTAL): x / dy hold bf16, dw is fp32.  dbias != NULL needs
+// `dy_f32`, an fp32 view of the same gradient.  No fallback: a shape the kernel does not take is an error.
+int mfvi_conv2d_wgrad_bf16(const MfviConvDesc* d, MfviView x, MfviView dy, float* dw, long long w_sstride, MfviView dy_f32,
+                           float* dbias, mfvi_stream_t st) {
+  MFVI_REQUIRE(d != nullptr && x.ptr != nullptr && dy.ptr != nullptr && dw != nullptr, "conv2d_wgrad_bf16: null argument");
+  MFVI_REQUIRE(dbias == nullptr || dy_f32.ptr != nullptr, "conv2d_wgrad_bf16: the bias gradient needs an fp32 view of dy");
+  const int rc = wgrad_tc_launch(d, x, dy, dw, dbias, w_sstride, st, true, dy_f32);
+  MFVI_REQUIRE(rc >= 0, "conv2d_wgrad_bf16: %d->%d k%dx%d s%d %dx%d is not taken by the tensor-core kernel", d->Cin, d->Cout,
+               d->KH, d->KW, d->stride, d->Hout, d->Wout);
+  return rc;
 }
 
 }  // extern "C"

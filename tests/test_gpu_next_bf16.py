@@ -64,6 +64,25 @@ def _reference(c):
     return y, dx, stats
 
 
+def _wgrad(c, bf16):
+    """dw (+ bias gradient) of the case: fp32 CUDA-core kernel on the rounded values, or the bf16 tensor-core kernel."""
+    from mfvi_dip_mia_b200 import _lib as L
+    S, cin, cout, k = c["S"], c["cin"], c["cout"], c["k"]
+    dev = c["xb"].device
+    P, boff = k * k * cout * cin + cout, k * k * cout * cin
+    dw = torch.zeros(S, (P + 3) // 4 * 4, device=dev)
+    dy32 = c["dyb"][..., :cout].float().contiguous()
+    d = L.ConvDesc(S, cin, cout, k, k, c["stride"], c["Hin"], c["Win"], c["H"], c["W"], L.MATH_TF32 if bf16 else L.MATH_FP32)
+    if bf16:
+        L.call("mfvi_conv2d_wgrad_bf16", C.byref(d), L.view(c["xb"][..., :cin]), L.view(c["dyb"][..., :cout]), dw.data_ptr(),
+               dw.stride(0), L.view(dy32), dw.data_ptr() + 4 * boff)
+    else:
+        x32 = c["xb"][..., :cin].float().contiguous()
+        L.call("mfvi_conv2d_wgrad", C.byref(d), L.view(x32), L.view(dy32), dw.data_ptr(), dw.data_ptr() + 4 * boff, dw.stride(0))
+    torch.cuda.synchronize()
+    return dw[:, :P]
+
+
 def _bf16(c, accumulate=False):
     from mfvi_dip_mia_b200 import _lib as L
     S, cin, cout, k = c["S"], c["cin"], c["cout"], c["k"]
@@ -89,6 +108,15 @@ def test_bf16_conv_equals_fp32_kernels_on_rounded_inputs(shape):
     for n, a, b in zip(["y", "dx", "bn stats"], got, ref):
         assert torch.isfinite(a).all(), (shape, n)
         assert rel_err(a, b) < TOL, (shape, n, rel_err(a, b))
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_bf16_wgrad_equals_fp32_kernel_on_rounded_inputs(shape):
+    """Sums over up to 65536 pixels in a different order (split-K atomics on both sides): 1e-4 of the largest entry."""
+    c = _case(shape)
+    ref, got = _wgrad(c, False), _wgrad(c, True)
+    assert torch.isfinite(got).all()
+    assert rel_err(got, ref) < 1e-4, (shape, rel_err(got, ref))
 
 
 def test_bf16_dgrad_accumulates():
