@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libmfvidip.so")
 ABI_VERSION = 1
 MATH_FP32 = 0
 MATH_TF32 = 1
+MATH_BF16 = 2      # host-side mode only (EXPERIMENTAL): the engine calls the *_bf16 entry points
 STREAM_WEIGHTS = 0
 STREAM_INPUT_JITTER = 1
 
@@ -146,6 +147,7 @@ def call(name: str, *args, stream=None, meta=None):
 
 
 PASS_FWD, PASS_DGRAD, PASS_WGRAD = 0, 1, 2
+PASS_BF16 = 3      # added to a pass: the bf16-operand entry point of that pass (views are then bf16 views)
 
 
 def conv_plan(desc: ConvDesc, pass_: int, a: View, b: View, w_sstride: int, accumulate: int = 0, with_bias: bool = True) -> dict:

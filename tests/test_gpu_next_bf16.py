@@ -210,3 +210,59 @@ def test_view_and_weight_conversions_round_like_torch():
         assert torch.equal(got[..., :c], w[:, a:a + r * c].view(S, r, c).to(torch.bfloat16))
         assert (got[..., c:] == 0).all()
     assert torch.isnan(w16[:, P16:]).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------- stage D
+@pytest.mark.parametrize("task", ["den", "inp", "sr", "ct"])
+def test_bf16_engine_step_close_to_reference(task):
+    """Whole step in the bf16-operand mode against the reference fixture (the recipe of
+    test_gpu_tc.py::test_tf32_engine_step_close_to_reference).  8-bit operand mantissa, fp32 accumulate; the bars below are the
+    tf32 ones times four and are to be re-measured on the first GPU run (the printed numbers go to DESIGN.md)."""
+    from mfvi_dip_mia_b200 import SkipEngine, _lib as L
+    from mfvi_dip_mia_b200.engine import NLL
+    from mfvi_dip_mia_b200.trainer import LossHead
+    from oracle import mfvi_oracle as O
+    from tests.test_gpu_parity import SMALL, _fixture, _head_kwargs, spec_of
+    dev = torch.device("cuda:0")
+    d, S, sd, eps, ex, grads = _fixture(task)
+    x = torch.from_numpy(d["net_input"])
+    eng = SkipEngine(spec_of(SMALL[task]), x.shape[2], x.shape[3], S, dev, math=L.MATH_BF16)
+    eng.load_params(sd, prefix="net.")
+    eng.pack_eps(eps, prefix="net.")
+    head = LossHead(eng, task, **_head_kwargs(task, ex))
+    temp, sigma = float(d["temp"]), float(d["sigma"])
+    eng.zero_accumulators()
+    eng.set_input(x[0].permute(1, 2, 0).contiguous().to(dev), None, 0.0, L.key(0))
+    eng.sample_weights(L.key(0))
+    eng.forward()
+    head.run()
+    eng.backward()
+    eng.reparam_kl(L.key(0), prior_mu=0.0, prior_sigma_plus_eps=O.prior_scale(temp, sigma), direction=0, kscale=temp)
+    out = eng.out_nchw().cpu()
+    e_out = max(rel_err(out[s:s + 1], d[f"out{s}"]) for s in range(S))
+    e_nll = rel_err(eng.arena[:2].cpu()[NLL], d["nll"])
+    ours = {"net." + k: v.cpu() for k, v in eng.param_views("grad").items()}
+    va = torch.cat([ours[k].double().reshape(-1) for k in grads])
+    vb = torch.cat([grads[k].double().reshape(-1) for k in grads])
+    e_l2, cos = float((va - vb).norm() / vb.norm()), float((va @ vb) / (va.norm() * vb.norm()))
+    print(f"bf16 {task}: out {e_out:.2e}  nll {e_nll:.2e}  grad relL2 {e_l2:.2e}  cos {cos:.6f}")
+    assert torch.isfinite(va).all()
+    assert e_out < 4e-2 and e_nll < 8e-3 and e_l2 < 0.12 and cos > 0.995
+
+
+def test_bf16_trainer_runs_graph_replayed_steps():
+    """The graph-captured trainer step in bf16 mode: finite, and the loss falls on a small denoising problem."""
+    from mfvi_dip_mia_b200 import MfviDipTrainer, SkipSpec, _lib as L
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(0)
+    spec = SkipSpec(8, 2, (8, 16, 16), (8, 16, 16), (4, 4, 4), 3, 3, 1, True, False, "bilinear")
+    x = torch.rand(1, 8, 64, 64, generator=g) * 0.1
+    target = torch.rand(1, 1, 64, 64, generator=g)
+    tr = MfviDipTrainer(spec, "den", x, temp=5.6e-7, sigma=1.5e-5, lr=1e-2, mc_samples=4, seed=3, device=dev, target=target,
+                        math_mode=L.MATH_BF16)
+    losses = []
+    for i in range(60):
+        tr.step()
+        if i % 20 == 19:
+            losses.append(tr.loss_terms()[0])
+    assert all(map(lambda v: v == v and abs(v) < 1e6, losses)) and losses[-1] < losses[0]

@@ -322,3 +322,32 @@ def test_plan_only_engine_cannot_execute():
     eng = SkipEngine(SkipSpec(), 64, 64, 2, "meta")
     with pytest.raises(L.MfviError, match="plan only"):
         eng.forward()
+
+
+@pytest.mark.parametrize("task", sorted(_TASK_NETS))
+def test_bf16_mode_plan_is_accepted_by_the_bf16_kernels(task):
+    """EXPERIMENTAL bf16-operand mode: the engine's plan — bf16 padded activations / gradients with the
+    channel pitch rounded up to 8, repacked bf16 weights — is taken by the bf16 tensor-core kernels for every convolution of the
+    four task networks (their host code runs here in planning-only mode), and every conv operand is a bf16 view while every
+    conv output stays fp32."""
+    import ctypes as C
+    from mfvi_dip_mia_b200 import SkipEngine, SkipSpec, _lib as L
+    kw, H = _TASK_NETS[task]
+    eng = SkipEngine(SkipSpec(**kw), H, H, 2, "meta", math=L.MATH_BF16)
+    rows = eng.conv_dispatch_table()
+    n_conv = len(eng.lay.convs)
+    assert sum(r["op"] == "fwd" for r in rows) == n_conv == sum(r["op"] == "wgrad" for r in rows)
+    assert {r["family"] for r in rows} == {"halo-bf16", "tc-bf16"}
+    for r in rows:
+        assert r["smem_bytes"] <= 227 * 1024 and r["plan"].get("tmem_cols", 32) <= 512, r
+    names = [op[0] for op in eng.fwd_ops + eng.bwd_ops]
+    assert not any(n in ("mfvi_conv2d_fwd", "mfvi_conv2d_dgrad", "mfvi_conv2d_wgrad", "mfvi_bn_act_pad_fwd") for n in names)
+    # the bf16 weight copy: blocks of [taps][Cout][Cin rounded up to 8], back to back
+    off = 0
+    for c in eng.lay.convs:
+        assert c.w16_off == off and c.cpitch % 8 == 0 and c.cpitch - c.cin in range(8)
+        off += c.k * c.k * c.cout * c.cpitch
+    assert eng.w16.shape == (2, off) and eng.w16.dtype == torch.bfloat16
+    # one launch more per direction than fp32 for the input / loss-gradient conversion, none for the BatchNorm backward
+    ref = SkipEngine(SkipSpec(**kw), H, H, 2, "meta", math=L.MATH_TF32)
+    assert len(eng.fwd_ops) == len(ref.fwd_ops) + 1 and len(eng.bwd_ops) == len(ref.bwd_ops) + 1
