@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) k_pack_weights_bf16(const float* __restri
     const long long row = gl / gpr;
     const int c0 = static_cast<int>(gl - row * gpr) * 8;
     const float* src = w + static_cast<size_t>(s) * w_sstride + t.w_off[l] + row * t.cin[l] + c0;
-    __nv_bfloat16 v[8];
+    __align__(16) __nv_bfloat16 v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = __float2bfloat16_rn(c0 + j < t.cin[l] ? src[j] : 0.f);
     // w16_off, cpitch and w16_sstride are multiples of 8 elements: one 16-byte store
