@@ -180,7 +180,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}"
     net_input, target = synthetic_problem(args.size)
-    math_mode = L.MATH_TF32 if args.math == "tf32" else L.MATH_FP32
+    # "bf16" is the EXPERIMENTAL bf16-operand mode: never the default, and not a valid bench line until its
+    # parity tests (tests/test_gpu_next_bf16.py) have passed on the GPU
+    math_mode = {"tf32": L.MATH_TF32, "fp32": L.MATH_FP32, "bf16": L.MATH_BF16}[args.math]
     tr = MfviDipTrainer(SkipSpec(), "den", net_input, temp=TEMP, sigma=SIGMA, lr=LR, mc_samples=args.mc, seed=1,
                         device=dev, target=target, rank=rank, world_size=world, math_mode=math_mode, use_graph=True)
 
@@ -263,11 +265,12 @@ def run_ours(args):
             traffic = json.load(f).get("bytes_per_step", {}).get(dom)
     if a["flops"] > 0:
         # the convolutions run tcgen05 kind::tf32: half the dense bf16 rate MEASURED_PEAKS.json reports
-        peak = pk["tensor"] / 2.0 if args.math == "tf32" else 75.0
+        peak = {"tf32": pk["tensor"] / 2.0, "bf16": pk["tensor"], "fp32": 75.0}[args.math]
         ach = a["flops"] / (a["ms"] * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak, "traffic": traffic,
-                "peak_source": pk["src"] + " bf16 sustained / 2 (kind::tf32)" if args.math == "tf32" else "fp32 CUDA-core nominal",
+                "peak_source": {"tf32": pk["src"] + " bf16 sustained / 2 (kind::tf32)", "bf16": pk["src"] + " bf16 sustained (kind::f16)",
+                                "fp32": "fp32 CUDA-core nominal"}[args.math],
                 "algorithmic_gbs": a["bytes"] / (a["ms"] * 1e-3) / 1e9, "hbm_peak_gbs": pk["hbm"],
                 "launches_per_step": a["n"], "ms_per_step": a["ms"], "share_of_step": a["ms"] / step_ms_eager}
     else:
@@ -306,7 +309,7 @@ def run_ours(args):
     ws_mb = sum(t.numel() for t in tr.eng._bufs) * 4 / 2 ** 20
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "tf32" if args.math == "tf32" else "f32", "data": "synthetic",
+            "dtype": {"tf32": "tf32", "bf16": "bf16", "fp32": "f32"}[args.math], "data": "synthetic",
             "config": {"workload": f"mfvi_den {args.size}x{args.size} 5-scale skip net, MC={args.mc} split over {world} GPU(s), AdamW",
                        "mc_per_gpu": tr.S, "l2": f"per-step activation working set {ws_mb:.0f} MiB > 126 MB L2 (no flush needed)",
                        "cuda_graph": True, "last_loss": loss},
@@ -326,7 +329,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mc", type=int, default=8)
     ap.add_argument("--size", type=int, default=256)
-    ap.add_argument("--math", default="tf32", choices=["fp32", "tf32"])
+    ap.add_argument("--math", default="tf32", choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

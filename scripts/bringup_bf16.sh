@@ -1,0 +1,18 @@
+#!/usr/bin/env bash
+# Bring-up of the bf16-operand mode on a B200 box, simplest stage first; every stage writes its log
+# under gpurun_out/ and a failing stage does not stop the later ones (they are independent kernels).
+#   gpurun --timeout 900 -- 'bash scripts/bringup_bf16.sh'
+set -u
+mkdir -p gpurun_out
+export MFVI_TEST_NEXT=1
+run() { # name, pytest -k expression
+  timeout 300 python -m pytest tests/test_gpu_next_bf16.py -m gpu_next -q -x -k "$2" > "gpurun_out/bf16_$1.txt" 2>&1
+  echo "stage $1: rc=$? $(tail -1 gpurun_out/bf16_$1.txt)"
+}
+run C_elementwise "bn_act_pad or bn_bwd_apply or conversions"
+run A_conv "conv_equals or accumulates or rejects"
+run B_wgrad "wgrad"
+run D_engine "engine_step or trainer"
+# only meaningful once the four stages are green
+timeout 300 python bench.py --math bf16 --steps 30 --warmup 5 --no-cpu > gpurun_out/bf16_bench.json 2> gpurun_out/bf16_bench.err
+echo "bench rc=$? $(head -c 300 gpurun_out/bf16_bench.json)"
