@@ -552,6 +552,9 @@ static int wgrad_tc_launch(const MfviConvDesc* d, MfviView x, MfviView dy, float
   int TH = TP / TW;
   if (TH > d->Hout) {        // tiny images: shrink the tile
     TH = d->Hout;
+    // bf16 has no CUDA-core fallback and contracts 16 pixel rows per MMA: keep the tile a multiple of 16 rows by letting its
+    // box reach below the image (TMA zero-fills those rows of x and dy, so they add nothing).  TW is a power of two here.
+    if (bf16 && TW < 16 && TH % (16 / TW)) TH = (TH + 16 / TW - 1) / (16 / TW) * (16 / TW);
     TP = TH * TW;
   }
   if (TP % (bf16 ? 16 : 8) || TW > 256 || TH > 256) return -1;

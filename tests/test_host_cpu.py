@@ -351,3 +351,29 @@ def test_bf16_mode_plan_is_accepted_by_the_bf16_kernels(task):
     # one launch more per direction than fp32 for the input / loss-gradient conversion, none for the BatchNorm backward
     ref = SkipEngine(SkipSpec(**kw), H, H, 2, "meta", math=L.MATH_TF32)
     assert len(eng.fwd_ops) == len(ref.fwd_ops) + 1 and len(eng.bwd_ops) == len(ref.bwd_ops) + 1
+
+
+@pytest.mark.parametrize("H,W", [(64, 96), (160, 64), (224, 352), (352, 288)])
+def test_conv_plans_on_non_square_images(H, W):
+    """The runners crop to multiples of 32, not to squares: tile plans keep their invariants on ragged sizes, only weight
+    gradients over fewer than 8 pixels may leave the tensor cores (tf32), and the bf16 mode — which has no fallback — still
+    takes every convolution (tiles reaching below a tiny map are zero-filled)."""
+    from mfvi_dip_mia_b200 import SkipEngine, SkipSpec, _lib as L
+    for S in (1, 3):
+        for r in SkipEngine(SkipSpec(), H, W, S, "meta", math=L.MATH_TF32).conv_dispatch_table():
+            where = f"{H}x{W} S={S} {r['op']} {r['layer']} {r['shape']}"
+            if r["family"] == "simt":
+                assert r["op"] == "wgrad" and r["Hout"] * r["Wout"] < 8, where
+                continue
+            assert r["smem_bytes"] <= 227 * 1024, where
+            if r["family"] == "halo":
+                p = r["plan"]
+                Mh, Mw = (r["Hin"], r["Win"]) if r["op"] == "dgrad" else (r["Hout"], r["Wout"])
+                if p["cls"] == 4:
+                    Mh, Mw = (Mh + 1) // 2, (Mw + 1) // 2
+                assert p["n_mt"] * 128 >= (p["TH"] - 1) * p["Pw"] + p["TW"], where
+                assert p["acc_stages"] * p["n_mt"] * p["BN"] <= p["tmem_cols"] <= 512, where
+                assert p["tiles"] == r["S"] * p["nb"] * p["cls"] * _cdiv(Mh, p["TH"]) * _cdiv(Mw, p["TW"]), where
+        rows16 = SkipEngine(SkipSpec(), H, W, S, "meta", math=L.MATH_BF16).conv_dispatch_table()
+        assert {r["family"] for r in rows16} == {"halo-bf16", "tc-bf16"}
+        assert all(r["plan"]["TP"] % 16 == 0 for r in rows16 if r["op"] == "wgrad")
