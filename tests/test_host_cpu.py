@@ -356,14 +356,14 @@ def test_bf16_mode_plan_is_accepted_by_the_bf16_kernels(task):
 @pytest.mark.parametrize("H,W", [(64, 96), (160, 64), (224, 352), (352, 288)])
 def test_conv_plans_on_non_square_images(H, W):
     """The runners crop to multiples of 32, not to squares: tile plans keep their invariants on ragged sizes, only weight
-    gradients over fewer than 8 pixels may leave the tensor cores (tf32), and the bf16 mode — which has no fallback — still
+    gradients over fewer than 16 pixels may leave the tensor cores (tf32), and the bf16 mode — which has no fallback — still
     takes every convolution (tiles reaching below a tiny map are zero-filled)."""
     from mfvi_dip_mia_b200 import SkipEngine, SkipSpec, _lib as L
     for S in (1, 3):
         for r in SkipEngine(SkipSpec(), H, W, S, "meta", math=L.MATH_TF32).conv_dispatch_table():
             where = f"{H}x{W} S={S} {r['op']} {r['layer']} {r['shape']}"
             if r["family"] == "simt":
-                assert r["op"] == "wgrad" and r["Hout"] * r["Wout"] < 8, where
+                assert r["op"] == "wgrad" and r["Hout"] * r["Wout"] < 16, where
                 continue
             assert r["smem_bytes"] <= 227 * 1024, where
             if r["family"] == "halo":
