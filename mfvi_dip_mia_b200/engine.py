@@ -194,11 +194,12 @@ class SkipEngine:
     """Forward/backward plan of one hour-glass net at a fixed (H, W, S)."""
 
     def __init__(self, spec: SkipSpec, H: int, W: int, S: int, device, *, math: int = L.MATH_FP32,
-                 layout: Optional[SkipLayout] = None, need_input_grad: bool = False):
+                 layout: Optional[SkipLayout] = None, need_input_grad: bool = False, plan_only: bool = False):
         device = torch.device(device)
-        # device "meta" builds the kernel plan only (buffer shapes, strides and alignments, no memory): conv_dispatch_table()
-        # can then be inspected on a machine without a GPU; nothing can be executed
-        self.plan_only = device.type == "meta"
+        # A plan-only engine builds the kernel plan (buffers, views, op lists) and can never execute it: device "meta" (shapes,
+        # strides and alignments, no memory) for conv_dispatch_table() on a machine without a GPU; plan_only=True on any device
+        # (real buffers) for the test-suite's CPU interpretation of the plan (tests/plan_interpreter.py)
+        self.plan_only = plan_only or device.type == "meta"
         if device.type != "cuda" and not self.plan_only:
             raise L.MfviError(f"SkipEngine needs a CUDA device, got {device}: there is no CPU fallback")
         n = len(spec.down)
@@ -605,7 +606,7 @@ class SkipEngine:
         (each waits for the lane that produced its inputs), everything else to the current stream; every lane used is
         joined back before returning.  With the per-kernel timeline on, everything runs on one stream."""
         if self.plan_only:
-            raise L.MfviError("this SkipEngine was built on device 'meta' (plan only): it cannot execute")
+            raise L.MfviError("this SkipEngine is plan only (device 'meta' or plan_only=True): it cannot execute")
         serial = L.timeline is not None
         main = torch.cuda.current_stream(self.device)
         streams = {"main": main, "wgrad": self._side, "skip": self._side2}

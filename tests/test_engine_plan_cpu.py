@@ -1,0 +1,98 @@
+"""The engine's kernel plan, interpreted on the CPU (tests/plan_interpreter.py), against the reference fixtures.
+
+A SkipEngine built with plan_only=True on the CPU holds the real plan — buffers, views, op lists — and cannot run it; the
+interpreter executes every op with PyTorch as include/mfvi_dip.h defines it.  What is checked is the host side of the engine
+(which buffer feeds which kernel, shapes, strides, paddings, accumulate flags, sample sharing of the input, the reparam chain
+around the plan), for the exact-fp32 plan to 1e-4 of the imported reference, and for the EXPERIMENTAL bf16-operand plan
+ to the accuracy 8-bit operand mantissas allow — before that mode has seen a GPU."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import mfvi_oracle as O
+from tests.helpers import grad_errs, group, load_npz, rel_err
+from tests.plan_interpreter import PlanInterpreter
+
+SMALL = {
+    "den": O.SkipCfg(4, 2, (8, 16, 16), (8, 16, 16), (2, 2, 2), 3, 3, 1, True, False, "bilinear"),
+    "sr": O.SkipCfg(4, 2, (8, 16, 16), (8, 16, 16), (2, 2, 2), 3, 3, 1, True, False, "bilinear"),
+    "ct": O.SkipCfg(4, 1, (8, 16, 16), (8, 16, 16), (2, 2, 2), 3, 3, 1, True, False, "bilinear"),
+    "inp": O.SkipCfg(4, 4, (8, 16, 16), (8, 16, 16), (0, 0, 0), 5, 3, 1, False, False, "nearest"),
+}
+
+
+def _head(task, ex, S):
+    """(S,C,H,W) network outputs -> mean over the samples of the task's data loss (oracle.mfvi_loss)."""
+    per = {
+        "den": lambda o: O.gaussian_nll(o[:, :1], o[:, 1:], ex["target"]),
+        "sr": lambda o: (lambda lr: O.gaussian_nll(lr[:, :1], lr[:, 1:], ex["target"]))(O.sr_downsample_nearest(o, 4)),
+        "inp": lambda o: O.gaussian_nll_inpainting(torch.sigmoid(o[:, :3]), o[:, 3:], ex["target"], ex["mask"]),
+        "ct": lambda o: F.mse_loss(O.radon_forward(o, ex["theta"]), ex["sino"]),
+    }[task]
+    return lambda out: torch.stack([per(out[s:s + 1]) for s in range(S)]).mean()
+
+
+def _run(task, math):
+    from mfvi_dip_mia_b200 import SkipEngine, SkipSpec
+    d = load_npz(f"skipnet_small_{task}.npz")
+    S, sd, ex, grads = int(d["S"]), group(d, "sd/"), group(d, "extra/"), group(d, "grad/")
+    eps = [group(d, f"eps{s}/") for s in range(S)]
+    cfg = SMALL[task]
+    spec = SkipSpec(cfg.num_input_channels, cfg.num_output_channels, tuple(cfg.down), tuple(cfg.up), tuple(cfg.skip),
+                    cfg.filter_down, cfg.filter_up, cfg.filter_skip, cfg.need1x1_up, cfg.need_sigmoid, cfg.upsample_mode)
+    x = torch.from_numpy(d["net_input"])
+    eng = SkipEngine(spec, x.shape[2], x.shape[3], S, "cpu", math=math, plan_only=True)
+    eng.load_params(sd, prefix="net.")
+    eng.pack_eps(eps, prefix="net.")
+    it = PlanInterpreter(eng)
+    nll = it.step(x[0], _head(task, ex, S))
+    # the reparameterisation chain and the tempered KL around the plan (mfvi_kl_reparam_fwd_bwd, include/mfvi_dip.h)
+    temp, sigma = float(d["temp"]), float(d["sigma"])
+    P = eng.lay.P
+    mu, rho = eng.mu.clone().requires_grad_(True), eng.rho.clone().requires_grad_(True)
+    kl = O.kl_elementwise(mu, rho, 0.0, O.prior_scale(temp, sigma)).sum()
+    kl.backward()
+    eng.g_mu.copy_(eng.dw[:, :P].sum(0) + temp * mu.grad)
+    eng.g_rho.copy_(torch.sigmoid(eng.rho) * (eng.eps[:, :P] * eng.dw[:, :P]).sum(0) + temp * rho.grad)
+    ours = {"net." + k: v.clone() for k, v in eng.param_views("grad").items()}
+    out = eng.out.permute(0, 3, 1, 2)
+    return d, S, out, nll, float(kl), ours, grads
+
+
+@pytest.mark.parametrize("task", ["den", "sr", "ct", "inp"])
+def test_fp32_plan_reproduces_the_reference_step(task):
+    from mfvi_dip_mia_b200 import _lib as L
+    d, S, out, nll, kl, ours, grads = _run(task, L.MATH_FP32)
+    for s in range(S):
+        assert rel_err(out[s:s + 1], d[f"out{s}"]) < 1e-4, s
+    assert rel_err(nll, d["nll"]) < 1e-5 and rel_err(kl, d["kl"]) < 1e-5
+    errs = grad_errs({k: ours[k] for k in grads}, grads)
+    worst = max(errs, key=errs.get)
+    assert errs[worst] < 1e-3, (worst, errs[worst])
+
+
+@pytest.mark.parametrize("task", ["den", "sr", "ct", "inp"])
+def test_bf16_plan_is_wired_like_the_fp32_plan(task):
+    """Same data flow with bf16 conv operands: every result stays within what 8-bit operand mantissas explain (a wiring bug —
+    a wrong buffer, a missing accumulate, a dropped branch — shows up as an O(1) error, cosine ~0).  Measured on these
+    32x32 fixtures: output 2-5e-2 of its max, NLL 0.2-2e-3, whole gradient 3-18 % relative L2, cosine 0.984-0.9997 — about 8x the
+    tf32 mode's figures, as three mantissa bits fewer predict.  Whether training tolerates that is a separate question:
+    scripts/bf16_quality_study.py."""
+    from mfvi_dip_mia_b200 import _lib as L
+    d, S, out, nll, kl, ours, grads = _run(task, L.MATH_BF16)
+    e_out = max(rel_err(out[s:s + 1], d[f"out{s}"]) for s in range(S))
+    va = torch.cat([ours[k].double().reshape(-1) for k in grads])
+    vb = torch.cat([grads[k].double().reshape(-1) for k in grads])
+    e_l2, cos = float((va - vb).norm() / vb.norm()), float((va @ vb) / (va.norm() * vb.norm()))
+    print(f"bf16 plan {task}: out {e_out:.2e}  nll {rel_err(nll, d['nll']):.2e}  grad relL2 {e_l2:.2e}  cos {cos:.6f}")
+    assert e_out < 0.1 and rel_err(nll, d["nll"]) < 1e-2
+    assert e_l2 < 0.3 and cos > 0.97
+
+
+def test_plan_only_engine_on_cpu_needs_the_flag():
+    from mfvi_dip_mia_b200 import SkipEngine, SkipSpec, _lib as L
+    with pytest.raises(L.MfviError, match="no CPU fallback"):
+        SkipEngine(SkipSpec(), 64, 64, 1, "cpu")
+    eng = SkipEngine(SkipSpec(), 64, 64, 1, "cpu", plan_only=True)
+    with pytest.raises(L.MfviError, match="plan only"):
+        eng.backward()

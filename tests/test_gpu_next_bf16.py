@@ -214,14 +214,17 @@ def test_view_and_weight_conversions_round_like_torch():
 
 # ---------------------------------------------------------------------------------------------------------------- stage D
 @pytest.mark.parametrize("task", ["den", "inp", "sr", "ct"])
-def test_bf16_engine_step_close_to_reference(task):
-    """Whole step in the bf16-operand mode against the reference fixture (the recipe of
-    test_gpu_tc.py::test_tf32_engine_step_close_to_reference).  8-bit operand mantissa, fp32 accumulate; the bars below are the
-    tf32 ones times four and are to be re-measured on the first GPU run (the printed numbers go to DESIGN.md)."""
+def test_bf16_engine_step_equals_its_cpu_interpretation(task):
+    """Whole step in the bf16-operand mode on the GPU against the SAME plan interpreted on the CPU with the kernels' rounding
+    points (tests/plan_interpreter.py; tests/test_engine_plan_cpu.py holds that interpretation to the reference within bf16
+    accuracy).  Both sides round the same values to bf16, so they differ only where an fp32 summation-order difference flips
+    a rounding: the bars are far below the bf16 error itself (output 2-5e-2, gradient 3-18 %), and a kernel bug cannot hide
+    behind a reduced-precision tolerance."""
     from mfvi_dip_mia_b200 import SkipEngine, _lib as L
     from mfvi_dip_mia_b200.engine import NLL
     from mfvi_dip_mia_b200.trainer import LossHead
     from oracle import mfvi_oracle as O
+    from tests.test_engine_plan_cpu import _run
     from tests.test_gpu_parity import SMALL, _fixture, _head_kwargs, spec_of
     dev = torch.device("cuda:0")
     d, S, sd, eps, ex, grads = _fixture(task)
@@ -239,15 +242,16 @@ def test_bf16_engine_step_close_to_reference(task):
     eng.backward()
     eng.reparam_kl(L.key(0), prior_mu=0.0, prior_sigma_plus_eps=O.prior_scale(temp, sigma), direction=0, kscale=temp)
     out = eng.out_nchw().cpu()
-    e_out = max(rel_err(out[s:s + 1], d[f"out{s}"]) for s in range(S))
-    e_nll = rel_err(eng.arena[:2].cpu()[NLL], d["nll"])
+    nll = float(eng.arena[:2].cpu()[NLL])
     ours = {"net." + k: v.cpu() for k, v in eng.param_views("grad").items()}
+    _, _, out_i, nll_i, _, interp, _ = _run(task, L.MATH_BF16)              # the CPU interpretation of the same plan
+    e_out = rel_err(out, out_i)
     va = torch.cat([ours[k].double().reshape(-1) for k in grads])
-    vb = torch.cat([grads[k].double().reshape(-1) for k in grads])
+    vb = torch.cat([interp[k].double().reshape(-1) for k in grads])
     e_l2, cos = float((va - vb).norm() / vb.norm()), float((va @ vb) / (va.norm() * vb.norm()))
-    print(f"bf16 {task}: out {e_out:.2e}  nll {e_nll:.2e}  grad relL2 {e_l2:.2e}  cos {cos:.6f}")
+    print(f"bf16 {task} GPU vs CPU interpretation: out {e_out:.2e}  nll {rel_err(nll, nll_i):.2e}  grad relL2 {e_l2:.2e}  cos {cos:.6f}")
     assert torch.isfinite(va).all()
-    assert e_out < 4e-2 and e_nll < 8e-3 and e_l2 < 0.12 and cos > 0.995
+    assert e_out < 5e-3 and rel_err(nll, nll_i) < 1e-3 and e_l2 < 2e-2 and cos > 0.9995
 
 
 def test_bf16_trainer_runs_graph_replayed_steps():
