@@ -16,3 +16,6 @@ run D_engine "engine_step or trainer"
 # only meaningful once the four stages are green
 timeout 300 python bench.py --math bf16 --steps 30 --warmup 5 --no-cpu > gpurun_out/bf16_bench.json 2> gpurun_out/bf16_bench.err
 echo "bench rc=$? $(head -c 300 gpurun_out/bf16_bench.json)"
+# issue rate of kind::f16 bf16 MMAs vs N (K-major and MN-major): the numbers the mode's cost models need
+(cd scripts && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o umma_rate_test umma_rate_test.cu -lcuda 2>/dev/null; \
+ timeout 60 ./umma_rate_test bf16 > ../gpurun_out/bf16_umma_rate_probe.txt 2>&1; echo "rate probe rc=$?")
