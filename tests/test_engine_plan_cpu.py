@@ -96,3 +96,61 @@ def test_plan_only_engine_on_cpu_needs_the_flag():
     eng = SkipEngine(SkipSpec(), 64, 64, 1, "cpu", plan_only=True)
     with pytest.raises(L.MfviError, match="plan only"):
         eng.backward()
+
+
+@pytest.mark.parametrize("math_name", ["fp32", "bf16"])
+def test_metric_network_plan_against_the_oracle(math_name):
+    """The 5-scale, 16-channel-input network of the metric (bilinear upsampling, skip branches, 1x1 up convs) at 128x128 with
+    random parameters: interpreted plan vs the oracle's autograd (no fixture: the oracle itself is pinned to the reference by
+    tests/test_oracle_golden.py).  Per-sample BatchNorm over the 4x4 maps of the deepest scale is badly conditioned — the fp32
+    oracle itself is 1e-3 away from its fp64 run on the smallest gradients — so fp64 is the yardstick and the fp32 plan has to
+    stay within 4x the fp32 oracle's own error (+1e-3)."""
+    from mfvi_dip_mia_b200 import SkipEngine, SkipSpec, _lib as L
+    S, H = 1, 128
+    g = torch.Generator().manual_seed(11)
+    eng = SkipEngine(SkipSpec(), H, H, S, "cpu", math=L.MATH_FP32 if math_name == "fp32" else L.MATH_BF16, plan_only=True)
+    eng.mu.copy_(0.1 * torch.randn(eng.lay.P, generator=g))
+    eng.rho.copy_(-3.0 + 0.1 * torch.randn(eng.lay.P, generator=g))
+    eng.gamma.copy_(1.0 + 0.1 * torch.randn(eng.lay.Q, generator=g))
+    eng.beta.copy_(0.1 * torch.randn(eng.lay.Q, generator=g))
+    eps = []
+    for _ in range(S):
+        e = {}
+        for c in eng.lay.convs:
+            e["net." + c.key + ".W"] = torch.randn(c.cout, c.cin, c.k, c.k, generator=g)
+            e["net." + c.key + ".b"] = torch.randn(c.cout, generator=g)
+        eps.append(e)
+    eng.pack_eps(eps, prefix="net.")
+    x = torch.rand(1, 16, H, H, generator=g) * 0.1
+    target = torch.rand(1, 1, H, H, generator=g)
+    it = PlanInterpreter(eng)
+    nll = it.step(x[0], lambda out: torch.stack([O.gaussian_nll(out[s:s + 1, :1], out[s:s + 1, 1:], target) for s in range(S)]).mean())
+    P = eng.lay.P
+    eng.g_mu.copy_(eng.dw[:, :P].sum(0))                         # data term only: the KL chain is not part of the plan
+    eng.g_rho.copy_(torch.sigmoid(eng.rho) * (eng.eps[:, :P] * eng.dw[:, :P]).sum(0))
+    ours = {"net." + k: v for k, v in eng.param_views("grad").items()}
+
+    def oracle(dtype):
+        sd = {"net." + k: v.detach().clone().to(dtype).requires_grad_("running" not in k) for k, v in eng.param_views("theta").items()}
+        ee = [{k: v.to(dtype) for k, v in e.items()} for e in eps]
+        _, nll_o, _, outs = O.mfvi_loss(sd, O.SkipCfg(16, 2), x.to(dtype), ee, task="den", temp=1.0, prior_sigma_plus_eps=1.0,
+                                        target=target.to(dtype))
+        nll_o.backward()
+        return float(nll_o), [o.detach() for o in outs], {k: v.grad for k, v in sd.items() if v.grad is not None}
+
+    nll64, outs64, g64 = oracle(torch.float64)
+    out = eng.out.permute(0, 3, 1, 2)
+    e_out = max(rel_err(out[s:s + 1], outs64[s]) for s in range(S))
+    assert len(g64) == len(ours)
+    if math_name == "fp32":
+        _, _, g32 = oracle(torch.float32)
+        assert e_out < 1e-4 and rel_err(nll, nll64) < 1e-5
+        e_plan, e_o32 = grad_errs(ours, g64), grad_errs(g32, g64)
+        for k in e_plan:
+            assert e_plan[k] < 4 * e_o32[k] + 1e-3, (k, e_plan[k], e_o32[k])
+    else:
+        va = torch.cat([ours[k].double().reshape(-1) for k in g64])
+        vb = torch.cat([g64[k].reshape(-1) for k in g64])
+        cos = float((va @ vb) / (va.norm() * vb.norm()))
+        print(f"bf16 metric-net plan: out {e_out:.2e}  grad relL2 {float((va - vb).norm() / vb.norm()):.2e}  cos {cos:.5f}")
+        assert e_out < 0.1 and cos > 0.95
