@@ -80,7 +80,7 @@ class MfviDipTrainer:
                  target=None, mask=None, theta_deg=None, sino=None, sr_factor: int = 4,
                  rank: int = 0, world_size: int = 1, process_group=None, use_graph: bool = True,
                  nan_guard: Optional[bool] = None, betas=(0.9, 0.999), adam_eps: float = 1e-8, weight_decay: float = 0.0,
-                 kl_type: str = "reverse", prior_mu: float = 0.0):
+                 kl_type: str = "reverse", prior_mu: float = 0.0, plan_only: bool = False):
         device = torch.device(device)
         assert net_input.dim() == 4 and net_input.shape[0] == 1, "net_input must be (1,C,H,W) like the reference's"
         _, Cin, H, W = net_input.shape
@@ -96,7 +96,9 @@ class MfviDipTrainer:
         self.betas, self.adam_eps, self.weight_decay = betas, adam_eps, weight_decay
         self.reg_noise_std = float(reg_noise_std)
         self.seed = int(seed)
-        self.eng = SkipEngine(spec, H, W, self.S, device, math=math_mode)
+        # plan_only: build every buffer and the kernel plan on any device without being able to launch it (the test-suite
+        # interprets such a trainer on the CPU: tests/plan_interpreter.py)
+        self.eng = SkipEngine(spec, H, W, self.S, device, math=math_mode, plan_only=plan_only)
         self.head = LossHead(self.eng, task, target=target, mask=mask, theta_deg=theta_deg, sino=sino, sr_factor=sr_factor)
         self.nan_guard = (task == "ct") if nan_guard is None else nan_guard   # CT runner skips the update on NaN loss
         e = self.eng
@@ -108,7 +110,7 @@ class MfviDipTrainer:
         self.losses = torch.zeros(2, dtype=torch.float64, device=device)
         self.init_parameters(self.seed)
         self.post_step_hooks = []               # callables enqueued after AdamW, before the step counter advances
-        self.use_graph = use_graph
+        self.use_graph = use_graph and not plan_only
         self._graph = None
         self._warm = 0
 

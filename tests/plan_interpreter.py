@@ -285,3 +285,178 @@ class PlanInterpreter:
         e.dout.copy_(out.grad.permute(0, 2, 3, 1))
         self.run(e.bwd_ops)
         return float(nll.detach())
+
+
+class TrainerInterpreter(PlanInterpreter):
+    """Interprets a whole `MfviDipTrainer(plan_only=True, device="cpu")`: inside `with TrainerInterpreter(tr):` every libmfvidip
+    call the trainer makes (`_lib.call`) and every op list its engine runs is executed here on the CPU, so `tr.step()` works —
+    host logic under test: Philox keys and the device step counter, MC-sample sharding and the gradient all-reduce (gloo), the
+    KL / reparameterisation scaling, AdamW, post-step hooks.  Denoising / SR / inpainting heads; no CT."""
+
+    def __init__(self, tr):
+        super().__init__(tr.eng)
+        self.tr = tr
+        e = tr.eng
+        for t in (tr.saved, tr.step_dev, tr.m, tr.v, tr.losses, e._bn_ch_off, e._bn_sums_off, e._bn_C, e._bn_count,
+                  getattr(tr.head, "target", None), getattr(tr.head, "mask", None)):
+            self.register(t)
+
+    def register(self, t):
+        if t is None:
+            return
+        st = t.untyped_storage()
+        if all(lo != st.data_ptr() for lo, _, _ in self.stores):
+            self.stores.append((st.data_ptr(), st.data_ptr() + st.nbytes(), st))
+
+    def __enter__(self):
+        from mfvi_dip_mia_b200 import _lib as L
+        from mfvi_dip_mia_b200.engine import SkipEngine
+        self._saved = (L.call, SkipEngine._run)
+        interp = self
+
+        def call(name, *args, stream=None, meta=None):
+            L.launch_count += 1
+            interp.dispatch(name, args)
+
+        def _run(engine, op_list):
+            assert engine is interp.eng
+            interp.run(op_list)
+        L.call, SkipEngine._run = call, _run
+        return self
+
+    def __exit__(self, *exc):
+        from mfvi_dip_mia_b200 import _lib as L
+        from mfvi_dip_mia_b200.engine import SkipEngine
+        L.call, SkipEngine._run = self._saved
+
+    def dispatch(self, name, args):
+        fn = self.OPS.get(name) or self.TRAINER_OPS.get(name)
+        if fn is None:
+            raise NotImplementedError(f"{name} is not interpreted")
+        if self.eng.eps is not None:
+            self.register(self.eng.eps)
+        if self.tr.noise is not None:
+            self.register(self.tr.noise)
+        fn(self, name, args)
+
+    # ------------------------------------------------------------------ Philox streams (oracle/philox.py restates the kernels')
+    def _step_of(self, key):
+        return int(key.step) + (int(self.vec(key.step_dev, 1, torch.int32)[0]) if key.step_dev else 0)
+
+    def _normals(self, n, key, stream, sample):
+        from oracle import philox
+        return torch.from_numpy(philox.philox_normal(n, int(key.seed), stream, int(key.sample0) + sample, self._step_of(key)))
+
+    # ------------------------------------------------------------------ trainer-level ops
+    def op_input_jitter_pad(self, name, args):
+        saved, noise, H, W, Cn, std, pad, key, xp = args
+        x = self.vec(saved, H * W * Cn).view(H, W, Cn)
+        if noise is not None:
+            z = self.vec(noise, H * W * Cn).view(H, W, Cn)
+        else:                               # the reference's noise tensor is NCHW: flat index (c*H + h)*W + w
+            z = self._normals(Cn * H * W, key, 1, 0).view(Cn, H, W).permute(1, 2, 0)
+        y = (x + std * z).permute(2, 0, 1)[None]
+        if pad:
+            y = F.pad(y, (pad,) * 4, mode="reflect")
+        self.view(xp, 1, H + 2 * pad, W + 2 * pad, Cn).copy_(y.permute(0, 2, 3, 1))
+
+    def _eps_rows(self, eps, eps_ss, n, S, key):
+        if eps is not None:
+            return torch.stack([self.vec(eps + 4 * s * eps_ss, n) for s in range(S)])
+        return torch.stack([self._normals(n, key, 0, s) for s in range(S)])
+
+    def op_sample_weights(self, name, args):
+        mu, rho, n, S, eps, eps_ss, key, w_out, w_ss = args
+        m, sg = self.vec(mu, n), F.softplus(self.vec(rho, n))
+        E = self._eps_rows(eps, eps_ss, n, S, key)
+        for s in range(S):
+            self.vec(w_out + 4 * s * w_ss, n).copy_(m + sg * E[s])
+
+    def op_pack_weights_bf16(self, name, args):
+        w, w_ss, S, n_layers, w_off, w16_off, rows, cin, w16, w16_ss = args
+        for l in range(n_layers):
+            cp = (cin[l] + 7) // 8 * 8
+            for s in range(S):
+                src = self.vec(w + 4 * (s * w_ss + w_off[l]), rows[l] * cin[l]).view(rows[l], cin[l])
+                dst = self.vec(w16 + 2 * (s * w16_ss + w16_off[l]), rows[l] * cp, torch.bfloat16).view(rows[l], cp)
+                dst.zero_()
+                dst[:, :cin[l]] = src
+
+    def op_gauss_nll(self, name, args):
+        from oracle import mfvi_oracle as O
+        mode, out, S, H, W, Cn, sub, target, mask, loss_out, dout = args
+        o = self.view(out, S, H, W, Cn).permute(0, 3, 1, 2).clone().requires_grad_(True)
+        if mode == 0:
+            t = self.vec(target, (H // sub) * (W // sub)).view(1, 1, H // sub, W // sub)
+            per = [O.gaussian_nll(q[:, :1], q[:, 1:2], t) for q in (O.sr_downsample_nearest(o[s:s + 1], sub) if sub > 1 else o[s:s + 1]
+                                                                      for s in range(S))]
+        elif mode == 1:
+            t = self.vec(target, H * W * 3).view(H, W, 3).permute(2, 0, 1)[None]
+            mk = self.vec(mask, H * W).view(1, 1, H, W)
+            per = [O.gaussian_nll_inpainting(torch.sigmoid(o[s:s + 1, :3]), o[s:s + 1, 3:], t, mk) for s in range(S)]
+        else:
+            raise NotImplementedError(f"nll mode {mode}")
+        loss = torch.stack(per).mean()
+        loss.backward()
+        self.vec(loss_out, 1, torch.float64).add_(float(loss.detach()))
+        self.view(dout, S, H, W, Cn).copy_(o.grad.permute(0, 2, 3, 1))
+
+    def op_kl_reparam(self, name, args):
+        from oracle import mfvi_oracle as O
+        (mu, rho, n, pm, ps, direction, kscale, kscale_dev, dw, dw_ss, S, eps, eps_ss, key, gscale, kl_out, gmu, grho, acc) = args
+        if kscale_dev is not None:
+            kscale = kscale * float(self.vec(kscale_dev, 1)[0])
+        m = self.vec(mu, n).clone().requires_grad_(True)
+        r = self.vec(rho, n).clone().requires_grad_(True)
+        kl = O.kl_elementwise(m, r, pm, ps, "reverse" if direction == 0 else "forward").sum()
+        kl.backward()
+        if kl_out is not None:
+            self.vec(kl_out, 1, torch.float64).add_(float(kl.detach()))
+        if gmu is None:
+            return
+        g_m, g_r = kscale * m.grad, kscale * r.grad
+        if dw is not None and S > 0:
+            D = torch.stack([self.vec(dw + 4 * s * dw_ss, n) for s in range(S)])
+            E = self._eps_rows(eps, eps_ss, n, S, key)
+            g_m = g_m + gscale * D.sum(0)
+            g_r = g_r + gscale * (D * E).sum(0) * torch.sigmoid(r.detach())
+        GM, GR = self.vec(gmu, n), self.vec(grho, n)
+        GM.copy_(GM + g_m if acc else g_m)
+        GR.copy_(GR + g_r if acc else g_r)
+
+    def op_bn_running_update(self, name, args):
+        arena, ch_off, sums_off, Cs, counts, n_bn, S, mom, rmean, rvar = args
+        ch, so = self.vec(ch_off, n_bn, torch.int32), self.vec(sums_off, n_bn, torch.int64)
+        Cv, cnt = self.vec(Cs, n_bn, torch.int32), self.vec(counts, n_bn, torch.int32)
+        for b in range(n_bn):
+            Cn, N = int(Cv[b]), int(cnt[b])
+            sums = self.vec(arena + 8 * int(so[b]), S * Cn * 2, torch.float64).view(S, Cn, 2)
+            rm, rv = self.vec(rmean + 4 * int(ch[b]), Cn), self.vec(rvar + 4 * int(ch[b]), Cn)
+            for s in range(S):
+                mean = sums[s, :, 0] / N
+                var = (sums[s, :, 1] / N - mean * mean).clamp_min(0.0) * (N / max(N - 1, 1))
+                rm.copy_((1 - mom) * rm + mom * mean.float())
+                rv.copy_((1 - mom) * rv + mom * var.float())
+
+    def op_adamw(self, name, args):
+        p, g, m, v, n, lr, b1, b2, eps, wd, step, step_dev, skip_ptr = args
+        if skip_ptr is not None:
+            l = float(self.vec(skip_ptr, 1, torch.float64)[0])
+            if l != l or abs(l) > 1.7e308:
+                return
+        t = step + (int(self.vec(step_dev, 1, torch.int32)[0]) if step_dev is not None else 0)
+        P, G, M, V = (self.vec(q, n) for q in (p, g, m, v))
+        bc1, bc2s = 1.0 - b1 ** t, (1.0 - b2 ** t) ** 0.5
+        P.mul_(1.0 - lr * wd)
+        M.copy_(b1 * M + (1 - b1) * G)
+        V.copy_(b2 * V + (1 - b2) * G * G)
+        P.sub_((lr / bc1) * M / (V.sqrt() / bc2s + eps))
+
+    def op_counter_add(self, name, args):
+        ptr, inc = args
+        self.vec(ptr, 1, torch.int32).add_(int(inc))
+
+    TRAINER_OPS = {"mfvi_input_jitter_pad": op_input_jitter_pad, "mfvi_sample_weights": op_sample_weights,
+                   "mfvi_pack_weights_bf16": op_pack_weights_bf16, "mfvi_gauss_nll_fwd_bwd": op_gauss_nll,
+                   "mfvi_kl_reparam_fwd_bwd": op_kl_reparam, "mfvi_bn_running_update": op_bn_running_update,
+                   "mfvi_adamw_step": op_adamw, "mfvi_counter_add": op_counter_add}
