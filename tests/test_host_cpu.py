@@ -377,3 +377,16 @@ def test_conv_plans_on_non_square_images(H, W):
         rows16 = SkipEngine(SkipSpec(), H, W, S, "meta", math=L.MATH_BF16).conv_dispatch_table()
         assert {r["family"] for r in rows16} == {"halo-bf16", "tc-bf16"}
         assert all(r["plan"]["TP"] % 16 == 0 for r in rows16 if r["op"] == "wgrad")
+
+
+def test_verified_kernels_are_byte_identical():
+    """profiles/r01_sass_hashes.json fingerprints the 60 kernels of the build that passed the GPU suite in round 1 (the
+    last B200 run of the round).  Everything added afterwards without a GPU — the planning-only query, the plan-only engine,
+    the experimental bf16 mode — must leave their machine code untouched.  After a deliberate kernel change that has been
+    re-verified on a GPU, refresh the file with `python scripts/sass_hashes.py --write profiles/<round>_sass_hashes.json`."""
+    import shutil
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not installed")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "sass_hashes.py"), "--check",
+                        os.path.join(ROOT, "profiles", "r01_sass_hashes.json")], capture_output=True, text=True, timeout=280)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
