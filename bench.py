@@ -161,15 +161,17 @@ def run_ours(args):
     os.dup2(2, 1)
 
     # A collective that never completes (a rank died, mismatched call counts) would otherwise hang until the caller's
-    # timeout: after 10 minutes every rank gives up on its own, rank 0 reporting why on the JSON channel.
+    # timeout: every rank gives up on its own — after 10 minutes alone (the run includes the CPU baseline leg), after 5 minutes
+    # in a multi-rank run (no CPU leg; a healthy 8-GPU run takes well under a minute) — rank 0 reporting why on the JSON channel.
     state = {"printed": False}
+    limit_s = 600.0 if world == 1 else 300.0
 
     def _give_up():
         if rank == 0 and not state["printed"]:
-            os.write(json_fd, (json.dumps({"metric": METRIC, "error": "bench.py watchdog: no result after 600 s "
+            os.write(json_fd, (json.dumps({"metric": METRIC, "error": f"bench.py watchdog: no result after {limit_s:.0f} s "
                                            "(hung collective or device?)", "n_gpus": world}) + "\n").encode())
         os._exit(0 if state["printed"] else 3)
-    watchdog = threading.Timer(600.0, _give_up)
+    watchdog = threading.Timer(limit_s, _give_up)
     watchdog.daemon = True
     watchdog.start()
     if not torch.cuda.is_available():
