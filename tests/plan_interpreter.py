@@ -43,7 +43,16 @@ class PlanInterpreter:
                 last = sum((n - 1) * s for n, s in zip(size, stride)) if all(n > 0 for n in size) else 0
                 assert ptr + (last + 1) * esz <= hi, "view reaches beyond its buffer"
                 return t
-        raise AssertionError(f"pointer {ptr:#x} is not inside any engine buffer")
+        # a buffer allocated after the interpreter was built (e.g. the outputs of DeviceBookkeeping.uncertainty()): look it up
+        # among the live CPU tensors once, then resolve again
+        import gc
+        for obj in gc.get_objects():
+            if isinstance(obj, torch.Tensor) and obj.device.type == "cpu" and obj.numel() > 0:
+                st = obj.untyped_storage()
+                if st.data_ptr() <= ptr < st.data_ptr() + st.nbytes() and all(lo != st.data_ptr() for lo, _, _ in self.stores):
+                    self.stores.append((st.data_ptr(), st.data_ptr() + st.nbytes(), st))
+                    return self._strided(ptr, size, stride, dtype)
+        raise AssertionError(f"pointer {ptr:#x} is not inside any live buffer")
 
     def view(self, v, S, H, W, Cn, dtype=torch.float32):
         """(S,H,W,Cn) tensor of an MfviView (sample stride 0 = broadcast)."""
@@ -329,10 +338,19 @@ class TrainerInterpreter(PlanInterpreter):
         from mfvi_dip_mia_b200.engine import SkipEngine
         L.call, SkipEngine._run = self._saved
 
+    def register_object(self, obj):
+        """registers every tensor attribute of `obj` (e.g. a runners.DeviceBookkeeping, or tensors it allocates on demand)"""
+        for v in vars(obj).values():
+            if isinstance(v, torch.Tensor):
+                self.register(v)
+
     def dispatch(self, name, args):
         fn = self.OPS.get(name) or self.TRAINER_OPS.get(name)
         if fn is None:
             raise NotImplementedError(f"{name} is not interpreted")
+        for hook in self.tr.post_step_hooks:
+            if hasattr(hook, "__self__"):
+                self.register_object(hook.__self__)
         if self.eng.eps is not None:
             self.register(self.eng.eps)
         if self.tr.noise is not None:
@@ -456,7 +474,54 @@ class TrainerInterpreter(PlanInterpreter):
         ptr, inc = args
         self.vec(ptr, 1, torch.int32).add_(int(inc))
 
-    TRAINER_OPS = {"mfvi_input_jitter_pad": op_input_jitter_pad, "mfvi_sample_weights": op_sample_weights,
+    # ------------------------------------------------------------------ runner bookkeeping (csrc/bookkeeping.cu)
+    def op_bookkeep_step(self, name, args):
+        out, S, H, W, expw, gt, noisy, out_avg, ring_epi, ring_ale, R, iter_dev, iter_off, acc = args
+        it = iter_off + (int(self.vec(iter_dev, 1, torch.int32)[0]) if iter_dev is not None else 0)
+        O_ = self.view(out, S, H, W, 2)
+        m, v = O_[..., 0].mean(0), torch.exp(-O_[..., 1]).mean(0)
+        AVG = self.vec(out_avg, 2 * H * W).view(2, H, W)
+        if it == 0:
+            AVG[0], AVG[1] = m, v
+        else:
+            AVG[0] = AVG[0] * expw + m * (1 - expw)
+            AVG[1] = AVG[1] * expw + v * (1 - expw)
+        mc = m.clamp(0, 1)
+        if R > 0:
+            self.vec(ring_epi, R * H * W).view(R, H, W)[it % R] = mc
+            self.vec(ring_ale, R * H * W).view(R, H, W)[it % R] = v.clamp(0, 1)
+        A = self.vec(acc, 5, torch.float64)
+        am, amc = AVG[0], AVG[0].clamp(0, 1)
+        if noisy is not None:
+            t = self.vec(noisy, H * W).view(H, W)
+            A[0] += ((t - mc) ** 2).double().sum()
+            A[3] += ((t - am) ** 2).double().sum()
+        if gt is not None:
+            t = self.vec(gt, H * W).view(H, W)
+            A[1] += ((t - mc) ** 2).double().sum()
+            A[2] += ((t - amc) ** 2).double().sum()
+            A[4] += ((t - am) ** 2).double().sum()
+
+    def op_ssim(self, name, args):
+        from oracle import mfvi_oracle as O
+        a, b, H, W, clip_b, out_sum = args
+        A, B = self.vec(a, H * W).view(1, 1, H, W), self.vec(b, H * W).view(1, 1, H, W)
+        if clip_b:
+            B = B.clamp(0, 1)
+        self.vec(out_sum, 1, torch.float64).add_(float(O.ssim(A, B)) * H * W)
+
+    def op_ring_uncertainty(self, name, args):
+        ring_epi, ring_ale, n, H, W, gt, epi, ale, err2 = args
+        RE = self.vec(ring_epi, n * H * W).view(n, H, W)
+        RA = self.vec(ring_ale, n * H * W).view(n, H, W)
+        self.vec(epi, H * W).view(H, W).copy_(RE.var(0) if n > 1 else torch.zeros(H, W))
+        self.vec(ale, H * W).view(H, W).copy_(RA.mean(0))
+        if err2 is not None:
+            t = self.vec(gt, H * W).view(H, W) if gt is not None else torch.zeros(H, W)
+            self.vec(err2, H * W).view(H, W).copy_(((RE - t) ** 2).mean(0))
+
+    TRAINER_OPS = {"mfvi_bookkeep_step": op_bookkeep_step, "mfvi_ssim": op_ssim, "mfvi_ring_uncertainty": op_ring_uncertainty,
+                   "mfvi_input_jitter_pad": op_input_jitter_pad, "mfvi_sample_weights": op_sample_weights,
                    "mfvi_pack_weights_bf16": op_pack_weights_bf16, "mfvi_gauss_nll_fwd_bwd": op_gauss_nll,
                    "mfvi_kl_reparam_fwd_bwd": op_kl_reparam, "mfvi_bn_running_update": op_bn_running_update,
                    "mfvi_adamw_step": op_adamw, "mfvi_counter_add": op_counter_add}

@@ -121,3 +121,46 @@ def test_two_rank_gloo_sharded_trainer_equals_single_process(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=280, env=dict(os.environ, OMP_NUM_THREADS="2"), cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "rank 0 vs single-process" in r.stdout and "rank 1 vs single-process" in r.stdout
+
+
+def test_device_bookkeeping_matches_the_reference_loop():
+    """runners.DeviceBookkeeping (reference bayesian_optimization.py:1374-1416) attached to an interpreted trainer: the
+    bookkeeping launch is a post-step hook that must see the output of the step just computed and the iteration index of the
+    device counter BEFORE it advances.  After 30 iterations (more than one turn of the 25-deep rings) the EMA output, the PSNR
+    values, SSIM, the uncertainty maps and the UCE equal the reference's per-iteration formulas applied to the recorded outputs."""
+    import math
+    import numpy as np
+    from mfvi_dip_mia_b200.runners import DeviceBookkeeping
+    from mfvi_dip_mia_b200.utils.uce import uceloss
+    from tests.plan_interpreter import TrainerInterpreter
+    S, n_it, ring, expw = 2, 30, 25, 0.99
+    tr = _trainer(S)
+    g = torch.Generator().manual_seed(5)
+    gt = torch.rand(32, 32, generator=g)
+    noisy = (gt + 0.1 * torch.randn(32, 32, generator=g)).clamp(0, 1)
+    bk = DeviceBookkeeping(tr, gt=gt.numpy(), noisy=noisy.numpy(), exp_weight=expw, ring=ring)
+    outs = []
+    with TrainerInterpreter(tr):
+        for _ in range(n_it):
+            tr.step()
+            outs.append(tr.eng.out.clone())                     # (S,H,W,2) of the step just taken
+        m = bk.metrics()
+        epi, ale, err2 = bk.uncertainty()
+        uce = bk.uce()
+    # the reference loop on the recorded outputs
+    out_avg, r_epi, r_ale = None, torch.zeros(ring, 32, 32), torch.zeros(ring, 32, 32)
+    for i, o in enumerate(outs):
+        cur = torch.stack([o[..., 0].mean(0), torch.exp(-o[..., 1]).mean(0)])
+        out_avg = cur if out_avg is None else out_avg * expw + cur * (1 - expw)
+        r_epi[i % ring], r_ale[i % ring] = cur[0].clamp(0, 1), cur[1].clamp(0, 1)
+    psnr = lambda a, b: 10 * math.log10(1.0 / float(((a - b) ** 2).mean()))
+    last = torch.stack([outs[-1][..., 0].mean(0), torch.exp(-outs[-1][..., 1]).mean(0)])
+    assert abs(m["psnr_noisy"] - psnr(noisy, last[0].clamp(0, 1))) < 1e-4
+    assert abs(m["psnr_gt"] - psnr(gt, last[0].clamp(0, 1))) < 1e-4
+    assert abs(m["psnr_gt_sm"] - psnr(gt, out_avg[0].clamp(0, 1))) < 1e-4
+    assert abs(m["ssim_gt_sm"] - O.ssim(gt[None, None], out_avg[0].clamp(0, 1)[None, None])) < 1e-5
+    assert torch.allclose(bk.out_avg, out_avg, atol=1e-6)
+    assert torch.allclose(epi, r_epi.var(0), atol=1e-7) and torch.allclose(ale, r_ale.mean(0), atol=1e-6)
+    ref_err2 = ((r_epi - gt) ** 2).mean(0)
+    assert torch.allclose(err2, ref_err2, atol=1e-6)
+    assert abs(uce - float(uceloss(ref_err2.reshape(-1), (r_epi.var(0) + r_ale.mean(0)).reshape(-1), n_bins=15)[0])) < 1e-6
