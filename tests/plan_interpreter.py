@@ -300,15 +300,15 @@ class TrainerInterpreter(PlanInterpreter):
     """Interprets a whole `MfviDipTrainer(plan_only=True, device="cpu")`: inside `with TrainerInterpreter(tr):` every libmfvidip
     call the trainer makes (`_lib.call`) and every op list its engine runs is executed here on the CPU, so `tr.step()` works —
     host logic under test: Philox keys and the device step counter, MC-sample sharding and the gradient all-reduce (gloo), the
-    KL / reparameterisation scaling, AdamW, post-step hooks.  Denoising / SR / inpainting heads; no CT."""
+    KL / reparameterisation scaling, AdamW, post-step hooks, the four task heads."""
 
     def __init__(self, tr):
         super().__init__(tr.eng)
         self.tr = tr
         e = tr.eng
-        for t in (tr.saved, tr.step_dev, tr.m, tr.v, tr.losses, e._bn_ch_off, e._bn_sums_off, e._bn_C, e._bn_count,
-                  getattr(tr.head, "target", None), getattr(tr.head, "mask", None)):
+        for t in (tr.saved, tr.step_dev, tr.m, tr.v, tr.losses, e._bn_ch_off, e._bn_sums_off, e._bn_C, e._bn_count):
             self.register(t)
+        self.register_object(tr.head)
 
     def register(self, t):
         if t is None:
@@ -474,6 +474,38 @@ class TrainerInterpreter(PlanInterpreter):
         ptr, inc = args
         self.vec(ptr, 1, torch.int32).add_(int(inc))
 
+    # ------------------------------------------------------------------ CT head: radon projector + sinogram MSE
+    def _theta_deg(self, theta_rad, T):
+        return torch.rad2deg(self.vec(theta_rad, T).double()).float()
+
+    def op_radon_fwd(self, name, args):
+        from oracle import mfvi_oracle as O
+        img, S, Cn, H, W, theta, T, sino = args
+        X = self.view(img, S, H, W, Cn).permute(0, 3, 1, 2)
+        out = self.vec(sino, S * Cn * T * W).view(S, Cn, T, W)
+        for s in range(S):
+            out[s] = O.radon_forward(X[s:s + 1].contiguous(), self._theta_deg(theta, T))[0]
+
+    def op_radon_bwd(self, name, args):
+        from oracle import mfvi_oracle as O
+        dsino, S, Cn, H, W, theta, T, dimg = args
+        D = self.vec(dsino, S * Cn * T * W).view(S, Cn, T, W)
+        G = self.view(dimg, S, H, W, Cn)
+        for s in range(S):
+            probe = torch.zeros(1, Cn, H, W, requires_grad=True)
+            O.radon_forward(probe, self._theta_deg(theta, T)).backward(D[s:s + 1])
+            G[s] = probe.grad[0].permute(1, 2, 0)
+
+    def op_mse(self, name, args):
+        a, a_ss, b, n, S, loss_out, da = args
+        B = self.vec(b, n)
+        for s in range(S):
+            diff = self.vec(a + 4 * s * a_ss, n) - B
+            if loss_out is not None:
+                self.vec(loss_out, 1, torch.float64).add_(float((diff.double() ** 2).sum()) / (n * S))
+            if da is not None:
+                self.vec(da + 4 * s * a_ss, n).copy_(2.0 * diff / (n * S))
+
     # ------------------------------------------------------------------ runner bookkeeping (csrc/bookkeeping.cu)
     def op_bookkeep_step(self, name, args):
         out, S, H, W, expw, gt, noisy, out_avg, ring_epi, ring_ale, R, iter_dev, iter_off, acc = args
@@ -520,7 +552,8 @@ class TrainerInterpreter(PlanInterpreter):
             t = self.vec(gt, H * W).view(H, W) if gt is not None else torch.zeros(H, W)
             self.vec(err2, H * W).view(H, W).copy_(((RE - t) ** 2).mean(0))
 
-    TRAINER_OPS = {"mfvi_bookkeep_step": op_bookkeep_step, "mfvi_ssim": op_ssim, "mfvi_ring_uncertainty": op_ring_uncertainty,
+    TRAINER_OPS = {"mfvi_radon_fwd": op_radon_fwd, "mfvi_radon_bwd": op_radon_bwd, "mfvi_mse_fwd_bwd": op_mse,
+                   "mfvi_bookkeep_step": op_bookkeep_step, "mfvi_ssim": op_ssim, "mfvi_ring_uncertainty": op_ring_uncertainty,
                    "mfvi_input_jitter_pad": op_input_jitter_pad, "mfvi_sample_weights": op_sample_weights,
                    "mfvi_pack_weights_bf16": op_pack_weights_bf16, "mfvi_gauss_nll_fwd_bwd": op_gauss_nll,
                    "mfvi_kl_reparam_fwd_bwd": op_kl_reparam, "mfvi_bn_running_update": op_bn_running_update,

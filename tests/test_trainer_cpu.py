@@ -18,24 +18,42 @@ TEMP, SIGMA, LR, SEED = 5.656911698337764e-07, 1.4616642493692077e-05, 1e-2, 7
 CFG = O.SkipCfg(4, 2, (8, 16, 16), (8, 16, 16), (2, 2, 2), 3, 3, 1, True, False, "bilinear")
 
 
-def _problem():
+TASK_CFG = {
+    "den": CFG,
+    "sr": CFG,
+    "ct": O.SkipCfg(4, 1, (8, 16, 16), (8, 16, 16), (2, 2, 2), 3, 3, 1, True, False, "bilinear"),
+    "inp": O.SkipCfg(4, 4, (8, 16, 16), (8, 16, 16), (0, 0, 0), 5, 3, 1, False, False, "nearest"),
+}
+
+
+def _problem(task="den"):
+    """(net input, head kwargs as MfviDipTrainer / oracle.mfvi_loss take them)"""
     g = torch.Generator().manual_seed(0)
-    return torch.rand(1, 4, 32, 32, generator=g) * 0.1, torch.rand(1, 1, 32, 32, generator=g)
+    x = torch.rand(1, 4, 32, 32, generator=g) * 0.1
+    if task == "den":
+        return x, dict(target=torch.rand(1, 1, 32, 32, generator=g))
+    if task == "sr":
+        return x, dict(target=torch.rand(1, 1, 8, 8, generator=g))
+    if task == "inp":
+        return x, dict(target=torch.rand(1, 3, 32, 32, generator=g), mask=(torch.rand(1, 1, 32, 32, generator=g) > 0.5).float())
+    theta = torch.arange(0., 180., 20.)
+    return x, dict(theta_deg=theta, sino=O.radon_forward(torch.rand(1, 1, 32, 32, generator=g), theta))
 
 
-def _trainer(S, rank=0, world=1):
+def _trainer(S, rank=0, world=1, task="den"):
     from mfvi_dip_mia_b200 import MfviDipTrainer, SkipSpec
-    x, tgt = _problem()
-    spec = SkipSpec(CFG.num_input_channels, CFG.num_output_channels, tuple(CFG.down), tuple(CFG.up), tuple(CFG.skip),
-                    CFG.filter_down, CFG.filter_up, CFG.filter_skip, CFG.need1x1_up, CFG.need_sigmoid, CFG.upsample_mode)
-    return MfviDipTrainer(spec, "den", x, temp=TEMP, sigma=SIGMA, lr=LR, mc_samples=S, seed=SEED, device="cpu", target=tgt,
-                          rank=rank, world_size=world, plan_only=True)
+    x, head = _problem(task)
+    cfg = TASK_CFG[task]
+    spec = SkipSpec(cfg.num_input_channels, cfg.num_output_channels, tuple(cfg.down), tuple(cfg.up), tuple(cfg.skip),
+                    cfg.filter_down, cfg.filter_up, cfg.filter_skip, cfg.need1x1_up, cfg.need_sigmoid, cfg.upsample_mode)
+    return MfviDipTrainer(spec, task, x, temp=TEMP, sigma=SIGMA, lr=LR, mc_samples=S, seed=SEED, device="cpu",
+                          rank=rank, world_size=world, plan_only=True, **head)
 
 
-def _oracle_loop(tr, S, n_steps):
+def _oracle_loop(tr, S, n_steps, task="den"):
     """The same optimisation written independently: oracle forward / autograd, torch's AdamW, eps and jitter drawn from the
     Philox streams by (seed, stream, GLOBAL sample id, step)."""
-    x, tgt = _problem()
+    x, head = _problem(task)
     lay = tr.eng.lay
     sd = {"net." + k: v.detach().clone().requires_grad_("running" not in k) for k, v in tr.eng.param_views("theta").items()}
     opt = torch.optim.AdamW([v for v in sd.values() if v.requires_grad], lr=LR, weight_decay=0)
@@ -48,25 +66,32 @@ def _oracle_loop(tr, S, n_steps):
             eps.append({**{"net." + c.key + ".W": flat[c.w_off:c.w_off + c.w_numel].view(c.k, c.k, c.cout, c.cin).permute(2, 3, 0, 1)
                            for c in lay.convs},
                         **{"net." + c.key + ".b": flat[c.b_off:c.b_off + c.cout] for c in lay.convs}})
-        loss, _, _, _ = O.mfvi_loss(sd, CFG, x + 0.1 * z, eps, task="den", temp=TEMP,
-                                    prior_sigma_plus_eps=O.prior_scale(TEMP, SIGMA), target=tgt)
+        loss, _, _, _ = O.mfvi_loss(sd, TASK_CFG[task], x + 0.1 * z, eps, task=task, temp=TEMP,
+                                    prior_sigma_plus_eps=O.prior_scale(TEMP, SIGMA), **head)
         loss.backward()
+        if step == 0:
+            first_grads = {k: v.grad.clone() for k, v in sd.items() if v.grad is not None}
         opt.step()
-    return sd, float(loss.detach())
+    return sd, float(loss.detach()), first_grads
 
 
-def test_interpreted_trainer_follows_the_oracle_optimisation():
+@pytest.mark.parametrize("task", ["den", "sr", "inp", "ct"])
+def test_interpreted_trainer_follows_the_oracle_optimisation(task):
     from tests.plan_interpreter import TrainerInterpreter
     S, n_steps = 2, 3
-    tr = _trainer(S)
+    tr = _trainer(S, task=task)
     theta0 = tr.eng.theta.clone()
-    sd, loss_ref = _oracle_loop(tr, S, n_steps)                      # reads the initial parameters: before the trainer moves them
+    sd, loss_ref, first_grads = _oracle_loop(tr, S, n_steps, task)                      # reads the initial parameters: before the trainer moves them
+    from tests.helpers import grad_errs
     with TrainerInterpreter(tr):
-        for _ in range(n_steps):
+        for i in range(n_steps):
             tr.step()
+            if i == 0:          # the gradient of the first step (data term over the samples + T * KL), before dynamics amplify anything
+                errs = grad_errs({"net." + k: v.clone() for k, v in tr.eng.param_views("grad").items()}, first_grads)
         loss = tr.loss_terms()[2]
+    assert max(errs.values()) < 1e-4, max(errs, key=errs.get)
     assert tr.steps_done == n_steps
-    assert abs(loss - loss_ref) < 1e-3 * abs(loss_ref)                # the third step's loss, after two Adam updates
+    assert abs(loss - loss_ref) < 2e-3 * abs(loss_ref)                # the third step's loss, after two Adam updates
     assert (tr.eng.theta - theta0).abs().max() > 0.5 * LR             # Adam moves every parameter by ~lr per step
     ours = tr.eng.param_views("theta")
     sq = n = 0.0
@@ -77,7 +102,7 @@ def test_interpreted_trainer_follows_the_oracle_optimisation():
     # parameters agree to a small fraction of the distance they travelled (Adam's normalisation turns the fp32 noise of the
     # smallest gradients into update noise, so the yardstick is the step length, not the parameter value)
     rms = (sq / n) ** 0.5 / (LR * n_steps)
-    assert rms < 2e-2, rms
+    assert rms < 5e-2, rms
 
 
 _WORKER = r'''
