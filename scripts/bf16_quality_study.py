@@ -9,7 +9,10 @@ input gradients, statistics and parameters in fp32.  Reported: PSNR / SSIM / UCE
 mean over seeds, and the PAIRED difference bf16 - fp32 with its standard error (the optimisation is chaotic, so single
 trajectories differ by ~0.5 dB; the ensemble mean is what north_star's 0.1 dB / 0.005 bar can be held to).
 
-    python scripts/bf16_quality_study.py [K seeds = 8] [n_it = 1200] [workers = 4]
+    python scripts/bf16_quality_study.py [K seeds = 8] [n_it = 1200] [workers = 4] [size = 64] [net = small | metric]
+
+`net = metric` is the 5-scale, 16-channel-input network of the metric configuration (test_configs/mfvi_den.json) instead of the
+3-scale network of the trajectory fixture.
 """
 import os
 import sys
@@ -47,7 +50,9 @@ class Bf16OperandConv(torch.autograd.Function):
         return dx, dw, (dy.sum((0, 2, 3)) if ctx.has_b else None), None
 
 
-def one_run(seed, n_it, bf16):
+def one_run(seed, n_it, bf16, size=64, net="small"):
+    global H, W
+    H = W = size
     torch.set_num_threads(2)
     from oracle import mfvi_oracle as O
     from mfvi_dip_mia_b200.utils.phantoms import ellipse_phantom, noisy
@@ -59,7 +64,7 @@ def one_run(seed, n_it, bf16):
             b = O.rsample(bias_mu, O.softplus(bias_rho), eps_b) if bias_mu is not None else None
             return Bf16OperandConv.apply(x, w, b, stride)
         O.conv2d_rt = conv2d_rt
-    cfg = O.SkipCfg(4, 2, (8, 16, 16), (8, 16, 16), (2, 2, 2), 3, 3, 1, True, False, "bilinear")
+    cfg = O.SkipCfg(4, 2, (8, 16, 16), (8, 16, 16), (2, 2, 2), 3, 3, 1, True, False, "bilinear") if net == "small" else O.SkipCfg(16, 2)
     g = torch.Generator().manual_seed(seed)
     gt = torch.from_numpy(ellipse_phantom(H))[None]
     tgt = torch.from_numpy(noisy(ellipse_phantom(H), 0.1, 1))[None]
@@ -116,13 +121,16 @@ if __name__ == "__main__":
     K = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     n_it = int(sys.argv[2]) if len(sys.argv) > 2 else 1200
     workers = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+    size = int(sys.argv[4]) if len(sys.argv) > 4 else 64
+    net = sys.argv[5] if len(sys.argv) > 5 else "small"
     t0 = time.time()
-    jobs = [(100 + k, n_it, b) for k in range(K) for b in (False, True)]
+    jobs = [(100 + k, n_it, b, size, net) for k in range(K) for b in (False, True)]
     with mp.get_context("spawn").Pool(workers) as pool:
         runs = pool.map(_worker, jobs)
     its = sorted(runs[0])
     arr = np.array([[r[i] for i in its] for r in runs]).reshape(K, 2, len(its), 3)        # (seed, arm, checkpoint, metric)
-    print(f"# {K} seeds x {n_it} iterations, 64x64 denoising, oracle fp32 vs emulated bf16 conv operands; wall {time.time() - t0:.0f} s")
+    print(f"# {K} seeds x {n_it} iterations, {size}x{size} denoising, {net} net, oracle fp32 vs emulated bf16 conv operands; "
+          f"wall {time.time() - t0:.0f} s")
     print("# it   arm    PSNR dB   SSIM     UCE      | paired difference bf16 - fp32 (mean +- standard error)")
     for j, i in enumerate(its):
         d = arr[:, 1, j] - arr[:, 0, j]
