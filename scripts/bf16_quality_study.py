@@ -9,7 +9,12 @@ input gradients, statistics and parameters in fp32.  Reported: PSNR / SSIM / UCE
 mean over seeds, and the PAIRED difference bf16 - fp32 with its standard error (the optimisation is chaotic, so single
 trajectories differ by ~0.5 dB; the ensemble mean is what north_star's 0.1 dB / 0.005 bar can be held to).
 
-    python scripts/bf16_quality_study.py [K seeds = 8] [n_it = 1200] [workers = 4] [size = 64] [net = small | metric]
+    python scripts/bf16_quality_study.py [K seeds = 8] [n_it = 1200] [workers = 4] [size = 64] [net = small | metric] [arm = bf16 | bf16s]
+
+`arm = bf16s` ("bf16 storage") goes one step further than the mode that is written: the convolution OUTPUTS and the input
+gradients the data-gradient kernels write are rounded to bf16 as well, i.e. every activation and activation gradient that
+touches HBM is bf16 and only accumulators, statistics, parameters and their gradients are fp32 — the variant that would halve the
+traffic of the elementwise kernels too.
 
 `net = metric` is the 5-scale, 16-channel-input network of the metric configuration (test_configs/mfvi_den.json) instead of the
 3-scale network of the trajectory fixture.
@@ -32,20 +37,25 @@ CHECK = (300, 600, 900, 1200)
 
 
 class Bf16OperandConv(torch.autograd.Function):
-    """conv2d with bf16 operands and fp32 accumulation, forward and both gradients (dy is a bf16 operand of dgrad / wgrad)."""
+    """conv2d with bf16 operands and fp32 accumulation, forward and both gradients (dy is a bf16 operand of dgrad / wgrad).
+    round_io: the stored results (y, dx) are rounded to bf16 too."""
+    round_io = False
 
     @staticmethod
     def forward(ctx, x, w, b, stride):
         xb, wb = x.bfloat16().float(), w.bfloat16().float()
         ctx.save_for_backward(xb, wb)
         ctx.stride, ctx.has_b = stride, b is not None
-        return F.conv2d(xb, wb, b, stride=stride)
+        y = F.conv2d(xb, wb, b, stride=stride)
+        return y.bfloat16().float() if Bf16OperandConv.round_io else y
 
     @staticmethod
     def backward(ctx, dy):
         xb, wb = ctx.saved_tensors
         dyb = dy.bfloat16().float()
         dx = torch.nn.grad.conv2d_input(xb.shape, wb, dyb, stride=ctx.stride)
+        if Bf16OperandConv.round_io:
+            dx = dx.bfloat16().float()
         dw = torch.nn.grad.conv2d_weight(xb, wb.shape, dyb, stride=ctx.stride)
         return dx, dw, (dy.sum((0, 2, 3)) if ctx.has_b else None), None
 
@@ -58,6 +68,7 @@ def one_run(seed, n_it, bf16, size=64, net="small"):
     from mfvi_dip_mia_b200.utils.phantoms import ellipse_phantom, noisy
     from mfvi_dip_mia_b200.utils.uce import uceloss
     if bf16:
+        Bf16OperandConv.round_io = bf16 == 2
         def conv2d_rt(x, W_mu, W_rho, bias_mu, bias_rho, eps_w, eps_b, stride=1, padding=0, training=True):
             assert padding == 0 and training
             w = O.rsample(W_mu, O.softplus(W_rho), eps_w)
@@ -123,19 +134,21 @@ if __name__ == "__main__":
     workers = int(sys.argv[3]) if len(sys.argv) > 3 else 4
     size = int(sys.argv[4]) if len(sys.argv) > 4 else 64
     net = sys.argv[5] if len(sys.argv) > 5 else "small"
+    arm = sys.argv[6] if len(sys.argv) > 6 else "bf16"
     t0 = time.time()
-    jobs = [(100 + k, n_it, b, size, net) for k in range(K) for b in (False, True)]
+    jobs = [(100 + k, n_it, b, size, net) for k in range(K) for b in (0, 2 if arm == "bf16s" else 1)]
     with mp.get_context("spawn").Pool(workers) as pool:
         runs = pool.map(_worker, jobs)
     its = sorted(runs[0])
     arr = np.array([[r[i] for i in its] for r in runs]).reshape(K, 2, len(its), 3)        # (seed, arm, checkpoint, metric)
-    print(f"# {K} seeds x {n_it} iterations, {size}x{size} denoising, {net} net, oracle fp32 vs emulated bf16 conv operands; "
+    print(f"# {K} seeds x {n_it} iterations, {size}x{size} denoising, {net} net, oracle fp32 vs emulated {arm} "
+          f"({'bf16 conv operands AND bf16 conv outputs / input gradients' if arm == 'bf16s' else 'bf16 conv operands'}); "
           f"wall {time.time() - t0:.0f} s")
     print("# it   arm    PSNR dB   SSIM     UCE      | paired difference bf16 - fp32 (mean +- standard error)")
     for j, i in enumerate(its):
         d = arr[:, 1, j] - arr[:, 0, j]
         se = d.std(0, ddof=1) / np.sqrt(K) if K > 1 else np.zeros(3)
-        for a, name in ((0, "fp32"), (1, "bf16")):
+        for a, name in ((0, "fp32"), (1, arm)):
             m = arr[:, a, j].mean(0)
             tail = f" | {d.mean(0)[0]:+.3f}+-{se[0]:.3f} dB  {d.mean(0)[1]:+.4f}+-{se[1]:.4f}  {d.mean(0)[2]:+.4f}+-{se[2]:.4f}" if a else ""
             print(f"{i:5d}  {name}  {m[0]:8.3f}  {m[1]:.4f}  {m[2]:.4f}{tail}")
