@@ -9,7 +9,7 @@ input gradients, statistics and parameters in fp32.  Reported: PSNR / SSIM / UCE
 mean over seeds, and the PAIRED difference bf16 - fp32 with its standard error (the optimisation is chaotic, so single
 trajectories differ by ~0.5 dB; the ensemble mean is what north_star's 0.1 dB / 0.005 bar can be held to).
 
-    python scripts/bf16_quality_study.py [K seeds = 8] [n_it = 1200] [workers = 4] [size = 64] [net = small | metric] [arm = bf16 | bf16s]
+    python scripts/bf16_quality_study.py [K seeds = 8] [n_it = 1200] [workers = 4] [size = 64] [net = small | metric] [arm = bf16 | bf16s] [lr = 1e-2]
 
 `arm = bf16s` ("bf16 storage") goes one step further than the mode that is written: the convolution OUTPUTS and the input
 gradients the data-gradient kernels write are rounded to bf16 as well, i.e. every activation and activation gradient that
@@ -60,9 +60,10 @@ class Bf16OperandConv(torch.autograd.Function):
         return dx, dw, (dy.sum((0, 2, 3)) if ctx.has_b else None), None
 
 
-def one_run(seed, n_it, bf16, size=64, net="small"):
-    global H, W
+def one_run(seed, n_it, bf16, size=64, net="small", lr=LR):
+    global H, W, LR
     H = W = size
+    LR = lr
     torch.set_num_threads(2)
     from oracle import mfvi_oracle as O
     from mfvi_dip_mia_b200.utils.phantoms import ellipse_phantom, noisy
@@ -135,13 +136,14 @@ if __name__ == "__main__":
     size = int(sys.argv[4]) if len(sys.argv) > 4 else 64
     net = sys.argv[5] if len(sys.argv) > 5 else "small"
     arm = sys.argv[6] if len(sys.argv) > 6 else "bf16"
+    lr = float(sys.argv[7]) if len(sys.argv) > 7 else LR
     t0 = time.time()
-    jobs = [(100 + k, n_it, b, size, net) for k in range(K) for b in (0, 2 if arm == "bf16s" else 1)]
+    jobs = [(100 + k, n_it, b, size, net, lr) for k in range(K) for b in (0, 2 if arm == "bf16s" else 1)]
     with mp.get_context("spawn").Pool(workers) as pool:
         runs = pool.map(_worker, jobs)
     its = sorted(runs[0])
     arr = np.array([[r[i] for i in its] for r in runs]).reshape(K, 2, len(its), 3)        # (seed, arm, checkpoint, metric)
-    print(f"# {K} seeds x {n_it} iterations, {size}x{size} denoising, {net} net, oracle fp32 vs emulated {arm} "
+    print(f"# {K} seeds x {n_it} iterations, lr {lr:g}, {size}x{size} denoising, {net} net, oracle fp32 vs emulated {arm} "
           f"({'bf16 conv operands AND bf16 conv outputs / input gradients' if arm == 'bf16s' else 'bf16 conv operands'}); "
           f"wall {time.time() - t0:.0f} s")
     print("# it   arm    PSNR dB   SSIM     UCE      | paired difference bf16 - fp32 (mean +- standard error)")
