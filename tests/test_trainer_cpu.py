@@ -154,7 +154,6 @@ def test_device_bookkeeping_matches_the_reference_loop():
     device counter BEFORE it advances.  After 30 iterations (more than one turn of the 25-deep rings) the EMA output, the PSNR
     values, SSIM, the uncertainty maps and the UCE equal the reference's per-iteration formulas applied to the recorded outputs."""
     import math
-    import numpy as np
     from mfvi_dip_mia_b200.runners import DeviceBookkeeping
     from mfvi_dip_mia_b200.utils.uce import uceloss
     from tests.plan_interpreter import TrainerInterpreter
