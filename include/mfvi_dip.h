@@ -128,6 +128,19 @@ int mfvi_pack_weights_bf16(const float* w, long long w_sstride, int S, int n_lay
                            const long long* w16_off, const int* rows, const int* cin, void* w16, long long w16_sstride,
                            mfvi_stream_t st);
 
+/* EXPERIMENTAL (engine switch MFVI_FUSED_BN_BWD=1, off by default; not yet run on a GPU): the pair mfvi_pad_act_bwd +
+ * mfvi_bn_bwd_apply without the intermediate gradient g in HBM.  Pass 1 only accumulates red[S][C][2] += (sum g, sum g*xhat);
+ * pass 2 recomputes g = fold_reflect(dxp) * act'(bn(y)) from the same inputs and writes
+ * dy = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)) (fp32, or bf16 for the bf16-operand mode) and dgamma / dbeta. */
+int mfvi_pad_act_bwd_reduce(MfviView dxp, int S, int H, int W, int C, int pad, MfviView y, const double* sums, const float* gamma,
+                            const float* beta, int act, double* red, mfvi_stream_t st);
+int mfvi_bn_bwd_apply_from_dxp(MfviView dxp, MfviView y, int S, int H, int W, int C, int pad, const double* sums, const double* red,
+                               const float* gamma, const float* beta, int act, MfviView dy, float* dgamma, float* dbeta,
+                               mfvi_stream_t st);
+int mfvi_bn_bwd_apply_from_dxp_bf16(MfviView dxp, MfviView y, int S, int H, int W, int C, int pad, const double* sums,
+                                    const double* red, const float* gamma, const float* beta, int act, MfviView dy, float* dgamma,
+                                    float* dbeta, mfvi_stream_t st);
+
 /* Planning-only query (no reference counterpart; host-only, touches no device, works without a GPU): which kernel family
  * mfvi_conv2d_{fwd,dgrad,wgrad} would run for this geometry and these views — "pointwise", "halo", "alias", "tc" (tcgen05
  * paths) or "simt" (fp32 CUDA cores) — with its launch geometry and a one-line tile plan.  pass: 0 = forward (a = x, b = y),

@@ -69,6 +69,10 @@ _SIGS = {
     "mfvi_bn_act_pad_fwd_bf16": [View, _I, _I, _I, _I, _P, _P, _P, _I, _I, View],
     "mfvi_bn_bwd_apply_bf16": [View, View, _I, _I, _I, _I, _P, _P, _P, View, _P, _P],
     "mfvi_view_f32_to_bf16": [View, _I, _I, _I, _I, View],
+    # BatchNorm/activation/pad backward without the intermediate gradient buffer (EXPERIMENTAL, MFVI_FUSED_BN_BWD=1)
+    "mfvi_pad_act_bwd_reduce": [View, _I, _I, _I, _I, _I, View, _P, _P, _P, _I, _P],
+    "mfvi_bn_bwd_apply_from_dxp": [View, View, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, View, _P, _P],
+    "mfvi_bn_bwd_apply_from_dxp_bf16": [View, View, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, View, _P, _P],
     "mfvi_pack_weights_bf16": [_P, _LL, _I, _I, _P, _P, _P, _P, _P, _LL],
     "mfvi_kl_reparam_fwd_bwd": [_P, _P, _SZ, _F, _D, _I, _F, _P, _P, _LL, _I, _P, _LL, PhiloxKey, _F, _P, _P, _P, _I],
     "mfvi_bn_act_pad_fwd": [View, _I, _I, _I, _I, _P, _P, _P, _I, _I, View],

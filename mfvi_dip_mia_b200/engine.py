@@ -269,6 +269,9 @@ class SkipEngine:
         # their inputs; ("__join__", (), {"lane": X}) makes the main stream wait for lane X.
         self.overlap_wgrad = True
         self.overlap_skip = os.environ.get("MFVI_SKIP_LANE", "1") != "0"
+        # EXPERIMENTAL, off by default: BatchNorm/activation/pad backward as reduce + recompute-and-apply, without the
+        # intermediate gradient buffer (csrc/elementwise_fused.cu)
+        self.fused_bn_bwd = os.environ.get("MFVI_FUSED_BN_BWD", "0") == "1"
         self._side = None if self.plan_only else torch.cuda.Stream(device=device)
         self._side2 = None if self.plan_only else torch.cuda.Stream(device=device)
         self._build_plan()
@@ -352,6 +355,15 @@ class SkipEngine:
         S, H, W, Cn = y.shape
         sums, gamma, beta = self._bn_args(bn)
         red = self._aptr(bn.red_off)
+        if self.fused_bn_bwd:
+            out16 = self.bf16 and to_conv
+            dy = (self._buf16 if out16 else self._buf)(H, W, Cn)
+            ops.append(("mfvi_pad_act_bwd_reduce", (L.view(dxp), S, H, W, Cn, pad, L.view(y), sums, gamma, beta, act, red),
+                        self._ew_meta(dxp, y)))
+            ops.append(("mfvi_bn_bwd_apply_from_dxp_bf16" if out16 else "mfvi_bn_bwd_apply_from_dxp",
+                        (L.view(dxp), L.view(y), S, H, W, Cn, pad, sums, red, gamma, beta, act, L.view(dy),
+                         self.g_gamma.data_ptr() + 4 * bn.ch_off, self.g_beta.data_ptr() + 4 * bn.ch_off), self._ew_meta(dxp, y, dy)))
+            return dy
         g = self._buf(H, W, Cn)
         ops.append(("mfvi_pad_act_bwd", (L.view(dxp), S, H, W, Cn, pad, L.view(y), sums, gamma, beta, act, L.view(g), red),
                     self._ew_meta(dxp, y, g)))

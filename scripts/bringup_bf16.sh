@@ -13,6 +13,13 @@ run C_elementwise "bn_act_pad or bn_bwd_apply or conversions"
 run A_conv "conv_equals or accumulates or rejects"
 run B_wgrad "wgrad"
 run D_engine "engine_step or trainer"
+# independent of bf16: the BatchNorm backward without its intermediate buffer (exact fp32 arithmetic) — kernel test, then the
+# whole verified suite and the bench with the switch on
+run F_fused_bn_bwd "fused_bn_backward"
+MFVI_FUSED_BN_BWD=1 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/fused_bn_bwd_suite.txt 2>&1
+echo "verified suite with MFVI_FUSED_BN_BWD=1: rc=$? $(tail -1 gpurun_out/fused_bn_bwd_suite.txt)"
+MFVI_FUSED_BN_BWD=1 timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu > gpurun_out/fused_bn_bwd_bench.json 2> gpurun_out/fused_bn_bwd_bench.err
+echo "bench with MFVI_FUSED_BN_BWD=1 rc=$? $(head -c 200 gpurun_out/fused_bn_bwd_bench.json)"
 # only meaningful once the four stages are green
 timeout 300 python bench.py --math bf16 --steps 30 --warmup 5 --no-cpu > gpurun_out/bf16_bench.json 2> gpurun_out/bf16_bench.err
 echo "bench rc=$? $(head -c 300 gpurun_out/bf16_bench.json)"

@@ -222,6 +222,37 @@ class PlanInterpreter:
             self.vec(dgamma, Cn).copy_(R[..., 1].sum(0).float())
             self.vec(dbeta, Cn).copy_(R[..., 0].sum(0).float())
 
+    # the experimental pair without the intermediate gradient buffer (csrc/elementwise_fused.cu): same contract, g recomputed
+    def _folded_g(self, dxp, S, H, W, Cn, pad, y, sums, gamma, beta, act):
+        DXP = self.view(dxp, S, H + 2 * pad, W + 2 * pad, Cn)
+        Y = self.view(y, S, H, W, Cn)
+        mean, invstd, sc, sh = self._bn(sums, gamma, beta, S, Cn, H * W)
+        if pad:
+            probe = torch.zeros(S, Cn, H, W, requires_grad=True)
+            F.pad(probe, (pad,) * 4, mode="reflect").backward(DXP.permute(0, 3, 1, 2).contiguous())
+            G = probe.grad.permute(0, 2, 3, 1)
+        else:
+            G = DXP.clone()
+        if act:
+            G = torch.where(Y * sc + sh > 0, G, SLOPE * G)
+        return G, (Y - mean) * invstd, sc
+
+    def op_pad_act_bwd_reduce(self, name, args):
+        dxp, S, H, W, Cn, pad, y, sums, gamma, beta, act, red = args
+        G, xhat, _ = self._folded_g(dxp, S, H, W, Cn, pad, y, sums, gamma, beta, act)
+        self._add_red(red, G, G * xhat)
+
+    def op_bn_bwd_apply_from_dxp(self, name, args):
+        dxp, y, S, H, W, Cn, pad, sums, red, gamma, beta, act, dy, dgamma, dbeta = args
+        G, xhat, sc = self._folded_g(dxp, S, H, W, Cn, pad, y, sums, gamma, beta, act)
+        R = self.vec(red, S * Cn * 2, torch.float64).view(S, Cn, 2)
+        m1 = (R[..., 0] / (H * W)).float().reshape(S, 1, 1, Cn)
+        m2 = (R[..., 1] / (H * W)).float().reshape(S, 1, 1, Cn)
+        self.view(dy, S, H, W, Cn, self._dtype_of(name)).copy_(sc * (G - m1 - xhat * m2))
+        if dgamma is not None:
+            self.vec(dgamma, Cn).copy_(R[..., 1].sum(0).float())
+            self.vec(dbeta, Cn).copy_(R[..., 0].sum(0).float())
+
     def op_cat_up_bwd(self, name, args):
         (dA, S, H, W, mode, ys, Cs, sums_s, gamma_s, beta_s, gs, red_s, yd, Cd, sums_d, gamma_d, beta_d, gd, red_d, part) = args
         DA = self.view(dA, S, H, W, Cs + Cd)
@@ -253,7 +284,9 @@ class PlanInterpreter:
            "mfvi_conv2d_dgrad_bf16": op_conv_dgrad, "mfvi_conv2d_wgrad": op_conv_wgrad, "mfvi_conv2d_wgrad_bf16": op_conv_wgrad,
            "mfvi_bn_act_pad_fwd": op_bn_act_pad_fwd, "mfvi_bn_act_pad_fwd_bf16": op_bn_act_pad_fwd, "mfvi_cat_up_fwd": op_cat_up_fwd,
            "mfvi_pad_act_bwd": op_pad_act_bwd, "mfvi_bn_bwd_apply": op_bn_bwd_apply, "mfvi_bn_bwd_apply_bf16": op_bn_bwd_apply,
-           "mfvi_cat_up_bwd": op_cat_up_bwd, "mfvi_fill_f32": op_fill, "mfvi_view_f32_to_bf16": op_view_to_bf16}
+           "mfvi_cat_up_bwd": op_cat_up_bwd, "mfvi_fill_f32": op_fill, "mfvi_view_f32_to_bf16": op_view_to_bf16,
+           "mfvi_pad_act_bwd_reduce": op_pad_act_bwd_reduce, "mfvi_bn_bwd_apply_from_dxp": op_bn_bwd_apply_from_dxp,
+           "mfvi_bn_bwd_apply_from_dxp_bf16": op_bn_bwd_apply_from_dxp}
 
     def run(self, ops):
         """Executes an op list in order (lanes only express concurrency: program order is a valid schedule)."""

@@ -154,3 +154,27 @@ def test_metric_network_plan_against_the_oracle(math_name):
         cos = float((va @ vb) / (va.norm() * vb.norm()))
         print(f"bf16 metric-net plan: out {e_out:.2e}  grad relL2 {float((va - vb).norm() / vb.norm()):.2e}  cos {cos:.5f}")
         assert e_out < 0.1 and cos > 0.95
+
+
+@pytest.mark.parametrize("math_name", ["fp32", "bf16"])
+@pytest.mark.parametrize("task", ["den", "inp"])
+def test_plan_without_the_intermediate_gradient_buffer(task, math_name, monkeypatch):
+    """MFVI_FUSED_BN_BWD=1 (EXPERIMENTAL, off by default): the BatchNorm/activation/pad backward as reduce + recompute-and-apply
+    (csrc/elementwise_fused.cu).  The plan loses its g buffers, keeps its launch count, and interprets to the same step: fp32
+    against the reference fixture at the usual bars, bf16 at bf16 accuracy."""
+    from mfvi_dip_mia_b200 import SkipEngine, SkipSpec, _lib as L
+    monkeypatch.setenv("MFVI_FUSED_BN_BWD", "1")
+    math = L.MATH_FP32 if math_name == "fp32" else L.MATH_BF16
+    d, S, out, nll, kl, ours, grads = _run(task, math)
+    names = [op[0] for op in SkipEngine(SkipSpec(), 64, 64, 1, "meta", math=math).bwd_ops]
+    assert "mfvi_pad_act_bwd" not in names and "mfvi_pad_act_bwd_reduce" in names
+    if math_name == "fp32":
+        for s in range(S):
+            assert rel_err(out[s:s + 1], d[f"out{s}"]) < 1e-4, s
+        errs = grad_errs({k: ours[k] for k in grads}, grads)
+        worst = max(errs, key=errs.get)
+        assert errs[worst] < 1e-3, (worst, errs[worst])
+    else:
+        va = torch.cat([ours[k].double().reshape(-1) for k in grads])
+        vb = torch.cat([grads[k].double().reshape(-1) for k in grads])
+        assert float((va @ vb) / (va.norm() * vb.norm())) > 0.97

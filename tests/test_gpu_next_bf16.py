@@ -270,3 +270,37 @@ def test_bf16_trainer_runs_graph_replayed_steps():
         if i % 20 == 19:
             losses.append(tr.loss_terms()[0])
     assert all(map(lambda v: v == v and abs(v) < 1e6, losses)) and losses[-1] < losses[0]
+
+
+# ------------------------------------------------------------------------------------------ fused BatchNorm backward (fp32)
+@pytest.mark.parametrize("Cn,H,W,pad,act", [(16, 32, 32, 1, 1), (36, 17, 23, 1, 0), (128, 8, 8, 0, 1), (20, 16, 16, 2, 1), (2, 9, 9, 1, 1)])
+def test_fused_bn_backward_equals_the_standard_pair(Cn, H, W, pad, act):
+    """mfvi_pad_act_bwd_reduce + mfvi_bn_bwd_apply_from_dxp against mfvi_pad_act_bwd + mfvi_bn_bwd_apply on the same inputs:
+    the same loads and the same arithmetic, so the results agree to fp32 rounding (1e-6 of the max), and the bf16 variant is the
+    rounded fp32 result up to one bf16 ulp."""
+    from mfvi_dip_mia_b200 import _lib as L
+    dev, S = torch.device("cuda:0"), 3
+    gen = torch.Generator(device=dev).manual_seed(4)
+    y = torch.randn(S, H, W, Cn, device=dev, generator=gen)
+    dxp = torch.randn(S, H + 2 * pad, W + 2 * pad, Cn, device=dev, generator=gen)
+    sums = torch.stack([y.double().sum((1, 2)), (y.double() ** 2).sum((1, 2))], -1).contiguous()
+    gamma, beta = torch.rand(Cn, device=dev, generator=gen) + 0.5, torch.randn(Cn, device=dev, generator=gen)
+    z = lambda: torch.zeros(Cn, device=dev)
+    # standard pair
+    g, red0, dy0, dg0, db0 = torch.zeros_like(y), torch.zeros(S, Cn, 2, dtype=torch.float64, device=dev), torch.zeros_like(y), z(), z()
+    L.call("mfvi_pad_act_bwd", L.view(dxp), S, H, W, Cn, pad, L.view(y), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), act,
+           L.view(g), red0.data_ptr())
+    L.call("mfvi_bn_bwd_apply", L.view(g), L.view(y), S, H, W, Cn, sums.data_ptr(), red0.data_ptr(), gamma.data_ptr(), L.view(dy0),
+           dg0.data_ptr(), db0.data_ptr())
+    # fused pair
+    red1, dy1, dg1, db1 = torch.zeros_like(red0), torch.zeros_like(y), z(), z()
+    _, dy16 = _padded_bf16(S, H, W, Cn, dev)
+    L.call("mfvi_pad_act_bwd_reduce", L.view(dxp), S, H, W, Cn, pad, L.view(y), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+           act, red1.data_ptr())
+    tail = (L.view(dxp), L.view(y), S, H, W, Cn, pad, sums.data_ptr(), red1.data_ptr(), gamma.data_ptr(), beta.data_ptr(), act)
+    L.call("mfvi_bn_bwd_apply_from_dxp", *tail, L.view(dy1), dg1.data_ptr(), db1.data_ptr())
+    L.call("mfvi_bn_bwd_apply_from_dxp_bf16", *tail, L.view(dy16), dg1.data_ptr(), db1.data_ptr())
+    torch.cuda.synchronize()
+    assert rel_err(red1, red0) < 1e-12 or torch.allclose(red1, red0, rtol=1e-9, atol=1e-9)
+    assert rel_err(dy1, dy0) < 1e-6 and rel_err(dg1, dg0) < 1e-6 and rel_err(db1, db0) < 1e-6
+    assert rel_err(dy16.float(), dy0) < 2 ** -8
