@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Does MFVI-DIP training survive bf16 conv operands?  A CPU study ahead of the GPU bring-up of the bf16-operand mode
- — development tooling, it uses the oracle and is not part of the package or of bench.py.
+ — test infrastructure (it runs the oracle), not part of the package or of bench.py.
 
 The denoising loop of tests/golden/make_trajectory_golden.py (64x64 phantom, 3-scale net, lr 1e-2, 25-deep rings, EMA 0.99)
 is run with the CPU oracle twice per seed on IDENTICAL random streams: once in fp32, once with every convolution emulating the
@@ -9,7 +9,7 @@ input gradients, statistics and parameters in fp32.  Reported: PSNR / SSIM / UCE
 mean over seeds, and the PAIRED difference bf16 - fp32 with its standard error (the optimisation is chaotic, so single
 trajectories differ by ~0.5 dB; the ensemble mean is what north_star's 0.1 dB / 0.005 bar can be held to).
 
-    python scripts/bf16_quality_study.py [K seeds = 8] [n_it = 1200] [workers = 4] [size = 64] [net = small | metric] [arm = bf16 | bf16s] [lr = 1e-2]
+    python tests/studies/bf16_quality_study.py [K seeds = 8] [n_it = 1200] [workers = 4] [size = 64] [net = small | metric] [arm = bf16 | bf16s] [lr = 1e-2]
 
 `arm = bf16s` ("bf16 storage") goes one step further than the mode that is written: the convolution OUTPUTS and the input
 gradients the data-gradient kernels write are rounded to bf16 as well, i.e. every activation and activation gradient that
@@ -27,7 +27,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 H = W = 64

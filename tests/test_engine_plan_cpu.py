@@ -77,7 +77,7 @@ def test_bf16_plan_is_wired_like_the_fp32_plan(task):
     a wrong buffer, a missing accumulate, a dropped branch — shows up as an O(1) error, cosine ~0).  Measured on these
     32x32 fixtures: output 2-5e-2 of its max, NLL 0.2-2e-3, whole gradient 3-18 % relative L2, cosine 0.984-0.9997 — about 8x the
     tf32 mode's figures, as three mantissa bits fewer predict.  Whether training tolerates that is a separate question:
-    scripts/bf16_quality_study.py."""
+    tests/studies/bf16_quality_study.py."""
     from mfvi_dip_mia_b200 import _lib as L
     d, S, out, nll, kl, ours, grads = _run(task, L.MATH_BF16)
     e_out = max(rel_err(out[s:s + 1], d[f"out{s}"]) for s in range(S))
