@@ -13,6 +13,7 @@ run C_elementwise "bn_act_pad or bn_bwd_apply or conversions"
 run A_conv "conv_equals or accumulates or rejects"
 run B_wgrad "wgrad"
 run D_engine "engine_step or trainer"
+run G_acceptance "reference_ensemble"      # 32 seeds x 1200 iterations in bf16 against the reference's distribution (~1 minute)
 # independent of bf16: the BatchNorm backward without its intermediate buffer (exact fp32 arithmetic) — kernel test, then the
 # whole verified suite and the bench with the switch on
 run F_fused_bn_bwd "fused_bn_backward"

@@ -304,3 +304,33 @@ def test_fused_bn_backward_equals_the_standard_pair(Cn, H, W, pad, act):
     assert rel_err(red1, red0) < 1e-12 or torch.allclose(red1, red0, rtol=1e-9, atol=1e-9)
     assert rel_err(dy1, dy0) < 1e-6 and rel_err(dg1, dg0) < 1e-6 and rel_err(db1, db0) < 1e-6
     assert rel_err(dy16.float(), dy0) < 2 ** -8
+
+
+# ---------------------------------------------------------------------------------------------------------- acceptance
+def test_bf16_final_metrics_match_reference_ensemble():
+    """The mode's acceptance test, the bf16 twin of test_gpu_parity.py::test_den_final_metrics_match_reference_ensemble: final
+    PSNR / SSIM / UCE of the denoising runner after 1200 iterations over 32 seeds against the imported reference's own
+    distribution (tests/golden/trajectory_den64.npz) — north_star's 0.1 dB / 0.005 bar on the ensemble means plus three
+    standard errors.  The CPU study (tests/studies/bf16_quality_study.py) predicts a shift of +0.09 +- 0.17 dB."""
+    import numpy as np
+    from mfvi_dip_mia_b200 import _lib as L
+    from mfvi_dip_mia_b200.runners import run_den_mfvi
+    from mfvi_dip_mia_b200.utils.phantoms import ellipse_phantom, noisy
+    from tests.helpers import load_npz
+    from tests.test_gpu_parity import SMALL, _TRAJ, spec_of
+    d = load_npz("trajectory_den64.npz")
+    its = [int(v) for v in d["its"]]
+    ref = np.asarray(d["metrics"])[:, its.index(1200)]
+    gt = ellipse_phantom(_TRAJ["H"])
+    ny = noisy(gt, 0.1, 1)
+    ours = []
+    for k in range(32):
+        _, h = run_den_mfvi(gt, temp=_TRAJ["temp"], sigma=_TRAJ["sigma"], lr=_TRAJ["lr"], num_iter=1199, mc_samples=1,
+                            seed=1000 + k, device=torch.device("cuda:0"), mc_ring=_TRAJ["ring"], show_every=10 ** 9,
+                            math_mode=L.MATH_BF16, return_history=True, spec=spec_of(SMALL["den"]), img_noisy=ny)
+        ours.append((h["psnr_gt_sm"][-1], h["ssim_gt_sm"][-1], h["uce"]))
+    ours = np.array(ours)
+    mo, mr = ours.mean(0), ref.mean(0)
+    se = np.sqrt(ours.var(0, ddof=1) / len(ours) + ref.var(0, ddof=1) / len(ref))
+    print(f"[ensemble bf16] ours PSNR {mo[0]:.3f} SSIM {mo[1]:.4f} UCE {mo[2]:.4f}   ref PSNR {mr[0]:.3f} SSIM {mr[1]:.4f} UCE {mr[2]:.4f}   se {se}")
+    assert np.all(np.abs(mo - mr) < np.array([0.1, 0.005, 0.005]) + 3 * se), (mo, mr, se)
