@@ -5,6 +5,9 @@
 set -u
 mkdir -p gpurun_out
 export MFVI_TEST_NEXT=1
+# 0. descriptor semantics of kind::f16 / bf16 operands in isolation (seconds): if this fails, fix tc_ptx / the constants first
+(cd scripts && nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -o umma_bf16_test umma_bf16_test.cu -lcuda 2>/dev/null; \
+ timeout 60 ./umma_bf16_test > ../gpurun_out/bf16_descriptor_probe.txt 2>&1; echo "descriptor probe rc=$? $(tail -1 ../gpurun_out/bf16_descriptor_probe.txt)")
 run() { # name, pytest -k expression
   timeout 300 python -m pytest tests/test_gpu_next_bf16.py -m gpu_next -q -x -k "$2" > "gpurun_out/bf16_$1.txt" 2>&1
   echo "stage $1: rc=$? $(tail -1 gpurun_out/bf16_$1.txt)"
