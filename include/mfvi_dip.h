@@ -102,45 +102,6 @@ int mfvi_conv2d_dgrad(const MfviConvDesc* d, MfviView dy, const float* w, long l
 int mfvi_conv2d_wgrad(const MfviConvDesc* d, MfviView x, MfviView dy, float* dw, float* dbias, long long w_sstride,
                       mfvi_stream_t st);
 
-/* EXPERIMENTAL — bf16-operand mode, stage A (north_star: "bf16 operands with fp32 accumulate stated
- * separately"); not called by the engine yet.  Same convolutions on tcgen05 kind::f16: x / dy / w hold bf16 (MfviView.ptr is
- * then a bf16 pointer; view strides, w_sstride and w_cpitch count bf16 elements and must be multiples of 8; a layer's weight
- * block is [KH][KW][Cout][w_cpitch]); y / dx, the bias (sample stride bias_sstride, in floats) and the BatchNorm statistics are
- * fp32.  No fallback: a shape the tensor-core kernel does not take is an error. */
-int mfvi_conv2d_fwd_bf16(const MfviConvDesc* d, MfviView x, const void* w, int w_cpitch, long long w_sstride, const float* bias,
-                         long long bias_sstride, MfviView y, double* stats, mfvi_stream_t st);
-int mfvi_conv2d_dgrad_bf16(const MfviConvDesc* d, MfviView dy, const void* w, int w_cpitch, long long w_sstride, MfviView dx,
-                           int accumulate, mfvi_stream_t st);
-/* stage B: weight gradient from bf16 x / dy into the fp32 dw block ([KH][KW][Cout][Cin], accumulated with atomics like
- * mfvi_conv2d_wgrad).  dbias != NULL additionally reduces the bias gradient from `dy_f32`, an fp32 view of the same gradient. */
-int mfvi_conv2d_wgrad_bf16(const MfviConvDesc* d, MfviView x, MfviView dy, float* dw, long long w_sstride, MfviView dy_f32,
-                           float* dbias, mfvi_stream_t st);
-/* stage C: producers of the bf16 operands.  mfvi_bn_act_pad_fwd / mfvi_bn_bwd_apply with a bf16 OUTPUT view (same arithmetic in
- * fp32, rounded to nearest-even at the store); an fp32 -> bf16 copy of an NHWC view (network input, loss gradient); and the
- * sampled weights of all layers repacked to bf16 rows of w_cpitch = Cin rounded up to 8 (HOST arrays of n_layers entries:
- * element offsets of each layer's block in the fp32 / bf16 storage of one sample, rows = KH*KW*Cout, Cin). */
-int mfvi_bn_act_pad_fwd_bf16(MfviView y, int S, int H, int W, int C, const double* sums, const float* gamma,
-                             const float* beta, int act, int pad, MfviView xp, mfvi_stream_t st);
-int mfvi_bn_bwd_apply_bf16(MfviView g, MfviView y, int S, int H, int W, int C, const double* sums, const double* red,
-                           const float* gamma, MfviView dy, float* dgamma, float* dbeta, mfvi_stream_t st);
-int mfvi_view_f32_to_bf16(MfviView src, int S, int H, int W, int C, MfviView dst, mfvi_stream_t st);
-int mfvi_pack_weights_bf16(const float* w, long long w_sstride, int S, int n_layers, const long long* w_off,
-                           const long long* w16_off, const int* rows, const int* cin, void* w16, long long w16_sstride,
-                           mfvi_stream_t st);
-
-/* EXPERIMENTAL (engine switch MFVI_FUSED_BN_BWD=1, off by default; not yet run on a GPU): the pair mfvi_pad_act_bwd +
- * mfvi_bn_bwd_apply without the intermediate gradient g in HBM.  Pass 1 only accumulates red[S][C][2] += (sum g, sum g*xhat);
- * pass 2 recomputes g = fold_reflect(dxp) * act'(bn(y)) from the same inputs and writes
- * dy = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)) (fp32, or bf16 for the bf16-operand mode) and dgamma / dbeta. */
-int mfvi_pad_act_bwd_reduce(MfviView dxp, int S, int H, int W, int C, int pad, MfviView y, const double* sums, const float* gamma,
-                            const float* beta, int act, double* red, mfvi_stream_t st);
-int mfvi_bn_bwd_apply_from_dxp(MfviView dxp, MfviView y, int S, int H, int W, int C, int pad, const double* sums, const double* red,
-                               const float* gamma, const float* beta, int act, MfviView dy, float* dgamma, float* dbeta,
-                               mfvi_stream_t st);
-int mfvi_bn_bwd_apply_from_dxp_bf16(MfviView dxp, MfviView y, int S, int H, int W, int C, int pad, const double* sums,
-                                    const double* red, const float* gamma, const float* beta, int act, MfviView dy, float* dgamma,
-                                    float* dbeta, mfvi_stream_t st);
-
 /* Planning-only query (no reference counterpart; host-only, touches no device, works without a GPU): which kernel family
  * mfvi_conv2d_{fwd,dgrad,wgrad} would run for this geometry and these views — "pointwise", "halo", "alias", "tc" (tcgen05
  * paths) or "simt" (fp32 CUDA cores) — with its launch geometry and a one-line tile plan.  pass: 0 = forward (a = x, b = y),

@@ -16,7 +16,6 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libmfvidip.so")
 ABI_VERSION = 1
 MATH_FP32 = 0
 MATH_TF32 = 1
-MATH_BF16 = 2      # host-side mode only (EXPERIMENTAL): the engine calls the *_bf16 entry points
 STREAM_WEIGHTS = 0
 STREAM_INPUT_JITTER = 1
 
@@ -62,18 +61,6 @@ _SIGS = {
     "mfvi_conv2d_fwd": [_CD, View, _P, _P, _LL, View, _P],
     "mfvi_conv2d_dgrad": [_CD, View, _P, _LL, View, _I],
     "mfvi_conv2d_wgrad": [_CD, View, View, _P, _P, _LL],
-    # bf16-operand convolutions (EXPERIMENTAL, stage A of DESIGN.md section 8; not used by the engine yet)
-    "mfvi_conv2d_fwd_bf16": [_CD, View, _P, _I, _LL, _P, _LL, View, _P],
-    "mfvi_conv2d_dgrad_bf16": [_CD, View, _P, _I, _LL, View, _I],
-    "mfvi_conv2d_wgrad_bf16": [_CD, View, View, _P, _LL, View, _P],
-    "mfvi_bn_act_pad_fwd_bf16": [View, _I, _I, _I, _I, _P, _P, _P, _I, _I, View],
-    "mfvi_bn_bwd_apply_bf16": [View, View, _I, _I, _I, _I, _P, _P, _P, View, _P, _P],
-    "mfvi_view_f32_to_bf16": [View, _I, _I, _I, _I, View],
-    # BatchNorm/activation/pad backward without the intermediate gradient buffer (EXPERIMENTAL, MFVI_FUSED_BN_BWD=1)
-    "mfvi_pad_act_bwd_reduce": [View, _I, _I, _I, _I, _I, View, _P, _P, _P, _I, _P],
-    "mfvi_bn_bwd_apply_from_dxp": [View, View, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, View, _P, _P],
-    "mfvi_bn_bwd_apply_from_dxp_bf16": [View, View, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, View, _P, _P],
-    "mfvi_pack_weights_bf16": [_P, _LL, _I, _I, _P, _P, _P, _P, _P, _LL],
     "mfvi_kl_reparam_fwd_bwd": [_P, _P, _SZ, _F, _D, _I, _F, _P, _P, _LL, _I, _P, _LL, PhiloxKey, _F, _P, _P, _P, _I],
     "mfvi_bn_act_pad_fwd": [View, _I, _I, _I, _I, _P, _P, _P, _I, _I, View],
     "mfvi_cat_up_fwd": [View, _I, _P, _P, _P, View, _I, _P, _P, _P, _I, _I, _I, _I, View, _P],
@@ -151,7 +138,6 @@ def call(name: str, *args, stream=None, meta=None):
 
 
 PASS_FWD, PASS_DGRAD, PASS_WGRAD = 0, 1, 2
-PASS_BF16 = 3      # added to a pass: the bf16-operand entry point of that pass (views are then bf16 views)
 
 
 def conv_plan(desc: ConvDesc, pass_: int, a: View, b: View, w_sstride: int, accumulate: int = 0, with_bias: bool = True) -> dict:
@@ -181,9 +167,8 @@ def ptr(t):
 
 
 def view(t: torch.Tensor, broadcast: bool = False) -> View:
-    """MfviView of an NHWC tensor (S,H,W,C) (channel stride must be 1; other strides arbitrary, in elements).
-    bf16 tensors are accepted for the bf16-operand entry points (strides then count bf16 elements)."""
-    assert t.dim() == 4 and t.dtype in (torch.float32, torch.bfloat16) and (t.stride(3) == 1 or t.shape[3] == 1), (t.shape, t.stride())
+    """MfviView of an NHWC fp32 tensor (S,H,W,C) (channel stride must be 1; other strides arbitrary, in elements)."""
+    assert t.dim() == 4 and t.dtype == torch.float32 and (t.stride(3) == 1 or t.shape[3] == 1), (t.shape, t.stride())
     ss = 0 if (broadcast or t.shape[0] == 1) else t.stride(0)
     return View(t.data_ptr(), ss, t.stride(1), t.stride(2))
 

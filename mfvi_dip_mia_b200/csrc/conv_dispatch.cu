@@ -95,7 +95,7 @@ int mfvi_conv2d_wgrad(const MfviConvDesc* d, MfviView x, MfviView dy, float* dw,
 int mfvi_conv2d_plan(const MfviConvDesc* d, int pass, MfviView a, MfviView b, long long w_sstride, int accumulate, int with_bias,
                      MfviPlanInfo* out) {
   MFVI_REQUIRE(d != nullptr && out != nullptr, "conv2d_plan: null argument");
-  MFVI_REQUIRE(pass >= 0 && pass <= 5, "conv2d_plan: pass must be 0 (fwd), 1 (dgrad), 2 (wgrad) or 3..5 (the same, bf16 operands)");
+  MFVI_REQUIRE(pass >= 0 && pass <= 2, "conv2d_plan: pass must be 0 (fwd), 1 (dgrad) or 2 (wgrad)");
   mfvi::DryRunInfo info{};
   // any 16-byte aligned non-null address stands in for the weight / bias / statistics buffers
   float* const fake = reinterpret_cast<float*>(static_cast<uintptr_t>(0x1000));
@@ -110,23 +110,8 @@ int mfvi_conv2d_plan(const MfviConvDesc* d, int pass, MfviView a, MfviView b, lo
     rc = fwd_chain(d, a, fake, with_bias ? fake : nullptr, w_sstride, b, reinterpret_cast<double*>(fake), nullptr, &family);
   else if (pass == 1)
     rc = dgrad_chain(d, a, fake, w_sstride, b, accumulate, nullptr, &family);
-  else if (pass == 2)
+  else
     rc = wgrad_chain(d, a, b, fake, with_bias ? fake : nullptr, w_sstride, nullptr, &family);
-  else {
-    // bf16-operand entry points (experimental): weight rows padded to 8 channels, w_sstride counts bf16 elements for the
-    // convolutions' weights and floats for dw
-    const int cpitch = (d->Cin + 7) / 8 * 8;
-    if (pass == 3) {
-      rc = mfvi_conv2d_fwd_bf16(d, a, fake, cpitch, w_sstride, with_bias ? fake : nullptr, 0, b, reinterpret_cast<double*>(fake), nullptr);
-      family = "halo-bf16";
-    } else if (pass == 4) {
-      rc = mfvi_conv2d_dgrad_bf16(d, a, fake, cpitch, w_sstride, b, accumulate, nullptr);
-      family = "halo-bf16";
-    } else {
-      rc = mfvi_conv2d_wgrad_bf16(d, a, b, fake, w_sstride, b, with_bias ? fake : nullptr, nullptr);
-      family = "tc-bf16";
-    }
-  }
   mfvi::set_dry_run(nullptr);
   if (rc != 0) return rc;
   memset(out, 0, sizeof(*out));

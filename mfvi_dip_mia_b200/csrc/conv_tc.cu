@@ -524,12 +524,10 @@ int mfvi_conv2d_bias_grad_tc(const MfviConvDesc* d, MfviView dy, float* dbias, l
 
 }  // extern "C"
 
-// bf16: x and dy are bf16 views (strides in bf16 elements); dw stays fp32 in the [tap][Cout][Cin] storage layout.  The bias
-// gradient is reduced from `dy_bias`, which must be an fp32 view of the same gradient (the engine keeps the loss gradient of the
-// final convolution, the only one with a bias gradient, in fp32 as well).
 static int wgrad_tc_launch(const MfviConvDesc* d, MfviView x, MfviView dy, float* dw, float* dbias, long long w_sstride,
-                           mfvi_stream_t st, bool bf16, MfviView dy_bias) {
+                           mfvi_stream_t st) {
   using namespace mfvi::tc;
+  constexpr bool bf16 = false;
   const bool views_ok = bf16 ? (view_tma_ok_bf16(x, d->Cin) && view_tma_ok_bf16(dy, d->Cout)) : (view_tma_ok(x, d->Cin) && view_tma_ok(dy, d->Cout));
   if (!tc_stride_ok(d->stride) || !views_ok || d->Cout > 128 || d->Cin > 256 ||
       (reinterpret_cast<uintptr_t>(dw) % 16) || (w_sstride % 4))
@@ -580,7 +578,6 @@ static int wgrad_tc_launch(const MfviConvDesc* d, MfviView x, MfviView dy, float
   static size_t attr = 0;
   if (smem > attr && dry_run() == nullptr) {
     cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    if (e == cudaSuccess) e = wgrad_tc_bf16_set_smem(220 * 1024);
     MFVI_REQUIRE(e == cudaSuccess, "conv2d_wgrad_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
     attr = 220 * 1024;
   }
@@ -588,10 +585,9 @@ static int wgrad_tc_launch(const MfviConvDesc* d, MfviView x, MfviView dy, float
   dim3 grid(chunks, taps, Sz);
   dry_detail("TH=%d TW=%d TP=%d MB=%d NB=%d sgrp=%d stages=%d tmem_cols=%u tiles_per_cta=%d", a.TH, a.TW, a.TP, a.MB, a.NB, a.sgrp,
              a.stages, a.tmem_cols, a.tiles_per_cta);
-  if (bf16) wgrad_tc_bf16_launch(grid, smem, as_stream(st), tmDy, tmX, a);
-  else launch_k(k_wgrad_tc<false>, grid, kThreads, smem, as_stream(st), tmDy, tmX, a);
+  launch_k(k_wgrad_tc<false>, grid, kThreads, smem, as_stream(st), tmDy, tmX, a);
   if (int rc = check_launch("conv2d_wgrad_tc")) return rc;
-  if (dbias != nullptr) return mfvi_conv2d_bias_grad_tc(d, bf16 ? dy_bias : dy, dbias, w_sstride, st);
+  if (dbias != nullptr) return mfvi_conv2d_bias_grad_tc(d, dy, dbias, w_sstride, st);
   return 0;
 }
 
@@ -600,19 +596,7 @@ extern "C" {
 
 int mfvi_conv2d_wgrad_tc(const MfviConvDesc* d, MfviView x, MfviView dy, float* dw, float* dbias, long long w_sstride,
                          mfvi_stream_t st) {
-  return wgrad_tc_launch(d, x, dy, dw, dbias, w_sstride, st, false, dy);
-}
-
-// bf16-operand mode, stage B of DESIGN.md section 8 (EXPERIMENTAL): x / dy hold bf16, dw is fp32.  dbias != NULL needs
-// `dy_f32`, an fp32 view of the same gradient.  No fallback: a shape the kernel does not take is an error.
-int mfvi_conv2d_wgrad_bf16(const MfviConvDesc* d, MfviView x, MfviView dy, float* dw, long long w_sstride, MfviView dy_f32,
-                           float* dbias, mfvi_stream_t st) {
-  MFVI_REQUIRE(d != nullptr && x.ptr != nullptr && dy.ptr != nullptr && dw != nullptr, "conv2d_wgrad_bf16: null argument");
-  MFVI_REQUIRE(dbias == nullptr || dy_f32.ptr != nullptr, "conv2d_wgrad_bf16: the bias gradient needs an fp32 view of dy");
-  const int rc = wgrad_tc_launch(d, x, dy, dw, dbias, w_sstride, st, true, dy_f32);
-  MFVI_REQUIRE(rc >= 0, "conv2d_wgrad_bf16: %d->%d k%dx%d s%d %dx%d is not taken by the tensor-core kernel", d->Cin, d->Cout,
-               d->KH, d->KW, d->stride, d->Hout, d->Wout);
-  return rc;
+  return wgrad_tc_launch(d, x, dy, dw, dbias, w_sstride, st);
 }
 
 }  // extern "C"

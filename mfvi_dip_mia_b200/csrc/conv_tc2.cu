@@ -679,24 +679,14 @@ static int launch(const MfviConvDesc* d, bool dgrad, MfviView a, int Ca, int Ha,
     MFVI_REQUIRE(e == cudaSuccess, "%s: cannot raise dynamic shared memory: %s", what, cudaGetErrorString(e));
     attr = 200 * 1024;
   }
-  static size_t attr16 = 0;
-  if (bf16 && pl.smem > attr16 && dry_run() == nullptr) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_halo<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    MFVI_REQUIRE(e == cudaSuccess, "%s: cannot raise dynamic shared memory: %s", what, cudaGetErrorString(e));
-    attr16 = 200 * 1024;
-  }
   if (env_int("MFVI_TC2_VERBOSE", 0))
     fprintf(stderr, "[tc2] %s Kc=%d N=%d k%d M=%dx%d S=%d: TH=%d TW=%d Pw=%d n_mt=%d BN=%d nb=%d g=%d acc_stages=%d smem=%zu grid=%d tiles=%d\n",
             what, Ca, Nvalid, d->KH, Mh, Mw, d->S, pl.TH, pl.TW, pl.Pw, pl.n_mt, pl.BN, pl.n_nb, pl.g, pl.acc_stages, pl.smem, pl.grid,
             p.total_tiles);
   dry_detail("TH=%d TW=%d Pw=%d n_mt=%d BN=%d nb=%d chunks=%d g=%d acc_stages=%d tmem_cols=%u tiles=%d cls=%d planes=%d", pl.TH, pl.TW,
              pl.Pw, pl.n_mt, pl.BN, pl.n_nb, p.n_chunks, pl.g, pl.acc_stages, pl.tmem_cols, p.total_tiles, n_cls, planes);
-  if (bf16 && dgrad)
-    launch_k(k_conv_halo<true, true>, pl.grid, kThreads, pl.smem, as_stream(st), tmA, tmAt, tmB, tmBt, p);
-  else if (bf16)
-    launch_k(k_conv_halo<false, true>, pl.grid, kThreads, pl.smem, as_stream(st), tmA, tmAt, tmB, tmBt, p);
-  else if (dgrad)
+  if (bf16) return -1;          // the kind::f16 instantiation was measured and dropped
+  if (dgrad)
     launch_k(k_conv_halo<true>, pl.grid, kThreads, pl.smem, as_stream(st), tmA, tmAt, tmB, tmBt, p);
   else
     launch_k(k_conv_halo<false>, pl.grid, kThreads, pl.smem, as_stream(st), tmA, tmAt, tmB, tmBt, p);
@@ -731,36 +721,6 @@ int mfvi_conv2d_dgrad_tc2(const MfviConvDesc* d, MfviView dy, const float* w, lo
     return -1;
   return tc2::launch(d, true, dy, d->Cout, d->Hout, d->Wout, w, w_sstride, dx, d->Hin, d->Win, d->Cin, nullptr, nullptr, accumulate, st,
                      "conv2d_dgrad_tc2");
-}
-
-// ---- bf16-operand mode, stage A of DESIGN.md section 8 (EXPERIMENTAL: not yet called by the engine).  x / dy / w hold bf16;
-// view strides, w_sstride and w_cpitch (row pitch of the [tap][Cout][w_cpitch] weight block, a multiple of 8) count bf16
-// elements; y / dx, the bias (sample stride bias_sstride, in floats) and the statistics are fp32.  Unlike the fp32 entry points
-// there is no fallback: a shape the halo kernel does not take is an error.
-int mfvi_conv2d_fwd_bf16(const MfviConvDesc* d, MfviView x, const void* w, int w_cpitch, long long w_sstride, const float* bias,
-                         long long bias_sstride, MfviView y, double* stats, mfvi_stream_t st) {
-  MFVI_REQUIRE(d != nullptr && x.ptr != nullptr && w != nullptr && y.ptr != nullptr, "conv2d_fwd_bf16: null argument");
-  MFVI_REQUIRE(tc2::view_ok(x, d->Cin, 8) && reinterpret_cast<uintptr_t>(w) % 16 == 0 && w_sstride % 8 == 0 && w_cpitch % 8 == 0 &&
-                   w_cpitch >= d->Cin && d->Cout <= 256 && (d->stride == 1 || d->stride == 2),
-               "conv2d_fwd_bf16: bf16 operands need 16-byte aligned pixels and weight rows (strides multiples of 8 elements)");
-  const int rc = tc2::launch(d, false, x, d->Cin, d->Hin, d->Win, w, w_sstride, y, d->Hout, d->Wout, d->Cout, bias, stats, 0, st,
-                             "conv2d_fwd_bf16", true, w_cpitch, bias != nullptr ? bias_sstride : 0);
-  MFVI_REQUIRE(rc >= 0, "conv2d_fwd_bf16: %d->%d k%dx%d s%d %dx%d is not taken by the halo kernel", d->Cin, d->Cout, d->KH, d->KW,
-               d->stride, d->Hout, d->Wout);
-  return rc;
-}
-
-int mfvi_conv2d_dgrad_bf16(const MfviConvDesc* d, MfviView dy, const void* w, int w_cpitch, long long w_sstride, MfviView dx,
-                           int accumulate, mfvi_stream_t st) {
-  MFVI_REQUIRE(d != nullptr && dy.ptr != nullptr && w != nullptr && dx.ptr != nullptr, "conv2d_dgrad_bf16: null argument");
-  MFVI_REQUIRE(tc2::view_ok(dy, d->Cout, 8) && reinterpret_cast<uintptr_t>(w) % 16 == 0 && w_sstride % 8 == 0 && w_cpitch % 8 == 0 &&
-                   w_cpitch >= d->Cin && d->Cin <= 256 && (d->stride == 1 || d->stride == 2),
-               "conv2d_dgrad_bf16: bf16 operands need 16-byte aligned pixels and weight rows (strides multiples of 8 elements)");
-  const int rc = tc2::launch(d, true, dy, d->Cout, d->Hout, d->Wout, w, w_sstride, dx, d->Hin, d->Win, d->Cin, nullptr, nullptr,
-                             accumulate, st, "conv2d_dgrad_bf16", true, w_cpitch);
-  MFVI_REQUIRE(rc >= 0, "conv2d_dgrad_bf16: %d->%d k%dx%d s%d %dx%d is not taken by the halo kernel", d->Cin, d->Cout, d->KH, d->KW,
-               d->stride, d->Hout, d->Wout);
-  return rc;
 }
 
 }  // extern "C"

@@ -1,6 +1,5 @@
-// Weight-gradient kernel of conv_tc.cu (tcgen05, both operands MN-major), shared by two translation units: conv_tc.cu
-// instantiates the tf32 version, conv_tc_bf16.cu the bf16 one.  (They are kept apart on purpose: adding a kernel to a module
-// changes ptxas' register allocation of its neighbours, and the tf32 kernels are kept byte-identical to the GPU-verified build.)
+// Weight-gradient kernel of conv_tc.cu (tcgen05 kind::tf32, both operands MN-major).  The BF16 template parameter is the
+// kind::f16 variant measured in round 2 (profiles/r02_bf16_mode_bench_negative.json: no faster on this net) — never instantiated.
 #pragma once
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -164,11 +163,6 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUt
   }
 }
 
-
-// conv_tc_bf16.cu: the bf16 instantiation and its launch (see the note at the top)
-cudaError_t wgrad_tc_bf16_set_smem(int bytes);
-cudaError_t wgrad_tc_bf16_launch(dim3 grid, size_t smem, cudaStream_t st, const CUtensorMap& tmDy, const CUtensorMap& tmX,
-                                 const TcWgradArgs& a);
 
 }  // namespace tc
 }  // namespace mfvi

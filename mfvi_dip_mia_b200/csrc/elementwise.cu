@@ -452,14 +452,6 @@ using namespace mfvi;
       launch_k(KERNEL<1>, GRID, kEwThreads, 0, as_stream(st), __VA_ARGS__, (GEOM).G, (GEOM).PPB);  \
   } while (0)
 
-#define MFVI_EW_DISPATCH_BF16(GEOM, KERNEL, GRID, ...)                                               \
-  do {                                                                                              \
-    if ((GEOM).V == 4)                                                                              \
-      launch_k(KERNEL<4, true>, GRID, kEwThreads, 0, as_stream(st), __VA_ARGS__, (GEOM).G, (GEOM).PPB); \
-    else                                                                                            \
-      launch_k(KERNEL<1, true>, GRID, kEwThreads, 0, as_stream(st), __VA_ARGS__, (GEOM).G, (GEOM).PPB); \
-  } while (0)
-
 extern "C" {
 
 int mfvi_bn_act_pad_fwd(MfviView y, int S, int H, int W, int C, const double* sums, const float* gamma,
@@ -472,32 +464,6 @@ int mfvi_bn_act_pad_fwd(MfviView y, int S, int H, int W, int C, const double* su
   dim3 grid(ew_grid((H + 2 * pad) * (W + 2 * pad), ge.PPB, S), S);
   MFVI_EW_DISPATCH(ge, k_bn_act_pad_fwd, grid, y, H, W, C, sums, gamma, beta, act, pad, xp);
   return check_launch("bn_act_pad_fwd");
-}
-
-// bf16-operand mode (EXPERIMENTAL, DESIGN.md section 8 stage C): the same kernels with a bf16 OUTPUT view (strides in bf16
-// elements); inputs, statistics and arithmetic stay fp32, the result is rounded to nearest-even at the store.
-int mfvi_bn_act_pad_fwd_bf16(MfviView y, int S, int H, int W, int C, const double* sums, const float* gamma,
-                             const float* beta, int act, int pad, MfviView xp, mfvi_stream_t st) {
-  MFVI_REQUIRE(y.ptr && xp.ptr, "bn_act_pad_fwd_bf16: null pointer");
-  MFVI_REQUIRE(C >= 1 && C <= kMaxC, "bn_act_pad_fwd_bf16: C=%d out of range (1..%d)", C, kMaxC);
-  MFVI_REQUIRE(pad >= 0 && pad < H && pad < W, "bn_act_pad_fwd_bf16: pad must be smaller than the image");
-  const EwGeom ge = ew_geom(C, view_vec_ok(y) && view_vec_ok(xp));      // 4 bf16 = one 8-byte store: the fp32 test suffices
-  MFVI_REQUIRE(ge.G <= kEwThreads, "bn_act_pad_fwd_bf16: too many channel groups");
-  dim3 grid(ew_grid((H + 2 * pad) * (W + 2 * pad), ge.PPB, S), S);
-  MFVI_EW_DISPATCH_BF16(ge, k_bn_act_pad_fwd, grid, y, H, W, C, sums, gamma, beta, act, pad, xp);
-  return check_launch("bn_act_pad_fwd_bf16");
-}
-
-int mfvi_bn_bwd_apply_bf16(MfviView g, MfviView y, int S, int H, int W, int C, const double* sums, const double* red,
-                           const float* gamma, MfviView dy, float* dgamma, float* dbeta, mfvi_stream_t st) {
-  MFVI_REQUIRE(g.ptr && y.ptr && dy.ptr && sums && red, "bn_bwd_apply_bf16: null pointer");
-  MFVI_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "bn_bwd_apply_bf16: dgamma/dbeta must both be set or NULL");
-  MFVI_REQUIRE(C >= 1 && C <= kMaxC, "bn_bwd_apply_bf16: C out of range");
-  const EwGeom ge = ew_geom(C, view_vec_ok(g) && view_vec_ok(y) && view_vec_ok(dy));
-  MFVI_REQUIRE(ge.G <= kEwThreads, "bn_bwd_apply_bf16: too many channel groups");
-  dim3 grid(ew_grid(H * W, ge.PPB, S), S);
-  MFVI_EW_DISPATCH_BF16(ge, k_bn_bwd_apply, grid, g, y, S, H, W, C, sums, red, gamma, dy, dgamma, dbeta);
-  return check_launch("bn_bwd_apply_bf16");
 }
 
 int mfvi_cat_up_fwd(MfviView ys, int Cs, const double* sums_s, const float* gamma_s, const float* beta_s,

@@ -54,13 +54,6 @@ class ConvLayer:
     index: int = -1   # position in eps-draw order
     w_off: int = 0    # offset of the [k][k][cout][cin] block inside mu / rho
     b_off: int = 0    # offset of the bias vector inside mu / rho
-    w16_off: int = 0  # bf16-operand mode: offset of the [k][k][cout][cpitch] block inside one sample's bf16 weight copy
-
-    @property
-    def cpitch(self):
-        """Row pitch of the bf16 weight copy: cin rounded up to 8 (16-byte rows for TMA)."""
-        return (self.cin + 7) // 8 * 8
-
     @property
     def w_numel(self):
         return self.cout * self.cin * self.k * self.k
@@ -211,10 +204,6 @@ class SkipEngine:
         if spec.upsample_mode not in ("bilinear", "nearest"):
             raise L.MfviError(f"upsample_mode={spec.upsample_mode!r} is not supported")
         self.spec, self.H, self.W, self.S, self.device, self.math = spec, H, W, S, device, math
-        # EXPERIMENTAL bf16-operand mode: every convolution operand — padded activations, the gradients
-        # fed to dgrad / wgrad, a repacked copy of the sampled weights — is bf16; conv outputs, input gradients, statistics,
-        # parameters and their gradients stay fp32
-        self.bf16 = math == L.MATH_BF16
         self.lay = layout or build_layout(spec)
         lay = self.lay
         P, Pp, Q = lay.P, lay.P_pad, lay.Q
@@ -244,17 +233,6 @@ class SkipEngine:
         self.dw = self.zbuf[:S * Pp].view(S, Pp)
         self.arena = self.zbuf[S * Pp:].view(torch.float64)
         self.w = torch.zeros(S, Pp, **f32)
-        self.w16 = None
-        if self.bf16:
-            off16 = 0
-            for c in lay.convs:
-                c.w16_off = off16
-                off16 += c.k * c.k * c.cout * c.cpitch
-            self.P16 = off16                                   # a multiple of 8: every block is
-            self.w16 = torch.zeros(S, off16, dtype=torch.bfloat16, device=device)
-            arr = lambda vals, ct: (ct * len(vals))(*vals)
-            self._pack_tables = (arr([c.w_off for c in lay.convs], C.c_longlong), arr([c.w16_off for c in lay.convs], C.c_longlong),
-                                 arr([c.k * c.k * c.cout for c in lay.convs], C.c_int), arr([c.cin for c in lay.convs], C.c_int))
         self.eps = None                      # [S][Pp] injected eps (allocated on demand)
         self.inject_eps = False
         self._bufs: List[torch.Tensor] = []
@@ -269,9 +247,6 @@ class SkipEngine:
         # their inputs; ("__join__", (), {"lane": X}) makes the main stream wait for lane X.
         self.overlap_wgrad = True
         self.overlap_skip = os.environ.get("MFVI_SKIP_LANE", "1") != "0"
-        # EXPERIMENTAL, off by default: BatchNorm/activation/pad backward as reduce + recompute-and-apply, without the
-        # intermediate gradient buffer (csrc/elementwise_fused.cu)
-        self.fused_bn_bwd = os.environ.get("MFVI_FUSED_BN_BWD", "0") == "1"
         self._side = None if self.plan_only else torch.cuda.Stream(device=device)
         self._side2 = None if self.plan_only else torch.cuda.Stream(device=device)
         self._build_plan()
@@ -286,12 +261,6 @@ class SkipEngine:
         t = torch.empty(self.S if S is None else S, H, W, Cn, dtype=torch.float32, device=self.device)
         self._bufs.append(t)
         return t
-
-    def _buf16(self, H, W, Cn, S=None):
-        """bf16 NHWC buffer whose channel pitch is rounded up to 8 (16-byte aligned pixels for TMA); returns the Cn-channel view."""
-        t = torch.empty(self.S if S is None else S, H, W, (Cn + 7) // 8 * 8, dtype=torch.bfloat16, device=self.device)
-        self._bufs.append(t)
-        return t[..., :Cn]
 
     def _aptr(self, off):
         return self.arena.data_ptr() + 8 * off
@@ -315,12 +284,6 @@ class SkipEngine:
         y = self._buf(Ho, Wo, (c.cout + 3) // 4 * 4)[..., :c.cout]
         if bn is not None:
             bn.count = Ho * Wo
-        if self.bf16:
-            self.fwd_ops.append(("mfvi_conv2d_fwd_bf16", (
-                C.byref(d), L.view(x), self.w16.data_ptr() + 2 * c.w16_off, c.cpitch, self.P16, self.w.data_ptr() + 4 * c.b_off,
-                self.lay.P_pad, L.view(y), None if bn is None else self._aptr(bn.sums_off)), self._conv_meta(c, d, x, y)))
-            self._keep.append(d)
-            return y, d
         self.fwd_ops.append(("mfvi_conv2d_fwd", (
             C.byref(d), L.view(x), self.w.data_ptr() + 4 * c.w_off, self.w.data_ptr() + 4 * c.b_off, self.lay.P_pad,
             L.view(y), None if bn is None else self._aptr(bn.sums_off)), self._conv_meta(c, d, x, y)))
@@ -331,7 +294,7 @@ class SkipEngine:
         """Algorithmic work of one conv launch (fwd, dgrad and wgrad all perform the same MACs):
         flops = 2*S*Hout*Wout*Cout*Cin*KH*KW; bytes = input read once + sampled weights read once + output written once."""
         flops = 2.0 * self.S * d.Hout * d.Wout * c.cout * c.cin * c.k * c.k
-        nbytes = x.element_size() * x.numel() + (2.0 if self.bf16 else 4.0) * self.S * c.w_numel + 4.0 * self.S * c.cout \
+        nbytes = x.element_size() * x.numel() + 4.0 * self.S * c.w_numel + 4.0 * self.S * c.cout \
             + y.element_size() * y.numel()
         return {"flops": flops, "bytes": nbytes, "layer": c.key.rsplit(".", 1)[-1],
                 "shape": f"{c.cin}->{c.cout} k{c.k} s{c.stride} out{d.Hout}x{d.Wout}"}
@@ -343,46 +306,23 @@ class SkipEngine:
 
     def _bn_act_pad(self, y, bn: BnLayer, sums_ptr, gamma_ptr, beta_ptr, act, pad):
         S, H, W, Cn = y.shape
-        xp = (self._buf16 if self.bf16 else self._buf)(H + 2 * pad, W + 2 * pad, Cn)
-        self.fwd_ops.append(("mfvi_bn_act_pad_fwd_bf16" if self.bf16 else "mfvi_bn_act_pad_fwd", (L.view(y), S, H, W, Cn, sums_ptr, gamma_ptr, beta_ptr, act, pad,
+        xp = self._buf(H + 2 * pad, W + 2 * pad, Cn)
+        self.fwd_ops.append(("mfvi_bn_act_pad_fwd", (L.view(y), S, H, W, Cn, sums_ptr, gamma_ptr, beta_ptr, act, pad,
                                                      L.view(xp)), self._ew_meta(y, xp)))
         return xp
 
     # backward of  x = pad(act(bn(y)))  followed by the BN statistics backward:  dxp -> dy (returned)
-    # `to_conv`: the result feeds the wgrad / dgrad of a convolution (a bf16 operand in the bf16 mode); False for the
-    # BatchNorm behind the concat, whose gradient goes on to the elementwise concat backward
-    def _bn_act_pad_bwd(self, ops, dxp, y, bn: BnLayer, act, pad, to_conv=True):
+    def _bn_act_pad_bwd(self, ops, dxp, y, bn: BnLayer, act, pad):
         S, H, W, Cn = y.shape
         sums, gamma, beta = self._bn_args(bn)
         red = self._aptr(bn.red_off)
-        if self.fused_bn_bwd:
-            out16 = self.bf16 and to_conv
-            dy = (self._buf16 if out16 else self._buf)(H, W, Cn)
-            ops.append(("mfvi_pad_act_bwd_reduce", (L.view(dxp), S, H, W, Cn, pad, L.view(y), sums, gamma, beta, act, red),
-                        self._ew_meta(dxp, y)))
-            ops.append(("mfvi_bn_bwd_apply_from_dxp_bf16" if out16 else "mfvi_bn_bwd_apply_from_dxp",
-                        (L.view(dxp), L.view(y), S, H, W, Cn, pad, sums, red, gamma, beta, act, L.view(dy),
-                         self.g_gamma.data_ptr() + 4 * bn.ch_off, self.g_beta.data_ptr() + 4 * bn.ch_off), self._ew_meta(dxp, y, dy)))
-            return dy
         g = self._buf(H, W, Cn)
         ops.append(("mfvi_pad_act_bwd", (L.view(dxp), S, H, W, Cn, pad, L.view(y), sums, gamma, beta, act, L.view(g), red),
                     self._ew_meta(dxp, y, g)))
-        if self.bf16 and to_conv:
-            return self._bn_bwd_apply16(ops, g, y, bn)
         ops.append(("mfvi_bn_bwd_apply", (L.view(g), L.view(y), S, H, W, Cn, sums, red, gamma, L.view(g),
                                           self.g_gamma.data_ptr() + 4 * bn.ch_off, self.g_beta.data_ptr() + 4 * bn.ch_off),
                     self._ew_meta(g, y, g)))
         return g
-
-    def _bn_bwd_apply16(self, ops, g, y, bn: BnLayer, **lane):
-        """bf16 mode: BatchNorm backward of the fp32 gradient g into a fresh bf16 buffer (the dy operand of a convolution)."""
-        S, H, W, Cn = y.shape
-        sums, gamma, _ = self._bn_args(bn)
-        g16 = self._buf16(H, W, Cn)
-        ops.append(("mfvi_bn_bwd_apply_bf16", (L.view(g), L.view(y), S, H, W, Cn, sums, self._aptr(bn.red_off), gamma, L.view(g16),
-                                               self.g_gamma.data_ptr() + 4 * bn.ch_off, self.g_beta.data_ptr() + 4 * bn.ch_off),
-                    dict(self._ew_meta(g, y, g16), **lane)))
-        return g16
 
     def _dbias_ptr(self, c: ConvLayer, bn_follows: bool):
         """A conv bias that feeds a train-mode BatchNorm has an identically zero data gradient (BN subtracts the
@@ -391,16 +331,9 @@ class SkipEngine:
         layers instead of reducing dy again; only the final conv (no BN behind it) computes a bias gradient."""
         return None if bn_follows else self.dw.data_ptr() + 4 * c.b_off
 
-    def _conv_bwd(self, ops, c: ConvLayer, d, x, dy, need_dx=True, bn_follows=True, dy_f32=None):
+    def _conv_bwd(self, ops, c: ConvLayer, d, x, dy, need_dx=True, bn_follows=True):
         """wgrad into dw[s] (+bias), dgrad into a fresh padded-input-sized buffer (returned)."""
         meta = self._conv_meta(c, d, x, dy)
-        if self.bf16:
-            self._wgrad16(ops, c, d, x, dy, bn_follows, dy_f32, meta)
-            if not need_dx:
-                return None
-            dx = self._buf(x.shape[1], x.shape[2], c.cin)
-            self._dgrad16(ops, c, d, dy, dx, 0, meta)
-            return dx
         ops.append(("mfvi_conv2d_wgrad", (C.byref(d), L.view(x), L.view(dy), self.dw.data_ptr() + 4 * c.w_off,
                                           self._dbias_ptr(c, bn_follows), self.lay.P_pad), meta))
         if not need_dx:
@@ -409,16 +342,6 @@ class SkipEngine:
         ops.append(("mfvi_conv2d_dgrad", (C.byref(d), L.view(dy), self.w.data_ptr() + 4 * c.w_off, self.lay.P_pad,
                                           L.view(dx), 0), meta))
         return dx
-
-    def _wgrad16(self, ops, c: ConvLayer, d, x, dy, bn_follows, dy_f32, meta):
-        dbias = self._dbias_ptr(c, bn_follows)
-        assert dbias is None or dy_f32 is not None, "the bias gradient is reduced from an fp32 view of dy"
-        ops.append(("mfvi_conv2d_wgrad_bf16", (C.byref(d), L.view(x), L.view(dy), self.dw.data_ptr() + 4 * c.w_off, self.lay.P_pad,
-                                               L.view(dy_f32) if dbias is not None else L.View(None, 0, 0, 0), dbias), meta))
-
-    def _dgrad16(self, ops, c: ConvLayer, d, dy, dx, accumulate, meta):
-        ops.append(("mfvi_conv2d_dgrad_bf16", (C.byref(d), L.view(dy), self.w16.data_ptr() + 2 * c.w16_off, c.cpitch, self.P16,
-                                               L.view(dx), accumulate), meta))
 
     # ---------------------------------------------------------------- plan
     def _build_plan(self):
@@ -483,7 +406,7 @@ class SkipEngine:
                 else:
                     dyu = dz_out
                 dXA = self._conv_bwd(ops, sc.up, d_u, XA, dyu)
-                dA = self._bn_act_pad_bwd(ops, dXA, A, sc.cat_bn, 0, pu, to_conv=False)
+                dA = self._bn_act_pad_bwd(ops, dXA, A, sc.cat_bn, 0, pu)
                 gd = self._buf(z.shape[1], z.shape[2], Cd)
                 gs = self._buf(Hs, Ws, Cs) if Cs else None
                 cat_args = (L.view(dA), S, Hs, Ws, mode, L.view(ys) if Cs else null_view, Cs, *sb,
@@ -498,15 +421,7 @@ class SkipEngine:
                 # first down conv's dgrad accumulates onto after the join.
                 need_dT = i > 0 or self.need_input_grad
                 dT = self._buf(T.shape[1], T.shape[2], T.shape[3]) if need_dT else None
-                if Cs and self.bf16:
-                    x_s = self._interior(T, Tpad - ps)
-                    ms = self._conv_meta(sc.skip_conv, d_s, x_s, gs)
-                    gs16 = self._bn_bwd_apply16(ops, gs, ys, sc.skip_bn, lane="skip", after="skip")
-                    self._wgrad16(ops, sc.skip_conv, d_s, x_s, gs16, True, None, dict(ms, after="skip"))
-                    if need_dT:
-                        ops.append(("mfvi_fill_f32", (dT.data_ptr(), dT.numel(), 0.0), dict(self._ew_meta(dT), lane="skip", after="skip")))
-                        self._dgrad16(ops, sc.skip_conv, d_s, gs16, self._interior(dT, Tpad - ps), 1, dict(ms, lane="skip", after="skip"))
-                elif Cs:
+                if Cs:
                     x_s = self._interior(T, Tpad - ps)
                     ms = self._conv_meta(sc.skip_conv, d_s, x_s, gs)
                     ops.append(("mfvi_bn_bwd_apply", (
@@ -520,13 +435,10 @@ class SkipEngine:
                         ops.append(("mfvi_conv2d_dgrad", (C.byref(d_s), L.view(gs), self.w.data_ptr() + 4 * sc.skip_conv.w_off,
                                                           lay.P_pad, L.view(self._interior(dT, Tpad - ps)), 1),
                                     dict(ms, lane="skip", after="skip")))
-                if self.bf16:
-                    gd = self._bn_bwd_apply16(ops, gd, z, z_bn)          # from here on gd is the bf16 operand
-                else:
-                    ops.append(("mfvi_bn_bwd_apply", (
-                        L.view(gd), L.view(z), S, z.shape[1], z.shape[2], Cd, zb[0], self._aptr(z_bn.red_off), zb[1], L.view(gd),
-                        self.g_gamma.data_ptr() + 4 * z_bn.ch_off, self.g_beta.data_ptr() + 4 * z_bn.ch_off),
-                        self._ew_meta(gd, z, gd)))
+                ops.append(("mfvi_bn_bwd_apply", (
+                    L.view(gd), L.view(z), S, z.shape[1], z.shape[2], Cd, zb[0], self._aptr(z_bn.red_off), zb[1], L.view(gd),
+                    self.g_gamma.data_ptr() + 4 * z_bn.ch_off, self.g_beta.data_ptr() + 4 * z_bn.ch_off),
+                    self._ew_meta(gd, z, gd)))
                 if inner_bwd is not None:
                     dTn = inner_bwd(ops, gd)
                     dy2 = self._bn_act_pad_bwd(ops, dTn, y2, sc.d2_bn, 1, Tn_pad)
@@ -535,45 +447,29 @@ class SkipEngine:
                 dX2 = self._conv_bwd(ops, sc.d2, d_2, X2, dy2)
                 dy1 = self._bn_act_pad_bwd(ops, dX2, y1, sc.d1_bn, 1, pd)
                 m1 = self._conv_meta(sc.d1, d_1, x_d1, dy1)
-                if self.bf16:
-                    self._wgrad16(ops, sc.d1, d_1, x_d1, dy1, True, None, m1)
-                else:
-                    ops.append(("mfvi_conv2d_wgrad", (C.byref(d_1), L.view(x_d1), L.view(dy1), self.dw.data_ptr() + 4 * sc.d1.w_off,
-                                                      self._dbias_ptr(sc.d1, True), lay.P_pad), m1))
+                ops.append(("mfvi_conv2d_wgrad", (C.byref(d_1), L.view(x_d1), L.view(dy1), self.dw.data_ptr() + 4 * sc.d1.w_off,
+                                                  self._dbias_ptr(sc.d1, True), lay.P_pad), m1))
                 if need_dT:
                     dT_d1 = self._interior(dT, Tpad - pd)
                     if Cs:
                         ops.append(("__join__", (), {"lane": "skip"}))      # dT holds the skip branch's contribution
                     elif Tpad != pd:
                         ops.append(("mfvi_fill_f32", (dT.data_ptr(), dT.numel(), 0.0), self._ew_meta(dT)))
-                    if self.bf16:
-                        self._dgrad16(ops, sc.d1, d_1, dy1, dT_d1, 1 if (Cs or Tpad != pd) else 0, m1)
-                    else:
-                        ops.append(("mfvi_conv2d_dgrad", (C.byref(d_1), L.view(dy1), self.w.data_ptr() + 4 * sc.d1.w_off, lay.P_pad,
-                                                          L.view(dT_d1), 1 if (Cs or Tpad != pd) else 0), m1))
+                    ops.append(("mfvi_conv2d_dgrad", (C.byref(d_1), L.view(dy1), self.w.data_ptr() + 4 * sc.d1.w_off, lay.P_pad,
+                                                      L.view(dT_d1), 1 if (Cs or Tpad != pd) else 0), m1))
                 return dT
 
             Tn_pad = in_pad(i + 1) if i < n - 1 else 0
             return z_out, z_out_bn, backward
 
         x_in = self.x0
-        if self.bf16:         # the jitter kernel writes the fp32 x0; the convolutions read its bf16 copy
-            x_in = self._buf16(self.x0.shape[1], self.x0.shape[2], spec.num_input_channels, S=1)
-            self.fwd_ops.append(("mfvi_view_f32_to_bf16", (L.view(self.x0), 1, self.x0.shape[1], self.x0.shape[2],
-                                                           spec.num_input_channels, L.view(x_in)), self._ew_meta(self.x0, x_in)))
         z0, z0_bn, bwd0 = run_scale(0, x_in, self.pad0)
         XF = self._bn_act_pad(z0, z0_bn, *self._bn_args(z0_bn), 1, 0)
         self.out, d_f = self._conv_fwd(lay.final, XF, None)
         self.dout = torch.zeros(self.out.shape[:3] + ((lay.final.cout + 3) // 4 * 4,), dtype=torch.float32,
                                 device=self.device)[..., :lay.final.cout]
         ops = self.bwd_ops
-        if self.bf16:         # the loss head writes the fp32 dout (also the source of the final bias gradient)
-            So, Ho, Wo, Co = self.out.shape
-            dout16 = self._buf16(Ho, Wo, Co)
-            ops.append(("mfvi_view_f32_to_bf16", (L.view(self.dout), So, Ho, Wo, Co, L.view(dout16)), self._ew_meta(self.dout, dout16)))
-            dXF = self._conv_bwd(ops, lay.final, d_f, XF, dout16, bn_follows=False, dy_f32=self.dout)
-        else:
-            dXF = self._conv_bwd(ops, lay.final, d_f, XF, self.dout, bn_follows=False)
+        dXF = self._conv_bwd(ops, lay.final, d_f, XF, self.dout, bn_follows=False)
         dz0 = self._bn_act_pad_bwd(ops, dXF, z0, z0_bn, 1, 0)
         self.dx0 = bwd0(ops, dz0)
 
@@ -598,20 +494,9 @@ class SkipEngine:
         L.call("mfvi_sample_weights", self.mu.data_ptr(), self.rho.data_ptr(), self.lay.P, self.S,
                self.eps.data_ptr() if inj else None, self.lay.P_pad, key, self.w.data_ptr(), self.lay.P_pad,
                meta={"bytes": 4.0 * self.lay.P * (2 + self.S)})
-        if self.bf16:
-            self._pack_w16()
-
-    def _pack_w16(self):
-        """bf16 mode: repack the sampled weight blocks of all layers into 16-byte aligned bf16 rows (one launch)."""
-        t = self._pack_tables
-        L.call("mfvi_pack_weights_bf16", self.w.data_ptr(), self.lay.P_pad, self.S, len(self.lay.convs), t[0], t[1], t[2], t[3],
-               self.w16.data_ptr(), self.P16, meta={"bytes": self.S * (4.0 * self.lay.P + 2.0 * self.P16)})
-
     def use_mean_weights(self):
         """Eval mode of RTLayer (reparam_layers.py:33-35): w = mu for every sample."""
         self.w[:, :self.lay.P].copy_(self.mu.unsqueeze(0).expand(self.S, -1))
-        if self.bf16:
-            self._pack_w16()
 
     def _run(self, op_list):
         """Launch an op list: ops tagged lane="skip" go to the skip stream, weight-gradient kernels to the wgrad stream
@@ -696,19 +581,10 @@ class SkipEngine:
             elif name == "mfvi_conv2d_wgrad":
                 d, x, dy, _, db, wss = args
                 info = L.conv_plan(d._obj, L.PASS_WGRAD, x, dy, wss, 0, db is not None)
-            elif name == "mfvi_conv2d_fwd_bf16":
-                d, x, _, _, wss, b, _, y, _ = args
-                info = L.conv_plan(d._obj, L.PASS_FWD + L.PASS_BF16, x, y, wss, 0, b is not None)
-            elif name == "mfvi_conv2d_dgrad_bf16":
-                d, dy, _, _, wss, dx, acc = args
-                info = L.conv_plan(d._obj, L.PASS_DGRAD + L.PASS_BF16, dy, dx, wss, acc)
-            elif name == "mfvi_conv2d_wgrad_bf16":
-                d, x, dy, _, wss, _, db = args
-                info = L.conv_plan(d._obj, L.PASS_WGRAD + L.PASS_BF16, x, dy, wss, 0, db is not None)
             else:
                 continue
             g = d._obj
-            rows.append(dict(info, op=name[len("mfvi_conv2d_"):].replace("_bf16", ""), layer=meta["layer"], shape=meta["shape"], S=g.S, Cin=g.Cin,
+            rows.append(dict(info, op=name[len("mfvi_conv2d_"):], layer=meta["layer"], shape=meta["shape"], S=g.S, Cin=g.Cin,
                              Cout=g.Cout, K=g.KH, stride=g.stride, Hin=g.Hin, Win=g.Win, Hout=g.Hout, Wout=g.Wout))
         return rows
 

@@ -353,6 +353,51 @@ def full_den256(S=2):
     save("den256_summary.npz", **arrs)
 
 
+def full_summary(task, size, S, fname, seed=1234):
+    """Full-size net of a BASELINE config (den 256^2 / sr, inp, ct 512^2), philox eps, summary outputs only:
+    sub-sampled outputs, loss terms, the norm / abs-max of EVERY gradient tensor and the first 1024 elements of each.  The
+    synthetic inputs are the ones bench.py --config <task> uses (mfvi_dip_mia_b200.utils.phantoms)."""
+    from mfvi_dip_mia_b200.utils import phantoms as ph
+    cfg = FULL[task]
+    temp, sigma = {"den": (5.656911698337764e-07, 1.4616642493692077e-05), "sr": (4.3817e-07, 4.9e-08),
+                   "inp": (1e-12, 6.506e-4), "ct": (2.2e-10, 1.7e-7)}[task]
+    torch.manual_seed(1)
+    net = build_ref_net(cfg, np.sqrt(temp) * sigma)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    lay = O.skip_layout(cfg)
+    g = torch.Generator().manual_seed(5)
+    net_input = torch.rand(1, cfg.num_input_channels, size, size, generator=g) * 0.1
+    extra = {}
+    if task == "den":
+        extra["target"] = torch.from_numpy(ph.noisy(ph.ellipse_phantom(size), 0.1, 1))[None]
+    elif task == "sr":
+        extra["factor"] = 4
+        extra["target"] = torch.from_numpy(ph.ellipse_phantom(size))[None][:, :, ::4, ::4].contiguous()
+    elif task == "inp":
+        extra["target"] = torch.from_numpy(ph.rgb_phantom(size))[None]
+        extra["mask"] = torch.from_numpy(ph.random_mask(size, 2))[None]
+    elif task == "ct":
+        theta = torch.arange(0, 180., step=2.)                       # 90 angles (BASELINE config 4)
+        extra["radon"] = R["Radon"]((1, 1, size, size), theta)
+        extra["sino"] = extra["radon"](torch.from_numpy(ph.shepp_logan(size))[None]).detach()
+    eps_list = make_eps(lay, sd, S, seed=seed, step=0, use_philox=True)
+    loss, nll, kl, outs, grads = run_ref_step(net, cfg, lay, net_input, eps_list, task, temp, extra)
+    arrs = {"loss": loss, "nll": nll, "kl": kl, "temp": np.float64(temp), "sigma": np.float64(sigma), "S": np.int64(S),
+            "philox_seed": np.int64(seed), "input_seed": np.int64(5), "init_seed": np.int64(1), "size": np.int64(size),
+            "task": np.array(task)}
+    for i, o in enumerate(outs):
+        arrs[f"out{i}_sub"] = o[:, :, ::8, ::8]
+        arrs[f"out{i}_mean"] = o.double().mean(dim=(0, 2, 3))
+    names = list(grads.keys())
+    arrs["grad_names"] = np.array(json.dumps(names))
+    arrs["grad_norms"] = np.array([float(grads[k].double().norm()) for k in names])
+    arrs["grad_absmax"] = np.array([float(grads[k].abs().max()) for k in names])
+    arrs["param_norms"] = np.array([float(dict(net.named_parameters())[k].double().norm()) for k in names])
+    for k in names:
+        arrs["grad/" + k] = grads[k].reshape(-1)[:1024]
+    save(fname, **arrs)
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["small", "layers", "keys", "den256"]
     if "small" in what:
@@ -364,3 +409,8 @@ if __name__ == "__main__":
         full_keys()
     if "den256" in what:
         full_den256()
+    if "full" in what:          # BASELINE configs at full size: the metric shape at MC=8, configs 2-4 at 512^2 with one sample
+        full_summary("den", 256, 8, "full_den256_s8.npz")
+        full_summary("sr", 512, 1, "full_sr512.npz")
+        full_summary("ct", 512, 1, "full_ct512.npz")
+        full_summary("inp", 512, 1, "full_inp512.npz")

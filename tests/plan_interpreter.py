@@ -22,8 +22,6 @@ class PlanInterpreter:
         self.stores = []
         seen = set()
         tensors = [eng.theta, eng.grad, eng.zbuf, eng.w, eng.dout, eng.running_mean, eng.running_var] + list(eng._bufs)
-        if eng.w16 is not None:
-            tensors.append(eng.w16)
         if eng.eps is not None:
             tensors.append(eng.eps)
         for t in tensors:
@@ -280,13 +278,10 @@ class PlanInterpreter:
         src, S, H, W, Cn, dst = args
         self.view(dst, S, H, W, Cn, torch.bfloat16).copy_(self.view(src, S, H, W, Cn))
 
-    OPS = {"mfvi_conv2d_fwd": op_conv_fwd, "mfvi_conv2d_fwd_bf16": op_conv_fwd, "mfvi_conv2d_dgrad": op_conv_dgrad,
-           "mfvi_conv2d_dgrad_bf16": op_conv_dgrad, "mfvi_conv2d_wgrad": op_conv_wgrad, "mfvi_conv2d_wgrad_bf16": op_conv_wgrad,
-           "mfvi_bn_act_pad_fwd": op_bn_act_pad_fwd, "mfvi_bn_act_pad_fwd_bf16": op_bn_act_pad_fwd, "mfvi_cat_up_fwd": op_cat_up_fwd,
-           "mfvi_pad_act_bwd": op_pad_act_bwd, "mfvi_bn_bwd_apply": op_bn_bwd_apply, "mfvi_bn_bwd_apply_bf16": op_bn_bwd_apply,
-           "mfvi_cat_up_bwd": op_cat_up_bwd, "mfvi_fill_f32": op_fill, "mfvi_view_f32_to_bf16": op_view_to_bf16,
-           "mfvi_pad_act_bwd_reduce": op_pad_act_bwd_reduce, "mfvi_bn_bwd_apply_from_dxp": op_bn_bwd_apply_from_dxp,
-           "mfvi_bn_bwd_apply_from_dxp_bf16": op_bn_bwd_apply_from_dxp}
+    OPS = {"mfvi_conv2d_fwd": op_conv_fwd, "mfvi_conv2d_dgrad": op_conv_dgrad, "mfvi_conv2d_wgrad": op_conv_wgrad,
+           "mfvi_bn_act_pad_fwd": op_bn_act_pad_fwd, "mfvi_cat_up_fwd": op_cat_up_fwd,
+           "mfvi_pad_act_bwd": op_pad_act_bwd, "mfvi_bn_bwd_apply": op_bn_bwd_apply,
+           "mfvi_cat_up_bwd": op_cat_up_bwd, "mfvi_fill_f32": op_fill}
 
     def run(self, ops):
         """Executes an op list in order (lanes only express concurrency: program order is a valid schedule)."""
@@ -308,11 +303,6 @@ class PlanInterpreter:
         e = self.eng
         P = e.lay.P
         e.w[:, :P] = e.mu[None] + F.softplus(e.rho)[None] * e.eps[:, :P]
-        if e.w16 is not None:
-            e.w16.zero_()
-            for c in e.lay.convs:
-                src = e.w[:, c.w_off:c.w_off + c.w_numel].view(e.S, c.k * c.k * c.cout, c.cin)
-                e.w16[:, c.w16_off:c.w16_off + c.k * c.k * c.cout * c.cpitch].view(e.S, -1, c.cpitch)[..., :c.cin] = src
 
     def step(self, x_chw, nll_of_out):
         """forward, loss head (`nll_of_out`: (S,C,H,W) -> scalar mean-over-samples data loss), backward.  Returns the loss."""
@@ -422,16 +412,6 @@ class TrainerInterpreter(PlanInterpreter):
         E = self._eps_rows(eps, eps_ss, n, S, key)
         for s in range(S):
             self.vec(w_out + 4 * s * w_ss, n).copy_(m + sg * E[s])
-
-    def op_pack_weights_bf16(self, name, args):
-        w, w_ss, S, n_layers, w_off, w16_off, rows, cin, w16, w16_ss = args
-        for l in range(n_layers):
-            cp = (cin[l] + 7) // 8 * 8
-            for s in range(S):
-                src = self.vec(w + 4 * (s * w_ss + w_off[l]), rows[l] * cin[l]).view(rows[l], cin[l])
-                dst = self.vec(w16 + 2 * (s * w16_ss + w16_off[l]), rows[l] * cp, torch.bfloat16).view(rows[l], cp)
-                dst.zero_()
-                dst[:, :cin[l]] = src
 
     def op_gauss_nll(self, name, args):
         from oracle import mfvi_oracle as O
@@ -588,6 +568,6 @@ class TrainerInterpreter(PlanInterpreter):
     TRAINER_OPS = {"mfvi_radon_fwd": op_radon_fwd, "mfvi_radon_bwd": op_radon_bwd, "mfvi_mse_fwd_bwd": op_mse,
                    "mfvi_bookkeep_step": op_bookkeep_step, "mfvi_ssim": op_ssim, "mfvi_ring_uncertainty": op_ring_uncertainty,
                    "mfvi_input_jitter_pad": op_input_jitter_pad, "mfvi_sample_weights": op_sample_weights,
-                   "mfvi_pack_weights_bf16": op_pack_weights_bf16, "mfvi_gauss_nll_fwd_bwd": op_gauss_nll,
+                   "mfvi_gauss_nll_fwd_bwd": op_gauss_nll,
                    "mfvi_kl_reparam_fwd_bwd": op_kl_reparam, "mfvi_bn_running_update": op_bn_running_update,
                    "mfvi_adamw_step": op_adamw, "mfvi_counter_add": op_counter_add}
