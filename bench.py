@@ -1,15 +1,24 @@
 #!/usr/bin/env python
 """MFVI-DIP ELBO steps/sec benchmark (BASELINE.json metric: 256x256 denoise net, MC=8).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mc 8] [--size 256]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config den|sr|inp|ct] [--math tf32|fp32]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one full optimiser step of the hot path (input jitter, S-sample forward, NLL, KL, backward,
-[all-reduce], AdamW) on synthetic data of the metric shape.  `value` = steps/s with everything resident in HBM
+A "step" is one full optimiser step of the hot path (input jitter, S-sample forward, data loss, KL, backward,
+[all-reduce], AdamW) on synthetic data of the named shape.  `value` = steps/s with everything resident in HBM
 (CUDA-graph replay, CUDA-event timing, max over ranks); `e2e` = the same through MfviDipTrainer.step_from_host with
 pinned HOST buffers (H2D of net input + target and D2H of the loss inside the timed region).  MC samples are split
-across GPUs (total work fixed => "strong" scaling).  `--impl reference` times the CPU restatement of the reference
-step (oracle/, PyTorch fp32 on all host threads; /root/reference itself does not exist on the GPU box).
+across GPUs (total work fixed => "strong" scaling).
+
+--config selects the BASELINE.json configuration (default `den` = the metric configuration):
+    den  test_configs/mfvi_den.json   256x256 denoising, MC = 8          (config 1 shape at the metric's MC)
+    sr   test_configs/mfvi_sr.json    512x512 4x super-resolution, MC = 1 (config 2)
+    inp  test_configs/mfvi_inp.json   512x512 inpainting, MC = 8          (config 3; 8 GPUs: one sample per GPU)
+    ct   test_configs/mfvi_ct.json    512x512 sparse-view CT, 90 angles, MC = 1 (config 4; adds a `radon` object)
+--math: tf32 = tcgen05 kind::tf32 tensor-core convolutions (the separately stated reduced-precision mode, tested to the bars in
+tests/test_gpu_fullsize_parity.py); fp32 = CUDA-core convolutions, the mode held to north_star's rtol 1e-3.  At N=1 the JSON
+line carries BOTH in `modes`.  `--impl reference` times the CPU restatement of the reference step (oracle/, PyTorch fp32 on all
+host threads; /root/reference itself does not exist on the GPU box).
 """
 import argparse
 import json
@@ -23,8 +32,28 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-TEMP, SIGMA, LR = 5.656911698337764e-07, 1.4616642493692077e-05, 1e-3   # test_configs/mfvi_den.json
 METRIC, UNIT = "mfvi_dip_elbo_steps_per_sec", "steps/s"
+
+# hyper-parameters of test_configs/mfvi_{den,sr,inp,ct}.json (temp, sigma, lr, input_depth) and the benchmark shape
+CONFIGS = {
+    "den": dict(temp=5.656911698337764e-07, sigma=1.4616642493692077e-05, lr=1e-3, depth=16, size=256, mc=8,
+                name="mfvi_den {n}x{n} 5-scale skip net"),
+    "sr": dict(temp=4.3817e-07, sigma=4.9e-08, lr=1e-3, depth=32, size=512, mc=1, name="mfvi_sr {n}x{n} 4x SR 5-scale skip net"),
+    "inp": dict(temp=1e-12, sigma=6.506e-4, lr=2e-3, depth=16, size=512, mc=8,
+                name="mfvi_inp {n}x{n} inpainting 6-scale 5x5 net"),
+    "ct": dict(temp=2.2e-10, sigma=1.7e-7, lr=1e-3, depth=16, size=512, mc=1,
+               name="mfvi_ct {n}x{n} sparse-view CT (90 angles) 5-scale skip net"),
+}
+TESTED_TO = {
+    "tf32": "tests/test_gpu_fullsize_parity.py BARS['tf32'] vs the imported reference (tcgen05 kind::tf32 operands, fp32 "
+            "accumulate; the separately stated reduced-precision mode)",
+    "fp32": "tests/test_gpu_fullsize_parity.py BARS['fp32'] vs the imported reference: north_star rtol 1e-3 (fp32 CUDA-core convs)",
+}
+
+
+def workload_name(cfg, size, mc):
+    """The SAME string in both arms (the driver compares them)."""
+    return f"{cfg['name'].format(n=size)}, MC={mc}, AdamW"
 
 
 def peaks():
@@ -80,13 +109,74 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def synthetic_problem(size, seed=1):
+def synthetic_problem(config, size, seed=1):
+    """(net_input (1,C,H,W), head kwargs) of a BASELINE configuration on the synthetic phantoms of SURVEY.md section 8d.
+    For CT the head carries the phantom (`image`); its sinogram is produced by the caller's projector (ours on the GPU,
+    the oracle's on the CPU)."""
     import torch
-    from mfvi_dip_mia_b200.utils.phantoms import ellipse_phantom, noisy
-    target = torch.from_numpy(noisy(ellipse_phantom(size), 0.1, seed))[None]          # (1,1,H,W)
+    from mfvi_dip_mia_b200.utils import phantoms as ph
+    cfg = CONFIGS[config]
     g = torch.Generator().manual_seed(seed)
-    net_input = torch.rand(1, 16, size, size, generator=g) * 0.1                      # get_noise('noise', 'u', 1/10)
-    return net_input, target
+    net_input = torch.rand(1, cfg["depth"], size, size, generator=g) * 0.1             # get_noise('noise', 'u', 1/10)
+    if config == "den":
+        head = dict(target=torch.from_numpy(ph.noisy(ph.ellipse_phantom(size), 0.1, seed))[None])
+    elif config == "sr":
+        head = dict(target=torch.from_numpy(ph.ellipse_phantom(size))[None][:, :, ::4, ::4].contiguous())
+    elif config == "inp":
+        head = dict(target=torch.from_numpy(ph.rgb_phantom(size))[None], mask=torch.from_numpy(ph.random_mask(size, 2))[None])
+    else:
+        head = dict(theta_deg=torch.arange(0, 180., step=2.), image=torch.from_numpy(ph.shepp_logan(size))[None])
+    return net_input, head
+
+
+def spec_kwargs(config):
+    d = CONFIGS[config]["depth"]
+    if config == "inp":
+        return dict(num_input_channels=d, num_output_channels=4, down=(16, 32, 64, 128, 128, 128), up=(16, 32, 64, 128, 128, 128),
+                    skip=(0,) * 6, filter_down=5, filter_up=3, filter_skip=1, need1x1_up=False, upsample_mode="nearest")
+    return dict(num_input_channels=d, num_output_channels=1 if config == "ct" else 2)
+
+
+def oracle_cfg(config):
+    from oracle import mfvi_oracle as O
+    k = spec_kwargs(config)
+    if config == "inp":
+        return O.SkipCfg(k["num_input_channels"], 4, k["down"], k["up"], k["skip"], 5, 3, 1, False, False, "nearest")
+    return O.SkipCfg(k["num_input_channels"], k["num_output_channels"])
+
+
+def oracle_stepper(config, size, mc, device="cpu"):
+    """The reference step restated with PyTorch (oracle/cpu_step.py) on `device` for a BASELINE configuration."""
+    from oracle import mfvi_oracle as O
+    from oracle.cpu_step import OracleStepper
+    cfg = CONFIGS[config]
+    _, head = synthetic_problem(config, size)
+    if config == "ct":
+        img = head.pop("image")
+        head["sino"] = O.radon_forward(img, head["theta_deg"])
+    return OracleStepper(oracle_cfg(config), size, size, mc_samples=mc, temp=cfg["temp"], sigma=cfg["sigma"], lr=cfg["lr"], seed=1,
+                         task=config, device=device, head=head)
+
+
+def time_oracle(config, size, mc, device, budget_s, n_steps, warmup):
+    """Bounded sample: probe one sample-forward/backward, evaluate `s_eval` of the mc samples per step so that the run fits the
+    budget, scale linearly.  Returns (seconds per full step, s_eval)."""
+    from oracle.cpu_step import time_steps
+    st = oracle_stepper(config, size, mc, device)
+    t0 = time.perf_counter()
+    st.step(1)
+    if st.device.type != "cpu":
+        import torch
+        torch.cuda.synchronize()
+    probe = time.perf_counter() - t0
+    s_eval = max(1, min(mc, int(budget_s / max(probe * (n_steps + warmup), 1e-9))))
+    sec = time_steps(st, n_steps, warmup, s_eval)
+    return sec * mc / s_eval, s_eval
+
+
+PORT_NOTE = ("oracle port of the reference step (the same ATen kernels for conv/BN/pad/upsample/AdamW; its closed-form kl() is "
+             "CHEAPER than the reference's 1951-op torch.distributions kl(), so this baseline is if anything faster than the "
+             "reference itself)")
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
@@ -95,28 +185,17 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
-    from oracle import mfvi_oracle as O
-    from oracle.cpu_step import OracleStepper, time_steps
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    st = OracleStepper(O.SkipCfg(16, 2), args.size, args.size, mc_samples=args.mc, temp=TEMP, sigma=SIGMA, lr=LR, seed=1)
-    # bound the run: probe one sample-forward/backward, then choose how many MC samples a "step" evaluates
-    t0 = time.perf_counter()
-    st.step(1)
-    probe = time.perf_counter() - t0
-    budget = 240.0
-    total = args.steps + args.warmup
-    s_eval = max(1, min(args.mc, int(budget / max(probe * total, 1e-9))))
-    sec = time_steps(st, args.steps, args.warmup, s_eval)
-    # a full step evaluates args.mc samples; the sample evaluated s_eval of them (cost is linear in samples)
-    sec_full = sec * args.mc / s_eval
+    cfg = CONFIGS[args.config]
+    sec_full, s_eval = time_oracle(args.config, args.size, args.mc, "cpu", 240.0, args.steps, args.warmup)
     v = 1.0 / sec_full
     sample = (f"{args.steps} steps x {s_eval} of {args.mc} MC samples per step (time scaled by {args.mc}/{s_eval}), "
-              f"{args.size}x{args.size}, oracle port of the reference step, torch {torch.__version__} CPU fp32")
+              f"{args.size}x{args.size}, {PORT_NOTE}, torch {torch.__version__} CPU fp32")
     line = {"metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec_full * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"mfvi_den {args.size}x{args.size} 5-scale skip net, MC={args.mc}, AdamW"},
+            "config": {"workload": workload_name(cfg, args.size, args.mc)},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -134,22 +213,36 @@ def kernel_breakdown(tr, iters=3):
         torch.cuda.synchronize()
         tl, L.timeline = L.timeline, None
         for name, e0, e1, meta in tl:
-            a = agg.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0})
+            a = agg.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0, "samples": 0.0})
             a["ms"] += e0.elapsed_time(e1)
             a["n"] += 1
             if meta:
                 a["flops"] += meta.get("flops", 0.0)
                 a["bytes"] += meta.get("bytes", 0.0)
+                a["samples"] += meta.get("samples", 0.0)
     for a in agg.values():
         for k in a:
             a[k] /= iters
     return agg
 
 
+def build_trainer(args, math_mode, dev, rank, world):
+    from mfvi_dip_mia_b200 import MfviDipTrainer, SkipSpec
+    from mfvi_dip_mia_b200.radon import FastRadonTransform
+    cfg = CONFIGS[args.config]
+    net_input, head = synthetic_problem(args.config, args.size)
+    if args.config == "ct":
+        img = head.pop("image").to(dev)
+        head["sino"] = FastRadonTransform(tuple(img.shape), head["theta_deg"]).to(dev)(img).detach()
+    return MfviDipTrainer(SkipSpec(**spec_kwargs(args.config)), args.config, net_input, temp=cfg["temp"], sigma=cfg["sigma"],
+                          lr=cfg["lr"], mc_samples=args.mc, seed=1, device=dev, rank=rank, world_size=world, math_mode=math_mode,
+                          use_graph=True, **head)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from mfvi_dip_mia_b200 import MfviDipTrainer, SkipSpec, _lib as L
+    from mfvi_dip_mia_b200 import _lib as L
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -181,12 +274,9 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}"
-    net_input, target = synthetic_problem(args.size)
-    # "bf16" is the EXPERIMENTAL bf16-operand mode: never the default, and not a valid bench line until its
-    # parity tests (tests/test_gpu_next_bf16.py) have passed on the GPU
-    math_mode = {"tf32": L.MATH_TF32, "fp32": L.MATH_FP32}[args.math]
-    tr = MfviDipTrainer(SkipSpec(), "den", net_input, temp=TEMP, sigma=SIGMA, lr=LR, mc_samples=args.mc, seed=1,
-                        device=dev, target=target, rank=rank, world_size=world, math_mode=math_mode, use_graph=True)
+    cfg = CONFIGS[args.config]
+    math_of = {"tf32": L.MATH_TF32, "fp32": L.MATH_FP32}
+    tr = build_trainer(args, math_of[args.math], dev, rank, world)
 
     def barrier():
         if world > 1:
@@ -212,6 +302,15 @@ def run_ours(args):
     torch.cuda.synchronize()
     with ClockSampler(local) as clk:
         ms_total = timed(tr.step, args.steps)
+        # the loss of optimiser step number warm + steps: the same step index on every GPU count (eps is keyed by the global
+        # sample id, parameters start from the same seed), so the N = 1 / 2 / 4 / 8 lines show G-invariance of the trajectory
+        nll_k, kl_k, loss_k = tr.loss_terms()
+        if world > 1:       # the data term is a mean over the samples: average the per-rank means
+            t = torch.tensor([nll_k], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            nll_k = float(t.item()) / world
+            loss_k = nll_k + cfg["temp"] * kl_k
+        step_index = tr.steps_done
         # K steps can be shorter than nvidia-smi's sampling period: keep the SAME load running (untimed) for ~1 s so that the
         # clock record describes the loaded state.  The number of extra steps is derived from ms_total, which is already the
         # max over ranks and therefore IDENTICAL on every rank — every rank must issue the same number of all-reduces (a
@@ -231,7 +330,7 @@ def run_ours(args):
     bufs = [tr.host_buffers() for _ in range(2)]
     for h_in, h_tgt, _ in bufs:
         h_in.copy_(tr.saved.cpu())
-        h_tgt.copy_(tr.head.target.cpu())
+        h_tgt.copy_(tr._target_tensor().cpu())
     io = [0, 0]
     pending = []
     losses = []
@@ -251,7 +350,6 @@ def run_ours(args):
     ms_e2e = timed(e2e_step, args.steps)
     e2e = {"value": args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": io[0], "d2h_bytes_per_step": io[1],
            "pipeline_depth": 1}
-    nll, kl, loss = tr.loss_terms()
 
     # ---- roofline of the dominant kernel family (eager pass with CUDA events around every C-ABI launch)
     pk = peaks()
@@ -259,20 +357,20 @@ def run_ours(args):
     step_ms_eager = sum(a["ms"] for a in agg.values())
     dom = max(agg, key=lambda k: agg[k]["ms"])
     a = agg[dom]
-    # measured DRAM bytes per step of every family (ncu dram__bytes_read+write, profiles/r01_dram_traffic.json)
+    # measured DRAM bytes per step of every kernel family: ncu dram__bytes_read.sum + dram__bytes_write.sum of THIS round's
+    # build (scripts/traffic_from_ncu.py writes profiles/r02_dram_traffic.json from the committed launch list); null otherwise
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
-    if os.path.exists(tp) and args.size == 256 and args.mc == 8 and world == 1:
+    tp = os.path.join(ROOT, "profiles", "r02_dram_traffic.json")
+    if os.path.exists(tp) and args.config == "den" and args.size == 256 and args.mc == 8 and world == 1 and args.math == "tf32":
         with open(tp) as f:
             traffic = json.load(f).get("bytes_per_step", {}).get(dom)
     if a["flops"] > 0:
         # the convolutions run tcgen05 kind::tf32: half the dense bf16 rate MEASURED_PEAKS.json reports
-        peak = {"tf32": pk["tensor"] / 2.0, "bf16": pk["tensor"], "fp32": 75.0}[args.math]
+        peak = {"tf32": pk["tensor"] / 2.0, "fp32": 75.0}[args.math]
         ach = a["flops"] / (a["ms"] * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak, "traffic": traffic,
-                "peak_source": {"tf32": pk["src"] + " bf16 sustained / 2 (kind::tf32)", "bf16": pk["src"] + " bf16 sustained (kind::f16)",
-                                "fp32": "fp32 CUDA-core nominal"}[args.math],
+                "peak_source": {"tf32": pk["src"] + " bf16 sustained / 2 (kind::tf32)", "fp32": "fp32 CUDA-core nominal"}[args.math],
                 "algorithmic_gbs": a["bytes"] / (a["ms"] * 1e-3) / 1e9, "hbm_peak_gbs": pk["hbm"],
                 "launches_per_step": a["n"], "ms_per_step": a["ms"], "share_of_step": a["ms"] / step_ms_eager}
     else:
@@ -289,33 +387,79 @@ def run_ours(args):
             e["gbs"] = round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)
         kernels[k] = e
 
+    # ---- CT: the radon projector on its own (samples/s and GB/s under both byte definitions)
+    radon = None
+    if args.config == "ct":
+        radon = {}
+        H = args.size
+        T = tr.head.T
+        for name in ("mfvi_radon_fwd", "mfvi_radon_bwd"):
+            v = agg[name]
+            sec = v["ms"] * 1e-3
+            ref_bytes = tr.S * (T * H * H * 8.0 + 2.0 * T * H * H * 4.0)     # reference: grid read + (T,C,H,W) intermediate write+read
+            radon[name] = {"ms": round(v["ms"], 4), "bilinear_samples_per_s": v["samples"] / sec,
+                           "algorithmic_gbs": v["bytes"] / sec / 1e9, "frac_of_hbm_peak": v["bytes"] / sec / 1e9 / pk["hbm"],
+                           "gbs_under_reference_traffic_model": ref_bytes / sec / 1e9,
+                           "frac_of_hbm_peak_reference_model": ref_bytes / sec / 1e9 / pk["hbm"]}
+        radon["note"] = (f"{T} angles, {H}x{H}, S={tr.S}: algorithmic bytes = image + sinogram once each "
+                         "(gather/issue-bound at this size); reference model = the bytes radon/radon.py moves")
+
+    # ---- the other arithmetic mode on the same workload (N=1 only): fp32 next to tf32
+    modes = None
+    if world == 1 and not args.no_modes:
+        modes = {args.math: {"value": value, "unit": UNIT, "ms_per_step": ms_total / args.steps, "tested_to": TESTED_TO[args.math]}}
+        other = "fp32" if args.math == "tf32" else "tf32"
+        del bufs
+        tr2 = build_trainer(args, math_of[other], dev, rank, world)
+        for _ in range(warm):
+            tr2.step()
+        n2 = max(5, args.steps // 3)
+        ms2 = timed(tr2.step, n2)
+        modes[other] = {"value": n2 / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / n2, "steps": n2, "tested_to": TESTED_TO[other]}
+        del tr2
+        torch.cuda.empty_cache()
+
     if rank != 0:
         return
+    # ---- the reference step as eager PyTorch on this GPU (cuDNN fp32, TF32 off): the GPU bar of SURVEY section 2a
+    gpu_eager = None
+    if world == 1 and not args.no_cpu:
+        old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            sec, s_eval = time_oracle(args.config, args.size, args.mc, dev, 10.0, 3, 2)
+            gpu_eager = {"value": 1.0 / sec, "unit": UNIT, "ms_per_step": sec * 1e3,
+                         "what": f"{PORT_NOTE} run as eager PyTorch {torch.__version__} on this GPU (cuDNN fp32, allow_tf32=False), "
+                                 f"3 steps x {s_eval} of {args.mc} MC samples (time scaled), wall clock with synchronise"}
+        except Exception as e:                           # never let the comparison arm break the bench line
+            gpu_eager = {"error": f"{type(e).__name__}: {e}"[:200]}
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
     # ---- CPU baseline on this box's host cores (bounded sample), N=1 only
     cpu = None
     if world == 1 and not args.no_cpu:
-        from oracle import mfvi_oracle as O
-        from oracle.cpu_step import OracleStepper, time_steps
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        st = OracleStepper(O.SkipCfg(16, 2), args.size, args.size, mc_samples=args.mc, temp=TEMP, sigma=SIGMA, lr=LR)
-        t0 = time.perf_counter()
-        st.step(1)
-        probe = time.perf_counter() - t0
         n_cpu = 3
-        s_eval = max(1, min(args.mc, int(20.0 / max(probe * (n_cpu + 1), 1e-9))))
-        sec = time_steps(st, n_cpu, 1, s_eval) * args.mc / s_eval
+        sec, s_eval = time_oracle(args.config, args.size, args.mc, "cpu", 20.0, n_cpu, 1)
         cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{n_cpu} steps x {s_eval} of {args.mc} MC samples (time scaled by {args.mc}/{s_eval}), oracle "
-                         f"port of the reference step, torch CPU fp32"}
+               "sample": f"{n_cpu} steps x {s_eval} of {args.mc} MC samples (time scaled by {args.mc}/{s_eval}), {PORT_NOTE}, "
+                         f"torch CPU fp32"}
     ws_mb = sum(t.numel() for t in tr.eng._bufs) * 4 / 2 ** 20
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": {"tf32": "tf32", "bf16": "bf16", "fp32": "f32"}[args.math], "data": "synthetic",
-            "config": {"workload": f"mfvi_den {args.size}x{args.size} 5-scale skip net, MC={args.mc} split over {world} GPU(s), AdamW",
+            "dtype": {"tf32": "tf32", "fp32": "f32"}[args.math], "data": "synthetic",
+            "config": {"workload": workload_name(cfg, args.size, args.mc), "mc_split": f"{args.mc} MC samples over {world} GPU(s)",
                        "mc_per_gpu": tr.S, "l2": f"per-step activation working set {ws_mb:.0f} MiB > 126 MB L2 (no flush needed)",
-                       "cuda_graph": True, "last_loss": loss},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "kernels": kernels}
+                       "cuda_graph": True, "loss_at_step": {"step": step_index, "nll": nll_k, "kl": kl_k, "loss": loss_k}},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "launches_per_step": tr.launches_per_step, "roofline": roof,
+            "kernels": kernels}
+    if modes is not None:
+        line["modes"] = modes
+    if radon is not None:
+        line["radon"] = radon
+    if gpu_eager is not None:
+        line["gpu_eager_baseline"] = gpu_eager
     if cpu is not None:
         line["cpu_baseline"] = cpu
     sys.stdout.flush()
@@ -329,11 +473,15 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mc", type=int, default=8)
-    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--config", default="den", choices=sorted(CONFIGS))
+    ap.add_argument("--mc", type=int, default=None, help="MC samples per step (default: the configuration's)")
+    ap.add_argument("--size", type=int, default=None, help="image size (default: the configuration's)")
     ap.add_argument("--math", default="tf32", choices=["fp32", "tf32"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and gpu_eager_baseline legs")
+    ap.add_argument("--no-modes", action="store_true", help="skip timing the other arithmetic mode")
     args = ap.parse_args()
+    args.mc = args.mc or CONFIGS[args.config]["mc"]
+    args.size = args.size or CONFIGS[args.config]["size"]
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -190,10 +190,15 @@ int mfvi_input_jitter_pad(const float* saved, const float* noise, int H, int W, 
                           MfviPhiloxKey key, MfviView xp, mfvi_stream_t st);
 
 /* ---- a8: optimiser (torch.optim.AdamW, bayesian_optimization.py:1357,1372) over one flat buffer --------
- * skip_if_nonfinite: device double* loss; when it is NaN/Inf the update is skipped (CT runner :581-582). */
+ * skip_if_nonfinite: device float* holding the step's loss nll + temp*kl; when it is NaN/Inf the update is skipped (CT runner
+ * :577-582: `if not torch.isnan(loss): optimizer.step()`).  The flag is written by mfvi_loss_flag into a slot that rides at the
+ * tail of the all-reduced gradient buffer, so every rank of a sharded run takes the same decision; the optimiser's own step
+ * count (mfvi_counter_add_if_finite) does not advance on a skipped update, as torch's does not. */
 int mfvi_adamw_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2,
-                    float eps, float weight_decay, int step, const uint32_t* step_dev, const double* skip_if_nonfinite,
+                    float eps, float weight_decay, int step, const uint32_t* step_dev, const float* skip_if_nonfinite,
                     mfvi_stream_t st);
+int mfvi_loss_flag(const double* kl, const double* nll, float temp, float* flag, mfvi_stream_t st);
+int mfvi_counter_add_if_finite(uint32_t* ctr, uint32_t inc, const float* flag, mfvi_stream_t st);
 /* *ctr += inc (one thread): the device-side step counter read through MfviPhiloxKey.step_dev / adamw step_dev
  * (effective AdamW step = step + *step_dev). */
 int mfvi_counter_add(uint32_t* ctr, uint32_t inc, mfvi_stream_t st);
@@ -208,6 +213,14 @@ int mfvi_counter_add(uint32_t* ctr, uint32_t inc, mfvi_stream_t st);
 int mfvi_bookkeep_step(MfviView out, int S, int H, int W, float exp_weight, const float* gt, const float* noisy,
                        float* out_avg, float* ring_epi, float* ring_ale, int ring, const uint32_t* iter_dev,
                        int iter_offset, double* acc, mfvi_stream_t st);
+/* The same for the other runners: Cm image channels (1 or 3), flags bit 0 = sigmoid on the image channels (inpainting,
+ * bayesian_optimization.py:3034), bit 1 = channel Cm is s = -log sigma^2 (absent in the CT net, :533); `mask` (H,W) or NULL
+ * multiplies both images of the gt comparisons acc[1], acc[2] (inpainting, :3064-3065).  gt / noisy are (Cm,H,W); out_avg is
+ * (Cm [+1],H,W); ring_epi is (Cm,ring,H,W) so that each channel's ring feeds mfvi_ring_uncertainty; ring_ale is (ring,H,W).
+ * mfvi_bookkeep_step(...) == mfvi_bookkeep_step_ex(..., Cm = 1, flags = 2, mask = NULL, ...). */
+int mfvi_bookkeep_step_ex(MfviView out, int S, int H, int W, int Cm, int flags, float exp_weight, const float* gt,
+                          const float* noisy, const float* mask, float* out_avg, float* ring_epi, float* ring_ale, int ring,
+                          const uint32_t* iter_dev, int iter_offset, double* acc, mfvi_stream_t st);
 /* out_sum[0] += sum over pixels of the SSIM map of (a, b) — 11x11 Gaussian window sigma 1.5, zero padding
  * (utils/common_utils.py:308-353); clip_b != 0 clips b to [0,1] first.  SSIM = out_sum/(H*W). */
 int mfvi_ssim(const float* a, const float* b, int H, int W, int clip_b, double* out_sum, mfvi_stream_t st);

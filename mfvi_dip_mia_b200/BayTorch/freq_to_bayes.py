@@ -33,16 +33,11 @@ class _FusedForward(torch.autograd.Function):
         L.call("mfvi_nchw_to_nhwc", xh.data_ptr(), nhwc.data_ptr(), 1, x.shape[1], x.shape[2], x.shape[3])
         eng.zero_accumulators()
         eng.set_input(nhwc, None, 0.0, L.key(0))
-        if owner.training:
-            ctx.key = L.key(owner.seed, owner._forward_calls, owner.sample0)
-            owner._forward_calls += 1
-            eng.sample_weights(ctx.key)
-        else:
-            ctx.key = None
-            eng.use_mean_weights()
+        ctx.key = L.key(owner.seed, owner._forward_calls, owner.sample0)
+        owner._forward_calls += 1
+        eng.sample_weights(ctx.key)
         eng.forward()
-        if owner.training:
-            eng.update_running_stats()
+        eng.update_running_stats()
         return eng.out_nchw()
 
     @staticmethod
@@ -51,8 +46,6 @@ class _FusedForward(torch.autograd.Function):
         if ctx.generation != owner._generation:
             raise L.MfviError("MeanFieldVI: backward through a stale forward — the fused engine keeps the activations "
                               "of the latest forward only")
-        if ctx.key is None:
-            raise L.MfviError("MeanFieldVI: backward in eval mode is not supported by the fused engine")
         d = dout.to(torch.float32).contiguous()
         S, Cn, H, W = d.shape
         dn = torch.empty(S, H, W, Cn, dtype=torch.float32, device=d.device)
@@ -127,9 +120,9 @@ class MeanFieldVI(nn.Module):
                 self._replace_deterministic_modules(child, prior, posteriors, kl_type)
             elif self._replace_layers in key:
                 if isinstance(child, nn.Linear):
-                    module._modules[key] = self._linear(child.in_features, child.out_features,
-                                                        torch.is_tensor(child.bias), prior=prior,
-                                                        posteriors=posteriors, kl_type=kl_type)
+                    # like the reference (freq_to_bayes.py:56-61): Linear layers keep the layer's DEFAULT prior / posterior
+                    # initialisation / kl_type — only the convolutions receive the ones passed in
+                    module._modules[key] = self._linear(child.in_features, child.out_features, torch.is_tensor(child.bias))
                 elif isinstance(child, nn.Conv2d):
                     module._modules[key] = self._conv2d(
                         in_channels=child.in_channels, out_channels=child.out_channels, kernel_size=child.kernel_size,
@@ -202,9 +195,12 @@ class MeanFieldVI(nn.Module):
 
     # ------------------------------------------------------------------ reference surface
     def forward(self, x):
-        if not self.fused:
-            if self._spec is not None and x.device.type != "cuda":
-                raise L.MfviError(f"MeanFieldVI: input on {x.device}; this implementation runs on CUDA only")
+        if self._spec is not None and x.device.type != "cuda":
+            raise L.MfviError(f"MeanFieldVI: input on {x.device}; this implementation runs on CUDA only")
+        if not self.fused or not self.training:
+            # eval mode (never used by a reference runner): module by module, so that nn.BatchNorm2d normalises with its
+            # RUNNING statistics and RTLayer uses w = mu exactly as the reference's net.eval() does (reparam_layers.py:33-35);
+            # the modules' parameters and buffers are views of the engine's flat storage, so they are current
             return self.net(x)
         L.require_cuda(x, "MeanFieldVI.forward")
         self._engine_for(x)

@@ -75,7 +75,10 @@ _SIGS = {
     "mfvi_input_jitter_pad": [_P, _P, _I, _I, _I, _F, _I, PhiloxKey, View],
     "mfvi_adamw_step": [_P, _P, _P, _P, _SZ, _F, _F, _F, _F, _F, _I, _P, _P],
     "mfvi_counter_add": [_P, _U32],
+    "mfvi_counter_add_if_finite": [_P, _U32, _P],
+    "mfvi_loss_flag": [_P, _P, _F, _P],
     "mfvi_bookkeep_step": [View, _I, _I, _I, _F, _P, _P, _P, _P, _P, _I, _P, _I, _P],
+    "mfvi_bookkeep_step_ex": [View, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P],
     "mfvi_ssim": [_P, _P, _I, _I, _I, _P],
     "mfvi_ring_uncertainty": [_P, _P, _I, _I, _I, _P, _P, _P, _P],
     "mfvi_softplus_sq_fwd": [_P, _SZ, _P],

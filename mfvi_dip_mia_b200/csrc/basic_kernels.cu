@@ -383,12 +383,12 @@ k_mse(const float* __restrict__ a, long long a_sstride, const float* __restrict_
 __global__ void __launch_bounds__(256)
 k_adamw(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n,
         float lr, float b1, float b2, float eps, float wd, int step, const uint32_t* __restrict__ step_dev,
-        const double* __restrict__ skip_if_nonfinite) {
+        const float* __restrict__ skip_if_nonfinite) {
   pdl_trigger();
   pdl_wait();
   if (skip_if_nonfinite != nullptr) {
-    const double l = *skip_if_nonfinite;
-    if (!(l == l) || l > 1.7e308 || l < -1.7e308) return;
+    const float l = *skip_if_nonfinite;
+    if (!(l == l) || fabsf(l) > 3.0e38f) return;
   }
   __shared__ float sm_bc[2];
   if (threadIdx.x == 0) {
@@ -495,10 +495,21 @@ k_input_jitter_pad(const float* __restrict__ saved, const float* __restrict__ no
   }
 }
 
-__global__ void k_counter_add(uint32_t* ctr, uint32_t inc) {
+__global__ void k_counter_add(uint32_t* ctr, uint32_t inc, const float* __restrict__ only_if_finite) {
   pdl_trigger();
   pdl_wait();
+  if (only_if_finite != nullptr) {
+    const float l = *only_if_finite;
+    if (!(l == l) || fabsf(l) > 3.0e38f) return;
+  }
   *ctr += inc;
+}
+
+// flag = (float)(data loss + temp * kl): the scalar the reference's NaN guard tests (bayesian_optimization.py:577,581)
+__global__ void k_loss_flag(const double* __restrict__ kl, const double* __restrict__ nll, float temp, float* __restrict__ flag) {
+  pdl_trigger();
+  pdl_wait();
+  *flag = static_cast<float>(*nll + static_cast<double>(temp) * *kl);
 }
 
 __global__ void k_fill(float* __restrict__ p, size_t n, float v) {
@@ -602,7 +613,7 @@ int mfvi_mse_fwd_bwd(const float* a, long long a_sstride, const float* b, size_t
 }
 
 int mfvi_adamw_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2,
-                    float eps, float weight_decay, int step, const uint32_t* step_dev, const double* skip_if_nonfinite,
+                    float eps, float weight_decay, int step, const uint32_t* step_dev, const float* skip_if_nonfinite,
                     mfvi_stream_t st) {
   MFVI_REQUIRE(p && g && m && v, "adamw: null pointer");
   MFVI_REQUIRE(step >= 1 || (step >= 0 && step_dev != nullptr), "adamw: step counts from 1");
@@ -615,8 +626,20 @@ int mfvi_adamw_step(float* p, const float* g, float* m, float* v, size_t n, floa
 
 int mfvi_counter_add(uint32_t* ctr, uint32_t inc, mfvi_stream_t st) {
   MFVI_REQUIRE(ctr != nullptr, "counter_add: null pointer");
-  launch_k(k_counter_add, 1, 1, 0, as_stream(st), ctr, inc);
+  launch_k(k_counter_add, 1, 1, 0, as_stream(st), ctr, inc, static_cast<const float*>(nullptr));
   return check_launch("counter_add");
+}
+
+int mfvi_counter_add_if_finite(uint32_t* ctr, uint32_t inc, const float* flag, mfvi_stream_t st) {
+  MFVI_REQUIRE(ctr != nullptr && flag != nullptr, "counter_add_if_finite: null pointer");
+  launch_k(k_counter_add, 1, 1, 0, as_stream(st), ctr, inc, flag);
+  return check_launch("counter_add_if_finite");
+}
+
+int mfvi_loss_flag(const double* kl, const double* nll, float temp, float* flag, mfvi_stream_t st) {
+  MFVI_REQUIRE(kl && nll && flag, "loss_flag: null pointer");
+  launch_k(k_loss_flag, 1, 1, 0, as_stream(st), kl, nll, temp, flag);
+  return check_launch("loss_flag");
 }
 
 int mfvi_input_jitter_pad(const float* saved, const float* noise, int H, int W, int C, float stdv, int pad,

@@ -28,54 +28,63 @@ __device__ __forceinline__ void block_atomic_add(double* __restrict__ dst, doubl
   }
 }
 
-// One pixel per thread (grid-stride).  cur_mean = mean_s out[s,p,0]; cur_var = mean_s exp(-out[s,p,1]).
+// One pixel per thread (grid-stride).  Cm image channels (1: denoising / SR / CT, 3: inpainting), optionally squashed by a
+// sigmoid (inpainting: out[:, :3].sigmoid(), bayesian_optimization.py:3034) and optionally followed by the channel
+// s = -log sigma^2 whose exp(-s) is the aleatoric variance (:1375; the CT net has no such channel, :533).
+//   cur_c = mean_s f(out[s,p,c]);  cur_var = mean_s exp(-out[s,p,Cm])
+// Layouts: gt / noisy (Cm,H,W); mask (H,W) or NULL; out_avg (Cm [+1],H,W); ring_epi (Cm,R,H,W); ring_ale (R,H,W).
+// `mask` (inpainting, :3064-3065) multiplies BOTH images of the gt comparisons acc[1], acc[2].
+constexpr int kBkSigmoid = 1, kBkAleatoric = 2;
+
 __global__ void __launch_bounds__(256)
-k_bookkeep(MfviView out, int S, int HW, int W, float exp_weight, const float* __restrict__ gt,
-           const float* __restrict__ noisy, float* __restrict__ out_avg, float* __restrict__ ring_epi,
-           float* __restrict__ ring_ale, int R, const uint32_t* __restrict__ iter_dev, int iter_offset,
-           double* __restrict__ acc) {
+k_bookkeep(MfviView out, int S, int HW, int W, int Cm, int flags, float exp_weight, const float* __restrict__ gt,
+           const float* __restrict__ noisy, const float* __restrict__ mask, float* __restrict__ out_avg,
+           float* __restrict__ ring_epi, float* __restrict__ ring_ale, int R, const uint32_t* __restrict__ iter_dev,
+           int iter_offset, double* __restrict__ acc) {
   pdl_trigger();
   pdl_wait();
   const int it = iter_offset + (iter_dev != nullptr ? static_cast<int>(*iter_dev) : 0);
   const int slot = R > 0 ? it % R : 0;
   const float inv_s = 1.f / static_cast<float>(S);
+  const bool sig = flags & kBkSigmoid, ale = flags & kBkAleatoric;
   double a[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
     const int h = p / W, w = p - h * W;
-    float m = 0.f, v = 0.f;
+    float m[3] = {0.f, 0.f, 0.f}, v = 0.f;
     for (int s = 0; s < S; ++s) {
-      const float2 o = *reinterpret_cast<const float2*>(out.ptr + view_off(out, s, h, w));
-      m += o.x;
-      v += expf(-o.y);                                           // aleatoric variance (:1375)
+      const float* o = out.ptr + view_off(out, s, h, w);
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        if (c < Cm) m[c] += sig ? 1.f / (1.f + expf(-o[c])) : o[c];
+      if (ale) v += expf(-o[Cm]);                                // aleatoric variance (:1375)
     }
-    m *= inv_s;
-    v *= inv_s;
-    float am, av;
-    if (it == 0) {                                               // out_avg = out (:1378-1379)
-      am = m;
-      av = v;
-    } else {                                                     // out_avg*w + out*(1-w) (:1381)
-      am = out_avg[p] * exp_weight + m * (1.f - exp_weight);
-      av = out_avg[HW + p] * exp_weight + v * (1.f - exp_weight);
+    const float mk = mask != nullptr ? mask[p] : 1.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (c >= Cm) break;
+      const float mc_raw = m[c] * inv_s;
+      const size_t q = static_cast<size_t>(c) * HW + p;
+      const float am = it == 0 ? mc_raw : out_avg[q] * exp_weight + mc_raw * (1.f - exp_weight);   // (:1378-1381)
+      out_avg[q] = am;
+      const float mc = clip01(mc_raw), amc = clip01(am);
+      if (R > 0) ring_epi[(static_cast<size_t>(c) * R + slot) * HW + p] = mc;                      // (:1396)
+      if (noisy != nullptr) {
+        const float t = noisy[q];
+        a[0] += static_cast<double>((t - mc) * (t - mc));          // PSNR_noisy / psnr_corrupted
+        a[3] += static_cast<double>((t - am) * (t - am));          // mse_corrupted (unclipped, :1388)
+      }
+      if (gt != nullptr) {
+        const float t = gt[q];
+        a[1] += static_cast<double>((t * mk - mc * mk) * (t * mk - mc * mk));      // PSNR_gt
+        a[2] += static_cast<double>((t * mk - amc * mk) * (t * mk - amc * mk));    // PSNR_gt_sm
+        a[4] += static_cast<double>((t - am) * (t - am));          // mse_gt (:1389)
+      }
     }
-    out_avg[p] = am;
-    out_avg[HW + p] = av;
-    const float mc = clip01(m);
-    if (R > 0) {
-      ring_epi[static_cast<size_t>(slot) * HW + p] = mc;         // (:1396-1397)
-      ring_ale[static_cast<size_t>(slot) * HW + p] = clip01(v);
-    }
-    const float amc = clip01(am);
-    if (noisy != nullptr) {
-      const float t = noisy[p];
-      a[0] += static_cast<double>((t - mc) * (t - mc));          // PSNR_noisy
-      a[3] += static_cast<double>((t - am) * (t - am));          // mse_corrupted (unclipped, :1388)
-    }
-    if (gt != nullptr) {
-      const float t = gt[p];
-      a[1] += static_cast<double>((t - mc) * (t - mc));          // PSNR_gt
-      a[2] += static_cast<double>((t - amc) * (t - amc));        // PSNR_gt_sm
-      a[4] += static_cast<double>((t - am) * (t - am));          // mse_gt (:1389)
+    if (ale) {
+      v *= inv_s;
+      const size_t q = static_cast<size_t>(Cm) * HW + p;
+      out_avg[q] = it == 0 ? v : out_avg[q] * exp_weight + v * (1.f - exp_weight);
+      if (R > 0) ring_ale[static_cast<size_t>(slot) * HW + p] = clip01(v);                         // (:1397)
     }
   }
   block_atomic_add(acc, a, 5);
@@ -188,17 +197,23 @@ using namespace mfvi;
 
 extern "C" {
 
+int mfvi_bookkeep_step_ex(MfviView out, int S, int H, int W, int Cm, int flags, float exp_weight, const float* gt,
+                          const float* noisy, const float* mask, float* out_avg, float* ring_epi, float* ring_ale, int ring,
+                          const uint32_t* iter_dev, int iter_offset, double* acc, mfvi_stream_t st) {
+  MFVI_REQUIRE(out.ptr && out_avg && acc, "bookkeep_step: null pointer");
+  MFVI_REQUIRE(S >= 1 && H >= 1 && W >= 1, "bookkeep_step: empty output");
+  MFVI_REQUIRE(Cm == 1 || Cm == 3, "bookkeep_step: 1 or 3 image channels");
+  MFVI_REQUIRE(ring == 0 || (ring_epi && (ring_ale || !(flags & kBkAleatoric))), "bookkeep_step: ring buffers missing");
+  launch_k(k_bookkeep, grid_1d((size_t)H * W, 256), 256, 0, as_stream(st), out, S, H * W, W, Cm, flags, exp_weight, gt, noisy, mask,
+           out_avg, ring_epi, ring_ale, ring, iter_dev, iter_offset, acc);
+  return check_launch("bookkeep_step");
+}
+
 int mfvi_bookkeep_step(MfviView out, int S, int H, int W, float exp_weight, const float* gt, const float* noisy,
                        float* out_avg, float* ring_epi, float* ring_ale, int ring, const uint32_t* iter_dev,
                        int iter_offset, double* acc, mfvi_stream_t st) {
-  MFVI_REQUIRE(out.ptr && out_avg && acc, "bookkeep_step: null pointer");
-  MFVI_REQUIRE(S >= 1 && H >= 1 && W >= 1, "bookkeep_step: empty output");
-  MFVI_REQUIRE(ring == 0 || (ring_epi && ring_ale), "bookkeep_step: ring buffers missing");
-  MFVI_REQUIRE(reinterpret_cast<uintptr_t>(out.ptr) % 8 == 0 && out.wstride % 2 == 0 && out.hstride % 2 == 0 &&
-               out.sstride % 2 == 0, "bookkeep_step: output view must be 8-byte aligned (channel pairs)");
-  launch_k(k_bookkeep, grid_1d((size_t)H * W, 256), 256, 0, as_stream(st), out, S, H * W, W, exp_weight, gt, noisy, out_avg,
-           ring_epi, ring_ale, ring, iter_dev, iter_offset, acc);
-  return check_launch("bookkeep_step");
+  return mfvi_bookkeep_step_ex(out, S, H, W, 1, kBkAleatoric, exp_weight, gt, noisy, nullptr, out_avg, ring_epi, ring_ale, ring,
+                               iter_dev, iter_offset, acc, st);
 }
 
 int mfvi_ssim(const float* a, const float* b, int H, int W, int clip_b, double* out_sum, mfvi_stream_t st) {

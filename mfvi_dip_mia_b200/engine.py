@@ -212,7 +212,9 @@ class SkipEngine:
         self.n_theta = 2 * Pp + 2 * Q
         self.n_theta_pad = (self.n_theta + 3) // 4 * 4
         self.theta = torch.zeros(self.n_theta_pad, **f32)
-        self.grad = torch.zeros(self.n_theta_pad, **f32)
+        # 4 floats beyond the parameters: [0] = the step's loss (NaN-guard flag), all-reduced together with the gradient
+        self.grad_buf = torch.zeros(self.n_theta_pad + 4, **f32)
+        self.grad = self.grad_buf[:self.n_theta_pad]
         self.mu, self.rho = self.theta[:P], self.theta[Pp:Pp + P]
         self.gamma, self.beta = self.theta[2 * Pp:2 * Pp + Q], self.theta[2 * Pp + Q:2 * Pp + 2 * Q]
         self.g_mu, self.g_rho = self.grad[:P], self.grad[Pp:Pp + P]

@@ -23,23 +23,31 @@ import torch
 
 
 class DeviceBookkeeping:
-    """Per-iteration bookkeeping of the runners (reference bayesian_optimization.py:1374-1416) as ONE kernel per
-    iteration, registered as a post-step hook of the trainer so that it is replayed inside the step's CUDA graph; the
-    iteration index comes from the trainer's device-side step counter.  Nothing is read back until `metrics()`."""
+    """Per-iteration bookkeeping of the runners (reference bayesian_optimization.py:1374-1416; SR :2190-2222, inpainting
+    :3041-3069, CT :583-610) as ONE kernel per iteration, registered as a post-step hook of the trainer so that it is replayed
+    inside the step's CUDA graph; the iteration index comes from the trainer's device-side step counter.  Nothing is read back
+    until `metrics()`.
+
+    `channels` = image channels of the network output (1; 3 for inpainting), `sigmoid` squashes them (inpainting),
+    `aleatoric` = the output carries s = -log sigma^2 behind them (False for CT), `mask` (H,W) multiplies both images of the
+    ground-truth comparisons (inpainting).  gt / noisy: (channels,H,W)."""
 
     N_ACC = 8
 
-    def __init__(self, trainer, gt=None, noisy=None, exp_weight: float = 0.99, ring: int = 25):
+    def __init__(self, trainer, gt=None, noisy=None, exp_weight: float = 0.99, ring: int = 25, *, channels: int = 1,
+                 sigmoid: bool = False, aleatoric: bool = True, mask=None):
         from . import _lib as L
         self.L, self.tr = L, trainer
         e = trainer.eng
         self.S, self.H, self.W, _ = e.out.shape
         dev = e.device
-        f = lambda t: None if t is None else torch.as_tensor(t, dtype=torch.float32).reshape(self.H, self.W).to(dev).contiguous()
-        self.gt, self.noisy = f(gt), f(noisy)
+        self.Cm, self.flags = int(channels), (1 if sigmoid else 0) | (2 if aleatoric else 0)
+        self.aleatoric = aleatoric
+        f = lambda t, c: None if t is None else torch.as_tensor(t, dtype=torch.float32).reshape(c, self.H, self.W).to(dev).contiguous()
+        self.gt, self.noisy, self.mask = f(gt, self.Cm), f(noisy, self.Cm), f(mask, 1)
         self.exp_weight, self.ring = float(exp_weight), int(ring)
-        self.out_avg = torch.zeros(2, self.H, self.W, device=dev)
-        self.ring_epi = torch.zeros(max(ring, 1), self.H, self.W, device=dev)
+        self.out_avg = torch.zeros(self.Cm + (1 if aleatoric else 0), self.H, self.W, device=dev)
+        self.ring_epi = torch.zeros(self.Cm, max(ring, 1), self.H, self.W, device=dev)
         self.ring_ale = torch.zeros(max(ring, 1), self.H, self.W, device=dev)
         self.acc = torch.zeros(self.N_ACC, dtype=torch.float64, device=dev)     # [0..4] squared errors, [5..6] SSIM sums
         trainer.post_step_hooks.append(self.record)
@@ -49,17 +57,22 @@ class DeviceBookkeeping:
         advances; asynchronous)."""
         L, e = self.L, self.tr.eng
         L.call("mfvi_fill_f32", self.acc.data_ptr(), 2 * self.N_ACC, 0.0)
-        L.call("mfvi_bookkeep_step", L.view(e.out), self.S, self.H, self.W, self.exp_weight, L.ptr(self.gt),
-               L.ptr(self.noisy), self.out_avg.data_ptr(), self.ring_epi.data_ptr(), self.ring_ale.data_ptr(), self.ring,
-               self.tr.step_dev.data_ptr(), 0, self.acc.data_ptr(),
-               meta={"bytes": 4.0 * self.H * self.W * (2 * self.S + 8)})
+        L.call("mfvi_bookkeep_step_ex", L.view(e.out), self.S, self.H, self.W, self.Cm, self.flags, self.exp_weight,
+               L.ptr(self.gt), L.ptr(self.noisy), L.ptr(self.mask), self.out_avg.data_ptr(), self.ring_epi.data_ptr(),
+               self.ring_ale.data_ptr(), self.ring, self.tr.step_dev.data_ptr(), 0, self.acc.data_ptr(),
+               meta={"bytes": 4.0 * self.H * self.W * ((self.Cm + 1) * self.S + 8 * self.Cm)})
 
     def metrics(self, ssim: bool = True) -> Dict[str, float]:
         """PSNR / MSE / SSIM of the last recorded iteration (one synchronising read of 8 doubles)."""
         L = self.L
-        n = self.H * self.W
+        n = self.Cm * self.H * self.W
         if ssim and self.gt is not None:
-            L.call("mfvi_ssim", self.gt.data_ptr(), self.out_avg.data_ptr(), self.H, self.W, 1, self.acc[5:].data_ptr())
+            L.call("mfvi_fill_f32", self.acc[5:].data_ptr(), 2 * (self.N_ACC - 5), 0.0)     # mfvi_ssim accumulates
+            a_img, b_img = self.gt, self.out_avg[:self.Cm]
+            if self.mask is not None:            # inpainting compares img*mask with clip(out_avg)*mask (:3065, :3068)
+                a_img, b_img = (a_img * self.mask).contiguous(), (b_img.clamp(0, 1) * self.mask).contiguous()
+            for c in range(self.Cm):             # the window is per channel; equal-sized planes => mean over channels
+                L.call("mfvi_ssim", a_img[c].data_ptr(), b_img[c].data_ptr(), self.H, self.W, 1, self.acc[5:].data_ptr())
         a = self.acc.cpu().tolist()
         psnr = lambda sse: 10.0 * math.log10(n / sse) if sse > 0 else float("inf")
         m = {"mse_corrupted": a[3] / n, "mse_gt": a[4] / n}
@@ -72,13 +85,21 @@ class DeviceBookkeeping:
         return m
 
     def uncertainty(self, n_valid: Optional[int] = None):
-        """(epistemic, aleatoric, err2) maps from the ring buffers (:1410-1411); err2 is None without a ground truth."""
+        """(epistemic, aleatoric, err2) maps from the ring buffers (:1410-1411), each (channels,H,W) — (H,W) for one channel;
+        err2 is None without a ground truth, aleatoric is zero for a net without the s channel."""
         L = self.L
         n = min(self.tr.steps_done, self.ring) if n_valid is None else n_valid
-        epi, ale = torch.empty_like(self.out_avg[0]), torch.empty_like(self.out_avg[0])
+        epi = torch.empty(self.Cm, self.H, self.W, device=self.out_avg.device)
+        ale = torch.zeros_like(epi)
         err2 = torch.empty_like(epi) if self.gt is not None else None
-        L.call("mfvi_ring_uncertainty", self.ring_epi.data_ptr(), self.ring_ale.data_ptr(), max(n, 1), self.H, self.W,
-               L.ptr(self.gt), epi.data_ptr(), ale.data_ptr(), L.ptr(err2))
+        for c in range(self.Cm):
+            L.call("mfvi_ring_uncertainty", self.ring_epi[c].data_ptr(), self.ring_ale.data_ptr(), max(n, 1), self.H, self.W,
+                   None if self.gt is None else self.gt[c].data_ptr(), epi[c].data_ptr(), ale[c].data_ptr(),
+                   None if err2 is None else err2[c].data_ptr())
+        if not self.aleatoric:
+            ale.zero_()
+        if self.Cm == 1:
+            return epi[0], ale[0], (None if err2 is None else err2[0])
         return epi, ale, err2
 
     def uce(self, n_bins: int = 15) -> float:
@@ -89,14 +110,43 @@ class DeviceBookkeeping:
         return float(uceloss(err2.reshape(-1), (epi + ale).reshape(-1), n_bins=n_bins)[0])
 
 
+def _run_loop(tr, bk, num_iter: int, show_every: int, return_history: bool):
+    """The runners' loop (:1359-1422): num_iter + 1 iterations (:1287) of hot loop + device bookkeeping, metrics read back every
+    `show_every`; returns the BO objective psnr_gt_sm of the last iteration (:1444)."""
+    n_steps = num_iter + 1
+    hist: Dict[str, list] = {"it": [], "psnr_noisy": [], "psnr_gt": [], "psnr_gt_sm": [], "ssim_gt_sm": [], "loss": []}
+    for i in range(n_steps):
+        tr.step()                                 # hot loop + bookkeeping kernel, no host synchronisation
+        if i % show_every == 0 or i == n_steps - 1:
+            m = bk.metrics()
+            hist["it"].append(i)
+            hist["loss"].append(tr.loss_terms()[2])
+            for k in ("psnr_noisy", "psnr_gt", "psnr_gt_sm", "ssim_gt_sm"):
+                hist[k].append(m.get(k, float("nan")))
+    psnr_gt_sm = hist["psnr_gt_sm"][-1]
+    if not return_history:
+        return psnr_gt_sm
+    epi, ale, _ = bk.uncertainty()
+    hist["epistemic"], hist["aleatoric"] = epi.cpu(), ale.cpu()
+    hist["uce"] = bk.uce()
+    hist["recon"] = bk.out_avg[:bk.Cm].clamp(0, 1).cpu()
+    return psnr_gt_sm, hist
+
+
+def _math(L, math_mode):
+    return L.MATH_TF32 if math_mode is None else math_mode
+
+
 def run_den_mfvi(img_gt: np.ndarray, *, temp: float, sigma: float, lr: float = 1e-3, num_iter: int = 100,
                  mc_samples: int = 1, p_sigma: float = 0.1, seed: int = 1, device="cuda:0", input_depth: int = 16,
                  reg_noise_std: float = 0.1, exp_weight: float = 0.99, mc_ring: int = 25, show_every: int = 100,
                  math_mode: Optional[int] = None, rank: int = 0, world_size: int = 1, process_group=None,
                  return_history: bool = False, spec=None, img_noisy: Optional[np.ndarray] = None):
-    """img_gt: (1,H,W) ground-truth image in [0,1] with H, W multiples of 32.  Returns psnr_gt_sm of the last
-    iteration (and, with return_history, a dict of the per-`show_every` metrics and the final uncertainty maps).
-    `spec` (a SkipSpec) overrides the runner's 5-scale net; `img_noisy` overrides the seeded noisy observation."""
+    """Denoising runner (reference run_den_mfvi, bayesian_optimization.py:1240-1444).  img_gt: (1,H,W) ground-truth image in
+    [0,1] with H, W multiples of 32.  Returns psnr_gt_sm of the last iteration (and, with return_history, a dict of the
+    per-`show_every` metrics and the final uncertainty maps).  `spec` (a SkipSpec) overrides the runner's 5-scale net;
+    `img_noisy` overrides the seeded noisy observation.  `math_mode` defaults to the tf32 tensor-core mode (the separately
+    stated reduced-precision mode); pass _lib.MATH_FP32 for reference arithmetic."""
     from . import MfviDipTrainer, SkipSpec, _lib as L
     from .utils.common_utils import get_noise
     dev = torch.device(device)
@@ -109,27 +159,96 @@ def run_den_mfvi(img_gt: np.ndarray, *, temp: float, sigma: float, lr: float = 1
     net_input = get_noise(spec.num_input_channels, 'noise', (H, W))
     tr = MfviDipTrainer(spec, "den", net_input, temp=temp, sigma=sigma, lr=lr, mc_samples=mc_samples,
                         seed=seed, reg_noise_std=reg_noise_std, device=dev, target=torch.from_numpy(img_noisy)[None],
-                        math_mode=L.MATH_TF32 if math_mode is None else math_mode, rank=rank, world_size=world_size,
-                        process_group=process_group)
+                        math_mode=_math(L, math_mode), rank=rank, world_size=world_size, process_group=process_group)
     bk = DeviceBookkeeping(tr, gt=img_gt, noisy=img_noisy, exp_weight=exp_weight, ring=mc_ring)
-    n_steps = num_iter + 1                       # the reference runs num_iter + 1 iterations (:1287)
-    hist: Dict[str, list] = {"it": [], "psnr_noisy": [], "psnr_gt": [], "psnr_gt_sm": [], "ssim_gt_sm": [], "loss": []}
-    for i in range(n_steps):
-        tr.step()                                 # hot loop + bookkeeping kernel, no host synchronisation
-        if i % show_every == 0 or i == n_steps - 1:
-            m = bk.metrics()
-            hist["it"].append(i)
-            hist["loss"].append(tr.loss_terms()[2])
-            for k in ("psnr_noisy", "psnr_gt", "psnr_gt_sm", "ssim_gt_sm"):
-                hist[k].append(m[k])
-    psnr_gt_sm = hist["psnr_gt_sm"][-1]
-    if not return_history:
-        return psnr_gt_sm
-    epi, ale, _ = bk.uncertainty()
-    hist["epistemic"], hist["aleatoric"] = epi.cpu(), ale.cpu()
-    hist["uce"] = bk.uce()
-    hist["recon"] = bk.out_avg[:1].clamp(0, 1).cpu()
-    return psnr_gt_sm, hist
+    return _run_loop(tr, bk, num_iter, show_every, return_history)
+
+
+def run_sr_mfvi(img_hr: np.ndarray, *, temp: float, sigma: float, factor: int = 4, lr: float = 1e-3, num_iter: int = 100,
+                mc_samples: int = 1, seed: int = 2, device="cuda:0", input_depth: int = 32, reg_noise_std: float = 0.1,
+                exp_weight: float = 0.99, mc_ring: int = 25, show_every: int = 100, math_mode: Optional[int] = None, rank: int = 0,
+                world_size: int = 1, process_group=None, return_history: bool = False, spec=None):
+    """4x super-resolution runner (reference run_sr_mfvi, bayesian_optimization.py:2048-2263): the low-resolution observation
+    is every `factor`-th pixel of img_hr (nearest, :2095-2102), the NLL is taken on the equally sub-sampled output (:2182-2185),
+    bookkeeping and the objective psnr_gt_sm on the full-resolution output (:2190-2222)."""
+    from . import MfviDipTrainer, SkipSpec, _lib as L
+    from .utils.common_utils import get_noise
+    dev = torch.device(device)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    H, W = img_hr.shape[-2:]
+    img_lr = np.ascontiguousarray(img_hr[..., ::factor, ::factor])
+    spec = spec or SkipSpec(input_depth, 2)
+    net_input = get_noise(spec.num_input_channels, 'noise', (H, W))
+    tr = MfviDipTrainer(spec, "sr", net_input, temp=temp, sigma=sigma, lr=lr, mc_samples=mc_samples, seed=seed,
+                        reg_noise_std=reg_noise_std, device=dev, target=torch.from_numpy(img_lr)[None], sr_factor=factor,
+                        math_mode=_math(L, math_mode), rank=rank, world_size=world_size, process_group=process_group)
+    bk = DeviceBookkeeping(tr, gt=img_hr, noisy=None, exp_weight=exp_weight, ring=mc_ring)
+    return _run_loop(tr, bk, num_iter, show_every, return_history)
+
+
+def run_inp_mfvi(img: np.ndarray, mask: np.ndarray, *, temp: float, sigma: float, lr: float = 2e-3, num_iter: int = 100,
+                 mc_samples: int = 1, seed: int = 2, device="cuda:0", input_depth: int = 16, reg_noise_std: float = 0.1,
+                 exp_weight: float = 0.99, mc_ring: int = 25, show_every: int = 100, math_mode: Optional[int] = None,
+                 rank: int = 0, world_size: int = 1, process_group=None, return_history: bool = False, spec=None):
+    """Inpainting runner (reference run_inp_mfvi, bayesian_optimization.py:2892-3114): img (3,H,W), mask (1,H,W) rounded to
+    {0,1} (:3024); 6-scale net with 5x5 down filters, no skip branches, no 1x1 up convs, nearest upsampling, 4 outputs
+    (:2970-2998); masked NLL on sigmoid(out[:, :3]) (:3033-3036); metrics on img*mask vs out*mask (:3064-3069)."""
+    from . import MfviDipTrainer, SkipSpec, _lib as L
+    from .utils.common_utils import get_noise
+    dev = torch.device(device)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    H, W = img.shape[-2:]
+    mask = np.round(mask).astype(np.float32)
+    spec = spec or SkipSpec(input_depth, 4, (16, 32, 64, 128, 128, 128), (16, 32, 64, 128, 128, 128), (0,) * 6, 5, 3, 1, False,
+                            False, "nearest")
+    net_input = get_noise(spec.num_input_channels, 'noise', (H, W))
+    tr = MfviDipTrainer(spec, "inp", net_input, temp=temp, sigma=sigma, lr=lr, mc_samples=mc_samples, seed=seed,
+                        reg_noise_std=reg_noise_std, device=dev, target=torch.from_numpy(img)[None],
+                        mask=torch.from_numpy(mask)[None], math_mode=_math(L, math_mode), rank=rank, world_size=world_size,
+                        process_group=process_group)
+    bk = DeviceBookkeeping(tr, gt=img, noisy=img, exp_weight=exp_weight, ring=mc_ring, channels=3, sigmoid=True, mask=mask)
+    return _run_loop(tr, bk, num_iter, show_every, return_history)
+
+
+def run_ct_mfvi(img_gt: np.ndarray, *, temp: float, sigma: float, theta_deg=None, lr: float = 1e-3, num_iter: int = 100,
+                mc_samples: int = 1, seed: int = 1, device="cuda:0", input_depth: int = 16, reg_noise_std: float = 0.1,
+                exp_weight: float = 0.99, mc_ring: int = 25, show_every: int = 100, math_mode: Optional[int] = None, rank: int = 0,
+                world_size: int = 1, process_group=None, return_history: bool = False, spec=None):
+    """Sparse-view CT runner (reference run_ct_mfvi, bayesian_optimization.py:442-648): img_gt (1,H,H); the observation is its
+    sinogram under FastRadonTransform at `theta_deg` (default arange(0,180,4) = 45 angles, :545-547); one output channel, plain
+    MSE in sinogram space (:533,576), AdamW skipped on a non-finite loss (:581-582)."""
+    from . import MfviDipTrainer, SkipSpec, _lib as L
+    from .radon import FastRadonTransform
+    from .utils.common_utils import get_noise
+    dev = torch.device(device)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    H, W = img_gt.shape[-2:]
+    theta = torch.arange(0, 180., step=4.) if theta_deg is None else torch.as_tensor(theta_deg, dtype=torch.float32)
+    img_t = torch.from_numpy(np.ascontiguousarray(img_gt))[None].to(dev)
+    sino = FastRadonTransform(tuple(img_t.shape), theta).to(dev)(img_t).detach()
+    spec = spec or SkipSpec(input_depth, 1)
+    net_input = get_noise(spec.num_input_channels, 'noise', (H, W))
+    tr = MfviDipTrainer(spec, "ct", net_input, temp=temp, sigma=sigma, lr=lr, mc_samples=mc_samples, seed=seed,
+                        reg_noise_std=reg_noise_std, device=dev, theta_deg=theta, sino=sino, math_mode=_math(L, math_mode),
+                        rank=rank, world_size=world_size, process_group=process_group)
+    bk = DeviceBookkeeping(tr, gt=img_gt, noisy=img_gt, exp_weight=exp_weight, ring=mc_ring, aleatoric=False)
+    return _run_loop(tr, bk, num_iter, show_every, return_history)
+
+
+RUNNERS = {"den": run_den_mfvi, "sr": run_sr_mfvi, "inp": run_inp_mfvi, "ct": run_ct_mfvi}
+_TASK_ALIASES = {"denoising": "den", "inpainting": "inp", "super-resolution": "sr", "ct": "ct", "den": "den", "sr": "sr", "inp": "inp"}
+
+
+def f(task: str, bayes: str, candidate: Sequence[float], device, params: dict) -> float:
+    """The reference's trial wrapper (bayesian_optimization.py:3709-3724): maps (task, bayes) to run_<task>_<bayes> and the
+    candidate to (temp, sigma).  Only bayes='mfvi' exists here (the other methods are the paper's baselines, out of scope)."""
+    if bayes != "mfvi":
+        raise ValueError(f"bayes={bayes!r}: only the MFVI runners are implemented")
+    run = RUNNERS[_TASK_ALIASES[task]]
+    return run(temp=candidate[0], sigma=candidate[1], device=device, **params)
 
 
 def _trial_entry(fn, kwargs, candidate, device, queue):

@@ -104,7 +104,9 @@ class MfviDipTrainer:
         e = self.eng
         self.saved = net_input[0].to(device, torch.float32).permute(1, 2, 0).contiguous()   # NHWC (H,W,C)
         self.noise = None                       # injected jitter normals (tests)
-        self.step_dev = torch.zeros(1, dtype=torch.int32, device=device)     # device-side step counter
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=device)     # device-side step counter (Philox key, bookkeeping)
+        # NaN guard (CT runner): AdamW's own step count, which — like torch's — does not advance on a skipped update
+        self.adam_dev = torch.zeros(1, dtype=torch.int32, device=device)
         self.m = torch.zeros_like(e.theta)
         self.v = torch.zeros_like(e.theta)
         self.losses = torch.zeros(2, dtype=torch.float64, device=device)
@@ -129,6 +131,7 @@ class MfviDipTrainer:
         self.m.zero_()
         self.v.zero_()
         self.step_dev.zero_()
+        self.adam_dev.zero_()
 
     def _keys(self):
         kw = L.key(self.seed, 0, self.sample0, self.step_dev)
@@ -146,12 +149,21 @@ class MfviDipTrainer:
         e.backward()
         e.reparam_kl(kw, prior_mu=self.prior_mu, prior_sigma_plus_eps=self.prior_sigma_plus_eps, direction=self.direction,
                      kscale=self.temp)
+        # NaN guard (reference :577-582 tests nll + temp*kl): this rank's loss goes into the tail slot of the gradient buffer,
+        # so after the all-reduce every rank tests the SAME value (NaN / Inf on any rank poisons the mean) and either all
+        # ranks apply the update or none does
+        flag = e.grad.data_ptr() + 4 * e.n_theta_pad
+        if self.nan_guard:
+            L.call("mfvi_loss_flag", e._aptr(KL), e._aptr(NLL), self.temp, flag)
         if self.world_size > 1:
-            allreduce_mean_(e.grad, self.pg)
+            allreduce_mean_(e.grad_buf if self.nan_guard else e.grad, self.pg)
         e.update_running_stats()
         L.call("mfvi_adamw_step", e.theta.data_ptr(), e.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                e.n_theta_pad, self.lr, self.betas[0], self.betas[1], self.adam_eps, self.weight_decay, 1,
-               self.step_dev.data_ptr(), e._aptr(NLL) if self.nan_guard else None, meta={"bytes": 28.0 * e.n_theta_pad})
+               (self.adam_dev if self.nan_guard else self.step_dev).data_ptr(), flag if self.nan_guard else None,
+               meta={"bytes": 28.0 * e.n_theta_pad})
+        if self.nan_guard:
+            L.call("mfvi_counter_add_if_finite", self.adam_dev.data_ptr(), 1, flag)
         for hook in self.post_step_hooks:      # e.g. runners.DeviceBookkeeping.record (captured into the graph)
             hook()
         L.call("mfvi_counter_add", self.step_dev.data_ptr(), 1)

@@ -105,7 +105,7 @@ def kl_elementwise(mu, rho, prior_mu: float, prior_sigma_plus_eps: float, kl_typ
 def kl_layers(params: Sequence[torch.Tensor], prior_mu, prior_sigma_plus_eps, kl_type="reverse"):
     """MeanFieldVI.kl (BayTorch/freq_to_bayes.py:43-48): sum over all layers of W and bias KL.
     `params` = flat sequence (mu0, rho0, mu1, rho1, ...). Returns shape-[1] tensor like the reference."""
-    total = torch.zeros(1, dtype=params[0].dtype)
+    total = torch.zeros(1, dtype=params[0].dtype, device=params[0].device)
     for mu, rho in zip(params[0::2], params[1::2]):
         total = total + kl_elementwise(mu, rho, prior_mu, prior_sigma_plus_eps, kl_type).sum()
     return total
@@ -345,10 +345,10 @@ def radon_forward(image: torch.Tensor, theta_deg: torch.Tensor) -> torch.Tensor:
     assert image.shape[0] == 1 and image.shape[2] == image.shape[3]
     _, C, H, W = image.shape
     dt = image.dtype
-    th = torch.deg2rad(theta_deg.to(dt))
+    th = torch.deg2rad(theta_deg.to(device=image.device, dtype=dt))
     ts, tc = torch.sin(th), torch.cos(th)
-    xs = (2 * torch.arange(W, dtype=dt) + 1) / W - 1
-    ys = (2 * torch.arange(H, dtype=dt) + 1) / H - 1
+    xs = (2 * torch.arange(W, dtype=dt, device=image.device) + 1) / W - 1
+    ys = (2 * torch.arange(H, dtype=dt, device=image.device) + 1) / H - 1
     gx = tc[:, None, None] * xs[None, None, :] - ts[:, None, None] * ys[None, :, None]   # (T,H,W)
     gy = ts[:, None, None] * xs[None, None, :] + tc[:, None, None] * ys[None, :, None]
     ix = ((gx + 1) * W - 1) / 2

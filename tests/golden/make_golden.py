@@ -395,6 +395,32 @@ def full_summary(task, size, S, fname, seed=1234):
     arrs["param_norms"] = np.array([float(dict(net.named_parameters())[k].double().norm()) for k in names])
     for k in names:
         arrs["grad/" + k] = grads[k].reshape(-1)[:1024]
+    # the same step by the reference in float64: the yardstick for both sides.  Per-sample BatchNorm over the small maps of the
+    # deep scales is badly conditioned, so the reference's OWN fp32 gradients are up to a few 1e-2 of a tensor's scale away from
+    # its fp64 run on the smallest tensors — `ref_err32` records that distance per tensor (same denominators as the test uses).
+    net.double()
+    extra64 = {k: (v.double() if isinstance(v, torch.Tensor) and v.is_floating_point() else v) for k, v in extra.items()}
+    if task == "ct":
+        extra64["radon"] = R["Radon"]((1, 1, size, size), theta).double()
+    eps64 = [{k: v.double() for k, v in e.items()} for e in eps_list]
+    loss64, nll64, kl64, outs64, grads64 = run_ref_step(net, cfg, lay, net_input.double(), eps64, task, temp, extra64)
+    gmax = max(float(grads64[k].abs().max()) for k in names)
+    ref_err = []
+    for k in names:
+        g64 = grads64[k].reshape(-1)[:1024]
+        arrs["grad64/" + k] = g64
+        den = max(float(grads64[k].abs().max()), 1e-3 * gmax)
+        if k.endswith("bias_mu") or k.endswith("bias_rho"):
+            wk = k.replace("bias_mu", "W_mu").replace("bias_rho", "W_rho")
+            den = max(den, 0.05 * float(grads64[wk].abs().max()))
+        ref_err.append(float((grads[k].reshape(-1)[:1024].double() - g64).abs().max()) / den)
+    arrs["ref_err32"] = np.array(ref_err)
+    arrs["grad64_absmax"] = np.array([float(grads64[k].abs().max()) for k in names])
+    arrs["nll64"], arrs["kl64"] = nll64, kl64
+    for i, o in enumerate(outs64):
+        arrs[f"out{i}_sub64"] = o[:, :, ::8, ::8]
+    print(f"  {fname}: reference fp32 vs fp64: worst tensor {max(ref_err):.2e} ({names[int(np.argmax(ref_err))].rsplit('.', 2)[-2:]}), "
+          f"median {float(np.median(ref_err)):.2e}")
     save(fname, **arrs)
 
 

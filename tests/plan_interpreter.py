@@ -21,7 +21,7 @@ class PlanInterpreter:
         self.eng = eng
         self.stores = []
         seen = set()
-        tensors = [eng.theta, eng.grad, eng.zbuf, eng.w, eng.dout, eng.running_mean, eng.running_var] + list(eng._bufs)
+        tensors = [eng.theta, eng.grad_buf, eng.zbuf, eng.w, eng.dout, eng.running_mean, eng.running_var] + list(eng._bufs)
         if eng.eps is not None:
             tensors.append(eng.eps)
         for t in tensors:
@@ -472,8 +472,8 @@ class TrainerInterpreter(PlanInterpreter):
     def op_adamw(self, name, args):
         p, g, m, v, n, lr, b1, b2, eps, wd, step, step_dev, skip_ptr = args
         if skip_ptr is not None:
-            l = float(self.vec(skip_ptr, 1, torch.float64)[0])
-            if l != l or abs(l) > 1.7e308:
+            l = float(self.vec(skip_ptr, 1)[0])
+            if l != l or abs(l) > 3.0e38:
                 return
         t = step + (int(self.vec(step_dev, 1, torch.int32)[0]) if step_dev is not None else 0)
         P, G, M, V = (self.vec(q, n) for q in (p, g, m, v))
@@ -486,6 +486,16 @@ class TrainerInterpreter(PlanInterpreter):
     def op_counter_add(self, name, args):
         ptr, inc = args
         self.vec(ptr, 1, torch.int32).add_(int(inc))
+
+    def op_counter_add_if_finite(self, name, args):
+        ptr, inc, flag = args
+        l = float(self.vec(flag, 1)[0])
+        if l == l and abs(l) <= 3.0e38:
+            self.vec(ptr, 1, torch.int32).add_(int(inc))
+
+    def op_loss_flag(self, name, args):
+        kl, nll, temp, flag = args
+        self.vec(flag, 1)[0] = float(self.vec(nll, 1, torch.float64)[0] + temp * self.vec(kl, 1, torch.float64)[0])
 
     # ------------------------------------------------------------------ CT head: radon projector + sinogram MSE
     def _theta_deg(self, theta_rad, T):
@@ -522,29 +532,37 @@ class TrainerInterpreter(PlanInterpreter):
     # ------------------------------------------------------------------ runner bookkeeping (csrc/bookkeeping.cu)
     def op_bookkeep_step(self, name, args):
         out, S, H, W, expw, gt, noisy, out_avg, ring_epi, ring_ale, R, iter_dev, iter_off, acc = args
+        return self.op_bookkeep_step_ex(name, (out, S, H, W, 1, 2, expw, gt, noisy, None, out_avg, ring_epi, ring_ale, R, iter_dev,
+                                               iter_off, acc))
+
+    def op_bookkeep_step_ex(self, name, args):
+        out, S, H, W, Cm, flags, expw, gt, noisy, mask, out_avg, ring_epi, ring_ale, R, iter_dev, iter_off, acc = args
         it = iter_off + (int(self.vec(iter_dev, 1, torch.int32)[0]) if iter_dev is not None else 0)
-        O_ = self.view(out, S, H, W, 2)
-        m, v = O_[..., 0].mean(0), torch.exp(-O_[..., 1]).mean(0)
-        AVG = self.vec(out_avg, 2 * H * W).view(2, H, W)
-        if it == 0:
-            AVG[0], AVG[1] = m, v
-        else:
-            AVG[0] = AVG[0] * expw + m * (1 - expw)
-            AVG[1] = AVG[1] * expw + v * (1 - expw)
+        sig, ale = bool(flags & 1), bool(flags & 2)
+        O_ = self.view(out, S, H, W, Cm + (1 if ale else 0))
+        img = O_[..., :Cm]
+        m = (torch.sigmoid(img) if sig else img).mean(0).permute(2, 0, 1)                # (Cm,H,W)
+        AVG = self.vec(out_avg, (Cm + (1 if ale else 0)) * H * W).view(-1, H, W)
+        AVG[:Cm] = m if it == 0 else AVG[:Cm] * expw + m * (1 - expw)
         mc = m.clamp(0, 1)
+        if ale:
+            v = torch.exp(-O_[..., Cm]).mean(0)
+            AVG[Cm] = v if it == 0 else AVG[Cm] * expw + v * (1 - expw)
         if R > 0:
-            self.vec(ring_epi, R * H * W).view(R, H, W)[it % R] = mc
-            self.vec(ring_ale, R * H * W).view(R, H, W)[it % R] = v.clamp(0, 1)
+            self.vec(ring_epi, Cm * R * H * W).view(Cm, R, H, W)[:, it % R] = mc
+            if ale:
+                self.vec(ring_ale, R * H * W).view(R, H, W)[it % R] = v.clamp(0, 1)
         A = self.vec(acc, 5, torch.float64)
-        am, amc = AVG[0], AVG[0].clamp(0, 1)
+        am, amc = AVG[:Cm], AVG[:Cm].clamp(0, 1)
+        mk = self.vec(mask, H * W).view(1, H, W) if mask is not None else 1.0
         if noisy is not None:
-            t = self.vec(noisy, H * W).view(H, W)
+            t = self.vec(noisy, Cm * H * W).view(Cm, H, W)
             A[0] += ((t - mc) ** 2).double().sum()
             A[3] += ((t - am) ** 2).double().sum()
         if gt is not None:
-            t = self.vec(gt, H * W).view(H, W)
-            A[1] += ((t - mc) ** 2).double().sum()
-            A[2] += ((t - amc) ** 2).double().sum()
+            t = self.vec(gt, Cm * H * W).view(Cm, H, W)
+            A[1] += ((t * mk - mc * mk) ** 2).double().sum()
+            A[2] += ((t * mk - amc * mk) ** 2).double().sum()
             A[4] += ((t - am) ** 2).double().sum()
 
     def op_ssim(self, name, args):
@@ -566,8 +584,9 @@ class TrainerInterpreter(PlanInterpreter):
             self.vec(err2, H * W).view(H, W).copy_(((RE - t) ** 2).mean(0))
 
     TRAINER_OPS = {"mfvi_radon_fwd": op_radon_fwd, "mfvi_radon_bwd": op_radon_bwd, "mfvi_mse_fwd_bwd": op_mse,
-                   "mfvi_bookkeep_step": op_bookkeep_step, "mfvi_ssim": op_ssim, "mfvi_ring_uncertainty": op_ring_uncertainty,
+                   "mfvi_bookkeep_step": op_bookkeep_step, "mfvi_bookkeep_step_ex": op_bookkeep_step_ex, "mfvi_ssim": op_ssim, "mfvi_ring_uncertainty": op_ring_uncertainty,
                    "mfvi_input_jitter_pad": op_input_jitter_pad, "mfvi_sample_weights": op_sample_weights,
                    "mfvi_gauss_nll_fwd_bwd": op_gauss_nll,
                    "mfvi_kl_reparam_fwd_bwd": op_kl_reparam, "mfvi_bn_running_update": op_bn_running_update,
-                   "mfvi_adamw_step": op_adamw, "mfvi_counter_add": op_counter_add}
+                   "mfvi_adamw_step": op_adamw, "mfvi_counter_add": op_counter_add,
+                   "mfvi_counter_add_if_finite": op_counter_add_if_finite, "mfvi_loss_flag": op_loss_flag}

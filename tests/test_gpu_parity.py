@@ -568,3 +568,129 @@ def test_den_final_metrics_match_reference_ensemble(dev, math):
     print(f"[ensemble {math}] ref   PSNR {mr[0]:.3f} SSIM {mr[1]:.4f} UCE {mr[2]:.4f}  (std {ref.std(0, ddof=1)})  se {se}")
     tol = np.array([0.1, 0.005, 0.005])
     assert np.all(np.abs(mo - mr) < tol + 3 * se), (mo, mr, se)
+
+
+# ----------------------------------------------------------------------------------------------- paired trajectories
+_PAIRED = dict(n_it=400, seeds=(31, 32, 33, 34, 35, 36), lr=1e-3)
+_paired_oracle_cache = {}
+
+
+def _paired_oracle_run(dev, seed, sd0, x, gt, tgt, n_it, lay_eng):
+    """The reference arithmetic (oracle port, PyTorch eager fp32 on the GPU, TF32 off) driven by the SAME Philox streams the
+    engine draws (weights eps keyed by step / sample, input jitter): returns (psnr_gt_sm, ssim_gt_sm, uce) after n_it steps."""
+    if seed in _paired_oracle_cache:
+        return _paired_oracle_cache[seed]
+    cfg = SMALL["den"]
+    H, W, Cn = x.shape[2], x.shape[3], x.shape[1]
+    temp, sigma, lr = _TRAJ["temp"], _TRAJ["sigma"], _PAIRED["lr"]
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        names = [k for k, v in sd0.items() if v.is_floating_point() and "running" not in k]
+        leaves = {k: sd0[k].clone().to(dev).requires_grad_(True) for k in names}
+        full = {k: v.to(dev) for k, v in sd0.items()}
+        full.update(leaves)
+        opt = torch.optim.AdamW(list(leaves.values()), lr=lr, weight_decay=0)
+        upd, met, _ = _host_bookkeeping(gt, _TRAJ["ring"])
+        xd, tg = x.to(dev), tgt.to(dev)
+        for it in range(n_it):
+            opt.zero_grad()
+            z = torch.from_numpy(philox.philox_normal(Cn * H * W, seed, 1, 0, it)).reshape(1, Cn, H, W).to(dev)
+            eps = [{k: v.to(dev) for k, v in e.items()} for e in _oracle_eps_from_stream(lay_eng, seed, it, 1)]
+            loss, _, _, outs = O.mfvi_loss(full, cfg, xd + 0.1 * z, eps, task="den", temp=temp,
+                                           prior_sigma_plus_eps=O.prior_scale(temp, sigma), target=tg)
+            loss.backward()
+            opt.step()
+            upd(outs[0].detach().cpu())
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    _paired_oracle_cache[seed] = met()
+    return _paired_oracle_cache[seed]
+
+
+@pytest.mark.parametrize("math", ["tf32", "fp32"])
+def test_den_paired_trajectories_match_reference_arithmetic(dev, math):
+    """north_star's final-metric bar (PSNR / SSIM / UCE within 0.1 dB / 0.005 / 0.005) as a PAIRED comparison: for every seed the
+    engine and the reference arithmetic (oracle port in eager fp32 on the same GPU) run 400 optimiser steps on identical
+    Philox streams at the denoising configuration's own learning rate (test_configs/mfvi_den.json: 1e-3), where trajectories
+    stay together.  Paired differences have a standard error of a few 0.001 dB, so the bar is enforced on the mean difference
+    WITHOUT an allowance, and every single pair has to stay within 3x the bar."""
+    from mfvi_dip_mia_b200 import MfviDipTrainer, _lib as L
+    from mfvi_dip_mia_b200.runners import DeviceBookkeeping
+    from mfvi_dip_mia_b200.utils.phantoms import ellipse_phantom, noisy
+    cfg = SMALL["den"]
+    H = W = _TRAJ["H"]
+    n_it, lr = _PAIRED["n_it"], _PAIRED["lr"]
+    gt = torch.from_numpy(ellipse_phantom(H))[None]
+    tgt = torch.from_numpy(noisy(ellipse_phantom(H), 0.1, 1))[None]
+    diffs = []
+    for seed in _PAIRED["seeds"]:
+        g = torch.Generator().manual_seed(seed)
+        x = torch.rand(1, cfg.num_input_channels, H, W, generator=g) * 0.1
+        tr = MfviDipTrainer(spec_of(cfg), "den", x, temp=_TRAJ["temp"], sigma=_TRAJ["sigma"], lr=lr, mc_samples=1, seed=seed,
+                            device=dev, target=tgt, math_mode=L.MATH_TF32 if math == "tf32" else L.MATH_FP32, use_graph=True)
+        bk = DeviceBookkeeping(tr, gt=gt, noisy=tgt, ring=_TRAJ["ring"])
+        sd0 = {"net." + k: v.detach().cpu().clone() for k, v in tr.eng.param_views("theta").items()}
+        for _ in range(n_it):
+            tr.step()
+        m = bk.metrics()
+        ours = np.array([m["psnr_gt_sm"], m["ssim_gt_sm"], bk.uce()])
+        ref = np.array(_paired_oracle_run(dev, seed, sd0, x, gt, tgt, n_it, tr.eng))
+        diffs.append(ours - ref)
+        print(f"[paired {math} seed {seed}] PSNR {ours[0]:.4f} / {ref[0]:.4f}  SSIM {ours[1]:.5f} / {ref[1]:.5f}  "
+              f"UCE {ours[2]:.5f} / {ref[2]:.5f}  (engine / reference arithmetic)")
+    diffs = np.array(diffs)
+    tol = np.array([0.1, 0.005, 0.005])
+    mean, se = diffs.mean(0), diffs.std(0, ddof=1) / np.sqrt(len(diffs))
+    print(f"[paired {math}] mean difference {mean}  standard error {se}  worst pair {np.abs(diffs).max(0)}")
+    assert np.all(np.abs(mean) < tol), (mean, se)
+    assert np.all(np.abs(diffs).max(0) < 3 * tol), np.abs(diffs).max(0)
+
+
+@pytest.mark.parametrize("variant", ["inp", "ct"])
+def test_bookkeeping_kernel_other_runners(dev, variant):
+    """mfvi_bookkeep_step_ex for the inpainting (3 sigmoid channels + s, masked gt comparisons: reference
+    bayesian_optimization.py:3041-3069) and CT (one channel, no aleatoric channel: :583-610) runners against the reference's
+    per-iteration formulas written with torch, over 9 iterations (ring of 4 wraps twice), S=2."""
+    from mfvi_dip_mia_b200 import _lib as L
+    S, H, W, ring, expw = 2, 24, 40, 4, 0.99
+    Cm, sig, ale = (3, True, True) if variant == "inp" else (1, False, False)
+    g = torch.Generator().manual_seed(9)
+    gt = torch.rand(Cm, H, W, generator=g)
+    noisy_t = gt.clone() if variant == "inp" else (gt + 0.05 * torch.randn(Cm, H, W, generator=g))
+    mask = (torch.rand(1, H, W, generator=g) < 0.6).float() if variant == "inp" else None
+    Ctot = Cm + (1 if ale else 0)
+    out_avg = torch.zeros(Ctot, H, W, device=dev)
+    r_epi, r_ale = torch.zeros(Cm, ring, H, W, device=dev), torch.zeros(ring, H, W, device=dev)
+    acc = torch.zeros(8, dtype=torch.float64, device=dev)
+    it_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+    gt_d, no_d = gt.to(dev).contiguous(), noisy_t.to(dev).contiguous()
+    mk_d = None if mask is None else mask.to(dev).contiguous()
+    avg_ref, ring_e, ring_a = None, torch.zeros(Cm, ring, H, W), torch.zeros(ring, H, W)
+    for it in range(9):
+        out = torch.randn(S, H, W, Ctot, generator=g) * 0.7 + 0.3
+        o = torch.zeros(S, H, W, 4, device=dev)                          # channel pitch 4 like the engine's output buffer
+        o[..., :Ctot] = out.to(dev)
+        acc.zero_()
+        L.call("mfvi_bookkeep_step_ex", L.view(o), S, H, W, Cm, (1 if sig else 0) | (2 if ale else 0), expw, gt_d.data_ptr(),
+               no_d.data_ptr(), L.ptr(mk_d), out_avg.data_ptr(), r_epi.data_ptr(), r_ale.data_ptr(), ring, it_dev.data_ptr(), 0,
+               acc.data_ptr())
+        L.call("mfvi_counter_add", it_dev.data_ptr(), 1)
+        img = out[..., :Cm]
+        cur = (torch.sigmoid(img) if sig else img).mean(0).permute(2, 0, 1)
+        parts = [cur] + ([torch.exp(-out[..., Cm]).mean(0)[None]] if ale else [])
+        cur_all = torch.cat(parts)
+        avg_ref = cur_all.clone() if avg_ref is None else avg_ref * expw + cur_all * (1 - expw)
+        ring_e[:, it % ring] = cur.clamp(0, 1)
+        if ale:
+            ring_a[it % ring] = cur_all[Cm].clamp(0, 1)
+    assert rel_err(out_avg.cpu(), avg_ref) < 1e-5
+    assert rel_err(r_epi.cpu(), ring_e) < 1e-6 and (not ale or rel_err(r_ale.cpu(), ring_a) < 1e-5)
+    a = acc.cpu().numpy()
+    mk = mask if mask is not None else torch.ones(1, H, W)
+    mc, am, amc = cur.clamp(0, 1), avg_ref[:Cm], avg_ref[:Cm].clamp(0, 1)
+    ref = [((noisy_t - mc) ** 2).sum(), ((gt * mk - mc * mk) ** 2).sum(), ((gt * mk - amc * mk) ** 2).sum(),
+           ((noisy_t - am) ** 2).sum(), ((gt - am) ** 2).sum()]
+    for k in range(5):
+        assert abs(a[k] - float(ref[k])) < 1e-4 * max(1.0, float(ref[k])), (k, a[k], float(ref[k]))

@@ -74,13 +74,18 @@ def test_tc_conv_broadcast_input(shape, S):
         assert rel_err(a, b) < TF32_TOL, (shape, S, n, rel_err(a, b))
 
 
-@pytest.mark.parametrize("task", ["den", "inp"])
+# whole-step bars of the tf32 mode on the four small task nets: ~2x the errors measured on a B200 (printed by the test,
+# profiles/r02_parity_errors.txt).  (output, nll, whole-gradient relative L2, cosine, worst per-tensor normalised max error)
+TF32_STEP_BARS = {"den": (1e-2, 2e-3, 3e-2, 0.9995, 0.25), "sr": (1e-2, 2e-3, 3e-2, 0.9995, 0.25),
+                  "ct": (1e-2, 2e-3, 3e-2, 0.9995, 0.25), "inp": (1e-2, 2e-3, 3e-2, 0.9995, 0.25)}
+
+
+@pytest.mark.parametrize("task", ["den", "sr", "ct", "inp"])
 def test_tf32_engine_step_close_to_reference(task):
-    """Whole step in TF32 mode against the reference fixture.  This is the separately stated reduced-precision mode
-    (10-bit operand mantissa, truncated by the tensor core; fp32 accumulate): output within 1e-2, loss terms within
-    2e-3, whole gradient within 3e-2 relative L2 / cosine > 0.9995 (observed: 3e-3, 2e-4, 0.4-1.6e-2, 0.9999).
-    Individual small tensors (BatchNorm biases, 1x1 skip convs) are off by up to ~0.2 of their own max through
-    cancellation in the BN backward; the fp32 mode (test_gpu_parity.py) is the one held to rtol 1e-3."""
+    """Whole step in TF32 mode against the reference fixture, all four tasks.  This is the separately stated
+    reduced-precision mode (10-bit operand mantissa, truncated by the tensor core; fp32 accumulate).  Individual small
+    tensors (BatchNorm biases, 1x1 skip convs) carry the largest relative error through cancellation in the BN backward;
+    the fp32 mode (test_gpu_parity.py) is the one held to rtol 1e-3."""
     from mfvi_dip_mia_b200 import SkipEngine, _lib as L
     from mfvi_dip_mia_b200.engine import KL, NLL
     from mfvi_dip_mia_b200.trainer import LossHead
@@ -103,15 +108,19 @@ def test_tf32_engine_step_close_to_reference(task):
     eng.backward()
     eng.reparam_kl(L.key(0), prior_mu=0.0, prior_sigma_plus_eps=O.prior_scale(temp, sigma), direction=0, kscale=temp)
     out = eng.out_nchw().cpu()
-    for s in range(S):
-        assert rel_err(out[s:s + 1], d[f"out{s}"]) < 1e-2, s
+    b_out, b_nll, b_l2, b_cos, b_tensor = TF32_STEP_BARS[task]
+    e_out = max(rel_err(out[s:s + 1], d[f"out{s}"]) for s in range(S))
     a = eng.arena[:2].cpu()
-    assert rel_err(a[NLL], d["nll"]) < 2e-3
+    e_nll = rel_err(a[NLL], d["nll"])
     ours = {"net." + k: v.cpu() for k, v in eng.param_views("grad").items()}
     va = torch.cat([ours[k].double().reshape(-1) for k in grads])
     vb = torch.cat([grads[k].double().reshape(-1) for k in grads])
-    assert float((va - vb).norm() / vb.norm()) < 3e-2
-    assert float((va @ vb) / (va.norm() * vb.norm())) > 0.9995
+    e_l2 = float((va - vb).norm() / vb.norm())
+    cos = float((va @ vb) / (va.norm() * vb.norm()))
     errs = grad_errs({k: ours[k] for k in grads}, grads)
     worst = max(errs, key=errs.get)
-    assert errs[worst] < 0.5, (worst, errs[worst])
+    print(f"[parity small {task} tf32] out {e_out:.2e}  nll {e_nll:.2e}  grad relL2 {e_l2:.2e}  cos {cos:.6f}  "
+          f"worst tensor {errs[worst]:.2e} ({worst})")
+    assert e_out < b_out and e_nll < b_nll, (e_out, e_nll)
+    assert e_l2 < b_l2 and cos > b_cos, (e_l2, cos)
+    assert errs[worst] < b_tensor, (worst, errs[worst])

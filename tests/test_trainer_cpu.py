@@ -188,3 +188,49 @@ def test_device_bookkeeping_matches_the_reference_loop():
     ref_err2 = ((r_epi - gt) ** 2).mean(0)
     assert torch.allclose(err2, ref_err2, atol=1e-6)
     assert abs(uce - float(uceloss(ref_err2.reshape(-1), (r_epi.var(0) + r_ale.mean(0)).reshape(-1), n_bins=15)[0])) < 1e-6
+
+
+_NAN_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as dist
+from tests.plan_interpreter import TrainerInterpreter
+from tests.test_trainer_cpu import _trainer
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+tr = _trainer(4, rank, world, task="ct")               # the CT trainer switches the NaN guard on by default
+assert tr.nan_guard
+theta0 = tr.eng.theta.clone()
+clean = tr.head.sino_t.clone()
+with TrainerInterpreter(tr):
+    if rank == 1:
+        tr.head.sino_t[0] = float("nan")               # ONE rank sees a non-finite data loss
+    tr.step()
+    skipped = torch.equal(tr.eng.theta, theta0) and int(tr.adam_dev) == 0 and tr.steps_done == 1
+    tr.head.sino_t.copy_(clean)
+    tr.step()                                          # a clean step: Adam's first update (bias correction of step 1)
+moved = float((tr.eng.theta - theta0).abs().max())
+mine = tr.eng.theta.clone()
+other = mine.clone()
+dist.broadcast(other, src=0)
+print(f"rank {rank} skipped={skipped} adam_steps={int(tr.adam_dev)} moved={moved:.2e} identical={torch.equal(mine, other)}")
+assert skipped, "a NaN loss on one rank must skip the update on EVERY rank"
+assert int(tr.adam_dev) == 1 and tr.steps_done == 2 and torch.isfinite(tr.eng.theta).all()
+assert 0.5e-2 < moved < 1.5e-2                         # first Adam update moves every parameter by ~lr (1e-2): bias correction of step 1
+assert torch.equal(mine, other)
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_nan_guard_is_rank_consistent(tmp_path):
+    """CT runner's NaN guard (reference bayesian_optimization.py:577-582) under MC-sample sharding: the tested scalar is
+    nll + temp*kl carried through the gradient all-reduce, so a non-finite loss on ONE rank skips AdamW on BOTH (no rank applies
+    NaN gradients, replicas stay bit-identical), and the optimiser's own step count does not advance on the skipped update."""
+    script = tmp_path / "nan_worker.py"
+    script.write_text(_NAN_WORKER)
+    port = 33600 + os.getpid() % 2000
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(script), ROOT]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=280, env=dict(os.environ, OMP_NUM_THREADS="2"), cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "rank 0 skipped=True" in r.stdout and "rank 1 skipped=True" in r.stdout
