@@ -102,6 +102,21 @@ int mfvi_conv2d_dgrad(const MfviConvDesc* d, MfviView dy, const float* w, long l
 int mfvi_conv2d_wgrad(const MfviConvDesc* d, MfviView x, MfviView dy, float* dw, float* dbias, long long w_sstride,
                       mfvi_stream_t st);
 
+/* ---- Persistent multi-stage execution of a sub-list of the plan (no reference counterpart: the reference launches one ATen
+ * kernel per op; models/skip.py:58-132 is the sub-network concerned).  Between mfvi_mega_begin and mfvi_mega_end the entry points
+ * mfvi_conv2d_{fwd,dgrad,wgrad}, mfvi_bn_act_pad_fwd, mfvi_cat_up_fwd, mfvi_pad_act_bwd, mfvi_bn_bwd_apply, mfvi_cat_up_bwd and
+ * mfvi_fill_f32 RECORD a stage (same arguments, nothing is launched; thread-local).  mfvi_mega_mark_nosync declares the next
+ * recorded stage independent of the one before it (no grid barrier in between).  mfvi_mega_end copies the program into
+ * caller-owned device memory (n_stages * mfvi_mega_stage_bytes() bytes; synchronous copy at plan-build time) and reports its
+ * size figures; mfvi_mega_run executes the whole program in ONE launch (grid barriers instead of kernel boundaries; `barrier`
+ * = two device counters the caller allocates zeroed; the kernel leaves them zero, runs on one buffer must not overlap).  Convolution stages run on mma.sync tf32 tensor-core
+ * tiles sized for the <= 32x32 scales; with desc.math == MFVI_MATH_FP32 they use 3xTF32 error-compensated products. */
+int mfvi_mega_begin(void);
+int mfvi_mega_mark_nosync(void);
+size_t mfvi_mega_stage_bytes(void);
+int mfvi_mega_end(void* program_dev, size_t capacity_bytes, int* n_stages, int* max_items, int* any_split3);
+int mfvi_mega_run(const void* program_dev, int n_stages, int max_items, int any_split3, unsigned* barrier, mfvi_stream_t st);
+
 /* Planning-only query (no reference counterpart; host-only, touches no device, works without a GPU): which kernel family
  * mfvi_conv2d_{fwd,dgrad,wgrad} would run for this geometry and these views — "pointwise", "halo", "alias", "tc" (tcgen05
  * paths) or "simt" (fp32 CUDA cores) — with its launch geometry and a one-line tile plan.  pass: 0 = forward (a = x, b = y),

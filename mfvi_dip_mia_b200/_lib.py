@@ -74,6 +74,7 @@ _SIGS = {
     "mfvi_radon_bwd": [_P, _I, _I, _I, _I, _P, _I, View],
     "mfvi_input_jitter_pad": [_P, _P, _I, _I, _I, _F, _I, PhiloxKey, View],
     "mfvi_adamw_step": [_P, _P, _P, _P, _SZ, _F, _F, _F, _F, _F, _I, _P, _P],
+    "mfvi_mega_run": [_P, _I, _I, _I, _P],
     "mfvi_counter_add": [_P, _U32],
     "mfvi_counter_add_if_finite": [_P, _U32, _P],
     "mfvi_loss_flag": [_P, _P, _F, _P],
@@ -92,7 +93,8 @@ _SIGS = {
     "mfvi_nhwc_to_nchw": [_P, _P, _I, _I, _I, _I],
 }
 
-EXPORTS = ["mfvi_abi_version", "mfvi_last_error", "mfvi_conv2d_plan"] + list(_SIGS)
+EXPORTS = ["mfvi_abi_version", "mfvi_last_error", "mfvi_conv2d_plan", "mfvi_mega_begin", "mfvi_mega_mark_nosync",
+           "mfvi_mega_stage_bytes", "mfvi_mega_end"] + list(_SIGS)
 
 
 def _load():
@@ -112,6 +114,12 @@ def _load():
         fn.restype = C.c_int
     lib.mfvi_conv2d_plan.argtypes = [_CD, _I, View, View, _LL, _I, _I, C.POINTER(PlanInfo)]   # no stream: nothing is launched
     lib.mfvi_conv2d_plan.restype = C.c_int
+    # program recording of the persistent multi-stage kernel (host-only calls, no stream)
+    lib.mfvi_mega_begin.argtypes, lib.mfvi_mega_begin.restype = [], C.c_int
+    lib.mfvi_mega_mark_nosync.argtypes, lib.mfvi_mega_mark_nosync.restype = [], C.c_int
+    lib.mfvi_mega_stage_bytes.argtypes, lib.mfvi_mega_stage_bytes.restype = [], C.c_size_t
+    lib.mfvi_mega_end.argtypes = [_P, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.mfvi_mega_end.restype = C.c_int
     return lib
 
 
@@ -156,6 +164,31 @@ def conv_plan(desc: ConvDesc, pass_: int, a: View, b: View, w_sstride: int, accu
         plan[k] = int(v) if v.lstrip("-").isdigit() else v
     return {"family": info.family.decode(), "grid": tuple(info.grid), "block": info.block, "smem_bytes": info.smem_bytes,
             "launches": info.launches, "plan": plan}
+
+
+def record_program(ops, device) -> dict:
+    """Record an op list [(name, args, meta), ...] as ONE program of the persistent multi-stage kernel (include/mfvi_dip.h,
+    mfvi_mega_*): every op is passed to its usual entry point, which appends a stage instead of launching.  An op whose meta
+    has "indep" runs without a grid barrier after the op before it.  Returns the arguments of mfvi_mega_run."""
+    global launch_count
+    n = len(ops)
+    prog = torch.empty(max(n, 1) * int(lib.mfvi_mega_stage_bytes()), dtype=torch.uint8, device=device)
+    bar = torch.zeros(4, dtype=torch.int32, device=device)
+    if lib.mfvi_mega_begin() != 0:
+        raise MfviError(f"mfvi_mega_begin failed: {lib.mfvi_last_error().decode()}")
+    n_st, items, s3 = C.c_int(0), C.c_int(0), C.c_int(0)
+    try:
+        before = launch_count
+        for name, args, meta in ops:
+            if meta.get("indep"):
+                lib.mfvi_mega_mark_nosync()
+            call(name, *args, stream=0)
+        launch_count = before                                  # nothing was launched
+    finally:
+        rc = lib.mfvi_mega_end(prog.data_ptr(), prog.numel(), C.byref(n_st), C.byref(items), C.byref(s3))
+    if rc != 0:
+        raise MfviError(f"mfvi_mega_end failed (rc={rc}): {lib.mfvi_last_error().decode()}")
+    return {"prog": prog, "bar": bar, "n_stages": n_st.value, "max_items": items.value, "split3": s3.value}
 
 
 def require_cuda(t: torch.Tensor, what: str):

@@ -5,6 +5,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "mega.cuh"
 
 namespace mfvi {
 
@@ -657,6 +658,10 @@ int mfvi_input_jitter_pad(const float* saved, const float* noise, int H, int W, 
 int mfvi_fill_f32(float* p, size_t n, float v, mfvi_stream_t st) {
   if (n == 0) return 0;
   MFVI_REQUIRE(p, "fill: null pointer");
+  if (mega::Stage* ms = mega::append(mega::OP_FILL)) {
+    ms->fill_ptr = p; ms->fill_n = n; ms->fill_v = v;
+    return 0;
+  }
   launch_k(k_fill, grid_for(n, 256), 256, 0, as_stream(st), p, n, v);
   return check_launch("fill");
 }

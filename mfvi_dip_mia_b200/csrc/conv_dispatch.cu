@@ -2,6 +2,14 @@
 // the tcgen05 kernels (conv_tc2.cu, conv_tc.cu) when the shape qualifies (each returns -1 otherwise), else the exact-fp32
 // CUDA-core kernels (conv_simt.cu).  mfvi_conv2d_plan walks the same chains in planning-only mode (common.cuh: dry_run).
 #include "common.cuh"
+#include "mega.cuh"
+
+namespace mfvi {
+namespace mega {
+int record_conv(int op, const MfviConvDesc* d, MfviView act_in, MfviView act_out, const float* w, const float* bias,
+                long long w_sstride, float* dw, double* stats, int accumulate);
+}
+}  // namespace mfvi
 
 extern "C" {
 int mfvi_conv2d_fwd_simt(const MfviConvDesc*, MfviView, const float*, const float*, long long, MfviView, double*, mfvi_stream_t);
@@ -72,18 +80,25 @@ static int wgrad_chain(const MfviConvDesc* d, MfviView x, MfviView dy, float* dw
 
 int mfvi_conv2d_fwd(const MfviConvDesc* d, MfviView x, const float* w, const float* bias, long long w_sstride,
                     MfviView y, double* stats, mfvi_stream_t st) {
+  if (mfvi::mega::recording()) return mfvi::mega::record_conv(mfvi::mega::OP_CONV_FWD, d, x, y, w, bias, w_sstride, nullptr, stats, 0);
   const char* family;
   return fwd_chain(d, x, w, bias, w_sstride, y, stats, st, &family);
 }
 
 int mfvi_conv2d_dgrad(const MfviConvDesc* d, MfviView dy, const float* w, long long w_sstride, MfviView dx,
                       int accumulate, mfvi_stream_t st) {
+  if (mfvi::mega::recording())
+    return mfvi::mega::record_conv(mfvi::mega::OP_CONV_DGRAD, d, dy, dx, w, nullptr, w_sstride, nullptr, nullptr, accumulate);
   const char* family;
   return dgrad_chain(d, dy, w, w_sstride, dx, accumulate, st, &family);
 }
 
 int mfvi_conv2d_wgrad(const MfviConvDesc* d, MfviView x, MfviView dy, float* dw, float* dbias, long long w_sstride,
                       mfvi_stream_t st) {
+  if (mfvi::mega::recording()) {
+    MFVI_REQUIRE(dbias == nullptr, "mega: a bias gradient is not part of the fused stages");
+    return mfvi::mega::record_conv(mfvi::mega::OP_CONV_WGRAD, d, x, dy, nullptr, nullptr, w_sstride, dw, nullptr, 0);
+  }
   const char* family;
   return wgrad_chain(d, x, dy, dw, dbias, w_sstride, st, &family);
 }

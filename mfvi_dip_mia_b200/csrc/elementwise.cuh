@@ -120,14 +120,28 @@ __device__ __forceinline__ void cta_reduce_2(double (&a)[V], double (&b)[V], int
 // per-channel reductions are carried in fp32 for kFlush pixels at a time before they are added to double accumulators.
 constexpr int kFlush = 8;
 
+// Virtual block coordinates: (bx, by) of a (gx, S) grid.  A stand-alone kernel passes its real blockIdx / gridDim; the persistent
+// multi-stage kernel (mega.cu) loops over virtual blocks.
+struct VGrid {
+  int bx, by, gx;
+};
+
+// shared-memory pieces a kernel body may use (each wrapper allocates only what its body touches)
+struct BnTable;
+struct EwSmem {
+  double* red;      // [2 * kEwThreads * 4] doubles: thread-private reduction cells
+  BnTable* tab;     // BatchNorm constants of one sample
+  float* misc;      // [5 * kMaxC] floats (bn_bwd_apply)
+};
+
 struct PixIter {
   int p, npix, h, w, W, step, dh, dw;
   // grid-stride over pixels (all CTAs sweep the image together, which keeps DRAM pages hot); (h, w) advance incrementally
-  __device__ __forceinline__ PixIter(int npix_, int Wd, int PPB, int slot) {
+  __device__ __forceinline__ PixIter(const VGrid& vg, int npix_, int Wd, int PPB, int slot) {
     npix = npix_;
-    p = blockIdx.x * PPB + slot;
+    p = vg.bx * PPB + slot;
     W = Wd;
-    step = gridDim.x * PPB;
+    step = vg.gx * PPB;
     dh = step / Wd;
     dw = step - dh * Wd;
     h = p / Wd;

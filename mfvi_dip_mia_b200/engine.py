@@ -187,7 +187,8 @@ class SkipEngine:
     """Forward/backward plan of one hour-glass net at a fixed (H, W, S)."""
 
     def __init__(self, spec: SkipSpec, H: int, W: int, S: int, device, *, math: int = L.MATH_FP32,
-                 layout: Optional[SkipLayout] = None, need_input_grad: bool = False, plan_only: bool = False):
+                 layout: Optional[SkipLayout] = None, need_input_grad: bool = False, plan_only: bool = False,
+                 mega_from: Optional[int] = None):
         device = torch.device(device)
         # A plan-only engine builds the kernel plan (buffers, views, op lists) and can never execute it: device "meta" (shapes,
         # strides and alignments, no memory) for conv_dispatch_table() on a machine without a GPU; plan_only=True on any device
@@ -249,6 +250,17 @@ class SkipEngine:
         # their inputs; ("__join__", (), {"lane": X}) makes the main stream wait for lane X.
         self.overlap_wgrad = True
         self.overlap_skip = os.environ.get("MFVI_SKIP_LANE", "1") != "0"
+        # Persistent multi-stage kernel (csrc/mega.cu): scales >= mega_from run as ONE launch per direction instead of one launch
+        # per op.  None = the library default (by map size, _default_mega_from); -1 or MFVI_MEGA=0 = off.
+        env = os.environ.get("MFVI_MEGA_FROM")
+        if mega_from is None and env is not None:
+            mega_from = int(env)
+        if mega_from is None:
+            mega_from = self._default_mega_from()
+        if self.plan_only or os.environ.get("MFVI_MEGA", "1") == "0" or mega_from < 0 or mega_from >= len(spec.down):
+            mega_from = None
+        self.mega_from = mega_from
+        self._mega = []                      # recorded programs (kept alive)
         self._side = None if self.plan_only else torch.cuda.Stream(device=device)
         self._side2 = None if self.plan_only else torch.cuda.Stream(device=device)
         self._build_plan()
@@ -259,6 +271,31 @@ class SkipEngine:
         self._bn_count = torch.tensor([b.count for b in lay.bns], dtype=torch.int32, device=device)
 
     # ---------------------------------------------------------------- helpers
+    def _default_mega_from(self) -> int:
+        """First scale whose maps are small enough for the persistent multi-stage kernel: S * (H / 2^(i+1)) * (W / 2^(i+1))
+        output pixels of the scale's convolutions <= MFVI_MEGA_PIXELS (default 0 = off until measured)."""
+        limit = int(os.environ.get("MFVI_MEGA_PIXELS", "0"))
+        for i in range(len(self.spec.down)):
+            if self.S * (self.H >> (i + 1)) * (self.W >> (i + 1)) <= limit:
+                return i
+        return -1
+
+    def _fuse(self, ops, n0: int, tag: str):
+        """Replace ops[n0:] by one mfvi_mega_run op (weight gradients stay separate launches on their lane, after it)."""
+        sub = ops[n0:]
+        del ops[n0:]
+        inner = [op for op in sub if op[0] not in ("__join__", "mfvi_conv2d_wgrad")]
+        later = [op for op in sub if op[0] == "mfvi_conv2d_wgrad"]
+        if not inner:
+            ops.extend(sub)
+            return
+        m = L.record_program(inner, self.device)
+        self._mega.append(m)
+        meta = {"flops": sum(o[2].get("flops", 0.0) for o in inner), "bytes": sum(o[2].get("bytes", 0.0) for o in inner),
+                "layer": f"mega_{tag}", "shape": f"{m['n_stages']} stages", "sub_ops": inner}
+        ops.append(("mfvi_mega_run", (m["prog"].data_ptr(), m["n_stages"], m["max_items"], m["split3"], m["bar"].data_ptr()), meta))
+        ops.extend(later)
+
     def _buf(self, H, W, Cn, S=None):
         t = torch.empty(self.S if S is None else S, H, W, Cn, dtype=torch.float32, device=self.device)
         self._bufs.append(t)
@@ -370,12 +407,17 @@ class SkipEngine:
                 self.fwd_ops[-1][2].update(lane="skip", after="main")
             x_d1 = self._interior(T, Tpad - pd)
             y1, d_1 = self._conv_fwd(sc.d1, x_d1, sc.d1_bn)
+            if sc.skip_conv is not None:
+                self.fwd_ops[-1][2]["indep"] = True        # reads the same input as the skip conv before it
             X2 = self._bn_act_pad(y1, sc.d1_bn, *self._bn_args(sc.d1_bn), 1, pd)
             y2, d_2 = self._conv_fwd(sc.d2, X2, sc.d2_bn)
             if i < n - 1:
                 npad = in_pad(i + 1)
                 Tn = self._bn_act_pad(y2, sc.d2_bn, *self._bn_args(sc.d2_bn), 1, npad)
+                n_before = len(self.fwd_ops)
                 z, z_bn, inner_bwd = run_scale(i + 1, Tn, npad)
+                if self.mega_from is not None and i + 1 == self.mega_from:
+                    self._fuse(self.fwd_ops, n_before, "fwd")
             else:
                 z, z_bn, inner_bwd = y2, sc.d2_bn, None
             Hs, Ws = 2 * z.shape[1], 2 * z.shape[2]
@@ -417,7 +459,8 @@ class SkipEngine:
                 # the upsampled branch continues the main chain; the skip branch's half goes to the skip lane
                 ops.append(("mfvi_cat_up_bwd", cat_args + (2,), self._ew_meta(dA[..., Cs:], z, gd)))
                 if Cs:
-                    ops.append(("mfvi_cat_up_bwd", cat_args + (1,), dict(self._ew_meta(dA[..., :Cs], ys, gs), lane="skip", after="main")))
+                    ops.append(("mfvi_cat_up_bwd", cat_args + (1,), dict(self._ew_meta(dA[..., :Cs], ys, gs), lane="skip", after="main",
+                                                                         indep=True)))        # reads dA like part 2 before it
                 # BN backward of the two branches (their LeakyReLU was folded into cat_up_bwd).  The skip branch goes to the
                 # "skip" lane: BN backward, then its dgrad into the (zero-filled) input gradient of this scale, which the
                 # first down conv's dgrad accumulates onto after the join.
@@ -433,7 +476,9 @@ class SkipEngine:
                     ops.append(("mfvi_conv2d_wgrad", (C.byref(d_s), L.view(x_s), L.view(gs), self.dw.data_ptr() + 4 * sc.skip_conv.w_off,
                                                       self._dbias_ptr(sc.skip_conv, True), lay.P_pad), dict(ms, after="skip")))
                     if need_dT:
-                        ops.append(("mfvi_fill_f32", (dT.data_ptr(), dT.numel(), 0.0), dict(self._ew_meta(dT), lane="skip", after="skip")))
+                        # dT is a fresh buffer: the fill depends on nothing before it
+                        ops.append(("mfvi_fill_f32", (dT.data_ptr(), dT.numel(), 0.0), dict(self._ew_meta(dT), lane="skip", after="skip",
+                                                                                           indep=True)))
                         ops.append(("mfvi_conv2d_dgrad", (C.byref(d_s), L.view(gs), self.w.data_ptr() + 4 * sc.skip_conv.w_off,
                                                           lay.P_pad, L.view(self._interior(dT, Tpad - ps)), 1),
                                     dict(ms, lane="skip", after="skip")))
@@ -442,7 +487,10 @@ class SkipEngine:
                     self.g_gamma.data_ptr() + 4 * z_bn.ch_off, self.g_beta.data_ptr() + 4 * z_bn.ch_off),
                     self._ew_meta(gd, z, gd)))
                 if inner_bwd is not None:
+                    n_before = len(ops)
                     dTn = inner_bwd(ops, gd)
+                    if self.mega_from is not None and i + 1 == self.mega_from:
+                        self._fuse(ops, n_before, "bwd")
                     dy2 = self._bn_act_pad_bwd(ops, dTn, y2, sc.d2_bn, 1, Tn_pad)
                 else:
                     dy2 = gd

@@ -75,9 +75,9 @@ def test_tc_conv_broadcast_input(shape, S):
 
 
 # whole-step bars of the tf32 mode on the four small task nets: ~2x the errors measured on a B200 (printed by the test,
-# profiles/r02_parity_errors.txt).  (output, nll, whole-gradient relative L2, cosine, worst per-tensor normalised max error)
-TF32_STEP_BARS = {"den": (1e-2, 2e-3, 3e-2, 0.9995, 0.25), "sr": (1e-2, 2e-3, 3e-2, 0.9995, 0.25),
-                  "ct": (1e-2, 2e-3, 3e-2, 0.9995, 0.25), "inp": (1e-2, 2e-3, 3e-2, 0.9995, 0.25)}
+# profiles/r02_parity_errors.txt: output 2.5e-3 .. 4.1e-3, nll 0.8e-4 .. 2.3e-4, gradient relL2 0.8e-2 .. 1.7e-2, cosine >= 0.99986,
+# worst tensor 0.03 .. 0.24).  (output, nll, whole-gradient relative L2, cosine, median / p90 / max per-tensor normalised error)
+TF32_STEP_BARS = (8e-3, 5e-4, 3.5e-2, 0.9995, 3e-2, 1.5e-1, 0.5)
 
 
 @pytest.mark.parametrize("task", ["den", "sr", "ct", "inp"])
@@ -108,7 +108,7 @@ def test_tf32_engine_step_close_to_reference(task):
     eng.backward()
     eng.reparam_kl(L.key(0), prior_mu=0.0, prior_sigma_plus_eps=O.prior_scale(temp, sigma), direction=0, kscale=temp)
     out = eng.out_nchw().cpu()
-    b_out, b_nll, b_l2, b_cos, b_tensor = TF32_STEP_BARS[task]
+    b_out, b_nll, b_l2, b_cos, b_med, b_p90, b_max = TF32_STEP_BARS
     e_out = max(rel_err(out[s:s + 1], d[f"out{s}"]) for s in range(S))
     a = eng.arena[:2].cpu()
     e_nll = rel_err(a[NLL], d["nll"])
@@ -119,8 +119,11 @@ def test_tf32_engine_step_close_to_reference(task):
     cos = float((va @ vb) / (va.norm() * vb.norm()))
     errs = grad_errs({k: ours[k] for k in grads}, grads)
     worst = max(errs, key=errs.get)
+    import numpy as np
+    ev = np.array(list(errs.values()))
+    med, p90 = float(np.median(ev)), float(np.percentile(ev, 90))
     print(f"[parity small {task} tf32] out {e_out:.2e}  nll {e_nll:.2e}  grad relL2 {e_l2:.2e}  cos {cos:.6f}  "
-          f"worst tensor {errs[worst]:.2e} ({worst})")
+          f"per-tensor median/p90/max {med:.2e}/{p90:.2e}/{errs[worst]:.2e} ({worst.rsplit('.', 2)[-2]}.{worst.rsplit('.', 1)[-1]})")
     assert e_out < b_out and e_nll < b_nll, (e_out, e_nll)
     assert e_l2 < b_l2 and cos > b_cos, (e_l2, cos)
-    assert errs[worst] < b_tensor, (worst, errs[worst])
+    assert med < b_med and p90 < b_p90 and errs[worst] < b_max, (med, p90, worst, errs[worst])
