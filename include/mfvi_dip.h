@@ -102,20 +102,44 @@ int mfvi_conv2d_dgrad(const MfviConvDesc* d, MfviView dy, const float* w, long l
 int mfvi_conv2d_wgrad(const MfviConvDesc* d, MfviView x, MfviView dy, float* dw, float* dbias, long long w_sstride,
                       mfvi_stream_t st);
 
+/* Explicit kernel families behind mfvi_conv2d_{fwd,dgrad,wgrad} (same arguments; used by the tests and for benchmarking one
+ * family against another): *_simt = the exact-fp32 CUDA-core kernels (conv_simt.cu), the fp32 mode's default; *_mma = mma.sync
+ * tf32 tensor-core tiles (mega.cu) as stand-alone launches — 3xTF32 error-compensated (fp32 accuracy) when desc.math ==
+ * MFVI_MATH_FP32.  Measured slower than *_simt on the metric shape, hence not the default. */
+int mfvi_conv2d_fwd_simt(const MfviConvDesc* d, MfviView x, const float* w, const float* bias, long long w_sstride, MfviView y,
+                         double* stats, mfvi_stream_t st);
+int mfvi_conv2d_dgrad_simt(const MfviConvDesc* d, MfviView dy, const float* w, long long w_sstride, MfviView dx, int accumulate,
+                           mfvi_stream_t st);
+int mfvi_conv2d_wgrad_simt(const MfviConvDesc* d, MfviView x, MfviView dy, float* dw, float* dbias, long long w_sstride,
+                           mfvi_stream_t st);
+int mfvi_conv2d_fwd_mma(const MfviConvDesc* d, MfviView x, const float* w, const float* bias, long long w_sstride, MfviView y,
+                        double* stats, mfvi_stream_t st);
+int mfvi_conv2d_dgrad_mma(const MfviConvDesc* d, MfviView dy, const float* w, long long w_sstride, MfviView dx, int accumulate,
+                          mfvi_stream_t st);
+int mfvi_conv2d_wgrad_mma(const MfviConvDesc* d, MfviView x, MfviView dy, float* dw, float* dbias, long long w_sstride,
+                          mfvi_stream_t st);
+
 /* ---- Persistent multi-stage execution of a sub-list of the plan (no reference counterpart: the reference launches one ATen
  * kernel per op; models/skip.py:58-132 is the sub-network concerned).  Between mfvi_mega_begin and mfvi_mega_end the entry points
  * mfvi_conv2d_{fwd,dgrad,wgrad}, mfvi_bn_act_pad_fwd, mfvi_cat_up_fwd, mfvi_pad_act_bwd, mfvi_bn_bwd_apply, mfvi_cat_up_bwd and
  * mfvi_fill_f32 RECORD a stage (same arguments, nothing is launched; thread-local).  mfvi_mega_mark_nosync declares the next
- * recorded stage independent of the one before it (no grid barrier in between).  mfvi_mega_end copies the program into
- * caller-owned device memory (n_stages * mfvi_mega_stage_bytes() bytes; synchronous copy at plan-build time) and reports its
- * size figures; mfvi_mega_run executes the whole program in ONE launch (grid barriers instead of kernel boundaries; `barrier`
- * = two device counters the caller allocates zeroed; the kernel leaves them zero, runs on one buffer must not overlap).  Convolution stages run on mma.sync tf32 tensor-core
- * tiles sized for the <= 32x32 scales; with desc.math == MFVI_MATH_FP32 they use 3xTF32 error-compensated products. */
+ * recorded stage independent of the one before it (no barrier in between).  mfvi_mega_end copies the program into caller-owned
+ * device memory (n_stages * mfvi_mega_stage_bytes() bytes; synchronous copy at plan-build time).  mfvi_mega_run executes the whole
+ * program for S MC samples in ONE launch: one 8-CTA thread-block cluster per sample, cluster barriers instead of kernel
+ * boundaries (every recorded op must be per-sample independent, which all ops of the network are; a recorded mfvi_fill_f32
+ * must cover S equal per-sample slices).  Convolution stages run on mma.sync tf32 tensor-core tiles sized for the <= 16x16
+ * scales; with desc.math == MFVI_MATH_FP32 they use 3xTF32 error-compensated products.  A recorded mfvi_bn_bwd_apply does NOT
+ * write dgamma / dbeta (they sum over all samples): call mfvi_bn_param_grads after the run with DEVICE tables of the n layers'
+ * reduction tables (red[S][C][2]), dgamma / dbeta addresses (int64) and channel counts.
+ * stage_times: NULL, or n_stages + 1 device int64 receiving %globaltimer (ns) at the start of every stage of sample 0 and at the
+ * end, as seen by CTA 0 — a profiling aid (scripts/mega_profile.py). */
 int mfvi_mega_begin(void);
 int mfvi_mega_mark_nosync(void);
 size_t mfvi_mega_stage_bytes(void);
-int mfvi_mega_end(void* program_dev, size_t capacity_bytes, int* n_stages, int* max_items, int* any_split3);
-int mfvi_mega_run(const void* program_dev, int n_stages, int max_items, int any_split3, unsigned* barrier, mfvi_stream_t st);
+int mfvi_mega_end(void* program_dev, size_t capacity_bytes, int* n_stages);
+int mfvi_mega_run(const void* program_dev, int n_stages, int S, long long* stage_times, mfvi_stream_t st);
+int mfvi_bn_param_grads(const long long* red_ptrs, const long long* dgamma_ptrs, const long long* dbeta_ptrs, const int* Cs, int n,
+                        int S, mfvi_stream_t st);
 
 /* Planning-only query (no reference counterpart; host-only, touches no device, works without a GPU): which kernel family
  * mfvi_conv2d_{fwd,dgrad,wgrad} would run for this geometry and these views — "pointwise", "halo", "alias", "tc" (tcgen05

@@ -74,7 +74,14 @@ _SIGS = {
     "mfvi_radon_bwd": [_P, _I, _I, _I, _I, _P, _I, View],
     "mfvi_input_jitter_pad": [_P, _P, _I, _I, _I, _F, _I, PhiloxKey, View],
     "mfvi_adamw_step": [_P, _P, _P, _P, _SZ, _F, _F, _F, _F, _F, _I, _P, _P],
-    "mfvi_mega_run": [_P, _I, _I, _I, _P],
+    "mfvi_mega_run": [_P, _I, _I, _P],
+    "mfvi_conv2d_fwd_simt": [_CD, View, _P, _P, _LL, View, _P],
+    "mfvi_conv2d_dgrad_simt": [_CD, View, _P, _LL, View, _I],
+    "mfvi_conv2d_wgrad_simt": [_CD, View, View, _P, _P, _LL],
+    "mfvi_conv2d_fwd_mma": [_CD, View, _P, _P, _LL, View, _P],
+    "mfvi_conv2d_dgrad_mma": [_CD, View, _P, _LL, View, _I],
+    "mfvi_conv2d_wgrad_mma": [_CD, View, View, _P, _P, _LL],
+    "mfvi_bn_param_grads": [_P, _P, _P, _P, _I, _I],
     "mfvi_counter_add": [_P, _U32],
     "mfvi_counter_add_if_finite": [_P, _U32, _P],
     "mfvi_loss_flag": [_P, _P, _F, _P],
@@ -118,7 +125,7 @@ def _load():
     lib.mfvi_mega_begin.argtypes, lib.mfvi_mega_begin.restype = [], C.c_int
     lib.mfvi_mega_mark_nosync.argtypes, lib.mfvi_mega_mark_nosync.restype = [], C.c_int
     lib.mfvi_mega_stage_bytes.argtypes, lib.mfvi_mega_stage_bytes.restype = [], C.c_size_t
-    lib.mfvi_mega_end.argtypes = [_P, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.mfvi_mega_end.argtypes = [_P, C.c_size_t, C.POINTER(C.c_int)]
     lib.mfvi_mega_end.restype = C.c_int
     return lib
 
@@ -169,14 +176,13 @@ def conv_plan(desc: ConvDesc, pass_: int, a: View, b: View, w_sstride: int, accu
 def record_program(ops, device) -> dict:
     """Record an op list [(name, args, meta), ...] as ONE program of the persistent multi-stage kernel (include/mfvi_dip.h,
     mfvi_mega_*): every op is passed to its usual entry point, which appends a stage instead of launching.  An op whose meta
-    has "indep" runs without a grid barrier after the op before it.  Returns the arguments of mfvi_mega_run."""
+    has "indep" runs without a barrier after the op before it.  Returns the program (device buffer, stage count, op names)."""
     global launch_count
     n = len(ops)
     prog = torch.empty(max(n, 1) * int(lib.mfvi_mega_stage_bytes()), dtype=torch.uint8, device=device)
-    bar = torch.zeros(4, dtype=torch.int32, device=device)
     if lib.mfvi_mega_begin() != 0:
         raise MfviError(f"mfvi_mega_begin failed: {lib.mfvi_last_error().decode()}")
-    n_st, items, s3 = C.c_int(0), C.c_int(0), C.c_int(0)
+    n_st = C.c_int(0)
     try:
         before = launch_count
         for name, args, meta in ops:
@@ -185,10 +191,12 @@ def record_program(ops, device) -> dict:
             call(name, *args, stream=0)
         launch_count = before                                  # nothing was launched
     finally:
-        rc = lib.mfvi_mega_end(prog.data_ptr(), prog.numel(), C.byref(n_st), C.byref(items), C.byref(s3))
+        rc = lib.mfvi_mega_end(prog.data_ptr(), prog.numel(), C.byref(n_st))
     if rc != 0:
         raise MfviError(f"mfvi_mega_end failed (rc={rc}): {lib.mfvi_last_error().decode()}")
-    return {"prog": prog, "bar": bar, "n_stages": n_st.value, "max_items": items.value, "split3": s3.value}
+    prof = torch.zeros(n_st.value + 1, dtype=torch.int64, device=device) if os.environ.get("MFVI_MEGA_PROFILE") else None
+    return {"prog": prog, "n_stages": n_st.value, "prof": prof,
+            "names": [op[0] + (":" + op[2].get("layer", "") if op[2].get("layer") else "") for op in ops]}
 
 
 def require_cuda(t: torch.Tensor, what: str):

@@ -8,6 +8,8 @@ namespace mfvi {
 namespace mega {
 int record_conv(int op, const MfviConvDesc* d, MfviView act_in, MfviView act_out, const float* w, const float* bias,
                 long long w_sstride, float* dw, double* stats, int accumulate);
+int launch_conv_mma(int op, const MfviConvDesc* d, MfviView act_in, MfviView act_out, const float* w, const float* bias,
+                    long long w_sstride, float* dw, double* stats, int accumulate, mfvi_stream_t stream, const char* what);
 }
 }  // namespace mfvi
 
@@ -28,6 +30,14 @@ int mfvi_conv2d_dgrad_pw(const MfviConvDesc*, MfviView, const float*, long long,
 
 // The chains name the kernel family that took the shape: "pointwise", "halo" (conv_tc2.cu), "alias" (conv_wgrad2.cu),
 // "tc" (conv_tc.cu) or "simt".
+// Exact-fp32 mode on 3xTF32 tensor-core tiles instead of the CUDA-core kernels: OFF by default — measured on a B200 the
+// mma.sync tiles of mega.cu run the 256x256 MC=8 step at 76 steps/s against 154 steps/s for conv_simt.cu
+// (profiles/r02_fp32_mma_negative.txt); MFVI_FP32_MMA=1 switches it on.
+static bool fp32_mma_on() {
+  static const bool on = [] { const char* e = getenv("MFVI_FP32_MMA"); return e != nullptr && e[0] == '1'; }();
+  return on;
+}
+
 static int fwd_chain(const MfviConvDesc* d, MfviView x, const float* w, const float* bias, long long w_sstride, MfviView y,
                      double* stats, mfvi_stream_t st, const char** family) {
   if (d != nullptr && d->math == MFVI_MATH_TF32) {
@@ -40,6 +50,12 @@ static int fwd_chain(const MfviConvDesc* d, MfviView x, const float* w, const fl
     if (rc >= 0) return rc;
     rc = mfvi_conv2d_fwd_tc(d, x, w, bias, w_sstride, y, stats, st);
     *family = "tc";
+    if (rc >= 0) return rc;
+  }
+  if (d != nullptr && d->math == MFVI_MATH_FP32 && fp32_mma_on()) {
+    // exact-fp32 mode: 3xTF32 tensor-core tiles (mega.cu) — fp32 accuracy, several times the CUDA-core rate
+    const int rc = mfvi::mega::launch_conv_mma(mfvi::mega::OP_CONV_FWD, d, x, y, w, bias, w_sstride, nullptr, stats, 0, st, "conv2d_fwd_mma");
+    *family = "mma3";
     if (rc >= 0) return rc;
   }
   *family = "simt";
@@ -59,6 +75,12 @@ static int dgrad_chain(const MfviConvDesc* d, MfviView dy, const float* w, long 
     *family = "tc";
     if (rc >= 0) return rc;
   }
+  if (d != nullptr && d->math == MFVI_MATH_FP32 && fp32_mma_on()) {
+    const int rc = mfvi::mega::launch_conv_mma(mfvi::mega::OP_CONV_DGRAD, d, dy, dx, w, nullptr, w_sstride, nullptr, nullptr, accumulate, st,
+                                               "conv2d_dgrad_mma");
+    *family = "mma3";
+    if (rc >= 0) return rc;
+  }
   *family = "simt";
   return mfvi_conv2d_dgrad_simt(d, dy, w, w_sstride, dx, accumulate, st);
 }
@@ -72,6 +94,13 @@ static int wgrad_chain(const MfviConvDesc* d, MfviView x, MfviView dy, float* dw
     if (rc >= 0) return rc;
     rc = mfvi_conv2d_wgrad_tc(d, x, dy, dw, dbias, w_sstride, st);
     *family = "tc";
+    if (rc >= 0) return rc;
+  }
+  if (d != nullptr && d->math == MFVI_MATH_FP32 && fp32_mma_on()) {
+    int rc = mfvi::mega::launch_conv_mma(mfvi::mega::OP_CONV_WGRAD, d, x, dy, nullptr, nullptr, w_sstride, dw, nullptr, 0, st,
+                                         "conv2d_wgrad_mma");
+    if (rc == 0 && dbias != nullptr) rc = mfvi_conv2d_bias_grad_tc(d, dy, dbias, w_sstride, st);      // exact fp32 reduction of dy
+    *family = "mma3";
     if (rc >= 0) return rc;
   }
   *family = "simt";
@@ -137,5 +166,28 @@ int mfvi_conv2d_plan(const MfviConvDesc* d, int pass, MfviView a, MfviView b, lo
   out->launches = info.launches;
   strncpy(out->detail, info.detail, sizeof(out->detail) - 1);
   return 0;
+}
+
+// explicit entry points of the mma.sync tile kernels (mega.cu) as stand-alone launches, whatever the dispatch default
+int mfvi_conv2d_fwd_mma(const MfviConvDesc* d, MfviView x, const float* w, const float* bias, long long w_sstride, MfviView y,
+                        double* stats, mfvi_stream_t st) {
+  const int rc = mfvi::mega::launch_conv_mma(mfvi::mega::OP_CONV_FWD, d, x, y, w, bias, w_sstride, nullptr, stats, 0, st, "conv2d_fwd_mma");
+  MFVI_REQUIRE(rc >= 0, "conv2d_fwd_mma: shape not taken (stride must be 1 or 2)");
+  return rc;
+}
+int mfvi_conv2d_dgrad_mma(const MfviConvDesc* d, MfviView dy, const float* w, long long w_sstride, MfviView dx, int accumulate,
+                          mfvi_stream_t st) {
+  const int rc = mfvi::mega::launch_conv_mma(mfvi::mega::OP_CONV_DGRAD, d, dy, dx, w, nullptr, w_sstride, nullptr, nullptr, accumulate, st,
+                                             "conv2d_dgrad_mma");
+  MFVI_REQUIRE(rc >= 0, "conv2d_dgrad_mma: shape not taken (stride must be 1 or 2)");
+  return rc;
+}
+int mfvi_conv2d_wgrad_mma(const MfviConvDesc* d, MfviView x, MfviView dy, float* dw, float* dbias, long long w_sstride,
+                          mfvi_stream_t st) {
+  int rc = mfvi::mega::launch_conv_mma(mfvi::mega::OP_CONV_WGRAD, d, x, dy, nullptr, nullptr, w_sstride, dw, nullptr, 0, st,
+                                       "conv2d_wgrad_mma");
+  MFVI_REQUIRE(rc >= 0, "conv2d_wgrad_mma: shape not taken (stride must be 1 or 2)");
+  if (rc == 0 && dbias != nullptr) rc = mfvi_conv2d_bias_grad_tc(d, dy, dbias, w_sstride, st);
+  return rc;
 }
 }

@@ -30,7 +30,7 @@ using namespace mfvi::tc;
 
 constexpr int kThreads = 224;
 constexpr int kMaxChunks = 9;
-constexpr int kMaxStages = 4;
+constexpr int kMaxStages = 8;
 constexpr int kTrLd = 17;
 
 struct Args {
@@ -107,7 +107,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* acc_full = b_empty + kMaxStages;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* tr_all = reinterpret_cast<float*>(ctrl + 256);      // [4 warps][32][kTrLd]
+  float* tr_all = reinterpret_cast<float*>(ctrl + 512);      // [4 warps][32][kTrLd]
 
   // warp index through a shuffle: ptxas then treats it (and every role branch on it) as warp-uniform and keeps the UMMA /
   // TMA operands in uniform registers instead of R2UR-ing them before every instruction
@@ -500,9 +500,25 @@ static Plan make_plan(int S, int Mh, int Mw, int hh, int hw, int taps, int plane
         pl.b_stage = static_cast<uint32_t>(rup(g * BN * rb_max, 1024));
         pl.n_a = 2;
         pl.n_b = (pl.n_groups * n_chunks > 1) ? 3 : 2;
-        pl.smem = 1024 + static_cast<size_t>(pl.n_a) * pl.a_stage + static_cast<size_t>(pl.n_b) * pl.b_stage + 256 + 4 * 32 * kTrLd * 4 +
-                  4 * BN * 16 + 64;
+        auto smem_of = [&](int na, int nb) {
+          return 1024 + static_cast<size_t>(na) * pl.a_stage + static_cast<size_t>(nb) * pl.b_stage + 512 + 4 * 32 * kTrLd * 4 +
+                 4 * BN * 16 + 64;
+        };
+        pl.smem = smem_of(pl.n_a, pl.n_b);
         if (pl.smem > 200 * 1024) break;
+        {
+          // Latency-bound tiles (few tiles per CTA, many operand stages per tile): every extra stage in flight saves a TMA round
+          // trip (~1.5 us).  Deepen the rings up to what a tile consumes while the CTA stays within `deep_cap` bytes
+          // (MFVI_TC2_DEEP, default 0 = the two/three-stage rings of round 1).
+          static const int deep_cap = env_int("MFVI_TC2_DEEP", 0) * 1024;
+          const int want_b = std::min(kMaxStages, pl.n_groups * n_chunks), want_a = std::min(4, n_chunks);
+          while (deep_cap > 0) {
+            if (pl.n_b < want_b && smem_of(pl.n_a, pl.n_b + 1) <= static_cast<size_t>(deep_cap)) { ++pl.n_b; continue; }
+            if (pl.n_a < want_a && smem_of(pl.n_a + 1, pl.n_b) <= static_cast<size_t>(deep_cap)) { ++pl.n_a; continue; }
+            break;
+          }
+          pl.smem = smem_of(pl.n_a, pl.n_b);
+        }
         const int tiles = S * split * n_cls * pl.tiles_h * pl.tiles_w;
         const int cpsm = (pl.smem <= 100 * 1024 && cols <= 256) ? 2 : 1;
         const int slots = kNumSMs * cpsm;

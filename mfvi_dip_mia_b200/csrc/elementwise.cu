@@ -129,7 +129,7 @@ int mfvi_bn_act_pad_fwd(MfviView y, int S, int H, int W, int C, const double* su
   MFVI_REQUIRE(ge.G <= kEwThreads, "bn_act_pad_fwd: too many channel groups");
   dim3 grid(ew_grid((H + 2 * pad) * (W + 2 * pad), ge.PPB, S), S);
   if (mega::Stage* ms = mega::append(mega::OP_BN_ACT_PAD_FWD)) {
-    ms->V = ge.V; ms->G = ge.G; ms->PPB = ge.PPB; ms->gx = grid.x; ms->S = S;
+    ms->V = ge.V; ms->G = ge.G; ms->PPB = ge.PPB; ms->gx = grid.x < 8u ? grid.x : 8u;      /* one virtual block per CTA of the sample's cluster */ ms->S = S;
     ms->a = y; ms->b = xp; ms->H = H; ms->W = W; ms->C = C; ms->sums = sums; ms->gamma = gamma; ms->beta = beta; ms->act = act;
     ms->pad = pad;
     return 0;
@@ -151,7 +151,7 @@ int mfvi_cat_up_fwd(MfviView ys, int Cs, const double* sums_s, const float* gamm
   MFVI_REQUIRE(ge.G <= kEwThreads, "cat_up_fwd: too many channel groups");
   dim3 grid(ew_grid((H / 2 + 1) * (W / 2 + 1), ge.PPB, S), S);
   if (mega::Stage* ms = mega::append(mega::OP_CAT_UP_FWD)) {
-    ms->V = ge.V; ms->G = ge.G; ms->PPB = ge.PPB; ms->gx = grid.x; ms->S = S;
+    ms->V = ge.V; ms->G = ge.G; ms->PPB = ge.PPB; ms->gx = grid.x < 8u ? grid.x : 8u;      /* one virtual block per CTA of the sample's cluster */ ms->S = S;
     ms->a = ys; ms->C = Cs; ms->sums = sums_s; ms->gamma = gamma_s; ms->beta = beta_s;
     ms->b = yd; ms->C2 = Cd; ms->sums2 = sums_d; ms->gamma2 = gamma_d; ms->beta2 = beta_d;
     ms->H = H; ms->W = W; ms->mode = mode; ms->c = A; ms->red = sumsA;
@@ -171,7 +171,7 @@ int mfvi_pad_act_bwd(MfviView dxp, int S, int H, int W, int C, int pad, MfviView
   MFVI_REQUIRE(ge.G <= kEwThreads, "pad_act_bwd: too many channel groups");
   dim3 grid(ew_grid(H * W, ge.PPB, S), S);
   if (mega::Stage* ms = mega::append(mega::OP_PAD_ACT_BWD)) {
-    ms->V = ge.V; ms->G = ge.G; ms->PPB = ge.PPB; ms->gx = grid.x; ms->S = S;
+    ms->V = ge.V; ms->G = ge.G; ms->PPB = ge.PPB; ms->gx = grid.x < 8u ? grid.x : 8u;      /* one virtual block per CTA of the sample's cluster */ ms->S = S;
     ms->a = dxp; ms->b = y; ms->c = g; ms->H = H; ms->W = W; ms->C = C; ms->pad = pad; ms->sums = sums; ms->gamma = gamma;
     ms->beta = beta; ms->act = act; ms->red = red;
     return 0;
@@ -189,7 +189,7 @@ int mfvi_bn_bwd_apply(MfviView g, MfviView y, int S, int H, int W, int C, const 
   MFVI_REQUIRE(ge.G <= kEwThreads, "bn_bwd_apply: too many channel groups");
   dim3 grid(ew_grid(H * W, ge.PPB, S), S);
   if (mega::Stage* ms = mega::append(mega::OP_BN_BWD_APPLY)) {
-    ms->V = ge.V; ms->G = ge.G; ms->PPB = ge.PPB; ms->gx = grid.x; ms->S = S;
+    ms->V = ge.V; ms->G = ge.G; ms->PPB = ge.PPB; ms->gx = grid.x < 8u ? grid.x : 8u;      /* one virtual block per CTA of the sample's cluster */ ms->S = S;
     ms->a = g; ms->b = y; ms->c = dy; ms->H = H; ms->W = W; ms->C = C; ms->sums = sums; ms->red = const_cast<double*>(red);
     ms->gamma = gamma; ms->dgamma = dgamma; ms->dbeta = dbeta;
     return 0;
@@ -211,7 +211,7 @@ int mfvi_cat_up_bwd(MfviView dA, int S, int H, int W, int mode, MfviView ys, int
     const EwGeom ge = ew_geom(Cs, view_vec_ok(dA) && view_vec_ok(ys) && view_vec_ok(gs));
     dim3 grid(ew_grid(H * W, ge.PPB, S), S);
     if (mega::Stage* ms = mega::append(mega::OP_CAT_BWD_SKIP)) {
-      ms->V = ge.V; ms->G = ge.G; ms->PPB = ge.PPB; ms->gx = grid.x; ms->S = S;
+      ms->V = ge.V; ms->G = ge.G; ms->PPB = ge.PPB; ms->gx = grid.x < 8u ? grid.x : 8u;      /* one virtual block per CTA of the sample's cluster */ ms->S = S;
       ms->a = dA; ms->b = ys; ms->c = gs; ms->H = H; ms->W = W; ms->C = Cs; ms->sums = sums_s; ms->gamma = gamma_s;
       ms->beta = beta_s; ms->red = red_s;
     } else {
@@ -225,7 +225,7 @@ int mfvi_cat_up_bwd(MfviView dA, int S, int H, int W, int mode, MfviView ys, int
   MFVI_REQUIRE(ge.G <= kEwThreads, "cat_up_bwd: too many channel groups");
   dim3 grid(ew_grid((H / 2) * (W / 2), ge.PPB, S), S);
   if (mega::Stage* ms = mega::append(mega::OP_CAT_BWD_UP)) {
-    ms->V = ge.V; ms->G = ge.G; ms->PPB = ge.PPB; ms->gx = grid.x; ms->S = S;
+    ms->V = ge.V; ms->G = ge.G; ms->PPB = ge.PPB; ms->gx = grid.x < 8u ? grid.x : 8u;      /* one virtual block per CTA of the sample's cluster */ ms->S = S;
     ms->a = dA; ms->b = yd; ms->c = gd; ms->H = H; ms->W = W; ms->mode = mode; ms->C = Cs; ms->C2 = Cd; ms->sums = sums_d;
     ms->gamma = gamma_d; ms->beta = beta_d; ms->red = red_d;
     return 0;

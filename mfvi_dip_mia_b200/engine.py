@@ -250,14 +250,16 @@ class SkipEngine:
         # their inputs; ("__join__", (), {"lane": X}) makes the main stream wait for lane X.
         self.overlap_wgrad = True
         self.overlap_skip = os.environ.get("MFVI_SKIP_LANE", "1") != "0"
-        # Persistent multi-stage kernel (csrc/mega.cu): scales >= mega_from run as ONE launch per direction instead of one launch
-        # per op.  None = the library default (by map size, _default_mega_from); -1 or MFVI_MEGA=0 = off.
+        # Persistent per-sample kernel (csrc/mega.cu): the down path of scale `mega_from`, everything below it and its upsample +
+        # concat run as ONE launch per direction instead of one launch per op (the scale's own skip and up convolutions, which
+        # work at twice the resolution, stay outside).  None = the library default (by map size, _default_mega_from); -1 or
+        # MFVI_MEGA=0 = off.
         env = os.environ.get("MFVI_MEGA_FROM")
         if mega_from is None and env is not None:
             mega_from = int(env)
         if mega_from is None:
             mega_from = self._default_mega_from()
-        if self.plan_only or os.environ.get("MFVI_MEGA", "1") == "0" or mega_from < 0 or mega_from >= len(spec.down):
+        if self.plan_only or os.environ.get("MFVI_MEGA", "1") == "0" or mega_from < 1 or mega_from >= len(spec.down):
             mega_from = None
         self.mega_from = mega_from
         self._mega = []                      # recorded programs (kept alive)
@@ -272,29 +274,38 @@ class SkipEngine:
 
     # ---------------------------------------------------------------- helpers
     def _default_mega_from(self) -> int:
-        """First scale whose maps are small enough for the persistent multi-stage kernel: S * (H / 2^(i+1)) * (W / 2^(i+1))
-        output pixels of the scale's convolutions <= MFVI_MEGA_PIXELS (default 0 = off until measured)."""
+        """First scale whose down-path maps are small enough for the persistent per-sample kernel: (H / 2^(i+1)) * (W / 2^(i+1))
+        pixels per sample <= MFVI_MEGA_PIXELS (default 0 = off until measured)."""
         limit = int(os.environ.get("MFVI_MEGA_PIXELS", "0"))
-        for i in range(len(self.spec.down)):
-            if self.S * (self.H >> (i + 1)) * (self.W >> (i + 1)) <= limit:
+        for i in range(1, len(self.spec.down)):
+            if (self.H >> (i + 1)) * (self.W >> (i + 1)) <= limit:
                 return i
         return -1
 
-    def _fuse(self, ops, n0: int, tag: str):
-        """Replace ops[n0:] by one mfvi_mega_run op (weight gradients stay separate launches on their lane, after it)."""
-        sub = ops[n0:]
-        del ops[n0:]
+    def _fuse(self, ops, n0: int, n1: int, tag: str):
+        """Replace ops[n0:n1] by one mfvi_mega_run op.  Lane joins of the slice are kept in front of it (the program runs on the
+        main lane), weight gradients stay separate launches on their lane behind it, and the gradients of the BatchNorm affine
+        parameters (a sum over all samples, which the per-sample program cannot form) follow as one mfvi_bn_param_grads."""
+        sub = ops[n0:n1]
         inner = [op for op in sub if op[0] not in ("__join__", "mfvi_conv2d_wgrad")]
-        later = [op for op in sub if op[0] == "mfvi_conv2d_wgrad"]
         if not inner:
-            ops.extend(sub)
             return
+        joins = [op for op in sub if op[0] == "__join__"]
+        later = [op for op in sub if op[0] == "mfvi_conv2d_wgrad"]
         m = L.record_program(inner, self.device)
         self._mega.append(m)
         meta = {"flops": sum(o[2].get("flops", 0.0) for o in inner), "bytes": sum(o[2].get("bytes", 0.0) for o in inner),
                 "layer": f"mega_{tag}", "shape": f"{m['n_stages']} stages", "sub_ops": inner}
-        ops.append(("mfvi_mega_run", (m["prog"].data_ptr(), m["n_stages"], m["max_items"], m["split3"], m["bar"].data_ptr()), meta))
-        ops.extend(later)
+        new = joins + [("mfvi_mega_run", (m["prog"].data_ptr(), m["n_stages"], self.S, L.ptr(m["prof"])), meta)]
+        bns = [op[1] for op in inner if op[0] == "mfvi_bn_bwd_apply" and op[1][10] is not None]
+        if bns:
+            i64 = lambda vals: torch.tensor(vals, dtype=torch.int64, device=self.device)
+            tabs = (i64([a[7] for a in bns]), i64([a[10] for a in bns]), i64([a[11] for a in bns]),
+                    torch.tensor([a[5] for a in bns], dtype=torch.int32, device=self.device))
+            m["bn_tables"] = tabs
+            new.append(("mfvi_bn_param_grads", (tabs[0].data_ptr(), tabs[1].data_ptr(), tabs[2].data_ptr(), tabs[3].data_ptr(),
+                                                len(bns), self.S), {"bytes": 16.0 * self.S * sum(a[5] for a in bns)}))
+        ops[n0:n1] = new + later
 
     def _buf(self, H, W, Cn, S=None):
         t = torch.empty(self.S if S is None else S, H, W, Cn, dtype=torch.float32, device=self.device)
@@ -405,19 +416,15 @@ class SkipEngine:
             if sc.skip_conv is not None:
                 ys, d_s = self._conv_fwd(sc.skip_conv, self._interior(T, Tpad - ps), sc.skip_bn)
                 self.fwd_ops[-1][2].update(lane="skip", after="main")
+            n_fuse0 = len(self.fwd_ops)
             x_d1 = self._interior(T, Tpad - pd)
             y1, d_1 = self._conv_fwd(sc.d1, x_d1, sc.d1_bn)
-            if sc.skip_conv is not None:
-                self.fwd_ops[-1][2]["indep"] = True        # reads the same input as the skip conv before it
             X2 = self._bn_act_pad(y1, sc.d1_bn, *self._bn_args(sc.d1_bn), 1, pd)
             y2, d_2 = self._conv_fwd(sc.d2, X2, sc.d2_bn)
             if i < n - 1:
                 npad = in_pad(i + 1)
                 Tn = self._bn_act_pad(y2, sc.d2_bn, *self._bn_args(sc.d2_bn), 1, npad)
-                n_before = len(self.fwd_ops)
                 z, z_bn, inner_bwd = run_scale(i + 1, Tn, npad)
-                if self.mega_from is not None and i + 1 == self.mega_from:
-                    self._fuse(self.fwd_ops, n_before, "fwd")
             else:
                 z, z_bn, inner_bwd = y2, sc.d2_bn, None
             Hs, Ws = 2 * z.shape[1], 2 * z.shape[2]
@@ -433,6 +440,8 @@ class SkipEngine:
             self.fwd_ops.append(("mfvi_cat_up_fwd", (L.view(ys) if Cs else null_view, Cs, *sb, L.view(z), Cd, *zb,
                                                      S, Hs, Ws, mode, L.view(A), self._aptr(sc.cat_bn.sums_off)),
                                  self._ew_meta(ys, z, A)))
+            if self.mega_from is not None and i == self.mega_from:
+                self._fuse(self.fwd_ops, n_fuse0, len(self.fwd_ops), "fwd")
             XA = self._bn_act_pad(A, sc.cat_bn, *self._bn_args(sc.cat_bn), 0, pu)
             yu, d_u = self._conv_fwd(sc.up, XA, sc.up_bn)
             if sc.up1 is not None:
@@ -456,17 +465,13 @@ class SkipEngine:
                 cat_args = (L.view(dA), S, Hs, Ws, mode, L.view(ys) if Cs else null_view, Cs, *sb,
                             L.view(gs) if Cs else null_view, self._aptr(sc.skip_bn.red_off) if Cs else None,
                             L.view(z), Cd, *zb, L.view(gd), self._aptr(z_bn.red_off))
-                # the upsampled branch continues the main chain; the skip branch's half goes to the skip lane
-                ops.append(("mfvi_cat_up_bwd", cat_args + (2,), self._ew_meta(dA[..., Cs:], z, gd)))
-                if Cs:
-                    ops.append(("mfvi_cat_up_bwd", cat_args + (1,), dict(self._ew_meta(dA[..., :Cs], ys, gs), lane="skip", after="main",
-                                                                         indep=True)))        # reads dA like part 2 before it
-                # BN backward of the two branches (their LeakyReLU was folded into cat_up_bwd).  The skip branch goes to the
-                # "skip" lane: BN backward, then its dgrad into the (zero-filled) input gradient of this scale, which the
-                # first down conv's dgrad accumulates onto after the join.
+                # The skip branch's half goes to the skip lane first (it only needs dA): LeakyReLU + BN backward, weight gradient,
+                # then its dgrad into the (zero-filled) input gradient of this scale, which the first down conv's dgrad accumulates
+                # onto after the join.  The upsampled branch then continues the main chain.
                 need_dT = i > 0 or self.need_input_grad
                 dT = self._buf(T.shape[1], T.shape[2], T.shape[3]) if need_dT else None
                 if Cs:
+                    ops.append(("mfvi_cat_up_bwd", cat_args + (1,), dict(self._ew_meta(dA[..., :Cs], ys, gs), lane="skip", after="main")))
                     x_s = self._interior(T, Tpad - ps)
                     ms = self._conv_meta(sc.skip_conv, d_s, x_s, gs)
                     ops.append(("mfvi_bn_bwd_apply", (
@@ -476,21 +481,18 @@ class SkipEngine:
                     ops.append(("mfvi_conv2d_wgrad", (C.byref(d_s), L.view(x_s), L.view(gs), self.dw.data_ptr() + 4 * sc.skip_conv.w_off,
                                                       self._dbias_ptr(sc.skip_conv, True), lay.P_pad), dict(ms, after="skip")))
                     if need_dT:
-                        # dT is a fresh buffer: the fill depends on nothing before it
-                        ops.append(("mfvi_fill_f32", (dT.data_ptr(), dT.numel(), 0.0), dict(self._ew_meta(dT), lane="skip", after="skip",
-                                                                                           indep=True)))
+                        ops.append(("mfvi_fill_f32", (dT.data_ptr(), dT.numel(), 0.0), dict(self._ew_meta(dT), lane="skip", after="skip")))
                         ops.append(("mfvi_conv2d_dgrad", (C.byref(d_s), L.view(gs), self.w.data_ptr() + 4 * sc.skip_conv.w_off,
                                                           lay.P_pad, L.view(self._interior(dT, Tpad - ps)), 1),
                                     dict(ms, lane="skip", after="skip")))
+                n_fuse0 = len(ops)
+                ops.append(("mfvi_cat_up_bwd", cat_args + (2,), self._ew_meta(dA[..., Cs:], z, gd)))
                 ops.append(("mfvi_bn_bwd_apply", (
                     L.view(gd), L.view(z), S, z.shape[1], z.shape[2], Cd, zb[0], self._aptr(z_bn.red_off), zb[1], L.view(gd),
                     self.g_gamma.data_ptr() + 4 * z_bn.ch_off, self.g_beta.data_ptr() + 4 * z_bn.ch_off),
                     self._ew_meta(gd, z, gd)))
                 if inner_bwd is not None:
-                    n_before = len(ops)
                     dTn = inner_bwd(ops, gd)
-                    if self.mega_from is not None and i + 1 == self.mega_from:
-                        self._fuse(ops, n_before, "bwd")
                     dy2 = self._bn_act_pad_bwd(ops, dTn, y2, sc.d2_bn, 1, Tn_pad)
                 else:
                     dy2 = gd
@@ -507,6 +509,8 @@ class SkipEngine:
                         ops.append(("mfvi_fill_f32", (dT.data_ptr(), dT.numel(), 0.0), self._ew_meta(dT)))
                     ops.append(("mfvi_conv2d_dgrad", (C.byref(d_1), L.view(dy1), self.w.data_ptr() + 4 * sc.d1.w_off, lay.P_pad,
                                                       L.view(dT_d1), 1 if (Cs or Tpad != pd) else 0), m1))
+                if self.mega_from is not None and i == self.mega_from:
+                    self._fuse(ops, n_fuse0, len(ops), "bwd")
                 return dT
 
             Tn_pad = in_pad(i + 1) if i < n - 1 else 0
