@@ -297,7 +297,7 @@ def run_ours(args):
         return float(ms.item())
 
     warm = max(args.warmup, 3)
-    for _ in range(warm):       # includes the 2 eager steps + graph capture
+    for _ in range(warm + 5):   # the first 2 steps run eagerly, the third captures the graph: 5 more replays settle NCCL / clocks
         tr.step()
     torch.cuda.synchronize()
     with ClockSampler(local) as clk:

@@ -22,6 +22,7 @@ from ..engine import SkipEngine
 from .modules import Conv2dLRT, Conv2dRT, LinearLRT, LinearRT, VIModule
 
 
+@L.device_guarded
 class _FusedForward(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, anchor, owner):
@@ -61,6 +62,7 @@ class _FusedForward(torch.autograd.Function):
         return None, torch.zeros_like(owner._anchor), None
 
 
+@L.device_guarded
 class _FusedKl(torch.autograd.Function):
     @staticmethod
     def forward(ctx, anchor, owner):

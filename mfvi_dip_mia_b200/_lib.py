@@ -199,6 +199,40 @@ def record_program(ops, device) -> dict:
             "names": [op[0] + (":" + op[2].get("layer", "") if op[2].get("layer") else "") for op in ops]}
 
 
+def on_device(fn):
+    """Method decorator: run with the object's CUDA device current.  The library launches on the CURRENT device and `call`
+    takes the current stream, so an engine living on cuda:k (trial fan-out: one runner per device; bayesian_optimization.py:3762)
+    must make that device current around every call — the reference gets this for free from ATen's device guards."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        dev = getattr(self, "device", None)
+        if dev is None or torch.device(dev).type != "cuda":
+            return fn(self, *a, **k)
+        with torch.cuda.device(dev):
+            return fn(self, *a, **k)
+    return wrapper
+
+
+def device_guarded(cls):
+    """Class decorator for torch.autograd.Function: forward / backward run with the device of their first CUDA tensor current."""
+    import functools
+
+    def guard(f):
+        @functools.wraps(f)
+        def wrapper(ctx, *a, **k):
+            t = next((x for x in a if torch.is_tensor(x) and x.is_cuda), None)
+            if t is None:
+                return f(ctx, *a, **k)
+            with torch.cuda.device(t.device):
+                return f(ctx, *a, **k)
+        return wrapper
+    cls.forward = staticmethod(guard(cls.forward))
+    cls.backward = staticmethod(guard(cls.backward))
+    return cls
+
+
 def require_cuda(t: torch.Tensor, what: str):
     if not t.is_cuda:
         raise MfviError(f"{what}: tensor is on {t.device}; this path runs only on a CUDA device (sm_100a) — "

@@ -394,6 +394,7 @@ class SkipEngine:
         return dx
 
     # ---------------------------------------------------------------- plan
+    @L.on_device
     def _build_plan(self):
         spec, lay, S = self.spec, self.lay, self.S
         self._keep = []
@@ -528,9 +529,11 @@ class SkipEngine:
         self.dx0 = bwd0(ops, dz0)
 
     # ---------------------------------------------------------------- execution
+    @L.on_device
     def zero_accumulators(self):
         L.call("mfvi_fill_f32", self.zbuf.data_ptr(), self.zbuf.numel(), 0.0, meta={"bytes": 4.0 * self.zbuf.numel()})
 
+    @L.on_device
     def set_input(self, x_nhwc: torch.Tensor, noise: Optional[torch.Tensor], std: float, key: L.PhiloxKey):
         """x0 = reflect_pad(saved + std * N(0,1))  (reference bayesian_optimization.py:1363-1364).
         x_nhwc: (H,W,C) contiguous.  noise (optional, (H,W,C)) injects the normals."""
@@ -542,12 +545,14 @@ class SkipEngine:
             self.eps = torch.zeros(self.S, self.lay.P_pad, dtype=torch.float32, device=self.device)
         return self.eps
 
+    @L.on_device
     def sample_weights(self, key: L.PhiloxKey):
         """w_s = mu + softplus(rho) * eps_s for every layer at once (reference module.py:82-85)."""
         inj = self.inject_eps
         L.call("mfvi_sample_weights", self.mu.data_ptr(), self.rho.data_ptr(), self.lay.P, self.S,
                self.eps.data_ptr() if inj else None, self.lay.P_pad, key, self.w.data_ptr(), self.lay.P_pad,
                meta={"bytes": 4.0 * self.lay.P * (2 + self.S)})
+    @L.on_device
     def use_mean_weights(self):
         """Eval mode of RTLayer (reparam_layers.py:33-35): w = mu for every sample."""
         self.w[:, :self.lay.P].copy_(self.mu.unsqueeze(0).expand(self.S, -1))
@@ -595,13 +600,16 @@ class SkipEngine:
         for lane in list(dirty):
             join(lane)
 
+    @L.on_device
     def forward(self):
         self._run(self.fwd_ops)
 
+    @L.on_device
     def backward(self):
         """Consumes self.dout; fills dw[s], BN gamma/beta grads (and dx0 when requested)."""
         self._run(self.bwd_ops)
 
+    @L.on_device
     def reparam_kl(self, key: L.PhiloxKey, *, prior_mu: float, prior_sigma_plus_eps: float, direction: int,
                    kscale: float, kscale_dev=None, data_term: bool = True, gscale: float = 1.0, accumulate: bool = False,
                    want_grad: bool = True, want_kl: bool = True):
@@ -615,6 +623,7 @@ class SkipEngine:
                self.g_rho.data_ptr() if want_grad else None, 1 if accumulate else 0,
                meta={"bytes": 4.0 * self.lay.P * (2 + (self.S if data_term else 0) + (2 if want_grad else 0))})
 
+    @L.on_device
     def update_running_stats(self, momentum: float = 0.1):
         L.call("mfvi_bn_running_update", self.arena.data_ptr(), self._bn_ch_off.data_ptr(), self._bn_sums_off.data_ptr(),
                self._bn_C.data_ptr(), self._bn_count.data_ptr(), len(self.lay.bns), self.S, float(momentum),
@@ -660,6 +669,7 @@ class SkipEngine:
                 out[f"{b.key}.running_var"] = self.running_var[b.ch_off:b.ch_off + b.C]
         return out
 
+    @L.on_device
     def load_params(self, sd: Dict[str, torch.Tensor], prefix: str = ""):
         """Copy a reference state_dict (keys optionally prefixed, e.g. 'net.') into the flat buffers."""
         views = self.param_views()
@@ -669,6 +679,7 @@ class SkipEngine:
                 raise KeyError(f"state dict lacks {prefix + k}")
             v.copy_(torch.as_tensor(src).to(self.device, torch.float32))
 
+    @L.on_device
     def pack_eps(self, eps: Sequence[Dict[str, torch.Tensor]], prefix: str = ""):
         """Injected eps: per sample a dict '<convkey>.W' (Cout,Cin,k,k) / '<convkey>.b' (Cout,) -> storage layout."""
         E = self.ensure_eps()
@@ -680,6 +691,7 @@ class SkipEngine:
                 E[s, c.b_off:c.b_off + c.cout].copy_(torch.as_tensor(d[prefix + c.key + ".b"]).to(self.device, torch.float32))
         self.inject_eps = True
 
+    @L.on_device
     def out_nchw(self) -> torch.Tensor:
         S, H, W, Cn = self.out.shape
         o = torch.empty(S, Cn, H, W, dtype=torch.float32, device=self.device)

@@ -69,6 +69,7 @@ def reparam_grads(mu, rho, eps, dw):
     return gm, gr
 
 
+@L.device_guarded
 class SampledConv2dFn(torch.autograd.Function):
     """RTLayer.forward with layer_fn=conv2d (reference reparam_layers.py:26-37, conv.py:6-38): one weight sample
     shared by the whole batch.  x (N,Cin,H,W); W_* (Cout,Cin,KH,KW); zero `padding`; dilation=groups=1."""
@@ -136,6 +137,7 @@ def _pad_nhwc(xh, padding):
     return xp
 
 
+@L.device_guarded
 class LrtConv2dFn(torch.autograd.Function):
     """LRTLayer.forward with layer_fn=conv2d (reference reparam_layers.py:39-72, conv.py:75-107):
         act_mu = conv(x, W_mu, b_mu);  act_var = conv(x^2, softplus(W_rho)^2, softplus(b_rho)^2)
@@ -222,6 +224,7 @@ class LrtConv2dFn(torch.autograd.Function):
         return dx, gWm, gWr, db, gbr, None, None, None, None, None
 
 
+@L.device_guarded
 class KlFn(torch.autograd.Function):
     """VIModule._kl (reference module.py:64-80) for one (mu, rho) pair: sum of closed-form Gaussian KLs,
     returned as a 0-dim fp32 tensor."""
@@ -249,6 +252,7 @@ class KlFn(torch.autograd.Function):
         return gm, gr, None, None, None
 
 
+@L.device_guarded
 class GaussianNllFn(torch.autograd.Function):
     """utils/bayesian_utils.py:29-39 of the reference.  mode 0: mu, s (N,1,H,W); mode 1 (inpainting): `mu` holds the
     PRE-sigmoid colour channels (N,3,H,W), s (N,1,H,W), mask (1,1,H,W)."""
@@ -284,6 +288,7 @@ class GaussianNllFn(torch.autograd.Function):
         return d[:, :Cm].contiguous(), d[:, Cm:].contiguous(), None, None, None, None
 
 
+@L.device_guarded
 class RadonFn(torch.autograd.Function):
     """FastRadonTransform.forward (reference radon/radon.py:48-55): image (1,C,H,W) -> sinogram (1,C,T,W)."""
 

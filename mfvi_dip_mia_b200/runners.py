@@ -22,6 +22,11 @@ import torch
 
 
 
+def _on_device(fn):
+    from ._lib import on_device
+    return on_device(fn)
+
+
 class DeviceBookkeeping:
     """Per-iteration bookkeeping of the runners (reference bayesian_optimization.py:1374-1416; SR :2190-2222, inpainting
     :3041-3069, CT :583-610) as ONE kernel per iteration, registered as a post-step hook of the trainer so that it is replayed
@@ -38,6 +43,7 @@ class DeviceBookkeeping:
                  sigmoid: bool = False, aleatoric: bool = True, mask=None):
         from . import _lib as L
         self.L, self.tr = L, trainer
+        self.device = trainer.eng.device
         e = trainer.eng
         self.S, self.H, self.W, _ = e.out.shape
         dev = e.device
@@ -52,6 +58,7 @@ class DeviceBookkeeping:
         self.acc = torch.zeros(self.N_ACC, dtype=torch.float64, device=dev)     # [0..4] squared errors, [5..6] SSIM sums
         trainer.post_step_hooks.append(self.record)
 
+    @_on_device
     def record(self):
         """Enqueue the bookkeeping of the step that was just computed (called by the trainer before the step counter
         advances; asynchronous)."""
@@ -62,6 +69,7 @@ class DeviceBookkeeping:
                self.ring_ale.data_ptr(), self.ring, self.tr.step_dev.data_ptr(), 0, self.acc.data_ptr(),
                meta={"bytes": 4.0 * self.H * self.W * ((self.Cm + 1) * self.S + 8 * self.Cm)})
 
+    @_on_device
     def metrics(self, ssim: bool = True) -> Dict[str, float]:
         """PSNR / MSE / SSIM of the last recorded iteration (one synchronising read of 8 doubles)."""
         L = self.L
@@ -84,6 +92,7 @@ class DeviceBookkeeping:
                 m["ssim_gt_sm"] = a[5] / n
         return m
 
+    @_on_device
     def uncertainty(self, n_valid: Optional[int] = None):
         """(epistemic, aleatoric, err2) maps from the ring buffers (:1410-1411), each (channels,H,W) — (H,W) for one channel;
         err2 is None without a ground truth, aleatoric is zero for a net without the s channel."""

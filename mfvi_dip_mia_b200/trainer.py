@@ -54,6 +54,11 @@ class LossHead:
         else:
             raise ValueError(f"unknown task {task!r}")
 
+    @property
+    def device(self):
+        return self.eng.device
+
+    @L.on_device
     def run(self):
         e = self.eng
         S, H, W, Cn = e.out.shape
@@ -88,6 +93,7 @@ class MfviDipTrainer:
         self.S_global = mc_samples
         self.S, self.sample0 = shard_samples(mc_samples, rank, world_size)
         self.rank, self.world_size, self.pg = rank, world_size, process_group
+        self.device = device
         self.temp, self.sigma, self.lr = float(temp), float(sigma), float(lr)
         self.prior_mu = float(prior_mu)
         # prior scale: sqrt(temp)*sigma handed to VIModule, which adds 1e-6 (bayesian_optimization.py:1335-1336, module.py:38)
@@ -117,6 +123,7 @@ class MfviDipTrainer:
         self._warm = 0
 
     # ------------------------------------------------------------------
+    @L.on_device
     def init_parameters(self, seed: int, mu=(0.0, 0.1), rho=(-3.0, 0.1)):
         """VIModule.reset_parameters (module.py:56-62): mu ~ N(0,0.1), rho ~ N(-3,0.1); BN gamma=1, beta=0.
         Same seed on every rank => identical replicas without a broadcast."""
@@ -138,6 +145,7 @@ class MfviDipTrainer:
         kj = L.key(self.seed, 0, 0, self.step_dev)
         return kw, kj
 
+    @L.on_device
     def _step_eager(self):
         e = self.eng
         kw, kj = self._keys()
@@ -168,6 +176,7 @@ class MfviDipTrainer:
             hook()
         L.call("mfvi_counter_add", self.step_dev.data_ptr(), 1)
 
+    @L.on_device
     def step(self):
         """One optimiser step, asynchronous on the current stream."""
         if not self.use_graph:
@@ -191,12 +200,14 @@ class MfviDipTrainer:
         tgt = getattr(self.head, "target", None)
         return self.head.sino_t if tgt is None else tgt
 
+    @L.on_device
     def host_buffers(self):
         """Pinned host staging buffers: (net_input NHWC (H,W,C), target as the head stores it, result[2] doubles)."""
         tgt = self._target_tensor()
         return (torch.empty_like(self.saved, device="cpu").pin_memory(), torch.empty_like(tgt, device="cpu").pin_memory(),
                 torch.zeros(2, dtype=torch.float64).pin_memory())
 
+    @L.on_device
     def step_from_host(self, net_input_host, target_host, result_host):
         """One step with HOST inputs: H2D copy of the net input and the target, the step, D2H of [kl, nll].
         Asynchronous and pipelined one step deep: the H2D copies go to one of two device staging slots on a copy stream
@@ -233,6 +244,7 @@ class MfviDipTrainer:
         return self.saved.numel() * 4 + tgt.numel() * 4, 16, done
 
     # ------------------------------------------------------------------
+    @L.on_device
     def loss_terms(self):
         """(nll, kl, loss) of the last step as Python floats (synchronises)."""
         a = self.eng.arena[:2].cpu()
