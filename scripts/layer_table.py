@@ -3,15 +3,15 @@ usage: python scripts/layer_table.py [fp32|tf32] [mc] [size]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from bench import synthetic_problem, TEMP, SIGMA, LR
-from mfvi_dip_mia_b200 import MfviDipTrainer, SkipSpec, _lib as L
+import bench
+from mfvi_dip_mia_b200 import _lib as L
 
 math = sys.argv[1] if len(sys.argv) > 1 else "tf32"
 mc = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 size = int(sys.argv[3]) if len(sys.argv) > 3 else 256
-x, t = synthetic_problem(size)
-tr = MfviDipTrainer(SkipSpec(), "den", x, temp=TEMP, sigma=SIGMA, lr=LR, mc_samples=mc, seed=1, device="cuda:0", target=t,
-                    math_mode=L.MATH_TF32 if math == "tf32" else L.MATH_FP32, use_graph=False)
+args = type("A", (), dict(config="den", size=size, mc=mc))()
+tr = bench.build_trainer(args, L.MATH_TF32 if math == "tf32" else L.MATH_FP32, torch.device("cuda:0"), 0, 1)
+tr.use_graph = False
 for _ in range(3):
     tr.step()
 torch.cuda.synchronize()

@@ -1,13 +1,16 @@
-"""Two eager MFVI-DIP steps (metric shape: 256^2, MC=8, tf32) — a short driver for `ncu --set full -k regex:<kernel>`."""
+"""Two eager steps of a BASELINE configuration (default: the metric shape 256^2, MC=8, tf32) — a short driver for
+`ncu --set full -k regex:<kernel>`.   usage: python scripts/one_step.py [den|sr|inp|ct] [tf32|fp32]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from bench import synthetic_problem, TEMP, SIGMA, LR
-from mfvi_dip_mia_b200 import MfviDipTrainer, SkipSpec, _lib as L
+import bench
+from mfvi_dip_mia_b200 import _lib as L
 
-x, t = synthetic_problem(256)
-tr = MfviDipTrainer(SkipSpec(), "den", x, temp=TEMP, sigma=SIGMA, lr=LR, mc_samples=8, seed=1, device="cuda:0", target=t,
-                    math_mode=L.MATH_TF32, use_graph=False)
+config = sys.argv[1] if len(sys.argv) > 1 else "den"
+math = sys.argv[2] if len(sys.argv) > 2 else "tf32"
+args = type("A", (), dict(config=config, size=bench.CONFIGS[config]["size"], mc=bench.CONFIGS[config]["mc"]))()
+tr = bench.build_trainer(args, L.MATH_TF32 if math == "tf32" else L.MATH_FP32, torch.device("cuda:0"), 0, 1)
+tr.use_graph = False
 for _ in range(2):
     tr.step()
 torch.cuda.synchronize()
