@@ -20,6 +20,7 @@
 // fused bias and per-sample BatchNorm (sum, sumsq) in double).  Accumulators are double-buffered in TMEM when they fit, so
 // the epilogue of tile i overlaps the loads and MMAs of tile i+1.
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -253,45 +254,37 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint32_t a_mt = (128u * rb) >> 4, rb16 = rb >> 4;
             const int tap0 = grp * p.g;
             const int ntap = min(p.g, p.taps - tap0);
-            for (int tt = 0; tt < ntap; ++tt) {
-              const int off_rows = p.tap_off[tcls][tap0 + tt];
-              if (off_rows < 0) continue;            // tap belongs to another output-parity class (stride-2 dgrad)
-              const uint32_t a_t = a_lo0 + static_cast<uint32_t>(off_rows) * rb16;
-              const uint32_t b_t = b_lo0 + static_cast<uint32_t>(tt) * b_tap;
-              const uint32_t acc0 = started ? 1u : 0u;
-              started = true;
-              uint32_t d_col = d_base;
-              if (ksteps == 4) {
-                // four k-steps of a 32-channel chunk: the eight descriptor low words stay live across the M tiles, so one
-                // MMA costs ~2 uniform-datapath instructions (each ~10 cycles) instead of ~8
-                uint32_t al0 = a_t, al1 = a_t + 2u, al2 = a_t + 4u, al3 = a_t + 6u;
-                const uint32_t bl0 = b_t, bl1 = b_t + b_k, bl2 = b_t + 2u * b_k, bl3 = b_t + 3u * b_k;
-                for (int j = 0; j < p.n_mt; ++j) {
-                  mma_elect<BF16>(d_col, desc_pack(al0, a_hi), desc_pack(bl0, b_hi), idesc, acc0);
-                  mma_elect<BF16>(d_col, desc_pack(al1, a_hi), desc_pack(bl1, b_hi), idesc, 1u);
-                  mma_elect<BF16>(d_col, desc_pack(al2, a_hi), desc_pack(bl2, b_hi), idesc, 1u);
-                  mma_elect<BF16>(d_col, desc_pack(al3, a_hi), desc_pack(bl3, b_hi), idesc, 1u);
-                  al0 += a_mt; al1 += a_mt; al2 += a_mt; al3 += a_mt;
-                  d_col += p.BN;
-                }
-              } else if (ksteps == 2) {
-                uint32_t al0 = a_t, al1 = a_t + 2u;
-                const uint32_t bl1 = b_t + b_k;
-                for (int j = 0; j < p.n_mt; ++j) {
-                  mma_elect<BF16>(d_col, desc_pack(al0, a_hi), desc_pack(b_t, b_hi), idesc, acc0);
-                  mma_elect<BF16>(d_col, desc_pack(al1, a_hi), desc_pack(bl1, b_hi), idesc, 1u);
-                  al0 += a_mt; al1 += a_mt;
-                  d_col += p.BN;
-                }
-              } else {
-                uint32_t al0 = a_t;
-                for (int j = 0; j < p.n_mt; ++j) {
-                  mma_elect<BF16>(d_col, desc_pack(al0, a_hi), desc_pack(b_t, b_hi), idesc, acc0);
-                  al0 += a_mt;
-                  d_col += p.BN;
+            // One specialised tap loop per chunk width (ksteps = 4 / 2 / 1): the single issuing thread spends most of its time
+            // in uniform-datapath bookkeeping, so everything loop-invariant (n_mt, BN, descriptor strides) sits in registers,
+            // the weight descriptor advances incrementally, and the tap's operand offset — a kernel-parameter table read with
+            // a run-time index in front of a branch — is fetched one tap ahead.
+            const int n_mt = p.n_mt;
+            const uint32_t BNu = static_cast<uint32_t>(p.BN);
+            int off_next = p.tap_off[tcls][tap0];
+            uint32_t b_t = b_lo0;
+            auto taps = [&](auto ks_tag) {
+              constexpr int KS = decltype(ks_tag)::value;
+              for (int tt = 0; tt < ntap; ++tt, b_t += b_tap) {
+                const int off_rows = off_next;
+                off_next = p.tap_off[tcls][tap0 + (tt + 1 < ntap ? tt + 1 : tt)];
+                if (off_rows < 0) continue;          // tap belongs to another output-parity class (stride-2 dgrad)
+                uint32_t al = a_lo0 + static_cast<uint32_t>(off_rows) * rb16;
+                const uint32_t acc0 = started ? 1u : 0u;
+                started = true;
+                uint32_t d_col = d_base;
+                for (int jm = 0; jm < n_mt; ++jm, al += a_mt, d_col += BNu) {
+                  mma_elect<BF16>(d_col, desc_pack(al, a_hi), desc_pack(b_t, b_hi), idesc, acc0);
+                  if (KS >= 2) mma_elect<BF16>(d_col, desc_pack(al + 2u, a_hi), desc_pack(b_t + b_k, b_hi), idesc, 1u);
+                  if (KS >= 4) {
+                    mma_elect<BF16>(d_col, desc_pack(al + 4u, a_hi), desc_pack(b_t + 2u * b_k, b_hi), idesc, 1u);
+                    mma_elect<BF16>(d_col, desc_pack(al + 6u, a_hi), desc_pack(b_t + 3u * b_k, b_hi), idesc, 1u);
+                  }
                 }
               }
-            }
+            };
+            if (ksteps == 4) taps(std::integral_constant<int, 4>{});
+            else if (ksteps == 2) taps(std::integral_constant<int, 2>{});
+            else taps(std::integral_constant<int, 1>{});
             tc_commit_elect(smem_u32(&b_empty[sb]));
             if (p.dbg) { cyc_issue += clock64() - ti0; n_mma += static_cast<long long>(p.g) * p.n_mt * ksteps; }
           }
