@@ -3,7 +3,7 @@
 #   1. launch list of the bench command (time + DRAM bytes per launch)  -> gpurun_out/r02_launches.csv
 #   2. --set full captures of the dominant kernels                        -> gpurun_out/r02_full_<name>.ncu-rep
 # In one eager step the launches of a kernel are ordered as the net executes, so `-s` picks a layer:
-#   k_conv_halo: forward launches 0..21 (up_9 = #19), then dgrad;  elementwise backward kernels start with the 256^2 layers.
+#   k_conv_halo: forward launches 0..21 (up_7 = #18, up_9 = #20, deeper_10 = #10), then dgrad (up_9 = #23);  elementwise backward kernels start with the 256^2 layers.
 set -u
 mkdir -p gpurun_out
 python bench.py --steps 2 --warmup 3 --profile > gpurun_out/r02_plain.log 2>&1 || { echo "plain bench run failed"; exit 1; }
@@ -17,9 +17,9 @@ run() {  # name script-args regex skip count
   echo "$1 rc=$?"
 }
 python scripts/one_step.py den > gpurun_out/r02_plain_one_step.log 2>&1 || { echo "plain one_step failed"; exit 1; }
-run conv_fwd_up9   den 'k_conv_halo'      19 1
-run conv_dgrad_up9 den 'k_conv_halo'      24 1
-run conv_fwd_up7   den 'k_conv_halo'      17 1
+run conv_fwd_up9   den 'k_conv_halo'      20 1
+run conv_dgrad_up9 den 'k_conv_halo'      23 1
+run conv_fwd_up7   den 'k_conv_halo'      18 1
 run conv_fwd_d10   den 'k_conv_halo'      10 1
 run wgrad_up9      den 'k_wgrad_alias'     2 1
 run pad_act_bwd    den 'k_pad_act_bwd'     2 1
