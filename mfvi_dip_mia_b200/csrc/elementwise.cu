@@ -41,7 +41,23 @@ k_pad_act_bwd(MfviView dxp, int H, int W, int C, int pad, MfviView y, const doub
   pdl_wait();
   __shared__ double sm_red[2 * kEwThreads * 4];
   __shared__ BnTable tab;
-  body_pad_act_bwd<V>(VGrid{(int)blockIdx.x, (int)blockIdx.y, (int)gridDim.x}, EwSmem{sm_red, &tab, nullptr}, dxp, H, W, C, pad, y, sums, gamma, beta, act, g, red, G, PPB);
+  body_pad_act_bwd<V, false>(VGrid{(int)blockIdx.x, (int)blockIdx.y, (int)gridDim.x}, EwSmem{sm_red, &tab, nullptr}, dxp, H, W, C, pad, y, sums, gamma, beta, act, g, red, G, PPB);
+}
+template <int V> __global__ void __launch_bounds__(kEwThreads, 5) k_pad_act_bwd5(MfviView dxp, int H, int W, int C, int pad, MfviView y, const double* __restrict__ sums,
+              const float* __restrict__ gamma, const float* __restrict__ beta, int act, MfviView g, double* __restrict__ red, int G, int PPB) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ double sm_red[2 * kEwThreads * 4];
+  __shared__ BnTable tab;
+  body_pad_act_bwd<V, false>(VGrid{(int)blockIdx.x, (int)blockIdx.y, (int)gridDim.x}, EwSmem{sm_red, &tab, nullptr}, dxp, H, W, C, pad, y, sums, gamma, beta, act, g, red, G, PPB);
+}
+template <int V> __global__ void __launch_bounds__(kEwThreads, 3) k_pad_act_bwd_u2(MfviView dxp, int H, int W, int C, int pad, MfviView y, const double* __restrict__ sums,
+              const float* __restrict__ gamma, const float* __restrict__ beta, int act, MfviView g, double* __restrict__ red, int G, int PPB) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ double sm_red[2 * kEwThreads * 4];
+  __shared__ BnTable tab;
+  body_pad_act_bwd<V, true>(VGrid{(int)blockIdx.x, (int)blockIdx.y, (int)gridDim.x}, EwSmem{sm_red, &tab, nullptr}, dxp, H, W, C, pad, y, sums, gamma, beta, act, g, red, G, PPB);
 }
 
 template <int V, bool OBF = false>       // OBF: dy is a bf16 view (strides in bf16 elements)
@@ -118,6 +134,22 @@ using namespace mfvi;
       launch_k(KERNEL<1>, GRID, kEwThreads, 0, as_stream(st), __VA_ARGS__, (GEOM).G, (GEOM).PPB);  \
   } while (0)
 
+// resident CTAs per SM of one elementwise kernel (both vector widths), asked of the runtime once per process
+template <typename K>
+static int ew_occupancy_of(K kernel) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kEwThreads, 0) != cudaSuccess || n < 1) {
+    cudaGetLastError();
+    n = 1;
+  }
+  return n;
+}
+#define MFVI_EW_OCC(GEOM, KERNEL)                                                         \
+  ([&]() -> int {                                                                         \
+    static const int occ4 = ew_occupancy_of(KERNEL<4>), occ1 = ew_occupancy_of(KERNEL<1>); \
+    return (GEOM).V == 4 ? occ4 : occ1;                                                   \
+  }())
+
 extern "C" {
 
 int mfvi_bn_act_pad_fwd(MfviView y, int S, int H, int W, int C, const double* sums, const float* gamma,
@@ -127,7 +159,7 @@ int mfvi_bn_act_pad_fwd(MfviView y, int S, int H, int W, int C, const double* su
   MFVI_REQUIRE(pad >= 0 && pad < H && pad < W, "bn_act_pad_fwd: pad must be smaller than the image");
   const EwGeom ge = ew_geom(C, view_vec_ok(y) && view_vec_ok(xp));
   MFVI_REQUIRE(ge.G <= kEwThreads, "bn_act_pad_fwd: too many channel groups");
-  dim3 grid(ew_grid((H + 2 * pad) * (W + 2 * pad), ge.PPB, S), S);
+  dim3 grid(ew_grid((H + 2 * pad) * (W + 2 * pad), ge.PPB, S, MFVI_EW_OCC(ge, k_bn_act_pad_fwd)), S);
   if (mega::Stage* ms = mega::append(mega::OP_BN_ACT_PAD_FWD)) {
     ms->V = ge.V; ms->G = ge.G; ms->PPB = ge.PPB; ms->gx = grid.x < 8u ? grid.x : 8u;      /* one virtual block per CTA of the sample's cluster */ ms->S = S;
     ms->a = y; ms->b = xp; ms->H = H; ms->W = W; ms->C = C; ms->sums = sums; ms->gamma = gamma; ms->beta = beta; ms->act = act;
@@ -149,7 +181,7 @@ int mfvi_cat_up_fwd(MfviView ys, int Cs, const double* sums_s, const float* gamm
   const bool al = view_vec_ok(yd) && view_vec_ok(A) && (Cs == 0 || view_vec_ok(ys)) && Cs % 4 == 0 && Cd % 4 == 0;
   const EwGeom ge = ew_geom(Cs + Cd, al);
   MFVI_REQUIRE(ge.G <= kEwThreads, "cat_up_fwd: too many channel groups");
-  dim3 grid(ew_grid((H / 2 + 1) * (W / 2 + 1), ge.PPB, S), S);
+  dim3 grid(ew_grid((H / 2 + 1) * (W / 2 + 1), ge.PPB, S, MFVI_EW_OCC(ge, k_cat_up_fwd)), S);
   if (mega::Stage* ms = mega::append(mega::OP_CAT_UP_FWD)) {
     ms->V = ge.V; ms->G = ge.G; ms->PPB = ge.PPB; ms->gx = grid.x < 8u ? grid.x : 8u;      /* one virtual block per CTA of the sample's cluster */ ms->S = S;
     ms->a = ys; ms->C = Cs; ms->sums = sums_s; ms->gamma = gamma_s; ms->beta = beta_s;
@@ -169,14 +201,22 @@ int mfvi_pad_act_bwd(MfviView dxp, int S, int H, int W, int C, int pad, MfviView
   MFVI_REQUIRE(pad >= 0 && pad < H && pad < W, "pad_act_bwd: pad must be smaller than the image");
   const EwGeom ge = ew_geom(C, view_vec_ok(dxp) && view_vec_ok(y) && view_vec_ok(g));
   MFVI_REQUIRE(ge.G <= kEwThreads, "pad_act_bwd: too many channel groups");
-  dim3 grid(ew_grid(H * W, ge.PPB, S), S);
+  static const int variant = ew_knob("MFVI_PAB", 0);          // measurement knob: 5 = 5 CTAs/SM build, 2 = two pixels per trip
+  const int occ = variant == 5 ? MFVI_EW_OCC(ge, k_pad_act_bwd5) : variant == 2 ? MFVI_EW_OCC(ge, k_pad_act_bwd_u2)
+                                                                                : MFVI_EW_OCC(ge, k_pad_act_bwd);
+  dim3 grid(ew_grid(H * W, ge.PPB, S, occ), S);
   if (mega::Stage* ms = mega::append(mega::OP_PAD_ACT_BWD)) {
     ms->V = ge.V; ms->G = ge.G; ms->PPB = ge.PPB; ms->gx = grid.x < 8u ? grid.x : 8u;      /* one virtual block per CTA of the sample's cluster */ ms->S = S;
     ms->a = dxp; ms->b = y; ms->c = g; ms->H = H; ms->W = W; ms->C = C; ms->pad = pad; ms->sums = sums; ms->gamma = gamma;
     ms->beta = beta; ms->act = act; ms->red = red;
     return 0;
   }
-  MFVI_EW_DISPATCH(ge, k_pad_act_bwd, grid, dxp, H, W, C, pad, y, sums, gamma, beta, act, g, red);
+  if (variant == 5)
+    MFVI_EW_DISPATCH(ge, k_pad_act_bwd5, grid, dxp, H, W, C, pad, y, sums, gamma, beta, act, g, red);
+  else if (variant == 2)
+    MFVI_EW_DISPATCH(ge, k_pad_act_bwd_u2, grid, dxp, H, W, C, pad, y, sums, gamma, beta, act, g, red);
+  else
+    MFVI_EW_DISPATCH(ge, k_pad_act_bwd, grid, dxp, H, W, C, pad, y, sums, gamma, beta, act, g, red);
   return check_launch("pad_act_bwd");
 }
 
@@ -187,7 +227,7 @@ int mfvi_bn_bwd_apply(MfviView g, MfviView y, int S, int H, int W, int C, const 
   MFVI_REQUIRE(C >= 1 && C <= kMaxC, "bn_bwd_apply: C out of range");
   const EwGeom ge = ew_geom(C, view_vec_ok(g) && view_vec_ok(y) && view_vec_ok(dy));
   MFVI_REQUIRE(ge.G <= kEwThreads, "bn_bwd_apply: too many channel groups");
-  dim3 grid(ew_grid(H * W, ge.PPB, S), S);
+  dim3 grid(ew_grid(H * W, ge.PPB, S, MFVI_EW_OCC(ge, k_bn_bwd_apply)), S);
   if (mega::Stage* ms = mega::append(mega::OP_BN_BWD_APPLY)) {
     ms->V = ge.V; ms->G = ge.G; ms->PPB = ge.PPB; ms->gx = grid.x < 8u ? grid.x : 8u;      /* one virtual block per CTA of the sample's cluster */ ms->S = S;
     ms->a = g; ms->b = y; ms->c = dy; ms->H = H; ms->W = W; ms->C = C; ms->sums = sums; ms->red = const_cast<double*>(red);
@@ -209,7 +249,7 @@ int mfvi_cat_up_bwd(MfviView dA, int S, int H, int W, int mode, MfviView ys, int
   if (Cs > 0 && part != 2) {
     MFVI_REQUIRE(ys.ptr && gs.ptr && red_s, "cat_up_bwd: null skip branch");
     const EwGeom ge = ew_geom(Cs, view_vec_ok(dA) && view_vec_ok(ys) && view_vec_ok(gs));
-    dim3 grid(ew_grid(H * W, ge.PPB, S), S);
+    dim3 grid(ew_grid(H * W, ge.PPB, S, MFVI_EW_OCC(ge, k_cat_bwd_skip)), S);
     if (mega::Stage* ms = mega::append(mega::OP_CAT_BWD_SKIP)) {
       ms->V = ge.V; ms->G = ge.G; ms->PPB = ge.PPB; ms->gx = grid.x < 8u ? grid.x : 8u;      /* one virtual block per CTA of the sample's cluster */ ms->S = S;
       ms->a = dA; ms->b = ys; ms->c = gs; ms->H = H; ms->W = W; ms->C = Cs; ms->sums = sums_s; ms->gamma = gamma_s;
@@ -223,7 +263,7 @@ int mfvi_cat_up_bwd(MfviView dA, int S, int H, int W, int mode, MfviView ys, int
   MFVI_REQUIRE(yd.ptr && gd.ptr && red_d, "cat_up_bwd: null upsampled branch");
   const EwGeom ge = ew_geom(Cd, view_vec_ok(dA) && view_vec_ok(yd) && view_vec_ok(gd) && Cs % 4 == 0);
   MFVI_REQUIRE(ge.G <= kEwThreads, "cat_up_bwd: too many channel groups");
-  dim3 grid(ew_grid((H / 2) * (W / 2), ge.PPB, S), S);
+  dim3 grid(ew_grid((H / 2) * (W / 2), ge.PPB, S, MFVI_EW_OCC(ge, k_cat_bwd_up)), S);
   if (mega::Stage* ms = mega::append(mega::OP_CAT_BWD_UP)) {
     ms->V = ge.V; ms->G = ge.G; ms->PPB = ge.PPB; ms->gx = grid.x < 8u ? grid.x : 8u;      /* one virtual block per CTA of the sample's cluster */ ms->S = S;
     ms->a = dA; ms->b = yd; ms->c = gd; ms->H = H; ms->W = W; ms->mode = mode; ms->C = Cs; ms->C2 = Cd; ms->sums = sums_d;

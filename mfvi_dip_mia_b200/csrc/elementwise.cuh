@@ -249,15 +249,31 @@ __device__ __forceinline__ int fold_sources(int h, int n, int pad, int (&q)[3]) 
   return cnt;
 }
 
-// chunks per sample: the whole launch (all S samples) gets about kCtasPerSM resident CTAs per SM, so that the
-// per-CTA prologue (BN tables) and epilogue (reductions, double atomics) are amortised over many pixels
-constexpr int kCtasPerSM = 6;
-static inline int ew_grid(int npix, int PPB, int S) {
-  int blocks = (npix + PPB - 1) / PPB;
-  int cap = (kNumSMs * kCtasPerSM + S - 1) / S;
-  if (cap < 1) cap = 1;
-  if (blocks > cap) blocks = cap;
-  return blocks < 1 ? 1 : blocks;
+// chunks per sample.  The whole launch (all S samples) is ONE resident wave: at most `occ` CTAs per SM -- the kernel's own
+// occupancy (MFVI_EW_OCC), capped by MFVI_EW_CTAS -- so that no partial second wave runs at a fraction of the machine (the
+// grid-stride sweep gives every CTA the same work).  Small launches take fewer CTAs still: every thread should sweep at least
+// kMinIter pixels, which amortises the per-CTA prologue (BN tables) and epilogue (reductions, double atomics), down to a floor
+// of kFloorCtas CTAs per SM.  MFVI_EW_CTAS / MFVI_EW_MINITER / MFVI_EW_FLOOR override the three constants (measurement knobs).
+constexpr int kCtasPerSM = 8, kMinIter = 4, kFloorCtas = 2;
+static inline int ew_knob(const char* name, int dflt) {
+  const char* e = getenv(name);
+  const int v = e ? atoi(e) : 0;
+  return v > 0 ? v : dflt;
+}
+static inline int ew_grid(int npix, int PPB, int S, int occ = kCtasPerSM) {
+  static const int cap = ew_knob("MFVI_EW_CTAS", kCtasPerSM), miniter = ew_knob("MFVI_EW_MINITER", kMinIter),
+                   floor_ctas = ew_knob("MFVI_EW_FLOOR", kFloorCtas);
+  const int blocks = (npix + PPB - 1) / PPB;                      // per sample, one pixel per thread
+  if (occ > cap) occ = cap;
+  if (occ < 1) occ = 1;
+  const long total = (long)blocks * S;
+  long want = (total + miniter - 1) / miniter;
+  const long lo = (long)kNumSMs * (floor_ctas < occ ? floor_ctas : occ), hi = (long)kNumSMs * occ;
+  if (want < lo) want = lo;
+  if (want > hi) want = hi;
+  long gx = want / S;
+  if (gx > blocks) gx = blocks;
+  return gx < 1 ? 1 : (int)gx;
 }
 
 }  // namespace mfvi

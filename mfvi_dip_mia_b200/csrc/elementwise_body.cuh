@@ -157,7 +157,7 @@ __device__ __forceinline__ void body_cat_up_fwd(const VGrid& vg, EwSmem sm, Mfvi
 
 
 // B1: g = fold_reflect(dxp) * act'(bn(y)), red += (sum g, sum g*xhat)      grid = (chunks, S)
-template <int V>
+template <int V, bool U2 = false>        // U2: two pixels per trip, their four loads issued before the first is used
 __device__ __forceinline__ void body_pad_act_bwd(const VGrid& vg, EwSmem sm, MfviView dxp, int H, int W, int C, int pad, MfviView y, const double* __restrict__ sums,
               const float* __restrict__ gamma, const float* __restrict__ beta, int act, MfviView g,
               double* __restrict__ red, int G, int PPB) {
@@ -176,10 +176,7 @@ __device__ __forceinline__ void body_pad_act_bwd(const VGrid& vg, EwSmem sm, Mfv
     const float* dbase = dxp.ptr + (size_t)s * dxp.sstride + c0;
     const float* ybase = y.ptr + (size_t)s * y.sstride + c0;
     float* gbase = g.ptr + (size_t)s * g.sstride + c0;
-    for (PixIter it(vg, H * W, W, PPB, slot); it.valid(); it.next()) {
-      const int h = it.h, w = it.w;
-      Vec<V> a;
-      a.load(dbase + (size_t)(h + pad) * dxp.hstride + (size_t)(w + pad) * dxp.wstride);
+    auto finish = [&](int h, int w, Vec<V>& a, const Vec<V>& yy) {
       const bool edge = pad > 0 && (h <= pad || w <= pad || h >= H - 1 - pad || w >= W - 1 - pad);
       if (edge) {          // reflected border positions fold back onto this pixel
         int qh[3], qw[3];
@@ -193,8 +190,6 @@ __device__ __forceinline__ void body_pad_act_bwd(const VGrid& vg, EwSmem sm, Mfv
             for (int j = 0; j < V; ++j) a.v[j] += t.v[j];
           }
       }
-      Vec<V> yy;
-      yy.load(ybase + (size_t)h * y.hstride + (size_t)w * y.wstride);
 #pragma unroll
       for (int j = 0; j < V; ++j) {
         const float z = fmaf(yy.v[j], bn.sc[j], bn.sh[j]);
@@ -207,6 +202,31 @@ __device__ __forceinline__ void body_pad_act_bwd(const VGrid& vg, EwSmem sm, Mfv
       }
       a.store(gbase + (size_t)h * g.hstride + (size_t)w * g.wstride);
       acc.tick();
+    };
+    PixIter it(vg, H * W, W, PPB, slot);
+    if constexpr (U2) {
+      while (it.valid()) {
+        const int h0 = it.h, w0 = it.w;
+        it.next();
+        const bool two = it.valid();
+        const int h1 = two ? it.h : h0, w1 = two ? it.w : w0;
+        if (two) it.next();
+        Vec<V> a0, y0, a1, y1;
+        a0.load(dbase + (size_t)(h0 + pad) * dxp.hstride + (size_t)(w0 + pad) * dxp.wstride);
+        y0.load(ybase + (size_t)h0 * y.hstride + (size_t)w0 * y.wstride);
+        a1.load(dbase + (size_t)(h1 + pad) * dxp.hstride + (size_t)(w1 + pad) * dxp.wstride);
+        y1.load(ybase + (size_t)h1 * y.hstride + (size_t)w1 * y.wstride);
+        finish(h0, w0, a0, y0);
+        if (two) finish(h1, w1, a1, y1);
+      }
+    } else {
+      for (; it.valid(); it.next()) {
+        const int h = it.h, w = it.w;
+        Vec<V> a, yy;
+        a.load(dbase + (size_t)(h + pad) * dxp.hstride + (size_t)(w + pad) * dxp.wstride);
+        yy.load(ybase + (size_t)h * y.hstride + (size_t)w * y.wstride);
+        finish(h, w, a, yy);
+      }
     }
     acc.flush();
   }

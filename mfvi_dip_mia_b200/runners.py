@@ -260,52 +260,125 @@ def f(task: str, bayes: str, candidate: Sequence[float], device, params: dict) -
     return run(temp=candidate[0], sigma=candidate[1], device=device, **params)
 
 
-def _trial_entry(fn, kwargs, candidate, device, queue):
-    """Body of one trial process (reference f(), bayesian_optimization.py:3709-3724)."""
+def _trial_value(fn, kwargs, candidate, device) -> float:
     try:
-        val = fn(temp=candidate[0], sigma=candidate[1], device=device, **kwargs)
+        return float(fn(temp=candidate[0], sigma=candidate[1], device=device, **kwargs))
     except Exception as e:  # a crashed trial is reported as NaN and dropped, like a diverged one
         print(f"[trial {candidate} on {device}] failed: {type(e).__name__}: {e}", flush=True)
-        val = float("nan")
-    queue.put((tuple(candidate), float(val)))
+        return float("nan")
+
+
+def _trial_entry(fn, kwargs, candidate, device, queue):
+    """Body of one trial process (reference f(), bayesian_optimization.py:3709-3724)."""
+    queue.put((tuple(candidate), _trial_value(fn, kwargs, candidate, device)))
+
+
+def _worker_entry(wid, fn, kwargs, device, tasks, results):
+    """Body of one persistent worker: trials of its device, one after the other, until the None sentinel.  The CUDA context,
+    the loaded library and whatever `fn` caches per process (runners.trial_cache) survive from trial to trial."""
+    while True:
+        cand = tasks.get()
+        if cand is None:
+            return
+        results.put((wid, tuple(cand), _trial_value(fn, kwargs, cand, device)))
+
+
+def _eval_trials_workers(ctx, cands, devices, fn, fn_kwargs, n_workers):
+    import queue as queue_mod
+    results_q = ctx.Queue()
+    results: Dict[Tuple[float, float], float] = {}
+    pending = list(cands)
+    workers = {}                                    # wid -> [process, task queue, device, candidate in flight]
+
+    def spawn(wid, device):
+        tq = ctx.Queue()
+        pr = ctx.Process(target=_worker_entry, args=(wid, fn, fn_kwargs, device, tq, results_q))
+        pr.start()
+        workers[wid] = [pr, tq, device, None]
+
+    def feed(wid):
+        w = workers[wid]
+        if pending:
+            w[3] = pending.pop(0)
+            w[1].put(w[3])
+        else:
+            w[3] = None
+
+    for wid in range(min(n_workers, len(cands))):
+        spawn(wid, devices[wid % len(devices)])
+        feed(wid)
+    while any(w[3] is not None for w in workers.values()):
+        try:
+            wid, c, v = results_q.get(timeout=0.5)
+            results[c] = v
+            feed(wid)
+        except queue_mod.Empty:
+            pass
+        for wid, w in list(workers.items()):
+            if w[3] is not None and not w[0].is_alive():
+                try:                                 # its last result may still sit in the queue
+                    while w[3] not in results:
+                        wid2, c2, v2 = results_q.get(timeout=0.5)
+                        results[c2] = v2
+                        if wid2 != wid:
+                            feed(wid2)
+                except queue_mod.Empty:
+                    results[w[3]] = float("nan")     # the worker died inside this trial: dropped like a NaN trial
+                w[0].join()
+                spawn(wid, w[2])                     # a fresh process (and CUDA context) for the rest of this device's trials
+                feed(wid)
+    for w in workers.values():
+        w[1].put(None)
+    for w in workers.values():
+        w[0].join(timeout=60)
+        if w[0].is_alive():
+            w[0].terminate()
+    return results
 
 
 def eval_trials(candidates: Iterable[Sequence[float]], devices: Sequence[str], fn: Callable[..., float],
                 fn_kwargs: Optional[dict] = None, *, max_parallel: Optional[int] = None,
-                start_method: str = "spawn") -> Tuple[List[Tuple[float, float]], List[float]]:
-    """Run `fn(temp=, sigma=, device=, **fn_kwargs)` once per candidate, one process per trial, devices assigned
-    round-robin; at most `max_parallel` (default: one per device) trials run at a time.  Returns (candidates, values)
-    with NaN results removed (bayesian_optimization.py:3772-3781)."""
+                start_method: str = "spawn", persistent: bool = False) -> Tuple[List[Tuple[float, float]], List[float]]:
+    """Run `fn(temp=, sigma=, device=, **fn_kwargs)` once per candidate, devices assigned round-robin; at most `max_parallel`
+    (default: one per device) trials run at a time.  Returns (candidates, values) with NaN results removed
+    (bayesian_optimization.py:3772-3781).
+    persistent=False: one OS process per trial, as the reference starts them.  persistent=True: one worker process per
+    device slot that runs its trials back to back -- the process start, `import torch`, the CUDA context and the library load
+    (seconds, against a 300-iteration trial's fraction of a second of kernels) are paid once per device instead of once per
+    trial; a trial that raises is NaN, a worker that dies takes only its current trial with it and is replaced."""
     import queue as queue_mod
     import torch.multiprocessing as mp
     ctx = mp.get_context(start_method)
     cands = [tuple(c) for c in candidates]
     max_parallel = max_parallel or len(devices)
-    queue = ctx.Queue()
-    dev_cycle = itertools.cycle(devices)
-    results: Dict[Tuple[float, float], float] = {}
-    pending = list(cands)
-    running = {}                                    # process -> candidate
-    while pending or running:
-        while pending and len(running) < max_parallel:
-            c = pending.pop(0)
-            pr = ctx.Process(target=_trial_entry, args=(fn, fn_kwargs or {}, c, next(dev_cycle), queue))
-            pr.start()
-            running[pr] = c
-        try:
-            c, v = queue.get(timeout=0.5)
-            results[c] = v
-        except queue_mod.Empty:
-            pass
-        for pr in [q for q in running if not q.is_alive()]:
-            pr.join()
-            c = running.pop(pr)
-            try:                                     # its result may still sit in the queue
-                while c not in results:
-                    c2, v2 = queue.get(timeout=0.5)
-                    results[c2] = v2
+    if persistent:
+        results = _eval_trials_workers(ctx, cands, list(devices), fn, fn_kwargs or {}, max_parallel)
+    else:
+        queue = ctx.Queue()
+        dev_cycle = itertools.cycle(devices)
+        results = {}
+        pending = list(cands)
+        running = {}                                    # process -> candidate
+        while pending or running:
+            while pending and len(running) < max_parallel:
+                c = pending.pop(0)
+                pr = ctx.Process(target=_trial_entry, args=(fn, fn_kwargs or {}, c, next(dev_cycle), queue))
+                pr.start()
+                running[pr] = c
+            try:
+                c, v = queue.get(timeout=0.5)
+                results[c] = v
             except queue_mod.Empty:
-                results.setdefault(c, float("nan"))  # the process died without reporting: dropped like a NaN trial
+                pass
+            for pr in [q for q in running if not q.is_alive()]:
+                pr.join()
+                c = running.pop(pr)
+                try:                                     # its result may still sit in the queue
+                    while c not in results:
+                        c2, v2 = queue.get(timeout=0.5)
+                        results[c2] = v2
+                except queue_mod.Empty:
+                    results.setdefault(c, float("nan"))  # the process died without reporting: dropped like a NaN trial
     X, Y = [], []
     for c in cands:
         v = results.get(c, float("nan"))

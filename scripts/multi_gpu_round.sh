@@ -16,7 +16,9 @@ except Exception as e:
     print("${tag} N=$n: FAILED", e)
 PY
 }
+if [ "$1" = sweep ]; then run 8 den; else
 for n in 1 2 4 8; do run $n den; done
 for n in 1 8; do run $n inp --config inp; done
+fi
 timeout 300 python -m pytest tests/test_gpu_trials.py -q -x 2>&1 | tail -2
 timeout 900 python scripts/run_bo_sweep.py --grid 8 --num-iter 300 --size 256 --out gpurun_out/r02_bo_sweep.json > gpurun_out/r02_bo_sweep.log 2>&1; tail -1 gpurun_out/r02_bo_sweep.log | cut -c1-400

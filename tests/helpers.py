@@ -66,6 +66,9 @@ def fake_trial(temp, sigma, device, offset=0.0):
         return float("nan")
     if temp == 4.0:
         raise RuntimeError("boom")
+    if temp == 6.0:
+        import os
+        os._exit(3)                       # the process dies without reporting
     return offset + math.log10(temp) - 2.0 * math.log10(sigma) + (0.0 if device == "cpu:0" else 0.5)
 
 

@@ -31,3 +31,17 @@ def test_trials_run_one_process_per_candidate_on_the_gpus():
     # atomics order + chaotic optimisation: ~0.15 dB after 40 steps at lr 1e-2)
     same = _den_trial(*cands[0], devices[0])
     assert abs(same - Y[0]) < 0.5, (same, Y[0])
+
+
+def test_trials_on_persistent_workers_match_per_trial_processes():
+    """persistent=True: one worker process per device runs its trials back to back (context, library and imports paid once);
+    the objectives are those of the one-process-per-trial fan-out, the NaN trial is dropped the same way."""
+    from mfvi_dip_mia_b200.runners import eval_trials
+    n_dev = torch.cuda.device_count()
+    devices = [f"cuda:{i}" for i in range(min(n_dev, 8))]
+    cands = [(5.6e-7, 1.5e-5), (1e-8, 1e-4), (1e-2, 1e-3), (1e-7, 1e-2), (3e-6, 1e-3)]
+    X, Y = eval_trials(cands, devices, _den_trial, {"poison": True}, persistent=True)
+    assert X == [c for c in cands if c[0] <= 1e-3], X
+    assert all(math.isfinite(v) and 5.0 < v < 40.0 for v in Y), Y
+    X1, Y1 = eval_trials(cands[:2], devices, _den_trial, {"poison": True}, max_parallel=max(2, len(devices)))
+    assert X1 == cands[:2] and all(abs(a - b) < 0.5 for a, b in zip(Y[:2], Y1)), (Y, Y1)

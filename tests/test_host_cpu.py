@@ -185,6 +185,22 @@ def test_trial_fanout_round_robin_and_nan_filter():
     assert len(g) == 64 and abs(g[0][0] - 1e-10) < 1e-20 and abs(g[-1][1] - 1.0) < 1e-12
 
 
+def test_trial_fanout_persistent_workers():
+    """eval_trials(persistent=True): one worker per device runs its trials back to back; a NaN trial and a raising trial are
+    dropped, a trial that kills its worker is dropped and the worker replaced, the rest of the candidates still finish."""
+    import math
+    from mfvi_dip_mia_b200.runners import eval_trials
+    from tests.helpers import fake_trial
+    cands = [(1.0, 0.1), (2.0, 0.1), (3.0, 0.1), (4.0, 0.1), (6.0, 0.1), (5.0, 0.01), (7.0, 0.1), (8.0, 0.1), (9.0, 0.1)]
+    X, Y = eval_trials(cands, ["cpu:0", "cpu:1"], fake_trial, {"offset": 1.0}, start_method="fork", persistent=True)
+    assert X == [c for c in cands if c[0] not in (3.0, 4.0, 6.0)]
+    for (t, s), y in zip(X, Y):          # which device ran a trial depends on timing: the value is one of the two
+        base = 1.0 + math.log10(t) - 2 * math.log10(s)
+        assert min(abs(y - base), abs(y - base - 0.5)) < 1e-12
+    X1, Y1 = eval_trials(cands[:1], ["cpu:0", "cpu:1"], fake_trial, {}, start_method="fork", persistent=True)
+    assert X1 == cands[:1] and abs(Y1[0] - (math.log10(1.0) + 2.0)) < 1e-12
+
+
 # ----------------------------------------------------------------------------------------------- BO outer loop (row f4)
 def test_gp_posterior_and_ei_match_closed_form():
     """ExactGPModel (constant mean + scaled RBF + Gaussian noise) against plain numpy GP algebra at the fitted
