@@ -33,7 +33,7 @@ k_cat_up_fwd(MfviView ys, int Cs, const double* __restrict__ sums_s, const float
 }
 
 template <int V>
-__global__ void __launch_bounds__(kEwThreads, 4)
+__global__ void __launch_bounds__(kEwThreads, 3)
 k_pad_act_bwd(MfviView dxp, int H, int W, int C, int pad, MfviView y, const double* __restrict__ sums,
               const float* __restrict__ gamma, const float* __restrict__ beta, int act, MfviView g,
               double* __restrict__ red, int G, int PPB) {
@@ -41,25 +41,8 @@ k_pad_act_bwd(MfviView dxp, int H, int W, int C, int pad, MfviView y, const doub
   pdl_wait();
   __shared__ double sm_red[2 * kEwThreads * 4];
   __shared__ BnTable tab;
-  body_pad_act_bwd<V, false>(VGrid{(int)blockIdx.x, (int)blockIdx.y, (int)gridDim.x}, EwSmem{sm_red, &tab, nullptr}, dxp, H, W, C, pad, y, sums, gamma, beta, act, g, red, G, PPB);
+  body_pad_act_bwd<V>(VGrid{(int)blockIdx.x, (int)blockIdx.y, (int)gridDim.x}, EwSmem{sm_red, &tab, nullptr}, dxp, H, W, C, pad, y, sums, gamma, beta, act, g, red, G, PPB);
 }
-template <int V> __global__ void __launch_bounds__(kEwThreads, 5) k_pad_act_bwd5(MfviView dxp, int H, int W, int C, int pad, MfviView y, const double* __restrict__ sums,
-              const float* __restrict__ gamma, const float* __restrict__ beta, int act, MfviView g, double* __restrict__ red, int G, int PPB) {
-  pdl_trigger();
-  pdl_wait();
-  __shared__ double sm_red[2 * kEwThreads * 4];
-  __shared__ BnTable tab;
-  body_pad_act_bwd<V, false>(VGrid{(int)blockIdx.x, (int)blockIdx.y, (int)gridDim.x}, EwSmem{sm_red, &tab, nullptr}, dxp, H, W, C, pad, y, sums, gamma, beta, act, g, red, G, PPB);
-}
-template <int V> __global__ void __launch_bounds__(kEwThreads, 3) k_pad_act_bwd_u2(MfviView dxp, int H, int W, int C, int pad, MfviView y, const double* __restrict__ sums,
-              const float* __restrict__ gamma, const float* __restrict__ beta, int act, MfviView g, double* __restrict__ red, int G, int PPB) {
-  pdl_trigger();
-  pdl_wait();
-  __shared__ double sm_red[2 * kEwThreads * 4];
-  __shared__ BnTable tab;
-  body_pad_act_bwd<V, true>(VGrid{(int)blockIdx.x, (int)blockIdx.y, (int)gridDim.x}, EwSmem{sm_red, &tab, nullptr}, dxp, H, W, C, pad, y, sums, gamma, beta, act, g, red, G, PPB);
-}
-
 template <int V, bool OBF = false>       // OBF: dy is a bf16 view (strides in bf16 elements)
 __global__ void __launch_bounds__(kEwThreads)
 k_bn_bwd_apply(MfviView g, MfviView y, int S, int H, int W, int C, const double* __restrict__ sums,
@@ -201,9 +184,7 @@ int mfvi_pad_act_bwd(MfviView dxp, int S, int H, int W, int C, int pad, MfviView
   MFVI_REQUIRE(pad >= 0 && pad < H && pad < W, "pad_act_bwd: pad must be smaller than the image");
   const EwGeom ge = ew_geom(C, view_vec_ok(dxp) && view_vec_ok(y) && view_vec_ok(g));
   MFVI_REQUIRE(ge.G <= kEwThreads, "pad_act_bwd: too many channel groups");
-  static const int variant = ew_knob("MFVI_PAB", 0);          // measurement knob: 5 = 5 CTAs/SM build, 2 = two pixels per trip
-  const int occ = variant == 5 ? MFVI_EW_OCC(ge, k_pad_act_bwd5) : variant == 2 ? MFVI_EW_OCC(ge, k_pad_act_bwd_u2)
-                                                                                : MFVI_EW_OCC(ge, k_pad_act_bwd);
+  const int occ = MFVI_EW_OCC(ge, k_pad_act_bwd);
   dim3 grid(ew_grid(H * W, ge.PPB, S, occ), S);
   if (mega::Stage* ms = mega::append(mega::OP_PAD_ACT_BWD)) {
     ms->V = ge.V; ms->G = ge.G; ms->PPB = ge.PPB; ms->gx = grid.x < 8u ? grid.x : 8u;      /* one virtual block per CTA of the sample's cluster */ ms->S = S;
@@ -211,12 +192,7 @@ int mfvi_pad_act_bwd(MfviView dxp, int S, int H, int W, int C, int pad, MfviView
     ms->beta = beta; ms->act = act; ms->red = red;
     return 0;
   }
-  if (variant == 5)
-    MFVI_EW_DISPATCH(ge, k_pad_act_bwd5, grid, dxp, H, W, C, pad, y, sums, gamma, beta, act, g, red);
-  else if (variant == 2)
-    MFVI_EW_DISPATCH(ge, k_pad_act_bwd_u2, grid, dxp, H, W, C, pad, y, sums, gamma, beta, act, g, red);
-  else
-    MFVI_EW_DISPATCH(ge, k_pad_act_bwd, grid, dxp, H, W, C, pad, y, sums, gamma, beta, act, g, red);
+  MFVI_EW_DISPATCH(ge, k_pad_act_bwd, grid, dxp, H, W, C, pad, y, sums, gamma, beta, act, g, red);
   return check_launch("pad_act_bwd");
 }
 

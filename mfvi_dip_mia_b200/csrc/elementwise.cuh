@@ -159,6 +159,30 @@ struct PixIter {
   }
 };
 
+// U consecutive positions of a PixIter: the kernels issue the loads of a whole batch before they use the first one (a thread
+// otherwise has one pixel's loads in flight -- the store to a possibly aliasing view keeps the compiler from hoisting the
+// next trip's loads -- and these kernels are latency-bound: profiles/r02_ew_load_batching.txt).  Positions past the end
+// repeat position 0 (their loads are harmless duplicates), n = the valid ones.
+template <int U>
+struct PixBatch {
+  int h[U], w[U], n;
+  __device__ __forceinline__ bool fill(PixIter& it) {
+    if (!it.valid()) return false;
+    h[0] = it.h; w[0] = it.w; n = 1;
+    it.next();
+#pragma unroll
+    for (int u = 1; u < U; ++u) {
+      if (it.valid()) {
+        h[u] = it.h; w[u] = it.w; n = u + 1;
+        it.next();
+      } else {
+        h[u] = h[0]; w[u] = w[0];
+      }
+    }
+    return true;
+  }
+};
+
 // BatchNorm constants of one sample: computed once per CTA (one thread per channel, double rsqrt) into shared memory,
 // then every thread keeps the V channels it owns in registers.  z = y*sc + sh ; xhat = (y - mean)*invstd
 struct BnTable {

@@ -24,18 +24,28 @@ __device__ __forceinline__ void body_bn_act_pad_fwd(const VGrid& vg, EwSmem sm, 
   const float* ybase = y.ptr + (size_t)s * y.sstride + c0;
   float* xbase = xp.ptr + (size_t)s * xp.sstride + c0;
   __nv_bfloat16* xbase16 = reinterpret_cast<__nv_bfloat16*>(xp.ptr) + (size_t)s * xp.sstride + c0;
-  for (PixIter it(vg, Hp * Wp, Wp, PPB, slot); it.valid(); it.next()) {
-    const int h = reflect_idx(it.h - pad, H), w = reflect_idx(it.w - pad, W);
-    Vec<V> t;
-    t.load(ybase + (size_t)h * y.hstride + (size_t)w * y.wstride);
+  constexpr int U = 4;
+  PixIter it(vg, Hp * Wp, Wp, PPB, slot);
+  PixBatch<U> b;
+  while (b.fill(it)) {
+    Vec<V> t[U];
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-      float z = fmaf(t.v[j], bn.sc[j], bn.sh[j]);
-      if (act) z = z > 0.f ? z : kLreluSlope * z;
-      t.v[j] = z;
+    for (int u = 0; u < U; ++u) {
+      const int h = reflect_idx(b.h[u] - pad, H), w = reflect_idx(b.w[u] - pad, W);
+      t[u].load(ybase + (size_t)h * y.hstride + (size_t)w * y.wstride);
     }
-    if (!OBF) t.store(xbase + (size_t)it.h * xp.hstride + (size_t)it.w * xp.wstride);
-    else store_bf16<V>(xbase16 + (size_t)it.h * xp.hstride + (size_t)it.w * xp.wstride, t.v);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (u >= b.n) break;
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        float z = fmaf(t[u].v[j], bn.sc[j], bn.sh[j]);
+        if (act) z = z > 0.f ? z : kLreluSlope * z;
+        t[u].v[j] = z;
+      }
+      if (!OBF) t[u].store(xbase + (size_t)b.h[u] * xp.hstride + (size_t)b.w[u] * xp.wstride);
+      else store_bf16<V>(xbase16 + (size_t)b.h[u] * xp.hstride + (size_t)b.w[u] * xp.wstride, t[u].v);
+    }
   }
 }
 
@@ -157,7 +167,7 @@ __device__ __forceinline__ void body_cat_up_fwd(const VGrid& vg, EwSmem sm, Mfvi
 
 
 // B1: g = fold_reflect(dxp) * act'(bn(y)), red += (sum g, sum g*xhat)      grid = (chunks, S)
-template <int V, bool U2 = false>        // U2: two pixels per trip, their four loads issued before the first is used
+template <int V>
 __device__ __forceinline__ void body_pad_act_bwd(const VGrid& vg, EwSmem sm, MfviView dxp, int H, int W, int C, int pad, MfviView y, const double* __restrict__ sums,
               const float* __restrict__ gamma, const float* __restrict__ beta, int act, MfviView g,
               double* __restrict__ red, int G, int PPB) {
@@ -203,29 +213,20 @@ __device__ __forceinline__ void body_pad_act_bwd(const VGrid& vg, EwSmem sm, Mfv
       a.store(gbase + (size_t)h * g.hstride + (size_t)w * g.wstride);
       acc.tick();
     };
+    constexpr int U = 2;
     PixIter it(vg, H * W, W, PPB, slot);
-    if constexpr (U2) {
-      while (it.valid()) {
-        const int h0 = it.h, w0 = it.w;
-        it.next();
-        const bool two = it.valid();
-        const int h1 = two ? it.h : h0, w1 = two ? it.w : w0;
-        if (two) it.next();
-        Vec<V> a0, y0, a1, y1;
-        a0.load(dbase + (size_t)(h0 + pad) * dxp.hstride + (size_t)(w0 + pad) * dxp.wstride);
-        y0.load(ybase + (size_t)h0 * y.hstride + (size_t)w0 * y.wstride);
-        a1.load(dbase + (size_t)(h1 + pad) * dxp.hstride + (size_t)(w1 + pad) * dxp.wstride);
-        y1.load(ybase + (size_t)h1 * y.hstride + (size_t)w1 * y.wstride);
-        finish(h0, w0, a0, y0);
-        if (two) finish(h1, w1, a1, y1);
+    PixBatch<U> b;
+    while (b.fill(it)) {
+      Vec<V> a[U], yy[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        a[u].load(dbase + (size_t)(b.h[u] + pad) * dxp.hstride + (size_t)(b.w[u] + pad) * dxp.wstride);
+        yy[u].load(ybase + (size_t)b.h[u] * y.hstride + (size_t)b.w[u] * y.wstride);
       }
-    } else {
-      for (; it.valid(); it.next()) {
-        const int h = it.h, w = it.w;
-        Vec<V> a, yy;
-        a.load(dbase + (size_t)(h + pad) * dxp.hstride + (size_t)(w + pad) * dxp.wstride);
-        yy.load(ybase + (size_t)h * y.hstride + (size_t)w * y.wstride);
-        finish(h, w, a, yy);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (u >= b.n) break;
+        finish(b.h[u], b.w[u], a[u], yy[u]);
       }
     }
     acc.flush();
@@ -280,18 +281,27 @@ __device__ __forceinline__ void body_bn_bwd_apply(const VGrid& vg, EwSmem sm, Mf
   const float* ybase = y.ptr + (size_t)s * y.sstride + c0;
   float* obase = dy.ptr + (size_t)s * dy.sstride + c0;
   __nv_bfloat16* obase16 = reinterpret_cast<__nv_bfloat16*>(dy.ptr) + (size_t)s * dy.sstride + c0;
-  for (PixIter it(vg, H * W, W, PPB, slot); it.valid(); it.next()) {
-    const int h = it.h, w = it.w;
-    Vec<V> gg, yy;
-    gg.load(gbase + (size_t)h * g.hstride + (size_t)w * g.wstride);
-    yy.load(ybase + (size_t)h * y.hstride + (size_t)w * y.wstride);
+  constexpr int U = 2;
+  PixIter it(vg, H * W, W, PPB, slot);
+  PixBatch<U> b;
+  while (b.fill(it)) {
+    Vec<V> gg[U], yy[U];
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-      const float xhat = (yy.v[j] - mean[j]) * invstd[j];
-      gg.v[j] = k[j] * (gg.v[j] - m1[j] - xhat * m2[j]);
+    for (int u = 0; u < U; ++u) {
+      gg[u].load(gbase + (size_t)b.h[u] * g.hstride + (size_t)b.w[u] * g.wstride);
+      yy[u].load(ybase + (size_t)b.h[u] * y.hstride + (size_t)b.w[u] * y.wstride);
     }
-    if (!OBF) gg.store(obase + (size_t)h * dy.hstride + (size_t)w * dy.wstride);
-    else store_bf16<V>(obase16 + (size_t)h * dy.hstride + (size_t)w * dy.wstride, gg.v);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (u >= b.n) break;
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const float xhat = (yy[u].v[j] - mean[j]) * invstd[j];
+        gg[u].v[j] = k[j] * (gg[u].v[j] - m1[j] - xhat * m2[j]);
+      }
+      if (!OBF) gg[u].store(obase + (size_t)b.h[u] * dy.hstride + (size_t)b.w[u] * dy.wstride);
+      else store_bf16<V>(obase16 + (size_t)b.h[u] * dy.hstride + (size_t)b.w[u] * dy.wstride, gg[u].v);
+    }
   }
 }
 
@@ -315,22 +325,31 @@ __device__ __forceinline__ void body_cat_bwd_skip(const VGrid& vg, EwSmem sm, Mf
     const float* dbase = dA.ptr + (size_t)s * dA.sstride + c0;
     const float* ybase = ys.ptr + (size_t)s * ys.sstride + c0;
     float* gbase = gs.ptr + (size_t)s * gs.sstride + c0;
-    for (PixIter it(vg, H * W, W, PPB, slot); it.valid(); it.next()) {
-      const int h = it.h, w = it.w;
-      Vec<V> d, yy;
-      d.load(dbase + (size_t)h * dA.hstride + (size_t)w * dA.wstride);
-      yy.load(ybase + (size_t)h * ys.hstride + (size_t)w * ys.wstride);
+    constexpr int U = 2;
+    PixIter it(vg, H * W, W, PPB, slot);
+    PixBatch<U> b;
+    while (b.fill(it)) {
+      Vec<V> d[U], yy[U];
 #pragma unroll
-      for (int j = 0; j < V; ++j) {
-        const float z = fmaf(yy.v[j], bn.sc[j], bn.sh[j]);
-        const float gg = z > 0.f ? d.v[j] : kLreluSlope * d.v[j];
-        const float xhat = (yy.v[j] - bn.mean[j]) * bn.invstd[j];
-        d.v[j] = gg;
-        acc.fa[j] += gg;
-        acc.fb[j] = fmaf(gg, xhat, acc.fb[j]);
+      for (int u = 0; u < U; ++u) {
+        d[u].load(dbase + (size_t)b.h[u] * dA.hstride + (size_t)b.w[u] * dA.wstride);
+        yy[u].load(ybase + (size_t)b.h[u] * ys.hstride + (size_t)b.w[u] * ys.wstride);
       }
-      d.store(gbase + (size_t)h * gs.hstride + (size_t)w * gs.wstride);
-      acc.tick();
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (u >= b.n) break;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const float z = fmaf(yy[u].v[j], bn.sc[j], bn.sh[j]);
+          const float gg = z > 0.f ? d[u].v[j] : kLreluSlope * d[u].v[j];
+          const float xhat = (yy[u].v[j] - bn.mean[j]) * bn.invstd[j];
+          d[u].v[j] = gg;
+          acc.fa[j] += gg;
+          acc.fb[j] = fmaf(gg, xhat, acc.fb[j]);
+        }
+        d[u].store(gbase + (size_t)b.h[u] * gs.hstride + (size_t)b.w[u] * gs.wstride);
+        acc.tick();
+      }
     }
     acc.flush();
   }
