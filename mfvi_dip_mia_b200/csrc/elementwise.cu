@@ -19,6 +19,17 @@ k_bn_act_pad_fwd(MfviView y, int H, int W, int C, const double* __restrict__ sum
   body_bn_act_pad_fwd<V, OBF>(VGrid{(int)blockIdx.x, (int)blockIdx.y, (int)gridDim.x}, EwSmem{nullptr, &tab, nullptr}, y, H, W, C, sums, gamma, beta, act, pad, xp, G, PPB);
 }
 
+template <int V>       // the same body behind the cp.async slots (kPipeBytes of dynamic shared memory)
+__global__ void __launch_bounds__(kEwThreads)
+k_bn_act_pad_fwd_p(MfviView y, int H, int W, int C, const double* __restrict__ sums, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, int act, int pad, MfviView xp, int G, int PPB) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) float ew_pipe[];
+  __shared__ BnTable tab;
+  body_bn_act_pad_fwd<V, false, true>(VGrid{(int)blockIdx.x, (int)blockIdx.y, (int)gridDim.x}, EwSmem{nullptr, &tab, nullptr, ew_pipe}, y, H, W, C, sums, gamma, beta, act, pad, xp, G, PPB);
+}
+
 template <int V>
 __global__ void __launch_bounds__(kEwThreads, 3)
 k_cat_up_fwd(MfviView ys, int Cs, const double* __restrict__ sums_s, const float* __restrict__ gamma_s,
@@ -43,6 +54,19 @@ k_pad_act_bwd(MfviView dxp, int H, int W, int C, int pad, MfviView y, const doub
   __shared__ BnTable tab;
   body_pad_act_bwd<V>(VGrid{(int)blockIdx.x, (int)blockIdx.y, (int)gridDim.x}, EwSmem{sm_red, &tab, nullptr}, dxp, H, W, C, pad, y, sums, gamma, beta, act, g, red, G, PPB);
 }
+template <int V>       // the same body behind the cp.async slots (kPipeBytes of dynamic shared memory)
+__global__ void __launch_bounds__(kEwThreads, 3)
+k_pad_act_bwd_p(MfviView dxp, int H, int W, int C, int pad, MfviView y, const double* __restrict__ sums,
+                const float* __restrict__ gamma, const float* __restrict__ beta, int act, MfviView g,
+                double* __restrict__ red, int G, int PPB) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) float ew_pipe[];
+  __shared__ double sm_red[2 * kEwThreads * 4];
+  __shared__ BnTable tab;
+  body_pad_act_bwd<V, true>(VGrid{(int)blockIdx.x, (int)blockIdx.y, (int)gridDim.x}, EwSmem{sm_red, &tab, nullptr, ew_pipe}, dxp, H, W, C, pad, y, sums, gamma, beta, act, g, red, G, PPB);
+}
+
 template <int V, bool OBF = false>       // OBF: dy is a bf16 view (strides in bf16 elements)
 __global__ void __launch_bounds__(kEwThreads)
 k_bn_bwd_apply(MfviView g, MfviView y, int S, int H, int W, int C, const double* __restrict__ sums,
@@ -52,6 +76,18 @@ k_bn_bwd_apply(MfviView g, MfviView y, int S, int H, int W, int C, const double*
   pdl_wait();
   __shared__ float sm_misc[5 * kMaxC];
   body_bn_bwd_apply<V, OBF>(VGrid{(int)blockIdx.x, (int)blockIdx.y, (int)gridDim.x}, EwSmem{nullptr, nullptr, sm_misc}, g, y, S, H, W, C, sums, red, gamma, dy, dgamma, dbeta, G, PPB);
+}
+
+template <int V>       // the same body behind the cp.async slots
+__global__ void __launch_bounds__(kEwThreads)
+k_bn_bwd_apply_p(MfviView g, MfviView y, int S, int H, int W, int C, const double* __restrict__ sums,
+                 const double* __restrict__ red, const float* __restrict__ gamma, MfviView dy,
+                 float* __restrict__ dgamma, float* __restrict__ dbeta, int G, int PPB) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) float ew_pipe[];
+  __shared__ float sm_misc[5 * kMaxC];
+  body_bn_bwd_apply<V, false, true>(VGrid{(int)blockIdx.x, (int)blockIdx.y, (int)gridDim.x}, EwSmem{nullptr, nullptr, sm_misc, ew_pipe}, g, y, S, H, W, C, sums, red, gamma, dy, dgamma, dbeta, G, PPB);
 }
 
 template <int V>
@@ -109,29 +145,61 @@ __global__ void k_bn_running(const double* __restrict__ arena, const int* __rest
 
 using namespace mfvi;
 
-#define MFVI_EW_DISPATCH(GEOM, KERNEL, GRID, ...)                                              \
+#define MFVI_EW_DISPATCH_SMEM(GEOM, KERNEL, GRID, SMEM, ...)                                   \
   do {                                                                                         \
     if ((GEOM).V == 4)                                                                         \
-      launch_k(KERNEL<4>, GRID, kEwThreads, 0, as_stream(st), __VA_ARGS__, (GEOM).G, (GEOM).PPB);  \
+      launch_k(KERNEL<4>, GRID, kEwThreads, SMEM, as_stream(st), __VA_ARGS__, (GEOM).G, (GEOM).PPB);  \
     else                                                                                       \
-      launch_k(KERNEL<1>, GRID, kEwThreads, 0, as_stream(st), __VA_ARGS__, (GEOM).G, (GEOM).PPB);  \
+      launch_k(KERNEL<1>, GRID, kEwThreads, SMEM, as_stream(st), __VA_ARGS__, (GEOM).G, (GEOM).PPB);  \
   } while (0)
+#define MFVI_EW_DISPATCH(GEOM, KERNEL, GRID, ...) MFVI_EW_DISPATCH_SMEM(GEOM, KERNEL, GRID, 0, __VA_ARGS__)
 
-// resident CTAs per SM of one elementwise kernel (both vector widths), asked of the runtime once per process
+// resident CTAs per SM of one elementwise kernel (both vector widths), asked of the runtime once per process; a kernel with
+// dynamic shared memory (the cp.async slots) is first allowed to exceed the 48 KB default together with its static arrays
 template <typename K>
-static int ew_occupancy_of(K kernel) {
+static void ew_allow_smem(K kernel, size_t dyn_smem, unsigned long long* done_mask) {      // once per device and kernel
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (*done_mask & bit) return;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn_smem));
+  *done_mask |= bit;
+}
+template <typename K>
+static int ew_occupancy_of(K kernel, size_t dyn_smem = 0) {
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kEwThreads, 0) != cudaSuccess || n < 1) {
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kEwThreads, dyn_smem) != cudaSuccess || n < 1) {
     cudaGetLastError();
     n = 1;
   }
   return n;
 }
-#define MFVI_EW_OCC(GEOM, KERNEL)                                                         \
-  ([&]() -> int {                                                                         \
-    static const int occ4 = ew_occupancy_of(KERNEL<4>), occ1 = ew_occupancy_of(KERNEL<1>); \
-    return (GEOM).V == 4 ? occ4 : occ1;                                                   \
+#define MFVI_EW_OCC_SMEM(GEOM, KERNEL, SMEM)                                                            \
+  ([&]() -> int {                                                                                       \
+    static unsigned long long allowed4 = 0, allowed1 = 0;                                               \
+    if ((SMEM) > 0) {                                                                                   \
+      if ((GEOM).V == 4) ew_allow_smem(KERNEL<4>, SMEM, &allowed4);                                     \
+      else ew_allow_smem(KERNEL<1>, SMEM, &allowed1);                                                   \
+    }                                                                                                   \
+    static const int occ4 = ew_occupancy_of(KERNEL<4>, SMEM), occ1 = ew_occupancy_of(KERNEL<1>, SMEM);  \
+    return (GEOM).V == 4 ? occ4 : occ1;                                                                 \
   }())
+#define MFVI_EW_OCC(GEOM, KERNEL) MFVI_EW_OCC_SMEM(GEOM, KERNEL, 0)
+// The cp.async kernels pay a longer prologue (D stages issued before the first pixel is used), so a launch takes them only
+// when its threads sweep at least kPipeMinIter pixels; below that the register-batched kernels are quicker
+// (profiles/r02_ew_load_batching.txt).  MFVI_EW_PIPE = bit mask of the kernels allowed to (1 pad_act_bwd, 2 bn_bwd_apply,
+// 4 bn_act_pad_fwd; measurement knob), MFVI_EW_PIPE_MINITER overrides the threshold.
+constexpr int kPipeMinIter = 8;
+static inline bool ew_piped(int bit, int npix, int PPB, int gx) {
+  static const int mask = [] {
+    const char* e = getenv("MFVI_EW_PIPE");
+    return e == nullptr ? 7 : atoi(e);
+  }();
+  static const int miniter = ew_knob("MFVI_EW_PIPE_MINITER", kPipeMinIter);
+  if (!(mask & bit)) return false;
+  const int blocks = (npix + PPB - 1) / PPB;
+  return blocks >= miniter * gx;
+}
 
 extern "C" {
 
@@ -142,14 +210,20 @@ int mfvi_bn_act_pad_fwd(MfviView y, int S, int H, int W, int C, const double* su
   MFVI_REQUIRE(pad >= 0 && pad < H && pad < W, "bn_act_pad_fwd: pad must be smaller than the image");
   const EwGeom ge = ew_geom(C, view_vec_ok(y) && view_vec_ok(xp));
   MFVI_REQUIRE(ge.G <= kEwThreads, "bn_act_pad_fwd: too many channel groups");
-  dim3 grid(ew_grid((H + 2 * pad) * (W + 2 * pad), ge.PPB, S, MFVI_EW_OCC(ge, k_bn_act_pad_fwd)), S);
+  const int npix_p = (H + 2 * pad) * (W + 2 * pad);
+  dim3 grid(ew_grid(npix_p, ge.PPB, S, MFVI_EW_OCC_SMEM(ge, k_bn_act_pad_fwd_p, kPipeBytes)), S);
+  const bool piped = ew_piped(4, npix_p, ge.PPB, grid.x);
+  if (!piped) grid.x = ew_grid(npix_p, ge.PPB, S, MFVI_EW_OCC(ge, k_bn_act_pad_fwd));
   if (mega::Stage* ms = mega::append(mega::OP_BN_ACT_PAD_FWD)) {
     ms->V = ge.V; ms->G = ge.G; ms->PPB = ge.PPB; ms->gx = grid.x < 8u ? grid.x : 8u;      /* one virtual block per CTA of the sample's cluster */ ms->S = S;
     ms->a = y; ms->b = xp; ms->H = H; ms->W = W; ms->C = C; ms->sums = sums; ms->gamma = gamma; ms->beta = beta; ms->act = act;
     ms->pad = pad;
     return 0;
   }
-  MFVI_EW_DISPATCH(ge, k_bn_act_pad_fwd, grid, y, H, W, C, sums, gamma, beta, act, pad, xp);
+  if (piped)
+    MFVI_EW_DISPATCH_SMEM(ge, k_bn_act_pad_fwd_p, grid, kPipeBytes, y, H, W, C, sums, gamma, beta, act, pad, xp);
+  else
+    MFVI_EW_DISPATCH(ge, k_bn_act_pad_fwd, grid, y, H, W, C, sums, gamma, beta, act, pad, xp);
   return check_launch("bn_act_pad_fwd");
 }
 
@@ -184,15 +258,20 @@ int mfvi_pad_act_bwd(MfviView dxp, int S, int H, int W, int C, int pad, MfviView
   MFVI_REQUIRE(pad >= 0 && pad < H && pad < W, "pad_act_bwd: pad must be smaller than the image");
   const EwGeom ge = ew_geom(C, view_vec_ok(dxp) && view_vec_ok(y) && view_vec_ok(g));
   MFVI_REQUIRE(ge.G <= kEwThreads, "pad_act_bwd: too many channel groups");
-  const int occ = MFVI_EW_OCC(ge, k_pad_act_bwd);
-  dim3 grid(ew_grid(H * W, ge.PPB, S, occ), S);
+  const int occ_p = MFVI_EW_OCC_SMEM(ge, k_pad_act_bwd_p, kPipeBytes);
+  dim3 grid(ew_grid(H * W, ge.PPB, S, occ_p), S);
+  const bool piped = ew_piped(1, H * W, ge.PPB, grid.x);
+  if (!piped) grid.x = ew_grid(H * W, ge.PPB, S, MFVI_EW_OCC(ge, k_pad_act_bwd));
   if (mega::Stage* ms = mega::append(mega::OP_PAD_ACT_BWD)) {
     ms->V = ge.V; ms->G = ge.G; ms->PPB = ge.PPB; ms->gx = grid.x < 8u ? grid.x : 8u;      /* one virtual block per CTA of the sample's cluster */ ms->S = S;
     ms->a = dxp; ms->b = y; ms->c = g; ms->H = H; ms->W = W; ms->C = C; ms->pad = pad; ms->sums = sums; ms->gamma = gamma;
     ms->beta = beta; ms->act = act; ms->red = red;
     return 0;
   }
-  MFVI_EW_DISPATCH(ge, k_pad_act_bwd, grid, dxp, H, W, C, pad, y, sums, gamma, beta, act, g, red);
+  if (piped)
+    MFVI_EW_DISPATCH_SMEM(ge, k_pad_act_bwd_p, grid, kPipeBytes, dxp, H, W, C, pad, y, sums, gamma, beta, act, g, red);
+  else
+    MFVI_EW_DISPATCH(ge, k_pad_act_bwd, grid, dxp, H, W, C, pad, y, sums, gamma, beta, act, g, red);
   return check_launch("pad_act_bwd");
 }
 
@@ -203,14 +282,19 @@ int mfvi_bn_bwd_apply(MfviView g, MfviView y, int S, int H, int W, int C, const 
   MFVI_REQUIRE(C >= 1 && C <= kMaxC, "bn_bwd_apply: C out of range");
   const EwGeom ge = ew_geom(C, view_vec_ok(g) && view_vec_ok(y) && view_vec_ok(dy));
   MFVI_REQUIRE(ge.G <= kEwThreads, "bn_bwd_apply: too many channel groups");
-  dim3 grid(ew_grid(H * W, ge.PPB, S, MFVI_EW_OCC(ge, k_bn_bwd_apply)), S);
+  dim3 grid(ew_grid(H * W, ge.PPB, S, MFVI_EW_OCC_SMEM(ge, k_bn_bwd_apply_p, kPipeBytes)), S);
+  const bool piped = ew_piped(2, H * W, ge.PPB, grid.x);
+  if (!piped) grid.x = ew_grid(H * W, ge.PPB, S, MFVI_EW_OCC(ge, k_bn_bwd_apply));
   if (mega::Stage* ms = mega::append(mega::OP_BN_BWD_APPLY)) {
     ms->V = ge.V; ms->G = ge.G; ms->PPB = ge.PPB; ms->gx = grid.x < 8u ? grid.x : 8u;      /* one virtual block per CTA of the sample's cluster */ ms->S = S;
     ms->a = g; ms->b = y; ms->c = dy; ms->H = H; ms->W = W; ms->C = C; ms->sums = sums; ms->red = const_cast<double*>(red);
     ms->gamma = gamma; ms->dgamma = dgamma; ms->dbeta = dbeta;
     return 0;
   }
-  MFVI_EW_DISPATCH(ge, k_bn_bwd_apply, grid, g, y, S, H, W, C, sums, red, gamma, dy, dgamma, dbeta);
+  if (piped)
+    MFVI_EW_DISPATCH_SMEM(ge, k_bn_bwd_apply_p, grid, kPipeBytes, g, y, S, H, W, C, sums, red, gamma, dy, dgamma, dbeta);
+  else
+    MFVI_EW_DISPATCH(ge, k_bn_bwd_apply, grid, g, y, S, H, W, C, sums, red, gamma, dy, dgamma, dbeta);
   return check_launch("bn_bwd_apply");
 }
 

@@ -132,6 +132,29 @@ struct EwSmem {
   double* red;      // [2 * kEwThreads * 4] doubles: thread-private reduction cells
   BnTable* tab;     // BatchNorm constants of one sample
   float* misc;      // [5 * kMaxC] floats (bn_bwd_apply)
+  float* pipe = nullptr;   // [kPipeBytes] thread-private cp.async slots of the PIPE variants (16-byte aligned)
+};
+
+// cp.async load pipeline of the stand-alone kernels.  Every thread owns D x NL slots of V floats in shared memory
+// ([stage][load][thread]: conflict-free) and keeps D pixels' loads in flight without holding registers for them; the slots are
+// thread-private, so the only synchronisation is cp.async.wait_group.  These kernels are latency-bound (one or two pixels of
+// register loads in flight per thread, profiles/r02_ew_load_batching.txt), which is what the deeper pipeline addresses.
+constexpr int kPipeBytes = 32 * 1024;
+template <int V>
+__device__ __forceinline__ void ew_cp_async(float* smem_dst, const float* g) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  if constexpr (V == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(g) : "memory");
+}
+__device__ __forceinline__ void ew_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void ew_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+template <int V, int NL>
+struct LdPipe {
+  static constexpr int D = kPipeBytes / (NL * kEwThreads * V * 4) > 8 ? 8 : kPipeBytes / (NL * kEwThreads * V * 4);   // stages
+  float* base;
+  __device__ __forceinline__ explicit LdPipe(float* pipe) : base(pipe + threadIdx.x * V) {}
+  __device__ __forceinline__ float* slot(int d, int l) const { return base + (d * NL + l) * (kEwThreads * V); }
 };
 
 struct PixIter {

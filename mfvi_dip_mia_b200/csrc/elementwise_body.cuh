@@ -8,7 +8,7 @@ namespace mfvi {
 
 
 // F1: xp = reflect_pad(act(bn(y)))            grid = (chunks, S)
-template <int V, bool OBF = false>       // OBF: xp is a bf16 view (strides in bf16 elements)
+template <int V, bool OBF = false, bool PIPE = false>       // OBF: xp is a bf16 view (strides in bf16 elements); PIPE: cp.async slots
 __device__ __forceinline__ void body_bn_act_pad_fwd(const VGrid& vg, EwSmem sm, MfviView y, int H, int W, int C, const double* __restrict__ sums, const float* __restrict__ gamma,
                  const float* __restrict__ beta, int act, int pad, MfviView xp, int G, int PPB) {
   BnTable& tab = *sm.tab;
@@ -24,8 +24,43 @@ __device__ __forceinline__ void body_bn_act_pad_fwd(const VGrid& vg, EwSmem sm, 
   const float* ybase = y.ptr + (size_t)s * y.sstride + c0;
   float* xbase = xp.ptr + (size_t)s * xp.sstride + c0;
   __nv_bfloat16* xbase16 = reinterpret_cast<__nv_bfloat16*>(xp.ptr) + (size_t)s * xp.sstride + c0;
-  constexpr int U = 4;
   PixIter it(vg, Hp * Wp, Wp, PPB, slot);
+  auto emit = [&](int hp, int wp, Vec<V>& t) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float z = fmaf(t.v[j], bn.sc[j], bn.sh[j]);
+      if (act) z = z > 0.f ? z : kLreluSlope * z;
+      t.v[j] = z;
+    }
+    if (!OBF) t.store(xbase + (size_t)hp * xp.hstride + (size_t)wp * xp.wstride);
+    else store_bf16<V>(xbase16 + (size_t)hp * xp.hstride + (size_t)wp * xp.wstride, t.v);
+  };
+  if constexpr (PIPE) {
+    using Pipe = LdPipe<V, 1>;
+    const Pipe pp(sm.pipe);
+    PixIter ld = it;
+    auto issue = [&](int d) {
+      if (ld.valid()) {
+        const int h = reflect_idx(ld.h - pad, H), w = reflect_idx(ld.w - pad, W);
+        ew_cp_async<V>(pp.slot(d, 0), ybase + (size_t)h * y.hstride + (size_t)w * y.wstride);
+        ld.next();
+      }
+      ew_cp_commit();
+    };
+#pragma unroll
+    for (int d = 0; d < Pipe::D; ++d) issue(d);
+    for (int d = 0; it.valid(); it.next()) {
+      ew_cp_wait<Pipe::D - 1>();
+      Vec<V> t;
+      t.load(pp.slot(d, 0));
+      emit(it.h, it.w, t);
+      issue(d);
+      d = d + 1 == Pipe::D ? 0 : d + 1;
+    }
+    ew_cp_wait<0>();
+    return;
+  }
+  constexpr int U = 4;
   PixBatch<U> b;
   while (b.fill(it)) {
     Vec<V> t[U];
@@ -37,14 +72,7 @@ __device__ __forceinline__ void body_bn_act_pad_fwd(const VGrid& vg, EwSmem sm, 
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (u >= b.n) break;
-#pragma unroll
-      for (int j = 0; j < V; ++j) {
-        float z = fmaf(t[u].v[j], bn.sc[j], bn.sh[j]);
-        if (act) z = z > 0.f ? z : kLreluSlope * z;
-        t[u].v[j] = z;
-      }
-      if (!OBF) t[u].store(xbase + (size_t)b.h[u] * xp.hstride + (size_t)b.w[u] * xp.wstride);
-      else store_bf16<V>(xbase16 + (size_t)b.h[u] * xp.hstride + (size_t)b.w[u] * xp.wstride, t[u].v);
+      emit(b.h[u], b.w[u], t[u]);
     }
   }
 }
@@ -167,7 +195,7 @@ __device__ __forceinline__ void body_cat_up_fwd(const VGrid& vg, EwSmem sm, Mfvi
 
 
 // B1: g = fold_reflect(dxp) * act'(bn(y)), red += (sum g, sum g*xhat)      grid = (chunks, S)
-template <int V>
+template <int V, bool PIPE = false>     // PIPE: loads through the cp.async slots of sm.pipe (stand-alone kernel only)
 __device__ __forceinline__ void body_pad_act_bwd(const VGrid& vg, EwSmem sm, MfviView dxp, int H, int W, int C, int pad, MfviView y, const double* __restrict__ sums,
               const float* __restrict__ gamma, const float* __restrict__ beta, int act, MfviView g,
               double* __restrict__ red, int G, int PPB) {
@@ -213,20 +241,46 @@ __device__ __forceinline__ void body_pad_act_bwd(const VGrid& vg, EwSmem sm, Mfv
       a.store(gbase + (size_t)h * g.hstride + (size_t)w * g.wstride);
       acc.tick();
     };
-    constexpr int U = 2;
     PixIter it(vg, H * W, W, PPB, slot);
-    PixBatch<U> b;
-    while (b.fill(it)) {
-      Vec<V> a[U], yy[U];
+    if constexpr (PIPE) {
+      using Pipe = LdPipe<V, 2>;
+      const Pipe pp(sm.pipe);
+      PixIter ld = it;
+      auto issue = [&](int d) {
+        if (ld.valid()) {
+          ew_cp_async<V>(pp.slot(d, 0), dbase + (size_t)(ld.h + pad) * dxp.hstride + (size_t)(ld.w + pad) * dxp.wstride);
+          ew_cp_async<V>(pp.slot(d, 1), ybase + (size_t)ld.h * y.hstride + (size_t)ld.w * y.wstride);
+          ld.next();
+        }
+        ew_cp_commit();
+      };
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        a[u].load(dbase + (size_t)(b.h[u] + pad) * dxp.hstride + (size_t)(b.w[u] + pad) * dxp.wstride);
-        yy[u].load(ybase + (size_t)b.h[u] * y.hstride + (size_t)b.w[u] * y.wstride);
+      for (int d = 0; d < Pipe::D; ++d) issue(d);
+      for (int d = 0; it.valid(); it.next()) {
+        ew_cp_wait<Pipe::D - 1>();
+        Vec<V> a, yy;
+        a.load(pp.slot(d, 0));
+        yy.load(pp.slot(d, 1));
+        finish(it.h, it.w, a, yy);
+        issue(d);                      // after the slot's values were consumed
+        d = d + 1 == Pipe::D ? 0 : d + 1;
       }
+      ew_cp_wait<0>();
+    } else {
+      constexpr int U = 2;
+      PixBatch<U> b;
+      while (b.fill(it)) {
+        Vec<V> a[U], yy[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (u >= b.n) break;
-        finish(b.h[u], b.w[u], a[u], yy[u]);
+        for (int u = 0; u < U; ++u) {
+          a[u].load(dbase + (size_t)(b.h[u] + pad) * dxp.hstride + (size_t)(b.w[u] + pad) * dxp.wstride);
+          yy[u].load(ybase + (size_t)b.h[u] * y.hstride + (size_t)b.w[u] * y.wstride);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (u >= b.n) break;
+          finish(b.h[u], b.w[u], a[u], yy[u]);
+        }
       }
     }
     acc.flush();
@@ -235,7 +289,7 @@ __device__ __forceinline__ void body_pad_act_bwd(const VGrid& vg, EwSmem sm, Mfv
 }
 
 // B2: dy = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)); block (0,0) also writes dgamma/dbeta.
-template <int V, bool OBF = false>       // OBF: dy is a bf16 view (strides in bf16 elements)
+template <int V, bool OBF = false, bool PIPE = false>       // OBF: dy is a bf16 view (strides in bf16 elements); PIPE: cp.async slots
 __device__ __forceinline__ void body_bn_bwd_apply(const VGrid& vg, EwSmem sm, MfviView g, MfviView y, int S, int H, int W, int C, const double* __restrict__ sums,
                const double* __restrict__ red, const float* __restrict__ gamma, MfviView dy,
                float* __restrict__ dgamma, float* __restrict__ dbeta, int G, int PPB) {
@@ -281,8 +335,43 @@ __device__ __forceinline__ void body_bn_bwd_apply(const VGrid& vg, EwSmem sm, Mf
   const float* ybase = y.ptr + (size_t)s * y.sstride + c0;
   float* obase = dy.ptr + (size_t)s * dy.sstride + c0;
   __nv_bfloat16* obase16 = reinterpret_cast<__nv_bfloat16*>(dy.ptr) + (size_t)s * dy.sstride + c0;
-  constexpr int U = 2;
   PixIter it(vg, H * W, W, PPB, slot);
+  auto emit = [&](int h, int w, Vec<V>& gg, const Vec<V>& yy) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float xhat = (yy.v[j] - mean[j]) * invstd[j];
+      gg.v[j] = k[j] * (gg.v[j] - m1[j] - xhat * m2[j]);
+    }
+    if (!OBF) gg.store(obase + (size_t)h * dy.hstride + (size_t)w * dy.wstride);
+    else store_bf16<V>(obase16 + (size_t)h * dy.hstride + (size_t)w * dy.wstride, gg.v);
+  };
+  if constexpr (PIPE) {
+    using Pipe = LdPipe<V, 2>;
+    const Pipe pp(sm.pipe);
+    PixIter ld = it;
+    auto issue = [&](int d) {
+      if (ld.valid()) {
+        ew_cp_async<V>(pp.slot(d, 0), gbase + (size_t)ld.h * g.hstride + (size_t)ld.w * g.wstride);
+        ew_cp_async<V>(pp.slot(d, 1), ybase + (size_t)ld.h * y.hstride + (size_t)ld.w * y.wstride);
+        ld.next();
+      }
+      ew_cp_commit();
+    };
+#pragma unroll
+    for (int d = 0; d < Pipe::D; ++d) issue(d);
+    for (int d = 0; it.valid(); it.next()) {
+      ew_cp_wait<Pipe::D - 1>();
+      Vec<V> gg, yy;
+      gg.load(pp.slot(d, 0));
+      yy.load(pp.slot(d, 1));
+      emit(it.h, it.w, gg, yy);
+      issue(d);
+      d = d + 1 == Pipe::D ? 0 : d + 1;
+    }
+    ew_cp_wait<0>();
+    return;
+  }
+  constexpr int U = 2;
   PixBatch<U> b;
   while (b.fill(it)) {
     Vec<V> gg[U], yy[U];
@@ -294,13 +383,7 @@ __device__ __forceinline__ void body_bn_bwd_apply(const VGrid& vg, EwSmem sm, Mf
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (u >= b.n) break;
-#pragma unroll
-      for (int j = 0; j < V; ++j) {
-        const float xhat = (yy[u].v[j] - mean[j]) * invstd[j];
-        gg[u].v[j] = k[j] * (gg[u].v[j] - m1[j] - xhat * m2[j]);
-      }
-      if (!OBF) gg[u].store(obase + (size_t)b.h[u] * dy.hstride + (size_t)b.w[u] * dy.wstride);
-      else store_bf16<V>(obase16 + (size_t)b.h[u] * dy.hstride + (size_t)b.w[u] * dy.wstride, gg[u].v);
+      emit(b.h[u], b.w[u], gg[u], yy[u]);
     }
   }
 }
