@@ -44,7 +44,7 @@ k_cat_up_fwd(MfviView ys, int Cs, const double* __restrict__ sums_s, const float
 }
 
 template <int V>
-__global__ void __launch_bounds__(kEwThreads, 3)
+__global__ void __launch_bounds__(kEwThreads, 2)
 k_pad_act_bwd(MfviView dxp, int H, int W, int C, int pad, MfviView y, const double* __restrict__ sums,
               const float* __restrict__ gamma, const float* __restrict__ beta, int act, MfviView g,
               double* __restrict__ red, int G, int PPB) {
@@ -91,7 +91,7 @@ k_bn_bwd_apply_p(MfviView g, MfviView y, int S, int H, int W, int C, const doubl
 }
 
 template <int V>
-__global__ void __launch_bounds__(kEwThreads, 4)
+__global__ void __launch_bounds__(kEwThreads, 3)
 k_cat_bwd_skip(MfviView dA, int H, int W, MfviView ys, int Cs, const double* __restrict__ sums_s,
                const float* __restrict__ gamma_s, const float* __restrict__ beta_s, MfviView gs,
                double* __restrict__ red_s, int G, int PPB) {

@@ -7,24 +7,24 @@
 namespace mfvi {
 
 
+// Every body issues the loads of its first pixels BEFORE it computes the BatchNorm tables (both depend only on the producer
+// kernels, not on each other), so the two L2 round trips of a small launch overlap instead of adding up.
+
 // F1: xp = reflect_pad(act(bn(y)))            grid = (chunks, S)
 template <int V, bool OBF = false, bool PIPE = false>       // OBF: xp is a bf16 view (strides in bf16 elements); PIPE: cp.async slots
 __device__ __forceinline__ void body_bn_act_pad_fwd(const VGrid& vg, EwSmem sm, MfviView y, int H, int W, int C, const double* __restrict__ sums, const float* __restrict__ gamma,
                  const float* __restrict__ beta, int act, int pad, MfviView xp, int G, int PPB) {
   BnTable& tab = *sm.tab;
   const int s = vg.by;
-  tab.fill(sums, gamma, beta, s, C, 1.0 / ((double)H * W));
-  __syncthreads();
   const int group = threadIdx.x % G, slot = threadIdx.x / G;
-  if (slot >= PPB) return;
+  const bool active = slot < PPB;
   const int c0 = group * V;
-  BnRegs<V> bn;
-  bn.load(tab, c0, C);
   const int Hp = H + 2 * pad, Wp = W + 2 * pad;
   const float* ybase = y.ptr + (size_t)s * y.sstride + c0;
   float* xbase = xp.ptr + (size_t)s * xp.sstride + c0;
   __nv_bfloat16* xbase16 = reinterpret_cast<__nv_bfloat16*>(xp.ptr) + (size_t)s * xp.sstride + c0;
-  PixIter it(vg, Hp * Wp, Wp, PPB, slot);
+  PixIter it(vg, active ? Hp * Wp : 0, Wp, PPB, slot);
+  BnRegs<V> bn;
   auto emit = [&](int hp, int wp, Vec<V>& t) {
 #pragma unroll
     for (int j = 0; j < V; ++j) {
@@ -49,6 +49,9 @@ __device__ __forceinline__ void body_bn_act_pad_fwd(const VGrid& vg, EwSmem sm, 
     };
 #pragma unroll
     for (int d = 0; d < Pipe::D; ++d) issue(d);
+    tab.fill(sums, gamma, beta, s, C, 1.0 / ((double)H * W));
+    __syncthreads();
+    bn.load(tab, c0, C);
     for (int d = 0; it.valid(); it.next()) {
       ew_cp_wait<Pipe::D - 1>();
       Vec<V> t;
@@ -58,21 +61,30 @@ __device__ __forceinline__ void body_bn_act_pad_fwd(const VGrid& vg, EwSmem sm, 
       d = d + 1 == Pipe::D ? 0 : d + 1;
     }
     ew_cp_wait<0>();
-    return;
-  }
-  constexpr int U = 4;
-  PixBatch<U> b;
-  while (b.fill(it)) {
+  } else {
+    constexpr int U = 4;
+    PixBatch<U> b;
     Vec<V> t[U];
+    auto fetch = [&]() {
+      if (!b.fill(it)) return false;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int h = reflect_idx(b.h[u] - pad, H), w = reflect_idx(b.w[u] - pad, W);
-      t[u].load(ybase + (size_t)h * y.hstride + (size_t)w * y.wstride);
-    }
+      for (int u = 0; u < U; ++u) {
+        const int h = reflect_idx(b.h[u] - pad, H), w = reflect_idx(b.w[u] - pad, W);
+        t[u].load(ybase + (size_t)h * y.hstride + (size_t)w * y.wstride);
+      }
+      return true;
+    };
+    bool have = fetch();
+    tab.fill(sums, gamma, beta, s, C, 1.0 / ((double)H * W));
+    __syncthreads();
+    bn.load(tab, c0, C);
+    while (have) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (u >= b.n) break;
-      emit(b.h[u], b.w[u], t[u]);
+      for (int u = 0; u < U; ++u) {
+        if (u >= b.n) break;
+        emit(b.h[u], b.w[u], t[u]);
+      }
+      have = fetch();
     }
   }
 }
@@ -206,85 +218,92 @@ __device__ __forceinline__ void body_pad_act_bwd(const VGrid& vg, EwSmem sm, Mfv
   const int c0 = group * V;
   Acc2<V> acc(sm_red);
   BnTable& tab = *sm.tab;
-  tab.fill(sums, gamma, beta, s, C, 1.0 / ((double)H * W));
-  __syncthreads();
-  if (active) {
-    BnRegs<V> bn;
-    bn.load(tab, c0, C);
-    const float* dbase = dxp.ptr + (size_t)s * dxp.sstride + c0;
-    const float* ybase = y.ptr + (size_t)s * y.sstride + c0;
-    float* gbase = g.ptr + (size_t)s * g.sstride + c0;
-    auto finish = [&](int h, int w, Vec<V>& a, const Vec<V>& yy) {
-      const bool edge = pad > 0 && (h <= pad || w <= pad || h >= H - 1 - pad || w >= W - 1 - pad);
-      if (edge) {          // reflected border positions fold back onto this pixel
-        int qh[3], qw[3];
-        const int nh = fold_sources(h, H, pad, qh), nw = fold_sources(w, W, pad, qw);
-        for (int ih = 0; ih < nh; ++ih)
-          for (int iw = 0; iw < nw; ++iw) {
-            if (ih == 0 && iw == 0) continue;
-            Vec<V> t;
-            t.load(dbase + (size_t)qh[ih] * dxp.hstride + (size_t)qw[iw] * dxp.wstride);
+  BnRegs<V> bn;
+  const float* dbase = dxp.ptr + (size_t)s * dxp.sstride + c0;
+  const float* ybase = y.ptr + (size_t)s * y.sstride + c0;
+  float* gbase = g.ptr + (size_t)s * g.sstride + c0;
+  auto finish = [&](int h, int w, Vec<V>& a, const Vec<V>& yy) {
+    const bool edge = pad > 0 && (h <= pad || w <= pad || h >= H - 1 - pad || w >= W - 1 - pad);
+    if (edge) {          // reflected border positions fold back onto this pixel
+      int qh[3], qw[3];
+      const int nh = fold_sources(h, H, pad, qh), nw = fold_sources(w, W, pad, qw);
+      for (int ih = 0; ih < nh; ++ih)
+        for (int iw = 0; iw < nw; ++iw) {
+          if (ih == 0 && iw == 0) continue;
+          Vec<V> t;
+          t.load(dbase + (size_t)qh[ih] * dxp.hstride + (size_t)qw[iw] * dxp.wstride);
 #pragma unroll
-            for (int j = 0; j < V; ++j) a.v[j] += t.v[j];
-          }
-      }
-#pragma unroll
-      for (int j = 0; j < V; ++j) {
-        const float z = fmaf(yy.v[j], bn.sc[j], bn.sh[j]);
-        float gg = a.v[j];
-        if (act && z <= 0.f) gg *= kLreluSlope;
-        const float xhat = (yy.v[j] - bn.mean[j]) * bn.invstd[j];
-        a.v[j] = gg;
-        acc.fa[j] += gg;
-        acc.fb[j] = fmaf(gg, xhat, acc.fb[j]);
-      }
-      a.store(gbase + (size_t)h * g.hstride + (size_t)w * g.wstride);
-      acc.tick();
-    };
-    PixIter it(vg, H * W, W, PPB, slot);
-    if constexpr (PIPE) {
-      using Pipe = LdPipe<V, 2>;
-      const Pipe pp(sm.pipe);
-      PixIter ld = it;
-      auto issue = [&](int d) {
-        if (ld.valid()) {
-          ew_cp_async<V>(pp.slot(d, 0), dbase + (size_t)(ld.h + pad) * dxp.hstride + (size_t)(ld.w + pad) * dxp.wstride);
-          ew_cp_async<V>(pp.slot(d, 1), ybase + (size_t)ld.h * y.hstride + (size_t)ld.w * y.wstride);
-          ld.next();
+          for (int j = 0; j < V; ++j) a.v[j] += t.v[j];
         }
-        ew_cp_commit();
-      };
-#pragma unroll
-      for (int d = 0; d < Pipe::D; ++d) issue(d);
-      for (int d = 0; it.valid(); it.next()) {
-        ew_cp_wait<Pipe::D - 1>();
-        Vec<V> a, yy;
-        a.load(pp.slot(d, 0));
-        yy.load(pp.slot(d, 1));
-        finish(it.h, it.w, a, yy);
-        issue(d);                      // after the slot's values were consumed
-        d = d + 1 == Pipe::D ? 0 : d + 1;
-      }
-      ew_cp_wait<0>();
-    } else {
-      constexpr int U = 2;
-      PixBatch<U> b;
-      while (b.fill(it)) {
-        Vec<V> a[U], yy[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          a[u].load(dbase + (size_t)(b.h[u] + pad) * dxp.hstride + (size_t)(b.w[u] + pad) * dxp.wstride);
-          yy[u].load(ybase + (size_t)b.h[u] * y.hstride + (size_t)b.w[u] * y.wstride);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (u >= b.n) break;
-          finish(b.h[u], b.w[u], a[u], yy[u]);
-        }
-      }
     }
-    acc.flush();
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float z = fmaf(yy.v[j], bn.sc[j], bn.sh[j]);
+      float gg = a.v[j];
+      if (act && z <= 0.f) gg *= kLreluSlope;
+      const float xhat = (yy.v[j] - bn.mean[j]) * bn.invstd[j];
+      a.v[j] = gg;
+      acc.fa[j] += gg;
+      acc.fb[j] = fmaf(gg, xhat, acc.fb[j]);
+    }
+    a.store(gbase + (size_t)h * g.hstride + (size_t)w * g.wstride);
+    acc.tick();
+  };
+  PixIter it(vg, active ? H * W : 0, W, PPB, slot);
+  if constexpr (PIPE) {
+    using Pipe = LdPipe<V, 2>;
+    const Pipe pp(sm.pipe);
+    PixIter ld = it;
+    auto issue = [&](int d) {
+      if (ld.valid()) {
+        ew_cp_async<V>(pp.slot(d, 0), dbase + (size_t)(ld.h + pad) * dxp.hstride + (size_t)(ld.w + pad) * dxp.wstride);
+        ew_cp_async<V>(pp.slot(d, 1), ybase + (size_t)ld.h * y.hstride + (size_t)ld.w * y.wstride);
+        ld.next();
+      }
+      ew_cp_commit();
+    };
+#pragma unroll
+    for (int d = 0; d < Pipe::D; ++d) issue(d);
+    tab.fill(sums, gamma, beta, s, C, 1.0 / ((double)H * W));
+    __syncthreads();
+    bn.load(tab, c0, C);
+    for (int d = 0; it.valid(); it.next()) {
+      ew_cp_wait<Pipe::D - 1>();
+      Vec<V> a, yy;
+      a.load(pp.slot(d, 0));
+      yy.load(pp.slot(d, 1));
+      finish(it.h, it.w, a, yy);
+      issue(d);                      // after the slot's values were consumed
+      d = d + 1 == Pipe::D ? 0 : d + 1;
+    }
+    ew_cp_wait<0>();
+  } else {
+    constexpr int U = 2;
+    PixBatch<U> b;
+    Vec<V> a[U], yy[U];
+    auto fetch = [&]() {
+      if (!b.fill(it)) return false;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        a[u].load(dbase + (size_t)(b.h[u] + pad) * dxp.hstride + (size_t)(b.w[u] + pad) * dxp.wstride);
+        yy[u].load(ybase + (size_t)b.h[u] * y.hstride + (size_t)b.w[u] * y.wstride);
+      }
+      return true;
+    };
+    bool have = fetch();
+    tab.fill(sums, gamma, beta, s, C, 1.0 / ((double)H * W));
+    __syncthreads();
+    bn.load(tab, c0, C);
+    while (have) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (u >= b.n) break;
+        finish(b.h[u], b.w[u], a[u], yy[u]);
+      }
+      have = fetch();
+    }
   }
+  acc.flush();
   cta_reduce_cells<V>(sm_red, G, PPB, C, red + (size_t)s * C * 2);
 }
 
@@ -295,47 +314,48 @@ __device__ __forceinline__ void body_bn_bwd_apply(const VGrid& vg, EwSmem sm, Mf
                float* __restrict__ dgamma, float* __restrict__ dbeta, int G, int PPB) {
   const int s = vg.by;
   const double inv_count = 1.0 / ((double)H * W);
-  if (vg.bx == 0 && vg.by == 0 && dgamma != nullptr) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      double dg = 0.0, db = 0.0;
-      for (int ss = 0; ss < S; ++ss) {
-        db += red[((size_t)ss * C + c) * 2 + 0];
-        dg += red[((size_t)ss * C + c) * 2 + 1];
-      }
-      dgamma[c] = (float)dg;
-      dbeta[c] = (float)db;
-    }
-  }
-  float *sm_k = sm.misc, *sm_mean = sm.misc + kMaxC, *sm_invstd = sm.misc + 2 * kMaxC, *sm_m1 = sm.misc + 3 * kMaxC,
-        *sm_m2 = sm.misc + 4 * kMaxC;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float mean_c, invstd_c;
-    bn_mean_invstd(sums + ((size_t)s * C + c) * 2, inv_count, mean_c, invstd_c);
-    sm_mean[c] = mean_c;
-    sm_invstd[c] = invstd_c;
-    sm_k[c] = (gamma != nullptr ? gamma[c] : 1.f) * invstd_c;
-    sm_m1[c] = (float)(red[((size_t)s * C + c) * 2 + 0] * inv_count);
-    sm_m2[c] = (float)(red[((size_t)s * C + c) * 2 + 1] * inv_count);
-  }
-  __syncthreads();
   const int group = threadIdx.x % G, slot = threadIdx.x / G;
-  if (slot >= PPB) return;
+  const bool active = slot < PPB;
   const int c0 = group * V;
-  float k[V], mean[V], invstd[V], m1[V], m2[V];
-#pragma unroll
-  for (int j = 0; j < V; ++j) {
-    const bool ok = c0 + j < C;
-    mean[j] = ok ? sm_mean[c0 + j] : 0.f;
-    invstd[j] = ok ? sm_invstd[c0 + j] : 1.f;
-    k[j] = ok ? sm_k[c0 + j] : 0.f;
-    m1[j] = ok ? sm_m1[c0 + j] : 0.f;
-    m2[j] = ok ? sm_m2[c0 + j] : 0.f;
-  }
   const float* gbase = g.ptr + (size_t)s * g.sstride + c0;
   const float* ybase = y.ptr + (size_t)s * y.sstride + c0;
   float* obase = dy.ptr + (size_t)s * dy.sstride + c0;
   __nv_bfloat16* obase16 = reinterpret_cast<__nv_bfloat16*>(dy.ptr) + (size_t)s * dy.sstride + c0;
-  PixIter it(vg, H * W, W, PPB, slot);
+  float *sm_k = sm.misc, *sm_mean = sm.misc + kMaxC, *sm_invstd = sm.misc + 2 * kMaxC, *sm_m1 = sm.misc + 3 * kMaxC,
+        *sm_m2 = sm.misc + 4 * kMaxC;
+  float k[V], mean[V], invstd[V], m1[V], m2[V];
+  auto tables = [&]() {            // per-channel constants of this sample: shared memory, then the V channels of this thread
+    if (vg.bx == 0 && vg.by == 0 && dgamma != nullptr) {
+      for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        double dg = 0.0, db = 0.0;
+        for (int ss = 0; ss < S; ++ss) {
+          db += red[((size_t)ss * C + c) * 2 + 0];
+          dg += red[((size_t)ss * C + c) * 2 + 1];
+        }
+        dgamma[c] = (float)dg;
+        dbeta[c] = (float)db;
+      }
+    }
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float mean_c, invstd_c;
+      bn_mean_invstd(sums + ((size_t)s * C + c) * 2, inv_count, mean_c, invstd_c);
+      sm_mean[c] = mean_c;
+      sm_invstd[c] = invstd_c;
+      sm_k[c] = (gamma != nullptr ? gamma[c] : 1.f) * invstd_c;
+      sm_m1[c] = (float)(red[((size_t)s * C + c) * 2 + 0] * inv_count);
+      sm_m2[c] = (float)(red[((size_t)s * C + c) * 2 + 1] * inv_count);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const bool ok = c0 + j < C;
+      mean[j] = ok ? sm_mean[c0 + j] : 0.f;
+      invstd[j] = ok ? sm_invstd[c0 + j] : 1.f;
+      k[j] = ok ? sm_k[c0 + j] : 0.f;
+      m1[j] = ok ? sm_m1[c0 + j] : 0.f;
+      m2[j] = ok ? sm_m2[c0 + j] : 0.f;
+    }
+  };
   auto emit = [&](int h, int w, Vec<V>& gg, const Vec<V>& yy) {
 #pragma unroll
     for (int j = 0; j < V; ++j) {
@@ -345,6 +365,7 @@ __device__ __forceinline__ void body_bn_bwd_apply(const VGrid& vg, EwSmem sm, Mf
     if (!OBF) gg.store(obase + (size_t)h * dy.hstride + (size_t)w * dy.wstride);
     else store_bf16<V>(obase16 + (size_t)h * dy.hstride + (size_t)w * dy.wstride, gg.v);
   };
+  PixIter it(vg, active ? H * W : 0, W, PPB, slot);
   if constexpr (PIPE) {
     using Pipe = LdPipe<V, 2>;
     const Pipe pp(sm.pipe);
@@ -359,6 +380,7 @@ __device__ __forceinline__ void body_bn_bwd_apply(const VGrid& vg, EwSmem sm, Mf
     };
 #pragma unroll
     for (int d = 0; d < Pipe::D; ++d) issue(d);
+    tables();
     for (int d = 0; it.valid(); it.next()) {
       ew_cp_wait<Pipe::D - 1>();
       Vec<V> gg, yy;
@@ -369,21 +391,28 @@ __device__ __forceinline__ void body_bn_bwd_apply(const VGrid& vg, EwSmem sm, Mf
       d = d + 1 == Pipe::D ? 0 : d + 1;
     }
     ew_cp_wait<0>();
-    return;
-  }
-  constexpr int U = 2;
-  PixBatch<U> b;
-  while (b.fill(it)) {
+  } else {
+    constexpr int U = 2;
+    PixBatch<U> b;
     Vec<V> gg[U], yy[U];
+    auto fetch = [&]() {
+      if (!b.fill(it)) return false;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      gg[u].load(gbase + (size_t)b.h[u] * g.hstride + (size_t)b.w[u] * g.wstride);
-      yy[u].load(ybase + (size_t)b.h[u] * y.hstride + (size_t)b.w[u] * y.wstride);
-    }
+      for (int u = 0; u < U; ++u) {
+        gg[u].load(gbase + (size_t)b.h[u] * g.hstride + (size_t)b.w[u] * g.wstride);
+        yy[u].load(ybase + (size_t)b.h[u] * y.hstride + (size_t)b.w[u] * y.wstride);
+      }
+      return true;
+    };
+    bool have = fetch();
+    tables();
+    while (have) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (u >= b.n) break;
-      emit(b.h[u], b.w[u], gg[u], yy[u]);
+      for (int u = 0; u < U; ++u) {
+        if (u >= b.n) break;
+        emit(b.h[u], b.w[u], gg[u], yy[u]);
+      }
+      have = fetch();
     }
   }
 }
@@ -400,42 +429,46 @@ __device__ __forceinline__ void body_cat_bwd_skip(const VGrid& vg, EwSmem sm, Mf
   const int c0 = group * V;
   Acc2<V> acc(sm_red);
   BnTable& tab = *sm.tab;
+  BnRegs<V> bn;
+  const float* dbase = dA.ptr + (size_t)s * dA.sstride + c0;
+  const float* ybase = ys.ptr + (size_t)s * ys.sstride + c0;
+  float* gbase = gs.ptr + (size_t)s * gs.sstride + c0;
+  constexpr int U = 2;
+  PixIter it(vg, active ? H * W : 0, W, PPB, slot);
+  PixBatch<U> b;
+  Vec<V> d[U], yy[U];
+  auto fetch = [&]() {
+    if (!b.fill(it)) return false;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      d[u].load(dbase + (size_t)b.h[u] * dA.hstride + (size_t)b.w[u] * dA.wstride);
+      yy[u].load(ybase + (size_t)b.h[u] * ys.hstride + (size_t)b.w[u] * ys.wstride);
+    }
+    return true;
+  };
+  bool have = fetch();
   tab.fill(sums_s, gamma_s, beta_s, s, Cs, 1.0 / ((double)H * W));
   __syncthreads();
-  if (active) {
-    BnRegs<V> bn;
-    bn.load(tab, c0, Cs);
-    const float* dbase = dA.ptr + (size_t)s * dA.sstride + c0;
-    const float* ybase = ys.ptr + (size_t)s * ys.sstride + c0;
-    float* gbase = gs.ptr + (size_t)s * gs.sstride + c0;
-    constexpr int U = 2;
-    PixIter it(vg, H * W, W, PPB, slot);
-    PixBatch<U> b;
-    while (b.fill(it)) {
-      Vec<V> d[U], yy[U];
+  bn.load(tab, c0, Cs);
+  while (have) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        d[u].load(dbase + (size_t)b.h[u] * dA.hstride + (size_t)b.w[u] * dA.wstride);
-        yy[u].load(ybase + (size_t)b.h[u] * ys.hstride + (size_t)b.w[u] * ys.wstride);
+    for (int u = 0; u < U; ++u) {
+      if (u >= b.n) break;
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const float z = fmaf(yy[u].v[j], bn.sc[j], bn.sh[j]);
+        const float gg = z > 0.f ? d[u].v[j] : kLreluSlope * d[u].v[j];
+        const float xhat = (yy[u].v[j] - bn.mean[j]) * bn.invstd[j];
+        d[u].v[j] = gg;
+        acc.fa[j] += gg;
+        acc.fb[j] = fmaf(gg, xhat, acc.fb[j]);
       }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (u >= b.n) break;
-#pragma unroll
-        for (int j = 0; j < V; ++j) {
-          const float z = fmaf(yy[u].v[j], bn.sc[j], bn.sh[j]);
-          const float gg = z > 0.f ? d[u].v[j] : kLreluSlope * d[u].v[j];
-          const float xhat = (yy[u].v[j] - bn.mean[j]) * bn.invstd[j];
-          d[u].v[j] = gg;
-          acc.fa[j] += gg;
-          acc.fb[j] = fmaf(gg, xhat, acc.fb[j]);
-        }
-        d[u].store(gbase + (size_t)b.h[u] * gs.hstride + (size_t)b.w[u] * gs.wstride);
-        acc.tick();
-      }
+      d[u].store(gbase + (size_t)b.h[u] * gs.hstride + (size_t)b.w[u] * gs.wstride);
+      acc.tick();
     }
-    acc.flush();
+    have = fetch();
   }
+  acc.flush();
   cta_reduce_cells<V>(sm_red, G, PPB, Cs, red_s + (size_t)s * Cs * 2);
 }
 
@@ -518,3 +551,4 @@ __device__ __forceinline__ void body_cat_bwd_up(const VGrid& vg, EwSmem sm, Mfvi
 }
 
 }  // namespace mfvi
+
