@@ -238,7 +238,7 @@ int mfvi_cat_up_fwd(MfviView ys, int Cs, const double* sums_s, const float* gamm
   const bool al = view_vec_ok(yd) && view_vec_ok(A) && (Cs == 0 || view_vec_ok(ys)) && Cs % 4 == 0 && Cd % 4 == 0;
   const EwGeom ge = ew_geom(Cs + Cd, al);
   MFVI_REQUIRE(ge.G <= kEwThreads, "cat_up_fwd: too many channel groups");
-  dim3 grid(ew_grid((H / 2 + 1) * (W / 2 + 1), ge.PPB, S, MFVI_EW_OCC(ge, k_cat_up_fwd)), S);
+  dim3 grid(ew_grid((H / 2 + 1) * (W / 2 + 1), ge.PPB, S, MFVI_EW_OCC(ge, k_cat_up_fwd), true), S);
   if (mega::Stage* ms = mega::append(mega::OP_CAT_UP_FWD)) {
     ms->V = ge.V; ms->G = ge.G; ms->PPB = ge.PPB; ms->gx = grid.x < 8u ? grid.x : 8u;      /* one virtual block per CTA of the sample's cluster */ ms->S = S;
     ms->a = ys; ms->C = Cs; ms->sums = sums_s; ms->gamma = gamma_s; ms->beta = beta_s;
@@ -259,9 +259,9 @@ int mfvi_pad_act_bwd(MfviView dxp, int S, int H, int W, int C, int pad, MfviView
   const EwGeom ge = ew_geom(C, view_vec_ok(dxp) && view_vec_ok(y) && view_vec_ok(g));
   MFVI_REQUIRE(ge.G <= kEwThreads, "pad_act_bwd: too many channel groups");
   const int occ_p = MFVI_EW_OCC_SMEM(ge, k_pad_act_bwd_p, kPipeBytes);
-  dim3 grid(ew_grid(H * W, ge.PPB, S, occ_p), S);
+  dim3 grid(ew_grid(H * W, ge.PPB, S, occ_p, true), S);
   const bool piped = ew_piped(1, H * W, ge.PPB, grid.x);
-  if (!piped) grid.x = ew_grid(H * W, ge.PPB, S, MFVI_EW_OCC(ge, k_pad_act_bwd));
+  if (!piped) grid.x = ew_grid(H * W, ge.PPB, S, MFVI_EW_OCC(ge, k_pad_act_bwd), true);
   if (mega::Stage* ms = mega::append(mega::OP_PAD_ACT_BWD)) {
     ms->V = ge.V; ms->G = ge.G; ms->PPB = ge.PPB; ms->gx = grid.x < 8u ? grid.x : 8u;      /* one virtual block per CTA of the sample's cluster */ ms->S = S;
     ms->a = dxp; ms->b = y; ms->c = g; ms->H = H; ms->W = W; ms->C = C; ms->pad = pad; ms->sums = sums; ms->gamma = gamma;
@@ -309,7 +309,7 @@ int mfvi_cat_up_bwd(MfviView dA, int S, int H, int W, int mode, MfviView ys, int
   if (Cs > 0 && part != 2) {
     MFVI_REQUIRE(ys.ptr && gs.ptr && red_s, "cat_up_bwd: null skip branch");
     const EwGeom ge = ew_geom(Cs, view_vec_ok(dA) && view_vec_ok(ys) && view_vec_ok(gs));
-    dim3 grid(ew_grid(H * W, ge.PPB, S, MFVI_EW_OCC(ge, k_cat_bwd_skip)), S);
+    dim3 grid(ew_grid(H * W, ge.PPB, S, MFVI_EW_OCC(ge, k_cat_bwd_skip), true), S);
     if (mega::Stage* ms = mega::append(mega::OP_CAT_BWD_SKIP)) {
       ms->V = ge.V; ms->G = ge.G; ms->PPB = ge.PPB; ms->gx = grid.x < 8u ? grid.x : 8u;      /* one virtual block per CTA of the sample's cluster */ ms->S = S;
       ms->a = dA; ms->b = ys; ms->c = gs; ms->H = H; ms->W = W; ms->C = Cs; ms->sums = sums_s; ms->gamma = gamma_s;
@@ -323,7 +323,7 @@ int mfvi_cat_up_bwd(MfviView dA, int S, int H, int W, int mode, MfviView ys, int
   MFVI_REQUIRE(yd.ptr && gd.ptr && red_d, "cat_up_bwd: null upsampled branch");
   const EwGeom ge = ew_geom(Cd, view_vec_ok(dA) && view_vec_ok(yd) && view_vec_ok(gd) && Cs % 4 == 0);
   MFVI_REQUIRE(ge.G <= kEwThreads, "cat_up_bwd: too many channel groups");
-  dim3 grid(ew_grid((H / 2) * (W / 2), ge.PPB, S, MFVI_EW_OCC(ge, k_cat_bwd_up)), S);
+  dim3 grid(ew_grid((H / 2) * (W / 2), ge.PPB, S, MFVI_EW_OCC(ge, k_cat_bwd_up), true), S);
   if (mega::Stage* ms = mega::append(mega::OP_CAT_BWD_UP)) {
     ms->V = ge.V; ms->G = ge.G; ms->PPB = ge.PPB; ms->gx = grid.x < 8u ? grid.x : 8u;      /* one virtual block per CTA of the sample's cluster */ ms->S = S;
     ms->a = dA; ms->b = yd; ms->c = gd; ms->H = H; ms->W = W; ms->mode = mode; ms->C = Cs; ms->C2 = Cd; ms->sums = sums_d;

@@ -301,13 +301,13 @@ __device__ __forceinline__ int fold_sources(int h, int n, int pad, int (&q)[3]) 
 // grid-stride sweep gives every CTA the same work).  Small launches take fewer CTAs still: every thread should sweep at least
 // kMinIter pixels, which amortises the per-CTA prologue (BN tables) and epilogue (reductions, double atomics), down to a floor
 // of kFloorCtas CTAs per SM.  MFVI_EW_CTAS / MFVI_EW_MINITER / MFVI_EW_FLOOR override the three constants (measurement knobs).
-constexpr int kCtasPerSM = 8, kMinIter = 4, kFloorCtas = 2;
+constexpr int kCtasPerSM = 8, kMinIter = 4, kFloorCtas = 2, kRedCtas = 128;
 static inline int ew_knob(const char* name, int dflt) {
   const char* e = getenv(name);
   const int v = e ? atoi(e) : 0;
   return v > 0 ? v : dflt;
 }
-static inline int ew_grid(int npix, int PPB, int S, int occ = kCtasPerSM) {
+static inline int ew_grid(int npix, int PPB, int S, int occ = kCtasPerSM, bool reducing = false) {
   static const int cap = ew_knob("MFVI_EW_CTAS", kCtasPerSM), miniter = ew_knob("MFVI_EW_MINITER", kMinIter),
                    floor_ctas = ew_knob("MFVI_EW_FLOOR", kFloorCtas);
   const int blocks = (npix + PPB - 1) / PPB;                      // per sample, one pixel per thread
@@ -320,6 +320,11 @@ static inline int ew_grid(int npix, int PPB, int S, int occ = kCtasPerSM) {
   if (want > hi) want = hi;
   long gx = want / S;
   if (gx > blocks) gx = blocks;
+  // a reducing kernel ends with one double atomic per channel and CTA on the sample's accumulators, which the L2 serialises
+  // per address (~12 ns each, profiles/r02_stat_atomics_negative.txt): more than kRedCtas CTAs per sample cost more in that
+  // burst than they save in the sweep (only reached with few MC samples per GPU)
+  static const int red_ctas = ew_knob("MFVI_EW_RED_CTAS", kRedCtas);
+  if (reducing && gx > red_ctas) gx = red_ctas;
   return gx < 1 ? 1 : (int)gx;
 }
 

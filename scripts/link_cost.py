@@ -66,3 +66,27 @@ for (Cn, H) in ((128, 8), (128, 16), (64, 32), (32, 64), (16, 128), (16, 256)):
     dxp = torch.zeros_like(xp)
     chain(f"conv dgrad tf32 {Cn}->{cout} k3 {H}x{H} S={S}", lambda: L.call("mfvi_conv2d_dgrad", C.byref(d), L.view(yo), w.data_ptr(), Pp,
                                                                            L.view(dxp), 0))
+
+# the concat / x2-upsample pair of every scale of the metric net (skip branch 4 channels, bilinear)
+for (Cd, H) in ((128, 16), (128, 32), (128, 64), (64, 128), (32, 256)):
+    Cs, h2 = 4, H // 2
+    ys = torch.randn(S, H, H, Cs, device=dev)
+    yd = torch.randn(S, h2, h2, Cd, device=dev)
+    mk = lambda t: torch.stack([t.double().sum((1, 2)), (t.double() ** 2).sum((1, 2))], -1).contiguous()
+    ss, sd = mk(ys), mk(yd)
+    gs_, bs_ = torch.ones(Cs, device=dev), torch.zeros(Cs, device=dev)
+    gd_, bd_ = torch.ones(Cd, device=dev), torch.zeros(Cd, device=dev)
+    A = torch.zeros(S, H + 2, H + 2, Cs + Cd, device=dev)
+    Ai = A[:, 1:-1, 1:-1, :]
+    sA = torch.zeros(S, Cs + Cd, 2, dtype=torch.float64, device=dev)
+    chain(f"cat_up_fwd  Cs=4 Cd={Cd} {H}x{H} S={S}", lambda: L.call("mfvi_cat_up_fwd", L.view(ys), Cs, ss.data_ptr(), gs_.data_ptr(),
+                                                                     bs_.data_ptr(), L.view(yd), Cd, sd.data_ptr(), gd_.data_ptr(),
+                                                                     bd_.data_ptr(), S, H, H, 0, L.view(Ai), sA.data_ptr()))
+    dA = torch.randn(S, H, H, Cs + Cd, device=dev)
+    g_s, g_d = torch.zeros_like(ys), torch.zeros_like(yd)
+    rs = torch.zeros(S, Cs, 2, dtype=torch.float64, device=dev)
+    rd = torch.zeros(S, Cd, 2, dtype=torch.float64, device=dev)
+    for part, nm in ((1, "skip"), (2, "up  ")):
+        chain(f"cat_up_bwd {nm} Cs=4 Cd={Cd} {H}x{H} S={S}", lambda: L.call(
+            "mfvi_cat_up_bwd", L.view(dA), S, H, H, 0, L.view(ys), Cs, ss.data_ptr(), gs_.data_ptr(), bs_.data_ptr(), L.view(g_s),
+            rs.data_ptr(), L.view(yd), Cd, sd.data_ptr(), gd_.data_ptr(), bd_.data_ptr(), L.view(g_d), rd.data_ptr(), part))
