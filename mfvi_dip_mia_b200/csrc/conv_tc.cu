@@ -257,7 +257,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
 // ---------------------------------------------------------------------------------------------- wgrad: conv_tc_wgrad.cuh
 
-// dbias[s][co] += sum over pixels of dy[s][.][.][co]   (HBM-bound column sum; V = 4 when C % 4 == 0, else scalar)
+// dbias[s][co] += sum over pixels of dy[s][.][.][co]   (column sum; V = 4 when C % 4 == 0, else scalar).  Few CTAs per sample
+// (every CTA ends with C float atomics on the same cache line, which the L2 serialises: profiles/r02_stat_atomics_negative.txt),
+// four independent loads per thread and trip, lanes of one channel group combined by shuffles before the shared-memory atomics.
 template <int V>
 __global__ void __launch_bounds__(256)
 k_bias_grad(MfviView dy, int H, int W, int C, float* __restrict__ dbias, long long sstride) {
@@ -274,16 +276,35 @@ k_bias_grad(MfviView dy, int H, int W, int C, float* __restrict__ dbias, long lo
 #pragma unroll
   for (int j = 0; j < V; ++j) acc[j] = 0.f;
   if (slot < PPB) {
-    const int npix = H * W;
-    for (int px = blockIdx.x * PPB + slot; px < npix; px += gridDim.x * PPB) {
-      const float* src = dy.ptr + view_off(dy, s, px / W, px % W) + V * g;
-      if (V == 4) {
-        const float4 v = *reinterpret_cast<const float4*>(src);
-        acc[0] += v.x; acc[1 % V] += v.y; acc[2 % V] += v.z; acc[3 % V] += v.w;
-      } else {
-        acc[0] += src[0];
+    const int npix = H * W, step = gridDim.x * PPB;
+    constexpr int U = 4;
+    for (int px0 = blockIdx.x * PPB + slot; px0 < npix; px0 += U * step) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int px = px0 + u * step;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (px < npix) {
+          const float* src = dy.ptr + view_off(dy, s, px / W, px % W) + V * g;
+          if (V == 4) v[u] = *reinterpret_cast<const float4*>(src);
+          else v[u].x = src[0];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        acc[0] += v[u].x; acc[1 % V] += V > 1 ? v[u].y : 0.f; acc[2 % V] += V > 2 ? v[u].z : 0.f; acc[3 % V] += V > 3 ? v[u].w : 0.f;
       }
     }
+  }
+  // lanes l and l + k*G of a warp hold the same channel group when G divides 32: fold them before touching shared memory
+  if (G <= 32 && (32 % G) == 0 && blockDim.x % 32 == 0) {
+    for (int off = 16; off >= G; off >>= 1)
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] += __shfl_down_sync(0xffffffffu, acc[j], off);
+    if ((threadIdx.x & 31) < G && slot < PPB)
+#pragma unroll
+      for (int j = 0; j < V; ++j) atomicAdd(&sm_part[V * g + j], acc[j]);
+  } else if (slot < PPB) {
 #pragma unroll
     for (int j = 0; j < V; ++j) atomicAdd(&sm_part[V * g + j], acc[j]);
   }
@@ -513,7 +534,8 @@ int mfvi_conv2d_bias_grad_tc(const MfviConvDesc* d, MfviView dy, float* dbias, l
                    dy.wstride % 4 == 0;
   const int groups = vec ? d->Cout / 4 : d->Cout;
   if (groups > 256) return -1;
-  int blocks = std::max(1, std::min(kNumSMs * 2, (d->Hout * d->Wout * groups + 255) / 256));
+  // one wave of about two CTAs per SM over all samples, at most 64 per sample (the float atomics at the end of every CTA)
+  int blocks = std::max(1, std::min(std::min(64, (kNumSMs * 2 + d->S - 1) / d->S), (d->Hout * d->Wout * groups + 255) / 256));
   dim3 g2(blocks, d->S);
   if (vec)
     launch_k(k_bias_grad<4>, g2, 256, d->Cout * sizeof(float), as_stream(st), dy, d->Hout, d->Wout, d->Cout, dbias, w_sstride);
