@@ -103,7 +103,7 @@ k_cat_bwd_skip(MfviView dA, int H, int W, MfviView ys, int Cs, const double* __r
 }
 
 template <int V>
-__global__ void __launch_bounds__(kEwThreads, 4)
+__global__ void __launch_bounds__(kEwThreads, 2)
 k_cat_bwd_up(MfviView dA, int H, int W, int mode, int Cs, MfviView yd, int Cd, const double* __restrict__ sums_d,
              const float* __restrict__ gamma_d, const float* __restrict__ beta_d, MfviView gd,
              double* __restrict__ red_d, int G, int PPB) {
@@ -323,7 +323,7 @@ int mfvi_cat_up_bwd(MfviView dA, int S, int H, int W, int mode, MfviView ys, int
   MFVI_REQUIRE(yd.ptr && gd.ptr && red_d, "cat_up_bwd: null upsampled branch");
   const EwGeom ge = ew_geom(Cd, view_vec_ok(dA) && view_vec_ok(yd) && view_vec_ok(gd) && Cs % 4 == 0);
   MFVI_REQUIRE(ge.G <= kEwThreads, "cat_up_bwd: too many channel groups");
-  dim3 grid(ew_grid((H / 2) * (W / 2), ge.PPB, S, MFVI_EW_OCC(ge, k_cat_bwd_up), true), S);
+  dim3 grid(ew_grid(((H / 2 + 1) / 2) * ((W / 2 + 1) / 2), ge.PPB, S, MFVI_EW_OCC(ge, k_cat_bwd_up), true), S);      // 2x2 low-res blocks
   if (mega::Stage* ms = mega::append(mega::OP_CAT_BWD_UP)) {
     ms->V = ge.V; ms->G = ge.G; ms->PPB = ge.PPB; ms->gx = grid.x < 8u ? grid.x : 8u;      /* one virtual block per CTA of the sample's cluster */ ms->S = S;
     ms->a = dA; ms->b = yd; ms->c = gd; ms->H = H; ms->W = W; ms->mode = mode; ms->C = Cs; ms->C2 = Cd; ms->sums = sums_d;

@@ -484,7 +484,12 @@ __device__ __forceinline__ float up_weight_of(int i, int k, int n, int mode) {
   return wgt;
 }
 
-// B3b: deeper branch: gd = up2x^T(dA[:, Cs:]) * lrelu'(bn(yd)), red_d += …   (iterates low-res pixels)
+// B3b: deeper branch: gd = up2x^T(dA[:, Cs:]) * lrelu'(bn(yd)), red_d += …
+// A thread owns a 2x2 block of low-resolution pixels (rows kh0, kh0+1 x columns kw0, kw0+1) and one channel group.  The block
+// receives the 6x6 high-resolution patch rows 2kh0-1..2kh0+4 x columns 2kw0-1..2kw0+4: 36 loads for 4 outputs instead of the
+// 16 per output of the per-pixel form, evaluated separably (each patch row is first combined along w for the two columns,
+// then added to the two rows with its vertical weights).  Weights come from up_weight_of, i.e. from the forward's up_taps,
+// and are 0 outside the image and for non-taps.
 template <int V>
 __device__ __forceinline__ void body_cat_bwd_up(const VGrid& vg, EwSmem sm, MfviView dA, int H, int W, int mode, int Cs, MfviView yd, int Cd, const double* __restrict__ sums_d,
              const float* __restrict__ gamma_d, const float* __restrict__ beta_d, MfviView gd,
@@ -492,6 +497,7 @@ __device__ __forceinline__ void body_cat_bwd_up(const VGrid& vg, EwSmem sm, Mfvi
   double* sm_red = sm.red;
   const int s = vg.by;
   const int h2 = H / 2, w2 = W / 2;
+  const int qh = (h2 + 1) / 2, qw = (w2 + 1) / 2;
   const int group = threadIdx.x % G, slot = threadIdx.x / G;
   const bool active = slot < PPB;
   const int c0 = group * V;
@@ -505,44 +511,76 @@ __device__ __forceinline__ void body_cat_bwd_up(const VGrid& vg, EwSmem sm, Mfvi
     const float* dbase = dA.ptr + (size_t)s * dA.sstride + Cs + c0;
     const float* ybase = yd.ptr + (size_t)s * yd.sstride + c0;
     float* gbase = gd.ptr + (size_t)s * gd.sstride + c0;
-    for (PixIter it(vg, h2 * w2, w2, PPB, slot); it.valid(); it.next()) {
-      const int kh = it.h, kw = it.w;
-      // hi-res rows 2kh-1 .. 2kh+2 receive low-res row kh with these weights (0 outside the image / when not a tap)
-      float wh[4], ww[4];
+    for (PixIter it(vg, qh * qw, qw, PPB, slot); it.valid(); it.next()) {
+      const int kh0 = 2 * it.h, kw0 = 2 * it.w;
+      const bool rin[2] = {true, kh0 + 1 < h2}, cin[2] = {true, kw0 + 1 < w2};
+      float wc[2][6];
 #pragma unroll
-      for (int d = 0; d < 4; ++d) {
-        wh[d] = up_weight_of(2 * kh + d - 1, kh, h2, mode);
-        ww[d] = up_weight_of(2 * kw + d - 1, kw, w2, mode);
+      for (int d = 0; d < 6; ++d) {
+        wc[0][d] = up_weight_of(2 * kw0 - 1 + d, kw0, w2, mode);
+        wc[1][d] = cin[1] ? up_weight_of(2 * kw0 - 1 + d, kw0 + 1, w2, mode) : 0.f;
       }
-      Vec<V> a;
+      Vec<V> a[2][2];
 #pragma unroll
-      for (int j = 0; j < V; ++j) a.v[j] = 0.f;
+      for (int u = 0; u < 2; ++u)
 #pragma unroll
-      for (int dh = 0; dh < 4; ++dh) {
-        if (wh[dh] == 0.f) continue;
-        const float* row = dbase + (size_t)(2 * kh + dh - 1) * dA.hstride;
+        for (int v = 0; v < 2; ++v)
 #pragma unroll
-        for (int dw = 0; dw < 4; ++dw) {
-          if (ww[dw] == 0.f) continue;
-          Vec<V> t;
-          t.load(row + (size_t)(2 * kw + dw - 1) * dA.wstride);
-          const float wgt = wh[dh] * ww[dw];
+          for (int j = 0; j < V; ++j) a[u][v].v[j] = 0.f;
 #pragma unroll
-          for (int j = 0; j < V; ++j) a.v[j] = fmaf(wgt, t.v[j], a.v[j]);
+      for (int dr = 0; dr < 6; ++dr) {
+        const int hr = 2 * kh0 - 1 + dr;
+        const float wr0 = up_weight_of(hr, kh0, h2, mode), wr1 = rin[1] ? up_weight_of(hr, kh0 + 1, h2, mode) : 0.f;
+        if (wr0 == 0.f && wr1 == 0.f) continue;          // also every row outside the image
+        const float* row = dbase + (size_t)hr * dA.hstride;
+        Vec<V> t[6];
+#pragma unroll
+        for (int dc = 0; dc < 6; ++dc) {
+          const bool on = wc[0][dc] != 0.f || wc[1][dc] != 0.f;
+          if (on) t[dc].load(row + (size_t)(2 * kw0 - 1 + dc) * dA.wstride);
+          else
+#pragma unroll
+            for (int j = 0; j < V; ++j) t[dc].v[j] = 0.f;
+        }
+        float t0[V], t1[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) t0[j] = t1[j] = 0.f;
+#pragma unroll
+        for (int dc = 0; dc < 6; ++dc)
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            t0[j] = fmaf(wc[0][dc], t[dc].v[j], t0[j]);
+            t1[j] = fmaf(wc[1][dc], t[dc].v[j], t1[j]);
+          }
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          a[0][0].v[j] = fmaf(wr0, t0[j], a[0][0].v[j]);
+          a[0][1].v[j] = fmaf(wr0, t1[j], a[0][1].v[j]);
+          a[1][0].v[j] = fmaf(wr1, t0[j], a[1][0].v[j]);
+          a[1][1].v[j] = fmaf(wr1, t1[j], a[1][1].v[j]);
         }
       }
-      Vec<V> yy;
-      yy.load(ybase + (size_t)kh * yd.hstride + (size_t)kw * yd.wstride);
 #pragma unroll
-      for (int j = 0; j < V; ++j) {
-        const float z = fmaf(yy.v[j], bn.sc[j], bn.sh[j]);
-        const float gg = z > 0.f ? a.v[j] : kLreluSlope * a.v[j];
-        const float xhat = (yy.v[j] - bn.mean[j]) * bn.invstd[j];
-        a.v[j] = gg;
-        acc.fa[j] += gg;
-        acc.fb[j] = fmaf(gg, xhat, acc.fb[j]);
+      for (int u = 0; u < 2; ++u) {
+        if (!rin[u]) continue;
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          if (!cin[v]) continue;
+          const int kh = kh0 + u, kw = kw0 + v;
+          Vec<V> yy;
+          yy.load(ybase + (size_t)kh * yd.hstride + (size_t)kw * yd.wstride);
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            const float z = fmaf(yy.v[j], bn.sc[j], bn.sh[j]);
+            const float gg = z > 0.f ? a[u][v].v[j] : kLreluSlope * a[u][v].v[j];
+            const float xhat = (yy.v[j] - bn.mean[j]) * bn.invstd[j];
+            a[u][v].v[j] = gg;
+            acc.fa[j] += gg;
+            acc.fb[j] = fmaf(gg, xhat, acc.fb[j]);
+          }
+          a[u][v].store(gbase + (size_t)kh * gd.hstride + (size_t)kw * gd.wstride);
+        }
       }
-      a.store(gbase + (size_t)kh * gd.hstride + (size_t)kw * gd.wstride);
       acc.tick();
     }
     acc.flush();
