@@ -197,13 +197,16 @@ def unnormalize_X(X_norm: torch.Tensor, x1_logbounds, x2_logbounds) -> torch.Ten
 
 
 def bo(trial_fn: Callable[..., float], bo_params: Dict[str, Dict[str, Sequence[float]]], run_params: Dict, *,
-       rounds: int = 20, gp_iters: int = 2000, start_method: str = "spawn", verbose: bool = True):
+       rounds: int = 20, gp_iters: int = 2000, start_method: str = "spawn", verbose: bool = True, persistent: bool = True):
     """The reference's `bo()` (:3726-3887) with the trial runner passed in: every round evaluates the current candidates
     (one process per candidate, devices round-robin, NaN results dropped), refits the GP on ALL observations, proposes
     the next candidates and writes `<bo_results_path>/<round>_fig_data.npz` with the reference's keys.
     bo_params: {"<name1>": {"logbounds": [lo, hi], "candidates": [...]}, "<name2>": {...}} (bo_configs/*.json);
-    run_params: keyword arguments of the trial runner plus "bo_results_path" and "devices".  Returns (X, Y)."""
-    from .runners import eval_trials
+    run_params: keyword arguments of the trial runner plus "bo_results_path" and "devices".  Returns (X, Y).
+    persistent (default): the trials of ALL rounds run on one worker process per device (runners.TrialPool), so that a round
+    costs the trials' kernels instead of a process start + CUDA context per trial; False = one process per trial, as the
+    reference starts them."""
+    from .runners import TrialPool, _finite, eval_trials
     run_params = dict(run_params)
     out_path = run_params.pop("bo_results_path")
     devices = list(run_params.pop("devices"))
@@ -217,8 +220,24 @@ def bo(trial_fn: Callable[..., float], bo_params: Dict[str, Dict[str, Sequence[f
     candidates = list(itertools.product(*[v["candidates"] for v in bo_params.values()]))
     X: List = []
     Y: List[float] = []
+    pool = TrialPool(devices, trial_fn, run_params, start_method=start_method) if persistent else None
+    try:
+        return _bo_rounds(pool, rounds, candidates, devices, trial_fn, run_params, start_method, verbose, bo_params, X, Y,
+                          p1_logbounds, p2_logbounds, gp_iters, X_test, XX_lr, XX_wd, out_path)
+    finally:
+        if pool is not None:
+            pool.close()
+
+
+def _bo_rounds(pool, rounds, candidates, devices, trial_fn, run_params, start_method, verbose, bo_params, X, Y, p1_logbounds,
+               p2_logbounds, gp_iters, X_test, XX_lr, XX_wd, out_path):
+    from .runners import _finite, eval_trials
     for r in range(rounds):
-        cands_run, y_run = eval_trials(candidates, devices, trial_fn, run_params, start_method=start_method)
+        if pool is not None:
+            cl = [tuple(c) for c in candidates]
+            cands_run, y_run = _finite(cl, pool.run(cl))
+        else:
+            cands_run, y_run = eval_trials(candidates, devices, trial_fn, run_params, start_method=start_method)
         if verbose:
             names = list(bo_params.keys())
             print(f"\n{names[0]}      {names[1]}       psnr")

@@ -273,67 +273,114 @@ def _trial_entry(fn, kwargs, candidate, device, queue):
     queue.put((tuple(candidate), _trial_value(fn, kwargs, candidate, device)))
 
 
-def _worker_entry(wid, fn, kwargs, device, tasks, results):
-    """Body of one persistent worker: trials of its device, one after the other, until the None sentinel.  The CUDA context,
-    the loaded library and whatever `fn` caches per process (runners.trial_cache) survive from trial to trial."""
+def _worker_entry(fn, kwargs, device, conn):
+    """Body of one persistent worker: trials of its device, one after the other, until the None sentinel (or the parent's end
+    of the pipe closes).  The CUDA context, the loaded library and whatever `fn` caches per process survive from trial to
+    trial.  Results go back synchronously over the worker's OWN pipe: a worker that dies cannot leave a lock of a shared queue
+    behind."""
     while True:
-        cand = tasks.get()
+        try:
+            cand = conn.recv()
+        except EOFError:
+            return
         if cand is None:
             return
-        results.put((wid, tuple(cand), _trial_value(fn, kwargs, cand, device)))
+        conn.send((tuple(cand), _trial_value(fn, kwargs, cand, device)))
 
 
-def _eval_trials_workers(ctx, cands, devices, fn, fn_kwargs, n_workers):
-    import queue as queue_mod
-    results_q = ctx.Queue()
-    results: Dict[Tuple[float, float], float] = {}
-    pending = list(cands)
-    workers = {}                                    # wid -> [process, task queue, device, candidate in flight]
+class TrialPool:
+    """Persistent trial workers: one process per device slot, alive from construction to close(); `run(candidates)` feeds each
+    worker its candidates one after the other and returns {candidate: value} (NaN for a trial that raised or whose worker
+    died; a dead worker is replaced).  Keeps `import torch`, the CUDA context and the loaded library across the trials of one
+    sweep AND across the rounds of `bo()`.  Use as a context manager."""
 
-    def spawn(wid, device):
-        tq = ctx.Queue()
-        pr = ctx.Process(target=_worker_entry, args=(wid, fn, fn_kwargs, device, tq, results_q))
+    def __init__(self, devices: Sequence[str], fn: Callable[..., float], fn_kwargs: Optional[dict] = None, *,
+                 n_workers: Optional[int] = None, start_method: str = "spawn"):
+        import torch.multiprocessing as mp
+        self._ctx = mp.get_context(start_method)
+        self._fn, self._kwargs = fn, dict(fn_kwargs or {})
+        self._devices = list(devices)
+        self._n = n_workers or len(self._devices)
+        self._workers: Dict[int, list] = {}           # wid -> [process, parent end of its pipe, candidate in flight]
+
+    def _spawn(self, wid: int):
+        device = self._devices[wid % len(self._devices)]
+        parent, child = self._ctx.Pipe(duplex=True)
+        pr = self._ctx.Process(target=_worker_entry, args=(self._fn, self._kwargs, device, child))
         pr.start()
-        workers[wid] = [pr, tq, device, None]
+        child.close()                                 # the worker holds the only other end: its death reads as EOF here
+        self._workers[wid] = [pr, parent, None]
 
-    def feed(wid):
-        w = workers[wid]
-        if pending:
-            w[3] = pending.pop(0)
-            w[1].put(w[3])
-        else:
-            w[3] = None
+    def run(self, candidates: Iterable[Sequence[float]]) -> Dict[Tuple[float, float], float]:
+        from multiprocessing.connection import wait
+        cands = [tuple(c) for c in candidates]
+        results: Dict[Tuple[float, float], float] = {}
+        pending = list(cands)
+        workers = self._workers
 
-    for wid in range(min(n_workers, len(cands))):
-        spawn(wid, devices[wid % len(devices)])
-        feed(wid)
-    while any(w[3] is not None for w in workers.values()):
-        try:
-            wid, c, v = results_q.get(timeout=0.5)
-            results[c] = v
+        def feed(wid):
+            w = workers[wid]
+            w[2] = pending.pop(0) if pending else None
+            if w[2] is not None:
+                w[1].send(w[2])
+
+        def replace(wid):                             # the worker died inside its trial: NaN, fresh process for the rest
+            w = workers[wid]
+            results[w[2]] = float("nan")
+            w[1].close()
+            w[0].join()
+            self._spawn(wid)
             feed(wid)
-        except queue_mod.Empty:
-            pass
-        for wid, w in list(workers.items()):
-            if w[3] is not None and not w[0].is_alive():
-                try:                                 # its last result may still sit in the queue
-                    while w[3] not in results:
-                        wid2, c2, v2 = results_q.get(timeout=0.5)
-                        results[c2] = v2
-                        if wid2 != wid:
-                            feed(wid2)
-                except queue_mod.Empty:
-                    results[w[3]] = float("nan")     # the worker died inside this trial: dropped like a NaN trial
-                w[0].join()
-                spawn(wid, w[2])                     # a fresh process (and CUDA context) for the rest of this device's trials
+
+        for wid in range(min(self._n, len(cands))):
+            if wid not in workers or not workers[wid][0].is_alive():
+                self._spawn(wid)
+            feed(wid)
+        while True:
+            busy = {w[1]: wid for wid, w in workers.items() if w[2] is not None}
+            if not busy:
+                break
+            for conn in wait(list(busy), timeout=0.5):
+                wid = busy[conn]
+                try:
+                    c, v = conn.recv()
+                except (EOFError, OSError):
+                    replace(wid)
+                    continue
+                results[c] = v
                 feed(wid)
-    for w in workers.values():
-        w[1].put(None)
-    for w in workers.values():
-        w[0].join(timeout=60)
-        if w[0].is_alive():
-            w[0].terminate()
-    return results
+        return results
+
+    def close(self):
+        for w in self._workers.values():
+            try:
+                w[1].send(None)
+            except (OSError, ValueError):
+                pass
+        for w in self._workers.values():
+            w[0].join(timeout=60)
+            if w[0].is_alive():
+                w[0].terminate()
+            w[1].close()
+        self._workers = {}
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+
+def _finite(cands, results):
+    """(candidates, values) in candidate order with the NaN results removed (bayesian_optimization.py:3778-3781)."""
+    X, Y = [], []
+    for c in cands:
+        v = results.get(c, float("nan"))
+        if not math.isnan(v):
+            X.append(c)
+            Y.append(v)
+    return X, Y
 
 
 def eval_trials(candidates: Iterable[Sequence[float]], devices: Sequence[str], fn: Callable[..., float],
@@ -352,7 +399,8 @@ def eval_trials(candidates: Iterable[Sequence[float]], devices: Sequence[str], f
     cands = [tuple(c) for c in candidates]
     max_parallel = max_parallel or len(devices)
     if persistent:
-        results = _eval_trials_workers(ctx, cands, list(devices), fn, fn_kwargs or {}, max_parallel)
+        with TrialPool(devices, fn, fn_kwargs, n_workers=max_parallel, start_method=start_method) as pool:
+            results = pool.run(cands)
     else:
         queue = ctx.Queue()
         dev_cycle = itertools.cycle(devices)
@@ -379,13 +427,7 @@ def eval_trials(candidates: Iterable[Sequence[float]], devices: Sequence[str], f
                         results[c2] = v2
                 except queue_mod.Empty:
                     results.setdefault(c, float("nan"))  # the process died without reporting: dropped like a NaN trial
-    X, Y = [], []
-    for c in cands:
-        v = results.get(c, float("nan"))
-        if not math.isnan(v):
-            X.append(c)
-            Y.append(v)
-    return X, Y
+    return _finite(cands, results)
 
 
 def log_grid(bounds_log10: Sequence[Sequence[float]], n: int) -> List[Tuple[float, float]]:

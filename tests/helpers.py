@@ -72,6 +72,12 @@ def fake_trial(temp, sigma, device, offset=0.0):
     return offset + math.log10(temp) - 2.0 * math.log10(sigma) + (0.0 if device == "cpu:0" else 0.5)
 
 
+def pid_trial(temp, sigma, device):
+    """Stand-in trial whose value is the id of the process that ran it (worker reuse in the TrialPool test)."""
+    import os
+    return float(os.getpid())
+
+
 def quadratic_trial(temp, sigma, device, peak=(1e-6, 1e-3)):
     """Analytic stand-in for a trial runner in the BO test: a smooth PSNR-like bowl in log10 space, maximum at `peak`."""
     import math

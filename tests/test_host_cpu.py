@@ -201,6 +201,20 @@ def test_trial_fanout_persistent_workers():
     assert X1 == cands[:1] and abs(Y1[0] - (math.log10(1.0) + 2.0)) < 1e-12
 
 
+def test_trial_pool_keeps_its_workers_across_runs():
+    """TrialPool (what bo() runs its rounds on): the worker processes of the first run serve the second one too."""
+    from mfvi_dip_mia_b200.runners import TrialPool
+    from tests.helpers import pid_trial
+    import os
+    with TrialPool(["cpu:0", "cpu:1"], pid_trial, start_method="fork") as pool:
+        r1 = pool.run([(float(i + 1), 0.1) for i in range(6)])
+        r2 = pool.run([(float(i + 10), 0.1) for i in range(5)])
+        r3 = pool.run([(99.0, 0.1)])                                    # fewer candidates than workers
+    pids1, pids2 = set(r1.values()), set(r2.values())
+    assert len(r1) == 6 and len(r2) == 5 and len(r3) == 1
+    assert 1 <= len(pids1) <= 2 and pids2 <= pids1 and set(r3.values()) <= pids1 and float(os.getpid()) not in pids1
+
+
 # ----------------------------------------------------------------------------------------------- BO outer loop (row f4)
 def test_gp_posterior_and_ei_match_closed_form():
     """ExactGPModel (constant mean + scaled RBF + Gaussian noise) against plain numpy GP algebra at the fitted
