@@ -23,6 +23,7 @@ int mfvi_conv2d_wgrad_tc(const MfviConvDesc*, MfviView, MfviView, float*, float*
 int mfvi_conv2d_fwd_tc2(const MfviConvDesc*, MfviView, const float*, const float*, long long, MfviView, double*, mfvi_stream_t);
 int mfvi_conv2d_dgrad_tc2(const MfviConvDesc*, MfviView, const float*, long long, MfviView, int, mfvi_stream_t);
 int mfvi_conv2d_wgrad_tc2(const MfviConvDesc*, MfviView, MfviView, float*, long long, mfvi_stream_t);
+int mfvi_conv2d_wgrad_pw(const MfviConvDesc*, MfviView, MfviView, float*, float*, long long, mfvi_stream_t);
 int mfvi_conv2d_bias_grad_tc(const MfviConvDesc*, MfviView, float*, long long, mfvi_stream_t);
 int mfvi_conv2d_fwd_pw(const MfviConvDesc*, MfviView, const float*, const float*, long long, MfviView, double*, mfvi_stream_t);
 int mfvi_conv2d_dgrad_pw(const MfviConvDesc*, MfviView, const float*, long long, MfviView, int, mfvi_stream_t);
@@ -88,7 +89,11 @@ static int dgrad_chain(const MfviConvDesc* d, MfviView dy, const float* w, long 
 static int wgrad_chain(const MfviConvDesc* d, MfviView x, MfviView dy, float* dw, float* dbias, long long w_sstride,
                        mfvi_stream_t st, const char** family) {
   if (d != nullptr && d->math == MFVI_MATH_TF32) {
-    int rc = mfvi_conv2d_wgrad_tc2(d, x, dy, dw, w_sstride, st);
+    // 1x1 layers with <= 4 output channels: a streaming reduction (weight and bias gradient in one launch)
+    int rc = mfvi_conv2d_wgrad_pw(d, x, dy, dw, dbias, w_sstride, st);
+    *family = "pointwise";
+    if (rc >= 0) return rc;
+    rc = mfvi_conv2d_wgrad_tc2(d, x, dy, dw, w_sstride, st);
     if (rc == 0 && dbias != nullptr) rc = mfvi_conv2d_bias_grad_tc(d, dy, dbias, w_sstride, st);
     *family = "alias";
     if (rc >= 0) return rc;

@@ -1,5 +1,5 @@
-// 1x1 (pointwise), stride-1 sampled-weight convolution with FEW output channels (Cout <= 4, Cin <= 32): forward and data
-// gradient on CUDA cores, exact fp32.
+// 1x1 (pointwise), stride-1 sampled-weight convolution with FEW output channels (Cout <= 4, Cin <= 32): forward, data
+// gradient and weight (+ bias) gradient on CUDA cores, exact fp32.
 //
 // These layers (the 16->4 / 32->4 skip convs and the final 16->2 conv of the metric net) are pure streaming: 70..150 bytes
 // per pixel against <= 256 FLOP, and an M=128 x N=16 tensor-core tile would compute 4..8x padding.  Measured against the
@@ -10,6 +10,7 @@
 //   forward : y[s,p,co] = b[s,co] + sum_ci x[s,p,ci] * w[s][co][ci]        (+ per-sample BatchNorm (sum, sumsq) in double)
 //   dgrad   : dx[s,p,ci] (+)= sum_co dy[s,p,co] * w[s][co][ci]
 // Both are out[p][n] = sum_k in[p][k] * M[k][n] with M = w^T (forward) or w (dgrad), zero-padded to [4*KP][4*NP].
+//   wgrad   : dw[s][co][ci] += sum_p dy[s,p,co] * x[s,p,ci],  dbias[s][co] += sum_p dy[s,p,co]   (k_wgrad_pointwise below)
 #include "common.cuh"
 
 namespace mfvi {
@@ -129,6 +130,97 @@ k_conv_pointwise(const Args p) {
   }
 }
 
+// Weight gradient of the same layers: a reduction over all pixels into Cout x Cin <= 128 numbers — 33 MB of x and 4..8 MB of
+// dy per launch at 256^2 / S = 8, i.e. streaming work (in the step's graph the tcgen05 alias kernel + bias-gradient kernel
+// took 29 us for 16->2 and 18 us for 16->4: profiles/r02_plan_link_cost_mc8.txt).  A thread owns one pixel slot and one
+// quad of input channels: per pixel one float4 of x, the pixel's <= 4 dy values (the lanes of a pixel read the same
+// addresses), 16 FMAs into acc[co][ci]; four pixels' loads are issued per trip.  Lanes of one channel quad are folded with
+// shuffles, the warps through shared memory, and a CTA ends with Cout x Cin (+ Cout) float atomics — at most 64 CTAs per sample.
+struct WArgs {
+  MfviView x, dy;
+  float* dw;               // [S][Cout][Cin], sample stride w_sstride
+  float* dbias;            // [S][Cout] (sample stride w_sstride) or null
+  long long w_sstride;
+  int Cin, Cout, HW, W, G;
+};
+
+__global__ void __launch_bounds__(kThreads)
+k_wgrad_pointwise(const WArgs p) {
+  __shared__ float part[kThreads / 32][8][20];          // [warp][channel quad][16 dw + 4 dbias]
+  pdl_trigger();
+  pdl_wait();
+  const int s = blockIdx.y;
+  const int G = p.G, PPB = kThreads / G;                // G = Cin / 4 in {1, 2, 4, 8}: divides the warp
+  const int g = threadIdx.x % G, slot = threadIdx.x / G;
+  float acc[4][4], bsum[4];
+#pragma unroll
+  for (int co = 0; co < 4; ++co) {
+    bsum[co] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[co][j] = 0.f;
+  }
+  const float* xb = p.x.ptr + static_cast<size_t>(s) * p.x.sstride + 4 * g;
+  const float* db = p.dy.ptr + static_cast<size_t>(s) * p.dy.sstride;
+  const int step = gridDim.x * PPB;
+  constexpr int U = 4;
+  for (int px0 = blockIdx.x * PPB + slot; px0 < p.HW; px0 += U * step) {
+    float4 xv[U];
+    float dv[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int px = px0 + u * step;
+      const bool ok = px < p.HW;
+      const int h = ok ? px / p.W : 0, w = ok ? px - h * p.W : 0;
+      xv[u] = ok ? __ldg(reinterpret_cast<const float4*>(xb + static_cast<size_t>(h) * p.x.hstride + static_cast<size_t>(w) * p.x.wstride))
+                 : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* dp = db + static_cast<size_t>(h) * p.dy.hstride + static_cast<size_t>(w) * p.dy.wstride;
+#pragma unroll
+      for (int co = 0; co < 4; ++co) dv[u][co] = (ok && co < p.Cout) ? __ldg(dp + co) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int co = 0; co < 4; ++co) {
+        acc[co][0] = fmaf(dv[u][co], xv[u].x, acc[co][0]);
+        acc[co][1] = fmaf(dv[u][co], xv[u].y, acc[co][1]);
+        acc[co][2] = fmaf(dv[u][co], xv[u].z, acc[co][2]);
+        acc[co][3] = fmaf(dv[u][co], xv[u].w, acc[co][3]);
+        bsum[co] += dv[u][co];
+      }
+  }
+  // lanes l, l + G, l + 2G, ... of a warp hold the same channel quad
+  for (int off = 16; off >= G; off >>= 1) {
+#pragma unroll
+    for (int co = 0; co < 4; ++co) {
+      bsum[co] += __shfl_down_sync(0xffffffffu, bsum[co], off);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[co][j] += __shfl_down_sync(0xffffffffu, acc[co][j], off);
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane < G) {
+#pragma unroll
+    for (int co = 0; co < 4; ++co) {
+      part[warp][lane][16 + co] = bsum[co];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) part[warp][lane][4 * co + j] = acc[co][j];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < G * 20; i += kThreads) {
+    const int gg = i / 20, v = i - gg * 20;
+    float t = 0.f;
+#pragma unroll
+    for (int wi = 0; wi < kThreads / 32; ++wi) t += part[wi][gg][v];
+    if (v < 16) {
+      const int co = v >> 2, j = v & 3;
+      if (co < p.Cout) atomicAdd(p.dw + static_cast<size_t>(s) * p.w_sstride + static_cast<size_t>(co) * p.Cin + 4 * gg + j, t);
+    } else if (gg == 0 && p.dbias != nullptr && v - 16 < p.Cout) {
+      atomicAdd(p.dbias + static_cast<size_t>(s) * p.w_sstride + (v - 16), t);
+    }
+  }
+}
+
 static inline int pad_quads(int c) { return c <= 4 ? 1 : (c <= 16 ? 4 : 8); }
 
 static bool ok_view(const MfviView& v, int C) {
@@ -189,6 +281,24 @@ int mfvi_conv2d_dgrad_pw(const MfviConvDesc* d, MfviView dy, const float* w, lon
                          mfvi_stream_t st) {
   if (!pw::enabled() || !pw::shape_ok(d) || !pw::ok_view(dy, d->Cout) || !pw::ok_view(dx, d->Cin)) return -1;
   return pw::launch(d, true, dy, dx, w, nullptr, w_sstride, nullptr, accumulate, st, "conv2d_dgrad_pw");
+}
+
+// dw (+)= x^T dy, dbias (+)= sum dy in ONE launch (both accumulate: zero them first, as for every weight-gradient kernel)
+int mfvi_conv2d_wgrad_pw(const MfviConvDesc* d, MfviView x, MfviView dy, float* dw, float* dbias, long long w_sstride,
+                         mfvi_stream_t st) {
+  const int G = d->Cin / 4;
+  if (!pw::enabled() || !pw::shape_ok(d) || d->Cin % 4 != 0 || !(G == 1 || G == 2 || G == 4 || G == 8) || !pw::ok_view(x, d->Cin) ||
+      (dy.sstride == 0 && d->S > 1))
+    return -1;
+  pw::WArgs p{};
+  p.x = x; p.dy = dy; p.dw = dw; p.dbias = dbias; p.w_sstride = w_sstride;
+  p.Cin = d->Cin; p.Cout = d->Cout; p.HW = d->Hout * d->Wout; p.W = d->Wout; p.G = G;
+  const int PPB = pw::kThreads / G;
+  int chunks = (p.HW + 4 * PPB - 1) / (4 * PPB);
+  chunks = std::max(1, std::min(chunks, std::min(64, (2 * kNumSMs + d->S - 1) / d->S)));
+  dry_detail("G=%d", G);
+  launch_k(pw::k_wgrad_pointwise, dim3(chunks, d->S), pw::kThreads, 0, as_stream(st), p);
+  return check_launch("conv2d_wgrad_pw");
 }
 
 }  // extern "C"
