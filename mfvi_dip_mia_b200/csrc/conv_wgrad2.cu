@@ -30,7 +30,8 @@ constexpr int kThreads = 192;
 constexpr int kMaxCblk = 5;
 
 struct WArgs {
-  int Cout, Cin, K3;            // K3 = 1 for 3x3, 0 for 1x1
+  int Cout, Cin, K3;            // K3 = 1 for 3x3, 0 for 1x1;  Cout = the <= 32 output channels THIS launch covers
+  int Cout_total, co0;          // the layer's output channels and the first one of this launch (dw row = co0 + co)
   int n_cblk;
   int Ho, Wo;
   int TH, TW, Pw;
@@ -144,7 +145,7 @@ k_wgrad_alias(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ 
           // 3x3: tap (r = n, s = 2 - q), lanes of block q = 3 are ignored;  1x1: only the diagonal block n == q counts
           const bool use = p.K3 ? (q < 3) : (n == q);
           const int tap = p.K3 ? n * 3 + (2 - q) : 0;
-          float* dst = dws + (static_cast<size_t>(tap) * p.Cout + co) * p.Cin + c * 32;
+          float* dst = dws + (static_cast<size_t>(tap) * p.Cout_total + p.co0 + co) * p.Cin + c * 32;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             float v[16];
@@ -200,18 +201,18 @@ static bool encode_act(CUtensorMap* m, const MfviView& a, int C, int H, int W, i
 
 using namespace mfvi;
 
-extern "C" {
-
-// dw only (the bias gradient is left to the caller).  Returns -1 when the shape is not taken.
-int mfvi_conv2d_wgrad_tc2(const MfviConvDesc* d, MfviView x, MfviView dy, float* dw, long long w_sstride, mfvi_stream_t st) {
+// One launch: output channels [co0, co0 + Cout) of the layer, dy already sliced to them.
+static int wgrad_alias_launch(const MfviConvDesc* d_layer, int Cout, int co0, MfviView x, MfviView dy, float* dw, long long w_sstride,
+                              mfvi_stream_t st) {
   using namespace mfvi::tc3;
-  static const bool on = env_int("MFVI_WGRAD2", 1) != 0;
-  const bool k3 = d->KH == 3 && d->KW == 3, k1 = d->KH == 1 && d->KW == 1;
-  if (!on || d->stride != 1 || !(k3 || k1) || d->Cout > 32 || d->Cin > 32 * kMaxCblk || !view_ok(x, d->Cin) || !view_ok(dy, d->Cout) ||
-      (reinterpret_cast<uintptr_t>(dw) % 16) || (w_sstride % 4) || d->Cin % 4)
-    return -1;
+  MfviConvDesc dd = *d_layer;
+  dd.Cout = Cout;
+  const MfviConvDesc* d = &dd;
+  const bool k3 = d->KH == 3 && d->KW == 3;
+  if (!view_ok(dy, d->Cout)) return -1;
   WArgs a{};
   a.Cout = d->Cout; a.Cin = d->Cin; a.K3 = k3 ? 1 : 0;
+  a.Cout_total = d_layer->Cout; a.co0 = co0;
   a.n_cblk = cdiv(d->Cin, 32);
   a.Ho = d->Hout; a.Wo = d->Wout;
   const int BN = k3 ? 96 : 128;
@@ -224,12 +225,14 @@ int mfvi_conv2d_wgrad_tc2(const MfviConvDesc* d, MfviView x, MfviView dy, float*
   int strips = 1;
   while (cdiv(d->Wout, strips) + halo > 256 || (k3 && a.n_cblk > 1 && cdiv(d->Wout, strips) > 64) || cdiv(d->Wout, strips) > 128) ++strips;
   if (const int f = env_int("MFVI_WGRAD2_STRIPS", 0)) strips = f;
-  a.TW = cdiv(d->Wout, strips);
-  a.Pw = a.TW + halo;
-  a.tiles_w = cdiv(d->Wout, a.TW);
   a.n_stages = 2;
   const size_t budget = 190 * 1024;
   int best_th = 0;
+  for (;; ++strips) {              // narrower strips when even a one-row tile of 5 channel blocks exceeds the two-stage budget
+  a.TW = cdiv(d->Wout, strips);
+  a.Pw = a.TW + halo;
+  a.tiles_w = cdiv(d->Wout, a.TW);
+  best_th = 0;
   for (int TH = 1; TH <= std::min(d->Hout, k3 ? 8 : 64); ++TH) {
     if (a.TW > 256 || TH + halo > 256) break;
     int n_k, dy_rows, x_rows;
@@ -247,6 +250,8 @@ int mfvi_conv2d_wgrad_tc2(const MfviConvDesc* d, MfviView x, MfviView dy, float*
     const int tiles = d->S * cdiv(d->Hout, TH) * a.tiles_w;
     if (best_th > 0 && tiles < kNumSMs) break;
     best_th = TH;
+  }
+  if (best_th > 0 || strips >= 4 || a.TW <= 16) break;
   }
   if (const int f = env_int("MFVI_WGRAD2_TH", 0)) best_th = f;
   if (best_th == 0) return -1;
@@ -288,6 +293,32 @@ int mfvi_conv2d_wgrad_tc2(const MfviConvDesc* d, MfviView x, MfviView dy, float*
              a.stage_bytes, a.tmem_cols, a.tiles_per_cta);
   launch_k(k_wgrad_alias, d->S * a.ctas_per_sample, kThreads, smem, as_stream(st), tmDy, tmX, a);
   return check_launch("conv2d_wgrad_tc2");
+}
+
+extern "C" {
+
+// dw only (the bias gradient is left to the caller).  Returns -1 when the shape is not taken.  Layers with 64 output channels
+// (MFVI_WGRAD2_SPLIT = the largest number of 32-channel launches taken, default 2) run as one launch per 32 output channels
+// over channel slices of dy.
+int mfvi_conv2d_wgrad_tc2(const MfviConvDesc* d, MfviView x, MfviView dy, float* dw, long long w_sstride, mfvi_stream_t st) {
+  using namespace mfvi::tc3;
+  static const bool on = env_int("MFVI_WGRAD2", 1) != 0;
+  static const int max_parts = env_int("MFVI_WGRAD2_SPLIT", 2);
+  const bool k3 = d->KH == 3 && d->KW == 3, k1 = d->KH == 1 && d->KW == 1;
+  // more than one launch only where the per-tap kernel is the slow one: long contractions (Cin x taps >= 512) over >= 4096
+  // pixels of >= 4 samples (measured: 132->64 at 64^2, S = 8: 52.6 -> 41.2 us; with one sample per GPU the per-tap kernel wins)
+  const bool big = d->Hout * d->Wout >= 4096 && d->Cin * d->KH * d->KW >= 512 && d->S >= 4;
+  const int parts = d->Cout <= 32 ? 1 : ((d->Cout % 32 == 0 && big) ? d->Cout / 32 : 0);
+  if (!on || d->stride != 1 || !(k3 || k1) || parts < 1 || parts > max_parts || d->Cin > 32 * kMaxCblk || !view_ok(x, d->Cin) ||
+      (reinterpret_cast<uintptr_t>(dw) % 16) || (w_sstride % 4) || d->Cin % 4)
+    return -1;
+  for (int h = 0; h < parts; ++h) {
+    MfviView dyh = dy;
+    dyh.ptr = dy.ptr + 32 * h;
+    const int rc = wgrad_alias_launch(d, parts == 1 ? d->Cout : 32, 32 * h, x, dyh, dw, w_sstride, st);
+    if (rc != 0) return h == 0 ? rc : (rc < 0 ? 1 : rc);      // a later slice cannot be declined once the first one ran
+  }
+  return 0;
 }
 
 }  // extern "C"
