@@ -67,6 +67,19 @@ static inline cudaError_t launch_k(void (*kernel)(P...), dim3 grid, dim3 block, 
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
 }
 
+// cudaFuncSetAttribute applies to the CURRENT device only: `done_mask` (a static at the call site, one per kernel) remembers the
+// devices that already have it, so that a process driving several GPUs opts every one of them in.
+template <typename K>
+static inline cudaError_t allow_dyn_smem(K kernel, int bytes, unsigned long long* done_mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (*done_mask & bit) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) *done_mask |= bit;
+  return e;
+}
+
 constexpr int kNumSMs = 148;  // B200
 constexpr float kBnEps = 1e-5f;
 constexpr float kLreluSlope = 0.2f;

@@ -427,11 +427,10 @@ int mfvi_conv2d_wgrad_simt(const MfviConvDesc* d, MfviView x, MfviView dy, float
   a.vec = (view_vec4(x) && view_vec4(dy)) ? 1 : 0;
   int threads = T * (a.BCO / 4) * (a.BCI / 4);
   threads = std::max(64, (threads + 31) / 32 * 32);
-  static thread_local size_t attr_set = 0;
-  if (smem > 48 * 1024 && smem > attr_set && dry_run() == nullptr) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  static unsigned long long attr_done = 0;
+  if (smem > 48 * 1024 && dry_run() == nullptr) {
+    const cudaError_t e = allow_dyn_smem(k_conv_wgrad, 200 * 1024, &attr_done);
     MFVI_REQUIRE(e == cudaSuccess, "conv2d_wgrad: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
-    attr_set = 200 * 1024;
   }
   dim3 grid(chunks, tiles, d->S);
   if (dry_run() != nullptr) {

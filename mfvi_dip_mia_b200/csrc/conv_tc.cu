@@ -465,11 +465,10 @@ int mfvi_conv2d_fwd_tc(const MfviConvDesc* d, MfviView x, const float* w, const 
     if (!encode_map(&tmB, w, dims, strides, box, estr)) return -1;
   }
   const size_t smem = conv_smem_bytes(a.stages, a.b_bytes, a.BN);
-  static size_t attr = 0;
-  if (smem > attr && dry_run() == nullptr) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  static unsigned long long attr_done = 0;
+  if (dry_run() == nullptr) {
+    const cudaError_t e = allow_dyn_smem(k_conv_tc, 200 * 1024, &attr_done);
     MFVI_REQUIRE(e == cudaSuccess, "conv2d_fwd_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
-    attr = 200 * 1024;
   }
   const int tiles_h = (a.Mh + a.TH - 1) / a.TH;
   dim3 grid(a.tiles_w * tiles_h, 1, d->S);
@@ -514,11 +513,10 @@ int mfvi_conv2d_dgrad_tc(const MfviConvDesc* d, MfviView dy, const float* w, lon
     if (!encode_map(&tmB, w, dims, strides, box, estr, true)) return -1;
   }
   const size_t smem = conv_smem_bytes(a.stages, a.b_bytes, a.BN);
-  static size_t attr = 0;
-  if (smem > attr && dry_run() == nullptr) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  static unsigned long long attr_done = 0;
+  if (dry_run() == nullptr) {
+    const cudaError_t e = allow_dyn_smem(k_conv_tc, 200 * 1024, &attr_done);
     MFVI_REQUIRE(e == cudaSuccess, "conv2d_dgrad_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
-    attr = 200 * 1024;
   }
   const int tiles_h = (a.Mh + a.TH - 1) / a.TH;
   dim3 grid(a.tiles_w * tiles_h, d->stride == 2 ? 4 : 1, d->S);
@@ -597,11 +595,10 @@ static int wgrad_tc_launch(const MfviConvDesc* d, MfviView x, MfviView dy, float
   if (!map_activation(&tmX, x, d->Cin, d->Hin, d->Win, d->S, TH, TW, xb, true, d->stride, bf16)) return -1;
   a.x_bcast = xb ? 1 : 0;
   const size_t smem = 1024 + static_cast<size_t>(a.stages) * (a_blocks + a.NB) * TP * 128 + 18 * 8 + 64;
-  static size_t attr = 0;
-  if (smem > attr && dry_run() == nullptr) {
-    cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  static unsigned long long attr_done = 0;
+  if (dry_run() == nullptr) {
+    const cudaError_t e = allow_dyn_smem(k_wgrad_tc<false>, 220 * 1024, &attr_done);
     MFVI_REQUIRE(e == cudaSuccess, "conv2d_wgrad_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
-    attr = 220 * 1024;
   }
   MFVI_REQUIRE(smem <= 220 * 1024, "conv2d_wgrad_tc: stage does not fit in shared memory");
   dim3 grid(chunks, taps, Sz);

@@ -681,12 +681,11 @@ static int launch(const MfviConvDesc* d, bool dgrad, MfviView a, int Ca, int Ha,
     tmA = tmAt;
     tmB = tmBt;
   }
-  static size_t attr = 0;
-  if (pl.smem > attr && dry_run() == nullptr) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_halo<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_halo<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  static unsigned long long attr_done[2] = {0, 0};
+  if (dry_run() == nullptr) {
+    cudaError_t e = allow_dyn_smem(k_conv_halo<false>, 200 * 1024, &attr_done[0]);
+    if (e == cudaSuccess) e = allow_dyn_smem(k_conv_halo<true>, 200 * 1024, &attr_done[1]);
     MFVI_REQUIRE(e == cudaSuccess, "%s: cannot raise dynamic shared memory: %s", what, cudaGetErrorString(e));
-    attr = 200 * 1024;
   }
   if (env_int("MFVI_TC2_VERBOSE", 0))
     fprintf(stderr, "[tc2] %s Kc=%d N=%d k%d M=%dx%d S=%d: TH=%d TW=%d Pw=%d n_mt=%d BN=%d nb=%d g=%d acc_stages=%d smem=%zu grid=%d tiles=%d\n",

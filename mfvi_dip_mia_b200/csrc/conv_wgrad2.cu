@@ -279,11 +279,10 @@ static int wgrad_alias_launch(const MfviConvDesc* d_layer, int Cout, int co0, Mf
   if (!encode_act(&tmDy, dy, d->Cout, d->Hout, d->Wout, d->S, d->S == 1, a.TW, k3 ? 1 : a.TH)) return -1;
   if (!encode_act(&tmX, x, d->Cin, d->Hin, d->Win, d->S, a.x_bcast != 0, a.Pw, a.TH + halo)) return -1;
   const size_t smem = 1024 + static_cast<size_t>(a.n_stages) * a.stage_bytes + 256;
-  static size_t attr = 0;
-  if (smem > attr && dry_run() == nullptr) {
-    cudaError_t e = cudaFuncSetAttribute(k_wgrad_alias, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  static unsigned long long attr_done = 0;
+  if (dry_run() == nullptr) {
+    const cudaError_t e = allow_dyn_smem(k_wgrad_alias, 200 * 1024, &attr_done);
     MFVI_REQUIRE(e == cudaSuccess, "conv2d_wgrad_tc2: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
-    attr = 200 * 1024;
   }
   MFVI_REQUIRE(smem <= 200 * 1024, "conv2d_wgrad_tc2: stage does not fit in shared memory");
   if (env_int("MFVI_TC2_VERBOSE", 0))

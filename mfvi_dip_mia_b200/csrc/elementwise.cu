@@ -158,12 +158,7 @@ using namespace mfvi;
 // dynamic shared memory (the cp.async slots) is first allowed to exceed the 48 KB default together with its static arrays
 template <typename K>
 static void ew_allow_smem(K kernel, size_t dyn_smem, unsigned long long* done_mask) {      // once per device and kernel
-  int dev = 0;
-  cudaGetDevice(&dev);
-  const unsigned long long bit = 1ull << (dev & 63);
-  if (*done_mask & bit) return;
-  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn_smem));
-  *done_mask |= bit;
+  allow_dyn_smem(kernel, static_cast<int>(dyn_smem), done_mask);
 }
 template <typename K>
 static int ew_occupancy_of(K kernel, size_t dyn_smem = 0) {

@@ -649,12 +649,11 @@ int launch_conv_mma(int op, const MfviConvDesc* d, MfviView act_in, MfviView act
   fill_conv(&s, op, d, act_in, act_out, w, bias, w_sstride, dw, stats, accumulate, 2 * kNumSMs);
   const int per_s = s.items / d->S;
   if (per_s < 1 || per_s > 65535 * 32) return -1;
-  static bool attr_set = false;
-  if (!attr_set && dry_run() == nullptr) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kStages * 2 * kOpFloats * 4));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kStages * 2 * kOpFloats * 4));
+  static unsigned long long attr_done[2] = {0, 0};
+  if (dry_run() == nullptr) {
+    cudaError_t e = allow_dyn_smem(k_conv_mma<true>, (int)(kStages * 2 * kOpFloats * 4), &attr_done[0]);
+    if (e == cudaSuccess) e = allow_dyn_smem(k_conv_mma<false>, (int)(kStages * 2 * kOpFloats * 4), &attr_done[1]);
     MFVI_REQUIRE(e == cudaSuccess, "%s: cannot raise dynamic shared memory: %s", what, cudaGetErrorString(e));
-    attr_set = true;
   }
   const size_t smem = static_cast<size_t>(kStages) * 2 * kOpFloats * sizeof(float);
   const dim3 grid(std::min(per_s, 4 * kNumSMs), d->S);
@@ -714,11 +713,10 @@ int mfvi_mega_end(void* program_dev, size_t capacity_bytes, int* n_stages) {
 int mfvi_mega_run(const void* program_dev, int n_stages, int S, long long* stage_times, mfvi_stream_t st) {
   MFVI_REQUIRE(program_dev != nullptr && n_stages >= 1 && S >= 1, "mega_run: null program / no samples");
   const size_t smem = std::max(mega::kEwSmemBytes, mega::kConvSmemBytes);
-  static bool attr_set = false;
-  if (!attr_set) {
-    const cudaError_t e = cudaFuncSetAttribute(mega::k_mega, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static unsigned long long attr_done = 0;
+  {
+    const cudaError_t e = allow_dyn_smem(mega::k_mega, (int)smem, &attr_done);
     MFVI_REQUIRE(e == cudaSuccess, "mega_run: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
-    attr_set = true;
   }
   const int clusters = std::min(S, 16);
   cudaLaunchConfig_t cfg = {};

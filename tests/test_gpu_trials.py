@@ -45,3 +45,16 @@ def test_trials_on_persistent_workers_match_per_trial_processes():
     assert all(math.isfinite(v) and 5.0 < v < 40.0 for v in Y), Y
     X1, Y1 = eval_trials(cands[:2], devices, _den_trial, {"poison": True}, max_parallel=max(2, len(devices)))
     assert X1 == cands[:2] and all(abs(a - b) < 0.5 for a, b in zip(Y[:2], Y1)), (Y, Y1)
+
+
+def test_one_process_drives_two_devices():
+    """Engines on cuda:0 and cuda:1 in ONE process: every entry point makes its device current, and the kernels' opt-in to
+    large dynamic shared memory is taken per device (cudaFuncSetAttribute applies to the current device only)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    c = (5.6e-7, 1.5e-5)
+    a = _den_trial(*c, "cuda:0")
+    b = _den_trial(*c, "cuda:1")
+    a2 = _den_trial(*c, "cuda:0")
+    assert all(math.isfinite(v) and 5.0 < v < 40.0 for v in (a, b, a2)), (a, b, a2)
+    assert abs(a - b) < 0.5 and abs(a - a2) < 0.5, (a, b, a2)
