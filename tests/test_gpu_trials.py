@@ -49,12 +49,31 @@ def test_trials_on_persistent_workers_match_per_trial_processes():
 
 def test_one_process_drives_two_devices():
     """Engines on cuda:0 and cuda:1 in ONE process: every entry point makes its device current, and the kernels' opt-in to
-    large dynamic shared memory is taken per device (cudaFuncSetAttribute applies to the current device only)."""
+    large dynamic shared memory is taken per device (cudaFuncSetAttribute applies to the current device only).  The same
+    seeded step on the two devices agrees to summation order (fp32 / double atomics, which the BatchNorm chain amplifies in the
+    gradient — measured 2.4e-3 relative L2 after three steps): loss terms to 1e-5, gradient to 1e-2, parameters to 1e-4."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
-    c = (5.6e-7, 1.5e-5)
-    a = _den_trial(*c, "cuda:0")
-    b = _den_trial(*c, "cuda:1")
-    a2 = _den_trial(*c, "cuda:0")
-    assert all(math.isfinite(v) and 5.0 < v < 40.0 for v in (a, b, a2)), (a, b, a2)
-    assert abs(a - b) < 0.5 and abs(a - a2) < 0.5, (a, b, a2)
+    import numpy as np
+    from mfvi_dip_mia_b200 import MfviDipTrainer, SkipSpec, _lib as L
+    from mfvi_dip_mia_b200.utils.common_utils import get_noise
+    from mfvi_dip_mia_b200.utils.phantoms import ellipse_phantom
+    img = ellipse_phantom(64)
+    res = []
+    for dev in ("cuda:0", "cuda:1", "cuda:0"):
+        np.random.seed(3)
+        torch.manual_seed(3)
+        noisy = np.clip(img + np.random.normal(scale=0.1, size=img.shape), 0, 1).astype(np.float32)
+        spec = SkipSpec(16, 2)
+        tr = MfviDipTrainer(spec, "den", get_noise(spec.num_input_channels, 'noise', (64, 64)), temp=1e-6, sigma=0.1, lr=1e-3,
+                            mc_samples=2, seed=3, reg_noise_std=0.1, device=torch.device(dev), target=torch.from_numpy(noisy)[None],
+                            math_mode=L.MATH_TF32)
+        tr.step()
+        torch.cuda.synchronize(torch.device(dev))
+        nll, kl, _ = tr.loss_terms()
+        res.append((float(nll), float(kl), tr.eng.grad.detach().double().cpu(), tr.eng.theta.detach().double().cpu()))
+    for other in (res[1], res[2]):
+        assert abs(other[0] - res[0][0]) <= 1e-5 * abs(res[0][0]) and abs(other[1] - res[0][1]) <= 1e-5 * abs(res[0][1]), (other[:2], res[0][:2])
+        for k, bar in ((2, 1e-2), (3, 1e-4)):
+            rel = float((other[k] - res[0][k]).norm() / res[0][k].norm())
+            assert rel < bar, (k, rel)
