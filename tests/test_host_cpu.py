@@ -351,6 +351,26 @@ def test_conv_dispatch_table_of_the_task_networks(task, S):
     assert len(rows32) == len(rows) and {r["family"] for r in rows32} == {"simt"}
 
 
+def test_weight_gradient_families_of_the_metric_net():
+    """Round-2 dispatch of the weight gradients: the 1x1 layers with <= 4 output channels take the
+    pointwise streaming kernel (weight and bias gradient in ONE launch, also for the last layer), and 132->64 at 64^2 runs
+    on the alias kernel as two 32-channel launches with 8 samples per GPU but stays on the per-tap kernel with one."""
+    from mfvi_dip_mia_b200 import SkipEngine, SkipSpec, _lib as L
+    kw, H = _TASK_NETS["den"]
+    by_s = {}
+    for S in (8, 1):
+        eng = SkipEngine(SkipSpec(**kw), H, H, S, "meta", math=L.MATH_TF32)
+        by_s[S] = {r["layer"]: r for r in eng.conv_dispatch_table() if r["op"] == "wgrad"}
+    for S, rows in by_s.items():
+        for name, r in rows.items():
+            if r["K"] == 1 and r["Cout"] <= 4 and r["Cin"] <= 32:
+                assert r["family"] == "pointwise" and r["launches"] == 1, (S, name, r["family"], r["launches"])
+        assert rows["Conv2d_up_11"]["family"] == "pointwise" and rows["Conv2d_skip_1"]["family"] == "pointwise"
+    assert by_s[8]["Conv2d_up_5"]["family"] == "alias" and by_s[8]["Conv2d_up_5"]["launches"] == 2
+    assert by_s[1]["Conv2d_up_5"]["family"] == "tc" and by_s[1]["Conv2d_up_5"]["launches"] == 1
+    assert by_s[8]["Conv2d_up_7"]["family"] == "alias" and by_s[8]["Conv2d_up_7"]["launches"] == 1
+
+
 def test_plan_only_engine_cannot_execute():
     from mfvi_dip_mia_b200 import SkipEngine, SkipSpec, _lib as L
     eng = SkipEngine(SkipSpec(), 64, 64, 2, "meta")
