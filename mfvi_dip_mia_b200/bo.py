@@ -222,41 +222,34 @@ def bo(trial_fn: Callable[..., float], bo_params: Dict[str, Dict[str, Sequence[f
     Y: List[float] = []
     pool = TrialPool(devices, trial_fn, run_params, start_method=start_method) if persistent else None
     try:
-        return _bo_rounds(pool, rounds, candidates, devices, trial_fn, run_params, start_method, verbose, bo_params, X, Y,
-                          p1_logbounds, p2_logbounds, gp_iters, X_test, XX_lr, XX_wd, out_path)
+        for r in range(rounds):
+            if pool is not None:
+                cl = [tuple(c) for c in candidates]
+                cands_run, y_run = _finite(cl, pool.run(cl))
+            else:
+                cands_run, y_run = eval_trials(candidates, devices, trial_fn, run_params, start_method=start_method)
+            if verbose:
+                names = list(bo_params.keys())
+                print(f"\n{names[0]}      {names[1]}       psnr")
+                for c, y in zip(cands_run, y_run):
+                    print(f"{c[0]:.6g}  {c[1]:.6g}  {y:.6f}")
+            X += [tuple(c) for c in cands_run]
+            Y += list(y_run)
+            X_train = normalize_X(torch.tensor(np.array(X), dtype=torch.double), p1_logbounds, p2_logbounds)
+            Y_train = torch.tensor(np.array(Y), dtype=torch.double)
+            gp = train_gp(X_train, Y_train, iter_max=gp_iters, verbose=False)
+            cands, exp_imp, acq = find_candidates(gp, X_test, X_train)
+            cands = torch.unique(torch.cat(cands), dim=0)
+            cand_np = unnormalize_X(cands, p1_logbounds, p2_logbounds).numpy()
+            with torch.no_grad():
+                mean, _ = gp.predict(X_test)
+                lo, hi = gp.confidence_region(X_test)
+            np.savez(os.path.join(out_path, f"{r}_fig_data.npz"), XX_lr=XX_lr.numpy(), XX_wd=XX_wd.numpy(),
+                     pred=mean.reshape(100, 100).numpy(), observed_X=np.array(X), observed_Y=np.array(Y),
+                     expected_improvement=np.array(exp_imp), confidence=(hi - lo).reshape(100, 100).numpy(),
+                     acq=acq.reshape(100, 100), candidates=cand_np)
+            candidates = [tuple(float(v) for v in c) for c in cand_np]
     finally:
         if pool is not None:
             pool.close()
-
-
-def _bo_rounds(pool, rounds, candidates, devices, trial_fn, run_params, start_method, verbose, bo_params, X, Y, p1_logbounds,
-               p2_logbounds, gp_iters, X_test, XX_lr, XX_wd, out_path):
-    from .runners import _finite, eval_trials
-    for r in range(rounds):
-        if pool is not None:
-            cl = [tuple(c) for c in candidates]
-            cands_run, y_run = _finite(cl, pool.run(cl))
-        else:
-            cands_run, y_run = eval_trials(candidates, devices, trial_fn, run_params, start_method=start_method)
-        if verbose:
-            names = list(bo_params.keys())
-            print(f"\n{names[0]}      {names[1]}       psnr")
-            for c, y in zip(cands_run, y_run):
-                print(f"{c[0]:.6g}  {c[1]:.6g}  {y:.6f}")
-        X += [tuple(c) for c in cands_run]
-        Y += list(y_run)
-        X_train = normalize_X(torch.tensor(np.array(X), dtype=torch.double), p1_logbounds, p2_logbounds)
-        Y_train = torch.tensor(np.array(Y), dtype=torch.double)
-        gp = train_gp(X_train, Y_train, iter_max=gp_iters, verbose=False)
-        cands, exp_imp, acq = find_candidates(gp, X_test, X_train)
-        cands = torch.unique(torch.cat(cands), dim=0)
-        cand_np = unnormalize_X(cands, p1_logbounds, p2_logbounds).numpy()
-        with torch.no_grad():
-            mean, _ = gp.predict(X_test)
-            lo, hi = gp.confidence_region(X_test)
-        np.savez(os.path.join(out_path, f"{r}_fig_data.npz"), XX_lr=XX_lr.numpy(), XX_wd=XX_wd.numpy(),
-                 pred=mean.reshape(100, 100).numpy(), observed_X=np.array(X), observed_Y=np.array(Y),
-                 expected_improvement=np.array(exp_imp), confidence=(hi - lo).reshape(100, 100).numpy(),
-                 acq=acq.reshape(100, 100), candidates=cand_np)
-        candidates = [tuple(float(v) for v in c) for c in cand_np]
     return X, Y
